@@ -1,0 +1,174 @@
+/*
+ * kintinuous_b200 -- C ABI of the B200-native dense tracking-and-fusion hot path.
+ *
+ * This header is the drop-in boundary: plain pointers and sizes, no torch /
+ * Eigen / OpenCV / PCL types.  Each entry point names the reference interface it replaces
+ * (paths relative to mp3guy/Kintinuous, src/frontend/).  The source-compatible C++ shim that
+ * re-creates the reference class / free-function names on top of this ABI is
+ * include/kintinuous_b200_shim.hpp; INTEGRATION.md shows how a maintainer wires it in.
+ *
+ * Conventions
+ *   - every function returns KT_OK (0) or a negative kt_status; kt_last_error() gives the text.
+ *     The reference's cudaSafeCall prints and exit(0)s (cuda/internal.h:76-86); this ABI never exits.
+ *   - "dev" pointers are device pointers on the context's GPU, images are compact row-major
+ *     (pitch = cols * sizeof(T)); vertex / normal maps are the reference's SoA layout: three float
+ *     planes x,y,z stacked vertically, 3*rows x cols (KintinuousTracker.cpp:373-377).
+ *   - Mat33 arguments are 9 floats row-major (Eigen::Matrix<float,3,3,RowMajor>, device_cast<Mat33>,
+ *     cuda/internal.h:481-485); float3 arguments are 3 floats; Intr is {fx, fy, cx, cy}.
+ *   - stream arguments are cudaStream_t passed as void* (NULL = the context's / default stream).
+ *   - there is NO CPU fallback: without a CUDA device every call fails with KT_ERR_CUDA.
+ */
+#ifndef KINTINUOUS_B200_H_
+#define KINTINUOUS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define KT_API __attribute__((visibility("default")))
+#else
+#define KT_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum kt_status {
+    KT_OK = 0,
+    KT_ERR_INVALID = -1,   /* bad argument / unsupported configuration */
+    KT_ERR_CUDA = -2,      /* CUDA runtime error (text in kt_last_error) */
+    KT_ERR_STATE = -3,     /* call out of order */
+    KT_ERR_CAPACITY = -4   /* output buffer too small */
+} kt_status;
+
+/* Replaces: the ConfigArgs flags the path reads (utils/ConfigArgs.h:111-185), Volume / Resolution
+ * singletons (Volume.h:26-57, Resolution.h:23-69), the cv::Mat K of KintinuousTracker(cv::Mat*)
+ * (KintinuousTracker.cpp:71-91) and the compile-time VOL macro (cuda/internal.h:243). */
+typedef struct kt_config {
+    int rows, cols;          /* Resolution (480 x 640) */
+    float fx, fy, cx, cy;    /* depth intrinsics (MainController.cpp:222-227) */
+    int vol;                 /* voxels per side; runtime here, '#define VOL 512' in the reference */
+    float volume_size;       /* metres, -s (default 6) */
+    int odometry;            /* 0 = ICP (default), 1 = RGB-D (-r), 2 = ICP + RGB-D (-ri) */
+    int fast_odometry;       /* -fod */
+    int voxel_shift;         /* -t (default 14) */
+    int overlap;             /* setOverlap (TrackerInterface.h:58, default 2) */
+    int angle_color;         /* !disableColorAngleWeight (-dc) */
+    int parked;              /* setParked / static mode: never shift */
+    int cloud_capacity;      /* slice point buffer; 0 = 3*rows*cols (KintinuousTracker.cpp:77) */
+    int device;              /* CUDA device ordinal (-gpu) */
+    /* multi-GPU z-slab sharding (no counterpart in the reference) */
+    int rank, world;         /* this process' rank / number of ranks sharing ONE volume (1 = single GPU) */
+} kt_config;
+
+typedef struct kt_pose {
+    float R[9];              /* camera -> volume rotation, row-major (rmats_.back()) */
+    float t[3];              /* camera position in the volume frame, metres (tvecs_.back()) */
+    float global_t[3];       /* currentGlobalCamera (KintinuousTracker.cpp:581-596) */
+    int voxel_wrap[3];       /* signed accumulated wrap (voxelWrap) */
+    int shifted;             /* number of CloudSlices produced by this frame */
+    int frame;               /* global_time_ after the frame */
+} kt_pose;
+
+/* 32-byte point, byte-compatible with pcl::PointXYZRGB / cuda/internal.h:156-184 */
+typedef struct kt_point_xyzrgb {
+    float x, y, z, _pad0;
+    uint8_t b, g, r, a;
+    uint8_t _pad1[12];
+} kt_point_xyzrgb;
+
+typedef struct kt_ctx kt_ctx;
+
+KT_API const char* kt_last_error(void);
+/* 1 when the library was built with the sm_100a kernels and a CUDA device is usable. */
+KT_API int kt_cuda_available(void);
+
+/* ---- tracker: replaces class KintinuousTracker (KintinuousTracker.h:85-172) ---- */
+KT_API int kt_create(const kt_config* cfg, kt_ctx** out);                 /* KintinuousTracker::KintinuousTracker (.cpp:71-182) */
+KT_API int kt_destroy(kt_ctx* ctx);                                       /* ~KintinuousTracker (.cpp:184-197) */
+KT_API int kt_reset(kt_ctx* ctx);                                         /* KintinuousTracker::reset (.cpp:262-354) */
+/* KintinuousTracker::processFrame (.cpp:444-915) together with the upload its caller does
+ * (backend/TrackerInterface.cpp:90-91).  depth: rows*cols u16 mm; rgb: rows*cols*3 u8 (PixelRGB r,g,b).
+ * Host buffers (pinned memory from kt_alloc_pinned makes the copy asynchronous). */
+KT_API int kt_process_frame(kt_ctx* ctx, const uint16_t* depth_host, const uint8_t* rgb_host, uint64_t utime, kt_pose* out);
+/* Same, inputs already resident in device memory (DeviceArray2D arguments of processFrame). */
+KT_API int kt_process_frame_device(kt_ctx* ctx, const uint16_t* depth_dev, const uint8_t* rgb_dev, uint64_t utime, kt_pose* out);
+KT_API int kt_finalise(kt_ctx* ctx);                                      /* KintinuousTracker::finalise (.cpp:1003-1048) */
+KT_API int kt_get_pose(kt_ctx* ctx, kt_pose* out);                        /* getLastRotation/getLastTranslation/getVolumeOffset */
+KT_API float kt_get_voxel_size(kt_ctx* ctx);                              /* getVoxelSize */
+KT_API float kt_get_trunc_dist(kt_ctx* ctx);                              /* TsdfVolume::getTsdfTruncDist (TSDFVolume.cpp:125-129) */
+KT_API int kt_set_overlap(kt_ctx* ctx, int overlap);                      /* setOverlap */
+KT_API int kt_set_parked(kt_ctx* ctx, int parked);                        /* setParked */
+/* getCloudSlices (.cpp:1055-1058): slices stay owned by the context until kt_reset / kt_destroy. */
+KT_API int kt_num_slices(kt_ctx* ctx);
+/* Copies up to max_points points of slice idx; *count = the slice's size; dimension = CloudSlice::Dimension
+ * (CloudSlice.h:33-44: XPlus..ZMinus, FIRST, FINAL, TSDF); camera_t = 3 floats, may be NULL. */
+KT_API int kt_get_slice(kt_ctx* ctx, int idx, kt_point_xyzrgb* points, size_t max_points, size_t* count, int* dimension, float* camera_t);
+/* Per-iteration normal equations of the last frame, n x 44 floats (A 6x6 row-major, b 6, residual, inliers):
+ * what icpStep / rgbStep hand back to the host each iteration (cuda/reduce.cu:404-418). */
+KT_API int kt_get_trace(kt_ctx* ctx, float* dst, int max_iters, int* n_iters);
+/* TsdfVolume::data() / ColorVolume::data() in the reference layout: short[V^3], uchar4[V^3], x fastest,
+ * storage (cyclic) order.  Either pointer may be NULL.  (TSDFVolume.h:154, ColorVolume.h:93) */
+KT_API int kt_volume_export_reference_layout(kt_ctx* ctx, int16_t* tsdf_host, uint8_t* color_host);
+/* which: 0 vmap_curr, 1 nmap_curr, 2 vmap_g_prev, 3 nmap_g_prev (3*rows_l*cols_l floats), 4 depth_curr (u16),
+ * 5 raycast colour (uchar4, level 0).  Test / GUI tap (getLiveImage inputs). */
+KT_API int kt_download_map(kt_ctx* ctx, int which, int level, void* dst_host);
+/* Stage timers (CUDA events) of the last frame, milliseconds: pyramid, odometry, shift, integrate, raycast, total. */
+KT_API int kt_get_stage_ms(kt_ctx* ctx, float* ms6);
+KT_API int kt_set_stage_timing(kt_ctx* ctx, int enabled);
+/* number of kernels this library launched since kt_create (for bench.py's gpu_launches) */
+KT_API long long kt_launch_count(kt_ctx* ctx);
+KT_API int kt_alloc_pinned(void** ptr, size_t bytes);
+KT_API int kt_free_pinned(void* ptr);
+
+/* ---- operators: one per free function of cuda/internal.h:299-536 ---- */
+KT_API int kt_op_bilateral(const uint16_t* src_dev, uint16_t* dst_dev, int rows, int cols, void* stream);                    /* bilateralFilter (bilateral_pyrdown.cu:333) */
+KT_API int kt_op_pyrdown(const uint16_t* src_dev, uint16_t* dst_dev, int src_rows, int src_cols, void* stream);             /* pyrDown (:345) */
+KT_API int kt_op_create_vmap(const float* intr4, const uint16_t* depth_dev, float* vmap_dev, int rows, int cols, void* stream);   /* createVMap (maps.cu:123) */
+KT_API int kt_op_create_nmap(const float* vmap_dev, float* nmap_dev, int rows, int cols, void* stream);                     /* createNMap (maps.cu:140) */
+/* fused createVMap + createNMap for one level (the product's own path) */
+KT_API int kt_op_create_maps(const float* intr4, const uint16_t* depth_dev, float* vmap_dev, float* nmap_dev, int rows, int cols, void* stream);
+KT_API int kt_op_transform_maps(const float* vmap_src, const float* nmap_src, const float* R9, const float* t3,
+                         float* vmap_dst, float* nmap_dst, int rows, int cols, void* stream);                        /* tranformMaps (maps.cu:204) */
+KT_API int kt_op_resize_vmap(const float* in_dev, float* out_dev, int in_rows, int in_cols, void* stream);                  /* resizeVMap (maps.cu:299) */
+KT_API int kt_op_resize_nmap(const float* in_dev, float* out_dev, int in_rows, int in_cols, void* stream);                  /* resizeNMap (maps.cu:305) */
+/* icpStep (reduce.cu:347-419): one normal-equation build; A_host 36, b_host 6, residual_host 2 floats. */
+KT_API int kt_op_icp_step(const float* Rcurr9, const float* tcurr3, const float* vmap_curr, const float* nmap_curr,
+                   const float* Rprev_inv9, const float* tprev3, const float* intr4,
+                   const float* vmap_g_prev, const float* nmap_g_prev, int rows, int cols,
+                   float dist_thres, float angle_thres, float* A_host, float* b_host, float* residual_host, void* stream);
+/* integrateTsdfVolume (tsdf_volume.cu:643-674): scaleDepth + tsdf23. tsdf: short[vol^3], color: uchar4[vol^3]. */
+KT_API int kt_op_integrate(const uint16_t* depth_raw_dev, int rows, int cols, const float* intr4, const float* volume_size3,
+                    const float* Rcurr_inv9, const float* tcurr3, float trunc_dist, int16_t* tsdf_dev, uint8_t* color_dev, int vol,
+                    const int* voxel_wrap3, const uint8_t* rgb_dev, const float* nmap_curr_dev, int angle_color,
+                    float* depth_scaled_dev, void* stream);
+/* raycast (ray_caster.cu:434-471) */
+KT_API int kt_op_raycast(const float* intr4, const float* Rcurr9, const float* tcurr3, float trunc_dist, const float* volume_size3,
+                  const int16_t* tsdf_dev, int vol, float* vmap_dev, float* nmap_dev, int rows, int cols,
+                  const int* voxel_wrap3, uint8_t* vmap_color_dev, const uint8_t* color_dev, void* stream);
+/* extractCloudSlice (extract.cu:325-419); *count = points written (<= capacity). Point order is unspecified. */
+KT_API int kt_op_extract_slice(const int16_t* tsdf_dev, const float* volume_size3, int vol, kt_point_xyzrgb* out_dev, size_t capacity,
+                        const int* voxel_wrap3, const uint8_t* color_dev, int minX, int maxX, int minY, int maxY, int minZ, int maxZ,
+                        int subsample, const int* real_voxel_wrap3, size_t* count, void* stream);
+/* clearVolume{X,Y,Z}[Back] + ...c on both volumes (tsdf_volume.cu:117-448). axis 0..2, back 0/1. */
+KT_API int kt_op_clear_volume(int axis, int back, int16_t* tsdf_dev, uint8_t* color_dev, int vol, int current_wrap, int delta_wrap, void* stream);
+/* initVolume + initColorVolume (tsdf_volume.cu:469, :77) */
+KT_API int kt_op_init_volume(int16_t* tsdf_dev, uint8_t* color_dev, int vol, void* stream);
+/* RGB-D odometry operators (bilateral_pyrdown.cu:300-420, maps.cu:331, reduce.cu:555,798) */
+KT_API int kt_op_short_depth_to_metres(const uint16_t* src_dev, float* dst_dev, int rows, int cols, int cut_off, void* stream);
+KT_API int kt_op_pyrdown_gauss_f(const float* src_dev, float* dst_dev, int src_rows, int src_cols, void* stream);
+KT_API int kt_op_bgr_to_intensity(const uint8_t* rgb_dev, uint8_t* dst_dev, int rows, int cols, void* stream);
+KT_API int kt_op_pyrdown_uchar_gauss(const uint8_t* src_dev, uint8_t* dst_dev, int src_rows, int src_cols, void* stream);
+KT_API int kt_op_derivative_images(const uint8_t* src_dev, int16_t* dx_dev, int16_t* dy_dev, int rows, int cols, void* stream);
+KT_API int kt_op_project_to_point_cloud(const float* depth_dev, float* cloud_dev, int rows, int cols, const double* intr4, int level, void* stream);
+KT_API int kt_op_rgb_residual(float min_scale, const int16_t* dIdx, const int16_t* dIdy, const float* last_depth, const float* next_depth,
+                       const uint8_t* last_image, const uint8_t* next_image, void* corres_dev, int rows, int cols,
+                       float max_depth_delta, const float* kt3, const float* krkinv9, int* sigma_sum, int* count, void* stream);
+KT_API int kt_op_rgb_step(const void* corres_dev, float sigma, const float* cloud_dev, float fx, float fy, const int16_t* dIdx, const int16_t* dIdy,
+                   float sobel_scale, int rows, int cols, float* A_host, float* b_host, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KINTINUOUS_B200_H_ */

@@ -1,0 +1,293 @@
+"""ctypes binding of include/kintinuous_b200.h (the drop-in C ABI)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class KtError(RuntimeError):
+    pass
+
+
+def lib_path() -> str:
+    return os.path.join(_HERE, "libkintinuous_b200.so")
+
+
+def load():
+    """Load the CUDA library; raises (loudly) if it was not built -- there is no fallback path."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    p = lib_path()
+    if not os.path.exists(p):
+        raise KtError(f"{p} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                      f"(or make -C kintinuous_b200/csrc); kintinuous_b200 has no CPU fallback")
+    lib = C.CDLL(p)
+    lib.kt_last_error.restype = C.c_char_p
+    lib.kt_get_voxel_size.restype = C.c_float
+    lib.kt_get_trunc_dist.restype = C.c_float
+    lib.kt_launch_count.restype = C.c_longlong
+    _LIB = lib
+    return lib
+
+
+def cuda_available() -> bool:
+    return bool(load().kt_cuda_available())
+
+
+def _check(status: int):
+    if status != 0:
+        raise KtError(f"kintinuous_b200 error {status}: {load().kt_last_error().decode()}")
+
+
+class Config(C.Structure):
+    """kt_config (include/kintinuous_b200.h)."""
+    _fields_ = [("rows", C.c_int), ("cols", C.c_int),
+                ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
+                ("vol", C.c_int), ("volume_size", C.c_float),
+                ("odometry", C.c_int), ("fast_odometry", C.c_int), ("voxel_shift", C.c_int), ("overlap", C.c_int),
+                ("angle_color", C.c_int), ("parked", C.c_int), ("cloud_capacity", C.c_int), ("device", C.c_int),
+                ("rank", C.c_int), ("world", C.c_int)]
+
+    @staticmethod
+    def default(rows=480, cols=640, vol=512, volume_size=6.0, odometry=0, **kw):
+        from . import synth
+        fx, fy, cx, cy = synth.intrinsics(cols, rows)
+        c = Config(rows=rows, cols=cols, fx=fx, fy=fy, cx=cx, cy=cy, vol=vol, volume_size=volume_size, odometry=odometry,
+                   fast_odometry=0, voxel_shift=14, overlap=2, angle_color=1, parked=0, cloud_capacity=0, device=0, rank=0, world=1)
+        for k, v in kw.items():
+            setattr(c, k, v)
+        return c
+
+
+class Pose(C.Structure):
+    _fields_ = [("R", C.c_float * 9), ("t", C.c_float * 3), ("global_t", C.c_float * 3), ("voxel_wrap", C.c_int * 3),
+                ("shifted", C.c_int), ("frame", C.c_int)]
+
+    def as_tuple(self):
+        return (np.array(self.R, dtype=np.float32).reshape(3, 3), np.array(self.t, dtype=np.float32),
+                np.array(self.global_t, dtype=np.float32), np.array(self.voxel_wrap, dtype=np.int32))
+
+
+POINT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("_p0", "<f4"),
+                        ("b", "u1"), ("g", "u1"), ("r", "u1"), ("a", "u1"), ("_p1", "u1", (12,))])
+assert POINT_DTYPE.itemsize == 32
+
+
+def _ptr(a):
+    """Device pointer of a torch tensor / int, host pointer of a numpy array."""
+    if a is None:
+        return C.c_void_p(0)
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    return C.c_void_p(a.data_ptr())
+
+
+def _f(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float32).reshape(-1))
+
+
+class Tracker:
+    """Mirror of the reference's KintinuousTracker (KintinuousTracker.h:85-172) over the C ABI."""
+
+    def __init__(self, cfg: Config):
+        self.lib = load()
+        self.cfg = cfg
+        self.h = C.c_void_p()
+        _check(self.lib.kt_create(C.byref(cfg), C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            self.lib.kt_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self):
+        _check(self.lib.kt_reset(self.h))
+
+    def process_frame(self, depth: np.ndarray, rgb: np.ndarray, utime: int = 0) -> Pose:
+        """processFrame with HOST buffers (numpy, or raw pinned pointers as ints)."""
+        p = Pose()
+        _check(self.lib.kt_process_frame(self.h, _ptr(depth), _ptr(rgb), C.c_uint64(utime), C.byref(p)))
+        return p
+
+    def process_frame_device(self, depth_dev, rgb_dev, utime: int = 0) -> Pose:
+        p = Pose()
+        _check(self.lib.kt_process_frame_device(self.h, _ptr(depth_dev), _ptr(rgb_dev), C.c_uint64(utime), C.byref(p)))
+        return p
+
+    def finalise(self):
+        _check(self.lib.kt_finalise(self.h))
+
+    def pose(self) -> Pose:
+        p = Pose()
+        _check(self.lib.kt_get_pose(self.h, C.byref(p)))
+        return p
+
+    @property
+    def voxel_size(self):
+        return float(self.lib.kt_get_voxel_size(self.h))
+
+    @property
+    def trunc_dist(self):
+        return float(self.lib.kt_get_trunc_dist(self.h))
+
+    def num_slices(self):
+        return int(self.lib.kt_num_slices(self.h))
+
+    def get_slice(self, idx):
+        n = C.c_size_t(0); dim = C.c_int(0); cam = (C.c_float * 3)()
+        _check(self.lib.kt_get_slice(self.h, idx, None, C.c_size_t(0), C.byref(n), C.byref(dim), cam))
+        pts = np.zeros(n.value, dtype=POINT_DTYPE)
+        if n.value:
+            _check(self.lib.kt_get_slice(self.h, idx, _ptr(pts), C.c_size_t(n.value), C.byref(n), C.byref(dim), cam))
+        return pts, dim.value, np.array(cam, dtype=np.float32)
+
+    def trace(self, max_iters=64):
+        n = C.c_int(0)
+        buf = np.zeros((max_iters, 44), dtype=np.float32)
+        _check(self.lib.kt_get_trace(self.h, _ptr(buf), max_iters, C.byref(n)))
+        return buf[:min(n.value, max_iters)]
+
+    def export_volume(self, tsdf=True, color=True):
+        V = self.cfg.vol
+        t = np.empty((V, V, V), dtype=np.int16) if tsdf else None
+        c = np.empty((V, V, V, 4), dtype=np.uint8) if color else None
+        _check(self.lib.kt_volume_export_reference_layout(self.h, _ptr(t), _ptr(c)))
+        return t, c
+
+    def download_map(self, which, level=0):
+        rows, cols = self.cfg.rows >> level, self.cfg.cols >> level
+        if which <= 3:
+            out = np.empty((3, rows, cols), dtype=np.float32)
+        elif which == 4:
+            out = np.empty((rows, cols), dtype=np.uint16)
+        else:
+            out = np.empty((rows, cols, 4), dtype=np.uint8)
+        _check(self.lib.kt_download_map(self.h, which, level, _ptr(out)))
+        return out
+
+    def set_stage_timing(self, on=True):
+        _check(self.lib.kt_set_stage_timing(self.h, int(on)))
+
+    def stage_ms(self):
+        ms = (C.c_float * 6)()
+        _check(self.lib.kt_get_stage_ms(self.h, ms))
+        return list(ms)
+
+    def launch_count(self):
+        return int(self.lib.kt_launch_count(self.h))
+
+
+class _Ops:
+    """Operator API: one function per free function of the reference's cuda/internal.h:299-536.
+    Arguments are torch CUDA tensors (or raw device pointers); outputs are written in place."""
+
+    def _l(self):
+        return load()
+
+    def bilateral(self, src, dst, rows, cols):
+        _check(self._l().kt_op_bilateral(_ptr(src), _ptr(dst), rows, cols, None))
+
+    def pyrdown(self, src, dst, src_rows, src_cols):
+        _check(self._l().kt_op_pyrdown(_ptr(src), _ptr(dst), src_rows, src_cols, None))
+
+    def create_vmap(self, intr, depth, vmap, rows, cols):
+        k = _f(intr); _check(self._l().kt_op_create_vmap(_ptr(k), _ptr(depth), _ptr(vmap), rows, cols, None))
+
+    def create_nmap(self, vmap, nmap, rows, cols):
+        _check(self._l().kt_op_create_nmap(_ptr(vmap), _ptr(nmap), rows, cols, None))
+
+    def create_maps(self, intr, depth, vmap, nmap, rows, cols):
+        k = _f(intr); _check(self._l().kt_op_create_maps(_ptr(k), _ptr(depth), _ptr(vmap), _ptr(nmap), rows, cols, None))
+
+    def transform_maps(self, vs, ns, R, t, vd, nd, rows, cols):
+        R = _f(R); t = _f(t)
+        _check(self._l().kt_op_transform_maps(_ptr(vs), _ptr(ns), _ptr(R), _ptr(t), _ptr(vd), _ptr(nd), rows, cols, None))
+
+    def resize_vmap(self, src, dst, in_rows, in_cols):
+        _check(self._l().kt_op_resize_vmap(_ptr(src), _ptr(dst), in_rows, in_cols, None))
+
+    def resize_nmap(self, src, dst, in_rows, in_cols):
+        _check(self._l().kt_op_resize_nmap(_ptr(src), _ptr(dst), in_rows, in_cols, None))
+
+    def icp_step(self, Rcurr, tcurr, vmap_curr, nmap_curr, Rprev_inv, tprev, intr, vmap_g_prev, nmap_g_prev, rows, cols,
+                 dist_thres=0.10, angle_thres=float(np.sin(np.float32(20.0) * np.float32(3.14159254) / np.float32(180.0)))):
+        A = np.zeros(36, np.float32); b = np.zeros(6, np.float32); res = np.zeros(2, np.float32)
+        Rc, tc, Rp, tp, k = _f(Rcurr), _f(tcurr), _f(Rprev_inv), _f(tprev), _f(intr)
+        _check(self._l().kt_op_icp_step(_ptr(Rc), _ptr(tc), _ptr(vmap_curr), _ptr(nmap_curr), _ptr(Rp), _ptr(tp), _ptr(k),
+                                        _ptr(vmap_g_prev), _ptr(nmap_g_prev), rows, cols, C.c_float(dist_thres), C.c_float(angle_thres),
+                                        _ptr(A), _ptr(b), _ptr(res), None))
+        return A.reshape(6, 6), b, res
+
+    def integrate(self, depth_raw, rows, cols, intr, volume_size, Rinv, t, trunc, tsdf, color, vol, wrap, rgb, nmap_curr, angle_color, depth_scaled):
+        k, vs, Ri, tt = _f(intr), _f(volume_size), _f(Rinv), _f(t)
+        w = np.ascontiguousarray(np.asarray(wrap, dtype=np.int32))
+        _check(self._l().kt_op_integrate(_ptr(depth_raw), rows, cols, _ptr(k), _ptr(vs), _ptr(Ri), _ptr(tt), C.c_float(trunc), _ptr(tsdf), _ptr(color),
+                                         vol, _ptr(w), _ptr(rgb), _ptr(nmap_curr), int(angle_color), _ptr(depth_scaled), None))
+
+    def raycast(self, intr, R, t, trunc, volume_size, tsdf, vol, vmap, nmap, rows, cols, wrap, vmap_color, color):
+        k, vs, Rr, tt = _f(intr), _f(volume_size), _f(R), _f(t)
+        w = np.ascontiguousarray(np.asarray(wrap, dtype=np.int32))
+        _check(self._l().kt_op_raycast(_ptr(k), _ptr(Rr), _ptr(tt), C.c_float(trunc), _ptr(vs), _ptr(tsdf), vol, _ptr(vmap), _ptr(nmap), rows, cols,
+                                       _ptr(w), _ptr(vmap_color), _ptr(color), None))
+
+    def extract_slice(self, tsdf, volume_size, vol, out, capacity, wrap, color, box, subsample, real_wrap):
+        vs = _f(volume_size)
+        w = np.ascontiguousarray(np.asarray(wrap, dtype=np.int32)); rw = np.ascontiguousarray(np.asarray(real_wrap, dtype=np.int32))
+        n = C.c_size_t(0)
+        _check(self._l().kt_op_extract_slice(_ptr(tsdf), _ptr(vs), vol, _ptr(out), C.c_size_t(capacity), _ptr(w), _ptr(color),
+                                             box[0], box[1], box[2], box[3], box[4], box[5], subsample, _ptr(rw), C.byref(n), None))
+        return n.value
+
+    def clear_volume(self, axis, back, tsdf, color, vol, current, delta):
+        _check(self._l().kt_op_clear_volume(axis, back, _ptr(tsdf), _ptr(color), vol, current, delta, None))
+
+    def init_volume(self, tsdf, color, vol):
+        _check(self._l().kt_op_init_volume(_ptr(tsdf), _ptr(color), vol, None))
+
+    def short_depth_to_metres(self, src, dst, rows, cols, cut_off):
+        _check(self._l().kt_op_short_depth_to_metres(_ptr(src), _ptr(dst), rows, cols, cut_off, None))
+
+    def pyrdown_gauss_f(self, src, dst, src_rows, src_cols):
+        _check(self._l().kt_op_pyrdown_gauss_f(_ptr(src), _ptr(dst), src_rows, src_cols, None))
+
+    def bgr_to_intensity(self, rgb, dst, rows, cols):
+        _check(self._l().kt_op_bgr_to_intensity(_ptr(rgb), _ptr(dst), rows, cols, None))
+
+    def pyrdown_uchar_gauss(self, src, dst, src_rows, src_cols):
+        _check(self._l().kt_op_pyrdown_uchar_gauss(_ptr(src), _ptr(dst), src_rows, src_cols, None))
+
+    def derivative_images(self, src, dx, dy, rows, cols):
+        _check(self._l().kt_op_derivative_images(_ptr(src), _ptr(dx), _ptr(dy), rows, cols, None))
+
+    def project_to_point_cloud(self, depth, cloud, rows, cols, intr_d, level):
+        k = np.ascontiguousarray(np.asarray(intr_d, dtype=np.float64))
+        _check(self._l().kt_op_project_to_point_cloud(_ptr(depth), _ptr(cloud), rows, cols, _ptr(k), level, None))
+
+    def rgb_residual(self, min_scale, dIdx, dIdy, last_depth, next_depth, last_image, next_image, corres, rows, cols, max_depth_delta, kt, krkinv):
+        ktf, kk = _f(kt), _f(krkinv)
+        sigma = C.c_int(0); count = C.c_int(0)
+        _check(self._l().kt_op_rgb_residual(C.c_float(min_scale), _ptr(dIdx), _ptr(dIdy), _ptr(last_depth), _ptr(next_depth), _ptr(last_image), _ptr(next_image),
+                                            _ptr(corres), rows, cols, C.c_float(max_depth_delta), _ptr(ktf), _ptr(kk), C.byref(sigma), C.byref(count), None))
+        return sigma.value, count.value
+
+    def rgb_step(self, corres, sigma, cloud, fx, fy, dIdx, dIdy, sobel_scale, rows, cols):
+        A = np.zeros(36, np.float32); b = np.zeros(6, np.float32)
+        _check(self._l().kt_op_rgb_step(_ptr(corres), C.c_float(sigma), _ptr(cloud), C.c_float(fx), C.c_float(fy), _ptr(dIdx), _ptr(dIdy),
+                                        C.c_float(sobel_scale), rows, cols, _ptr(A), _ptr(b), None))
+        return A.reshape(6, 6), b
+
+
+ops = _Ops()

@@ -1,0 +1,61 @@
+// kintinuous_b200 -- shared device/host helpers for the sm_100a kernels.
+//
+// Numerics contract: every kernel in csrc/ is compiled with the reference's own nvcc numerics
+// flags (--ftz=true --prec-div=false --prec-sqrt=false, reference CMakeLists.txt:47) and keeps the
+// reference's per-element expression order, so that per-pixel / per-voxel results agree with the
+// reference's CUDA path bit-for-bit wherever the compiler contracts the same way; reductions use a
+// different (fixed, deterministic) summation tree and agree to float rounding.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+namespace kt {
+
+struct Intr { float fx, fy, cx, cy; };
+struct Mat33 { float3 r0, r1, r2; };          // row-major rows, same bytes as 9 floats
+
+__host__ __device__ __forceinline__ Intr intr_level(const Intr& k, int level)   // cuda/internal.h:255-259
+{
+    int div = 1 << level;
+    Intr r = {k.fx / div, k.fy / div, k.cx / div, k.cy / div};
+    return r;
+}
+
+__device__ __forceinline__ float dot3(const float3& a, const float3& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ float3 cross3(const float3& a, const float3& b)
+{
+    return make_float3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+__device__ __forceinline__ float3 sub3(const float3& a, const float3& b) { return make_float3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ float3 add3(const float3& a, const float3& b) { return make_float3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ float3 scale3(const float3& a, float s) { return make_float3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ float norm3(const float3& a) { return sqrtf(dot3(a, a)); }
+__device__ __forceinline__ float3 normalized3(const float3& a) { return scale3(a, rsqrtf(dot3(a, a))); }
+__device__ __forceinline__ float3 mul33(const Mat33& m, const float3& v)
+{
+    return make_float3(dot3(m.r0, v), dot3(m.r1, v), dot3(m.r2, v));
+}
+
+__host__ __device__ __forceinline__ int div_up(int a, int b) { return (a + b - 1) / b; }
+
+// TSDF fixed point (cuda/device.hpp:67-83, cuda/internal.h:237)
+#define KT_DIVISOR 32767
+__device__ __forceinline__ short pack_tsdf(float tsdf)
+{
+    return (short)max(-KT_DIVISOR, min(KT_DIVISOR, __float2int_rz(tsdf * KT_DIVISOR)));
+}
+__device__ __forceinline__ float unpack_tsdf(short v) { return static_cast<float>(v) / KT_DIVISOR; }
+
+__device__ __forceinline__ float qnan() { return __int_as_float(0x7fffffff); }
+
+} // namespace kt
+
+// error plumbing shared by the host translation units
+namespace kt {
+void set_error(const char* fmt, ...);
+int cuda_check(cudaError_t e, const char* what, const char* file, int line);
+extern long long g_launches;      // kernels launched by this library (bench.py: gpu_launches)
+}
+#define KT_CUDA(expr) do { int _s = kt::cuda_check((expr), #expr, __FILE__, __LINE__); if (_s) return _s; } while (0)
+#define KT_LAUNCH_CHECK() do { ++kt::g_launches; int _s = kt::cuda_check(cudaGetLastError(), "kernel launch", __FILE__, __LINE__); if (_s) return _s; } while (0)

@@ -1,0 +1,90 @@
+// kintinuous_b200 -- internal C++ launch API (one function per operator; the C ABI in kt_capi.cu and
+// the tracker in kt_tracker.cu call these).  All pointers are device pointers, compact pitch.
+#pragma once
+#include "kt_common.cuh"
+
+namespace kt {
+
+static const int LEVELS = 4;                 // ICPOdometry.h:52 / RGBDOdometry.h:96
+
+// ---- pyramid (kt_pyramid.cu) ----
+int bilateral(const uint16_t* src, uint16_t* dst, int rows, int cols, cudaStream_t s);
+int pyrdown(const uint16_t* src, uint16_t* dst, int src_rows, int src_cols, cudaStream_t s);
+int create_vmap(const Intr& k, const uint16_t* depth, float* vmap, int rows, int cols, cudaStream_t s);
+int create_nmap(const float* vmap, float* nmap, int rows, int cols, cudaStream_t s);
+struct MapsLevel { const uint16_t* depth; float* vmap; float* nmap; int rows, cols; Intr k; float fx_inv, fy_inv; };
+int create_maps_pyramid(const MapsLevel* levels, int n_levels, cudaStream_t s);      // fused vmap+nmap, all levels, one launch
+int transform_maps(const float* vs, const float* ns, const Mat33& R, const float3& t, float* vd, float* nd, int rows, int cols, cudaStream_t s);
+struct TransformLevel { const float* vs; const float* ns; float* vd; float* nd; int rows, cols; };
+int transform_maps_pyramid(const TransformLevel* levels, int n_levels, const Mat33& R, const float3& t, cudaStream_t s);
+int resize_map(const float* in, float* out, int in_rows, int in_cols, bool normalize, cudaStream_t s);
+
+// ---- RGB-D preprocessing (kt_rgb.cu) ----
+int short_depth_to_metres(const uint16_t* src, float* dst, int rows, int cols, int cut_off, cudaStream_t s);
+int pyrdown_gauss_f(const float* src, float* dst, int src_rows, int src_cols, cudaStream_t s);
+int bgr_to_intensity(const uint8_t* rgb, uint8_t* dst, int rows, int cols, cudaStream_t s);
+int pyrdown_uchar_gauss(const uint8_t* src, uint8_t* dst, int src_rows, int src_cols, cudaStream_t s);
+int derivative_images(const uint8_t* src, int16_t* dx, int16_t* dy, int rows, int cols, cudaStream_t s);
+int project_to_point_cloud(const float* depth, float* cloud, int rows, int cols, double fx, double fy, double cx, double cy, cudaStream_t s);
+
+// ---- odometry reductions (kt_icp.cu, kt_rgb.cu) ----
+// Device-resident Gauss-Newton state shared by all iterations of one frame.
+struct OdomState {
+    // inputs of the frame
+    float Rprev[9], tprev[3], Rprev_inv[9];
+    // running estimate (ICPOdometry.cpp:73-74,177-178)
+    float Rcurr[9], tcurr[3];
+    double resultRt[16];                    // cv::Mat resultRt (ICPOdometry.cpp:83)
+    // photometric warp of the current iteration (RGBDOdometry.cpp:209-231)
+    float krkinv[9], kt[3];
+    int rgb_count, rgb_sigma;               // computeRgbResidual outputs
+    float sums_icp[32], sums_rgb[32];       // reduced [JtJ|Jtr] (27) + residual + inliers
+    int iter;                               // iterations done this frame
+    unsigned int blocks_done;               // last-block-done counter
+    unsigned int blocks_done_rgb;
+};
+static const int TRACE_STRIDE = 44;          // A(36) b(6) residual(2)
+static const int MAX_PARTIALS = 1024;
+
+struct IcpLevelArgs {
+    const float* vmap_curr; const float* nmap_curr; const float* vmap_g_prev; const float* nmap_g_prev;
+    int rows, cols; Intr k; float dist_thres, angle_thres;
+};
+// One ICP normal-equation build + (optionally) the on-device solve and pose update.
+//   mode 0: reduce only, result left in state->sums_icp (used by the operator API and by -ri before rgb_step)
+//   mode 1: reduce + LDLT solve + pose update on device (ICP-only odometry)
+int icp_iteration(const IcpLevelArgs& a, OdomState* state, float* partials, float* trace, int mode, cudaStream_t s);
+
+struct RgbLevelArgs {
+    const int16_t* dIdx; const int16_t* dIdy; const float* last_depth; const float* next_depth;
+    const uint8_t* last_image; const uint8_t* next_image; void* corres; const float* cloud;
+    int rows, cols; float min_scale, max_depth_delta, fx, fy, sobel_scale; double Kfx, Kfy, Kcx, Kcy;
+};
+// use_state_warp 1: (K R K^-1, K t) rebuilt on the device from state->resultRt; 0: taken from state->krkinv / kt
+int rgb_residual(const RgbLevelArgs& a, OdomState* state, int* partials, int use_state_warp, cudaStream_t s);
+// mode 0: reduce only; 1: solve RGB-only; 2: solve A_rgb + 100 A_icp (RGBDOdometry.cpp:316-321)
+int rgb_iteration(const RgbLevelArgs& a, OdomState* state, float* partials, float* trace, int mode, float sigma_override, cudaStream_t s);
+// pose12_dev: Rprev (9) + tprev (3) in device memory
+int odom_begin_frame(OdomState* state, const float* pose12_dev, cudaStream_t s);
+int reduce_grid_for(int n_items);
+
+// ---- volume (kt_tsdf.cu, kt_raycast.cu, kt_extract.cu) ----
+int init_volume(int16_t* tsdf, uint8_t* color, int vol, cudaStream_t s);
+int clear_volume(int axis, int back, int16_t* tsdf, uint8_t* color, int vol, int current_wrap, int delta_wrap, cudaStream_t s);
+int scale_depth(const uint16_t* depth, float* scaled, int rows, int cols, const Intr& k, bool angle_color, cudaStream_t s);
+struct IntegrateArgs {
+    const float* depth_scaled; int rows, cols; Intr k; float3 volume_size; Mat33 Rinv; float3 t; float trunc;
+    int16_t* tsdf; uint8_t* color; int vol; int3 wrap; const uint8_t* rgb; const float* nmap_curr; bool angle_color;
+    int z_begin, z_end;          // storage-z slab owned by this GPU ([0, vol) on a single GPU)
+};
+int integrate(const IntegrateArgs& a, float* ztable_dev /* 2*vol floats */, cudaStream_t s);
+struct RaycastArgs {
+    Intr k; Mat33 R; float3 t; float trunc; float3 volume_size; const int16_t* tsdf; const uint8_t* color; int vol; int3 wrap;
+    float* vmap[LEVELS]; float* nmap[LEVELS]; int rows, cols; uint8_t* vmap_color; int n_levels;   // n_levels>1: fused model pyramid
+};
+int raycast(const RaycastArgs& a, cudaStream_t s);
+int extract_slice(const int16_t* tsdf, const float3& volume_size, int vol, void* out, size_t capacity, const int3& wrap,
+                  const uint8_t* color, int minX, int maxX, int minY, int maxY, int minZ, int maxZ, int subsample,
+                  const int3& real_wrap, unsigned int* counter_dev, cudaStream_t s);
+
+} // namespace kt

@@ -1,0 +1,327 @@
+// kintinuous_b200 -- surface prediction: ray-cast the TSDF from the current pose and build the model
+// vertex / normal pyramid in the same launch.
+//
+// Replaces (reference, src/frontend/cuda/):
+//   raycast / RayCaster / rayCastKernel          ray_caster.cu:56-471
+//   resizeVMap / resizeNMap (x3 levels)          maps.cu:225-308  (KintinuousTracker.cpp:892-899)
+// B200 design: one CTA = a 32x8 pixel tile; after the march the tile's vertices / normals sit in shared
+// memory and the 2x2 means of levels 1..3 (16x4, 8x2, 4x1 pixels per tile) are produced by the same CTA,
+// which removes 6 launches + 6 cudaDeviceSynchronize per frame and the 12 MB re-read of the level-0 maps.
+// Per-ray arithmetic (march step, trilinear taps, gradient normal) keeps the reference's expression
+// order; the volume is read through the read-only path with cyclic addressing by compare-subtract.
+// Bound: L2 / latency (scattered 2-byte reads, about 60-100 per ray); DESIGN.md section 3.5.
+#include "kt_ops.h"
+
+namespace kt {
+
+namespace {
+
+struct RayParams {
+    Intr intr; Mat33 Rcurr; float3 tcurr; float time_step; float3 volume_size; float3 cell_size;
+    const int16_t* volume; const uchar4* color_volume; int V; int3 wrap;
+    float* vmap[LEVELS]; float* nmap[LEVELS]; uchar4* vmap_color; int rows, cols; int n_levels;
+    int z_begin;            // storage-z offset of the local slab (0 on a single GPU)
+};
+
+struct Caster {
+    const RayParams& p;
+    __device__ __forceinline__ Caster(const RayParams& p_) : p(p_) {}
+
+    __device__ __forceinline__ size_t addr(int x, int y, int z) const
+    {
+        int sx = x + p.wrap.x; if (sx >= p.V) sx -= p.V;
+        int sy = y + p.wrap.y; if (sy >= p.V) sy -= p.V;
+        int sz = z + p.wrap.z; if (sz >= p.V) sz -= p.V;
+        return ((size_t)sz * p.V + sy) * p.V + sx;
+    }
+    __device__ __forceinline__ float readTsdf(int x, int y, int z) const { return unpack_tsdf(__ldg(&p.volume[addr(x, y, z)])); }
+    __device__ __forceinline__ uchar4 readColor(int x, int y, int z) const { return __ldg(&p.color_volume[addr(x, y, z)]); }
+
+    __device__ __forceinline__ int3 getVoxel(float3 point) const
+    {
+        int vx = __float2int_rd(point.x / p.cell_size.x);
+        int vy = __float2int_rd(point.y / p.cell_size.y);
+        int vz = __float2int_rd(point.z / p.cell_size.z);
+        return make_int3(vx, vy, vz);
+    }
+    __device__ __forceinline__ bool checkInds(const int3& g) const
+    {
+        return (g.x >= 0 && g.y >= 0 && g.z >= 0 && g.x < p.V && g.y < p.V && g.z < p.V);
+    }
+
+    // trilinear weights and base voxel of a point; false if the base voxel is outside [1, V-2]
+    __device__ __forceinline__ bool trilinearSetup(const float3& point, int3& g, float& a, float& b, float& c) const
+    {
+        g = getVoxel(point);
+        if (g.x <= 0 || g.x >= p.V - 1) return false;
+        if (g.y <= 0 || g.y >= p.V - 1) return false;
+        if (g.z <= 0 || g.z >= p.V - 1) return false;
+        float vx = (g.x + 0.5f) * p.cell_size.x;
+        float vy = (g.y + 0.5f) * p.cell_size.y;
+        float vz = (g.z + 0.5f) * p.cell_size.z;
+        g.x = (point.x < vx) ? (g.x - 1) : g.x;
+        g.y = (point.y < vy) ? (g.y - 1) : g.y;
+        g.z = (point.z < vz) ? (g.z - 1) : g.z;
+        a = (point.x - (g.x + 0.5f) * p.cell_size.x) / p.cell_size.x;
+        b = (point.y - (g.y + 0.5f) * p.cell_size.y) / p.cell_size.y;
+        c = (point.z - (g.z + 0.5f) * p.cell_size.z) / p.cell_size.z;
+        return true;
+    }
+
+    __device__ __forceinline__ float interpolateTrilineary(const float3& point) const
+    {
+        int3 g; float a, b, c;
+        if (!trilinearSetup(point, g, a, b, c)) return qnan();
+        float res = readTsdf(g.x + 0, g.y + 0, g.z + 0) * (1 - a) * (1 - b) * (1 - c) +
+                    readTsdf(g.x + 0, g.y + 0, g.z + 1) * (1 - a) * (1 - b) * c +
+                    readTsdf(g.x + 0, g.y + 1, g.z + 0) * (1 - a) * b * (1 - c) +
+                    readTsdf(g.x + 0, g.y + 1, g.z + 1) * (1 - a) * b * c +
+                    readTsdf(g.x + 1, g.y + 0, g.z + 0) * a * (1 - b) * (1 - c) +
+                    readTsdf(g.x + 1, g.y + 0, g.z + 1) * a * (1 - b) * c +
+                    readTsdf(g.x + 1, g.y + 1, g.z + 0) * a * b * (1 - c) +
+                    readTsdf(g.x + 1, g.y + 1, g.z + 1) * a * b * c;
+        return res;
+    }
+
+    // colour (r,g,b truncated to u8) and weight ("heat") trilinear taps share the 8 uchar4 loads
+    __device__ __forceinline__ uchar4 interpolateColorHeat(const float3& point) const
+    {
+        int3 g; float a, b, c;
+        if (!trilinearSetup(point, g, a, b, c)) {
+            // interpolateColorTrilineary returns black, interpolateHeatTrilineary NaN -> (unsigned char)NaN
+            uchar4 r; r.x = 0; r.y = 0; r.z = 0; r.w = (unsigned char)qnan();
+            return r;
+        }
+        const uchar4 c000 = readColor(g.x + 0, g.y + 0, g.z + 0), c001 = readColor(g.x + 0, g.y + 0, g.z + 1);
+        const uchar4 c010 = readColor(g.x + 0, g.y + 1, g.z + 0), c011 = readColor(g.x + 0, g.y + 1, g.z + 1);
+        const uchar4 c100 = readColor(g.x + 1, g.y + 0, g.z + 0), c101 = readColor(g.x + 1, g.y + 0, g.z + 1);
+        const uchar4 c110 = readColor(g.x + 1, g.y + 1, g.z + 0), c111 = readColor(g.x + 1, g.y + 1, g.z + 1);
+#define KT_TRI(f) ((float)c000.f * (1 - a) * (1 - b) * (1 - c) + (float)c001.f * (1 - a) * (1 - b) * c + \
+                   (float)c010.f * (1 - a) * b * (1 - c) + (float)c011.f * (1 - a) * b * c + \
+                   (float)c100.f * a * (1 - b) * (1 - c) + (float)c101.f * a * (1 - b) * c + \
+                   (float)c110.f * a * b * (1 - c) + (float)c111.f * a * b * c)
+        uchar4 r;
+        r.x = KT_TRI(x); r.y = KT_TRI(y); r.z = KT_TRI(z);
+        float heat = KT_TRI(w);
+        r.w = heat;
+#undef KT_TRI
+        return r;
+    }
+};
+
+__device__ __forceinline__ float getMinTime(const float3& volume_max, const float3& origin, const float3& dir)
+{
+    float txmin = ((dir.x > 0 ? 0.f : volume_max.x) - origin.x) / dir.x;
+    float tymin = ((dir.y > 0 ? 0.f : volume_max.y) - origin.y) / dir.y;
+    float tzmin = ((dir.z > 0 ? 0.f : volume_max.z) - origin.z) / dir.z;
+    return fmax(fmax(txmin, tymin), tzmin);
+}
+__device__ __forceinline__ float getMaxTime(const float3& volume_max, const float3& origin, const float3& dir)
+{
+    float txmax = ((dir.x > 0 ? volume_max.x : 0.f) - origin.x) / dir.x;
+    float tymax = ((dir.y > 0 ? volume_max.y : 0.f) - origin.y) / dir.y;
+    float tzmax = ((dir.z > 0 ? volume_max.z : 0.f) - origin.z) / dir.z;
+    return fmin(fmin(txmax, tymax), tzmax);
+}
+
+enum { RC_X = 32, RC_Y = 8 };
+
+// One ray.  Returns validity of vertex / normal; outputs by reference.
+__device__ __forceinline__ void cast_ray(const RayParams& p, int x, int y, bool& v_ok, float3& vtx, bool& n_ok, float3& nrm,
+                                         bool& c_ok, uchar4& col)
+{
+    v_ok = false; n_ok = false; c_ok = false;
+    Caster rc(p);
+    float3 ray_start = p.tcurr;
+    float3 ray_next_c;
+    ray_next_c.x = (x - p.intr.cx) / p.intr.fx;
+    ray_next_c.y = (y - p.intr.cy) / p.intr.fy;
+    ray_next_c.z = 1;
+    float3 ray_next = add3(mul33(p.Rcurr, ray_next_c), p.tcurr);
+    float3 ray_dir = normalized3(sub3(ray_next, ray_start));
+    ray_dir.x = (ray_dir.x == 0.f) ? 1e-15 : ray_dir.x;
+    ray_dir.y = (ray_dir.y == 0.f) ? 1e-15 : ray_dir.y;
+    ray_dir.z = (ray_dir.z == 0.f) ? 1e-15 : ray_dir.z;
+
+    float time_start_volume = getMinTime(p.volume_size, ray_start, ray_dir);
+    float time_exit_volume = getMaxTime(p.volume_size, ray_start, ray_dir);
+    const float min_dist = 0.f;
+    time_start_volume = fmax(time_start_volume, min_dist);
+    if (time_start_volume >= time_exit_volume) return;
+
+    const float time_step = p.time_step;
+    float time_curr = time_start_volume;
+    int3 g = rc.getVoxel(add3(ray_start, scale3(ray_dir, time_curr)));
+    g.x = max(0, min(g.x, p.V - 1));
+    g.y = max(0, min(g.y, p.V - 1));
+    g.z = max(0, min(g.z, p.V - 1));
+    float tsdf = rc.readTsdf(g.x, g.y, g.z);
+
+    const float max_time = 3 * (p.volume_size.x + p.volume_size.y + p.volume_size.z);
+    for (; time_curr < max_time; time_curr += time_step) {
+        float tsdf_prev = tsdf;
+        int3 gn = rc.getVoxel(add3(ray_start, scale3(ray_dir, (time_curr + time_step))));
+        if (!rc.checkInds(gn)) break;
+        tsdf = rc.readTsdf(gn.x, gn.y, gn.z);
+        if (tsdf_prev < 0.f && tsdf > 0.f) break;
+        if (tsdf_prev > 0.f && tsdf < 0.f) {
+            float Ftdt = rc.interpolateTrilineary(add3(ray_start, scale3(ray_dir, (time_curr + time_step))));
+            if (isnan(Ftdt)) break;
+            float Ft = rc.interpolateTrilineary(add3(ray_start, scale3(ray_dir, time_curr)));
+            if (isnan(Ft)) break;
+
+            float Ts = time_curr - time_step * Ft / (Ftdt - Ft);
+            float3 vetex_found = add3(ray_start, scale3(ray_dir, Ts));
+            vtx = vetex_found; v_ok = true;
+
+            int3 gc = rc.getVoxel(add3(ray_start, scale3(ray_dir, time_curr)));
+            col = rc.interpolateColorHeat(vetex_found); c_ok = true;
+
+            if (gc.x > 1 && gc.y > 1 && gc.z > 1 && gc.x < p.V - 2 && gc.y < p.V - 2 && gc.z < p.V - 2) {
+                float3 t, n;
+                t = vetex_found; t.x += p.cell_size.x; float Fx1 = rc.interpolateTrilineary(t);
+                t = vetex_found; t.x -= p.cell_size.x; float Fx2 = rc.interpolateTrilineary(t);
+                n.x = (Fx1 - Fx2);
+                t = vetex_found; t.y += p.cell_size.y; float Fy1 = rc.interpolateTrilineary(t);
+                t = vetex_found; t.y -= p.cell_size.y; float Fy2 = rc.interpolateTrilineary(t);
+                n.y = (Fy1 - Fy2);
+                t = vetex_found; t.z += p.cell_size.z; float Fz1 = rc.interpolateTrilineary(t);
+                t = vetex_found; t.z -= p.cell_size.z; float Fz2 = rc.interpolateTrilineary(t);
+                n.z = (Fz1 - Fz2);
+                nrm = normalized3(n); n_ok = true;
+            }
+            break;
+        }
+    }
+}
+
+// 2x2 mean of one pyramid step inside the CTA (maps.cu:225-277): in/out are [3][H][W] tiles in smem.
+template <bool normalize>
+__device__ __forceinline__ bool resize_tile(const float* in, int W, int H, int ox, int oy, float3& out)
+{
+    const int xs = ox * 2, ys = oy * 2;
+    const int plane = W * H;
+    float x00 = in[ys * W + xs], x01 = in[ys * W + xs + 1], x10 = in[(ys + 1) * W + xs], x11 = in[(ys + 1) * W + xs + 1];
+    if (isnan(x00) || isnan(x01) || isnan(x10) || isnan(x11)) return false;
+    float3 n;
+    n.x = (x00 + x01 + x10 + x11) / 4;
+    const float* iy = in + plane;
+    n.y = (iy[ys * W + xs] + iy[ys * W + xs + 1] + iy[(ys + 1) * W + xs] + iy[(ys + 1) * W + xs + 1]) / 4;
+    const float* iz = in + 2 * plane;
+    n.z = (iz[ys * W + xs] + iz[ys * W + xs + 1] + iz[(ys + 1) * W + xs] + iz[(ys + 1) * W + xs + 1]) / 4;
+    if (normalize) n = normalized3(n);
+    out = n;
+    return true;
+}
+
+__global__ void __launch_bounds__(RC_X * RC_Y)
+raycast_kernel(const RayParams p)
+{
+    // level-0 tile, then levels 1..3 (each [v|n][3 planes][H][W])
+    __shared__ float s0[2][3][RC_Y][RC_X];
+    __shared__ float s1[2][3][RC_Y / 2][RC_X / 2];
+    __shared__ float s2[2][3][RC_Y / 4][RC_X / 4];
+
+    const int x = threadIdx.x + blockIdx.x * RC_X;
+    const int y = threadIdx.y + blockIdx.y * RC_Y;
+    const float nan = qnan();
+    const bool inside = (x < p.cols && y < p.rows);
+
+    bool v_ok = false, n_ok = false, c_ok = false;
+    float3 vtx = make_float3(nan, nan, nan), nrm = make_float3(nan, nan, nan);
+    uchar4 col;
+    if (inside) {
+        cast_ray(p, x, y, v_ok, vtx, n_ok, nrm, c_ok, col);
+        const size_t P = (size_t)p.rows * p.cols, i = (size_t)y * p.cols + x;
+        // like the reference: x planes are always written (NaN = no surface), y/z only on success
+        if (v_ok) { p.vmap[0][i] = vtx.x; p.vmap[0][i + P] = vtx.y; p.vmap[0][i + 2 * P] = vtx.z; }
+        else p.vmap[0][i] = nan;
+        if (n_ok) { p.nmap[0][i] = nrm.x; p.nmap[0][i + P] = nrm.y; p.nmap[0][i + 2 * P] = nrm.z; }
+        else p.nmap[0][i] = nan;
+        if (c_ok) p.vmap_color[i] = col;
+    }
+    if (p.n_levels <= 1) return;
+
+    s0[0][0][threadIdx.y][threadIdx.x] = v_ok ? vtx.x : nan; s0[0][1][threadIdx.y][threadIdx.x] = vtx.y; s0[0][2][threadIdx.y][threadIdx.x] = vtx.z;
+    s0[1][0][threadIdx.y][threadIdx.x] = n_ok ? nrm.x : nan; s0[1][1][threadIdx.y][threadIdx.x] = nrm.y; s0[1][2][threadIdx.y][threadIdx.x] = nrm.z;
+    __syncthreads();
+
+    // level 1: 16 x 4 outputs per tile
+    {
+        const int W = RC_X / 2, H = RC_Y / 2;
+        const int rows1 = p.rows >> 1, cols1 = p.cols >> 1;
+        if (threadIdx.x < W && threadIdx.y < H) {
+            const int ox = threadIdx.x, oy = threadIdx.y;
+            const int gx = blockIdx.x * W + ox, gy = blockIdx.y * H + oy;
+            float3 v, n;
+            bool okv = resize_tile<false>(&s0[0][0][0][0], RC_X, RC_Y, ox, oy, v);
+            bool okn = resize_tile<true>(&s0[1][0][0][0], RC_X, RC_Y, ox, oy, n);
+            s1[0][0][oy][ox] = okv ? v.x : nan; s1[0][1][oy][ox] = v.y; s1[0][2][oy][ox] = v.z;
+            s1[1][0][oy][ox] = okn ? n.x : nan; s1[1][1][oy][ox] = n.y; s1[1][2][oy][ox] = n.z;
+            if (gx < cols1 && gy < rows1) {
+                const size_t P = (size_t)rows1 * cols1, i = (size_t)gy * cols1 + gx;
+                if (okv) { p.vmap[1][i] = v.x; p.vmap[1][i + P] = v.y; p.vmap[1][i + 2 * P] = v.z; } else p.vmap[1][i] = nan;
+                if (okn) { p.nmap[1][i] = n.x; p.nmap[1][i + P] = n.y; p.nmap[1][i + 2 * P] = n.z; } else p.nmap[1][i] = nan;
+            }
+        }
+    }
+    if (p.n_levels <= 2) return;
+    __syncthreads();
+    {
+        const int W = RC_X / 4, H = RC_Y / 4;
+        const int rows2 = p.rows >> 2, cols2 = p.cols >> 2;
+        if (threadIdx.x < W && threadIdx.y < H) {
+            const int ox = threadIdx.x, oy = threadIdx.y;
+            const int gx = blockIdx.x * W + ox, gy = blockIdx.y * H + oy;
+            float3 v, n;
+            bool okv = resize_tile<false>(&s1[0][0][0][0], RC_X / 2, RC_Y / 2, ox, oy, v);
+            bool okn = resize_tile<true>(&s1[1][0][0][0], RC_X / 2, RC_Y / 2, ox, oy, n);
+            s2[0][0][oy][ox] = okv ? v.x : nan; s2[0][1][oy][ox] = v.y; s2[0][2][oy][ox] = v.z;
+            s2[1][0][oy][ox] = okn ? n.x : nan; s2[1][1][oy][ox] = n.y; s2[1][2][oy][ox] = n.z;
+            if (gx < cols2 && gy < rows2) {
+                const size_t P = (size_t)rows2 * cols2, i = (size_t)gy * cols2 + gx;
+                if (okv) { p.vmap[2][i] = v.x; p.vmap[2][i + P] = v.y; p.vmap[2][i + 2 * P] = v.z; } else p.vmap[2][i] = nan;
+                if (okn) { p.nmap[2][i] = n.x; p.nmap[2][i + P] = n.y; p.nmap[2][i + 2 * P] = n.z; } else p.nmap[2][i] = nan;
+            }
+        }
+    }
+    if (p.n_levels <= 3) return;
+    __syncthreads();
+    {
+        const int W = RC_X / 8, H = RC_Y / 8;
+        const int rows3 = p.rows >> 3, cols3 = p.cols >> 3;
+        if (threadIdx.x < W && threadIdx.y < H) {
+            const int ox = threadIdx.x, oy = threadIdx.y;
+            const int gx = blockIdx.x * W + ox, gy = blockIdx.y * H + oy;
+            float3 v, n;
+            bool okv = resize_tile<false>(&s2[0][0][0][0], RC_X / 4, RC_Y / 4, ox, oy, v);
+            bool okn = resize_tile<true>(&s2[1][0][0][0], RC_X / 4, RC_Y / 4, ox, oy, n);
+            if (gx < cols3 && gy < rows3) {
+                const size_t P = (size_t)rows3 * cols3, i = (size_t)gy * cols3 + gx;
+                if (okv) { p.vmap[3][i] = v.x; p.vmap[3][i + P] = v.y; p.vmap[3][i + 2 * P] = v.z; } else p.vmap[3][i] = nan;
+                if (okn) { p.nmap[3][i] = n.x; p.nmap[3][i + P] = n.y; p.nmap[3][i + 2 * P] = n.z; } else p.nmap[3][i] = nan;
+            }
+        }
+    }
+}
+
+} // namespace
+
+int raycast(const RaycastArgs& a, cudaStream_t s)
+{
+    RayParams p;
+    p.intr = a.k; p.Rcurr = a.R; p.tcurr = a.t; p.time_step = a.trunc * 0.8f; p.volume_size = a.volume_size;
+    p.cell_size = make_float3(a.volume_size.x / a.vol, a.volume_size.y / a.vol, a.volume_size.z / a.vol);
+    p.volume = a.tsdf; p.color_volume = (const uchar4*)a.color; p.V = a.vol; p.wrap = a.wrap;
+    for (int l = 0; l < LEVELS; ++l) { p.vmap[l] = a.vmap[l]; p.nmap[l] = a.nmap[l]; }
+    p.vmap_color = (uchar4*)a.vmap_color; p.rows = a.rows; p.cols = a.cols;
+    p.n_levels = a.n_levels; p.z_begin = 0;
+    // the in-tile pyramid needs every level's tile to be whole
+    if (p.n_levels > 1 && ((a.cols % RC_X) != 0 || (a.rows % RC_Y) != 0)) { set_error("raycast: fused pyramid needs cols %% 32 == 0 and rows %% 8 == 0"); return -1; }
+    dim3 block(RC_X, RC_Y), grid(div_up(a.cols, RC_X), div_up(a.rows, RC_Y));
+    raycast_kernel<<<grid, block, 0, s>>>(p);
+    KT_LAUNCH_CHECK();
+    return 0;
+}
+
+} // namespace kt

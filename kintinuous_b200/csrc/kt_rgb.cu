@@ -1,0 +1,359 @@
+// kintinuous_b200 -- photometric RGB-D odometry: pre-processing, per-pixel correspondence / residual,
+// Jacobian row and the 6x6 reduction (optionally merged with the ICP normal equations, "-ri").
+//
+// Replaces (reference, src/frontend/):
+//   shortDepthToMetres / short2FloatKernel              cuda/bilateral_pyrdown.cu:235-245, :404-411
+//   imageBGRToIntensity / bgr2IntensityKernel           cuda/bilateral_pyrdown.cu:247-259, :413-420
+//   pyrDownGaussF / pyrDownKernelGaussF                 cuda/bilateral_pyrdown.cu:201-233, :356-378
+//   pyrDownUcharGauss / pyrDownKernelIntensityGauss     cuda/bilateral_pyrdown.cu:172-199, :380-402
+//   computeDerivativeImages / applyKernel               cuda/bilateral_pyrdown.cu:271-331
+//   projectToPointCloud / projectPointsKernel           cuda/maps.cu:311-345
+//   computeRgbResidual / RGBResidual / residualKernel   cuda/reduce.cu:668-864
+//   rgbStep / RGBReduction / rgbKernel                  cuda/reduce.cu:423-607
+//   host half of RGBDOdometry::getIncrementalTransformation   RGBDOdometry.cpp:205-370
+// B200 design: no per-call cudaMalloc/cudaFree (the reference allocates the 25-tap table and the reduce
+// scratch on every call); the warp (K R K^-1, K t) of each iteration is rebuilt on the
+// device from the running estimate; the sigma of the robust weight and the Gauss-Newton solve live in the
+// reduction tails, so an iteration is 2 launches (3 with ICP) and no host round trip.
+#include "kt_ops.h"
+#include "kt_solve.cuh"
+#include "kt_reduce.cuh"
+
+namespace kt {
+
+namespace {
+
+__global__ void __launch_bounds__(256)
+short2float_kernel(const uint16_t* __restrict__ src, float* __restrict__ dst, int rows, int cols, int cutOff)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= cols || y >= rows) return;
+    size_t i = (size_t)y * cols + x;
+    dst[i] = src[i] > cutOff || src[i] <= 0 ? qnan() : ((float)src[i]) / 1000.0f;
+}
+
+__global__ void __launch_bounds__(256)
+bgr2intensity_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int rows, int cols)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= cols || y >= rows) return;
+    size_t i = (size_t)y * cols + x;
+    const uint8_t r = src[i * 3 + 0], g = src[i * 3 + 1], b = src[i * 3 + 2];     // PixelRGB {r,g,b}
+    int value = (float)r * 0.114f + (float)b * 0.299f + (float)g * 0.587f;
+    dst[i] = value;
+}
+
+__constant__ float c_gauss5[25] = {1, 4, 6, 4, 1, 4, 16, 24, 16, 4, 6, 24, 36, 24, 6, 4, 16, 24, 16, 4, 1, 4, 6, 4, 1};
+
+__global__ void __launch_bounds__(256)
+pyrdown_gauss_f_kernel(const float* __restrict__ src, float* __restrict__ dst, int srows, int scols, int drows, int dcols)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= dcols || y >= drows) return;
+    const int D = 5;
+    int tx = min(2 * x - D / 2 + D, scols - 1);
+    int ty = min(2 * y - D / 2 + D, srows - 1);
+    int cy = max(0, 2 * y - D / 2);
+    float sum = 0;
+    int count = 0;                                             // Q2: float weights accumulate into an int
+    for (; cy < ty; ++cy)
+        for (int cx = max(0, 2 * x - D / 2); cx < tx; ++cx) {
+            float v = src[(size_t)cy * scols + cx];
+            if (!isnan(v)) {
+                sum += v * c_gauss5[(ty - cy - 1) * 5 + (tx - cx - 1)];
+                count += c_gauss5[(ty - cy - 1) * 5 + (tx - cx - 1)];
+            }
+        }
+    dst[(size_t)y * dcols + x] = (float)(sum / (float)count);
+}
+
+__global__ void __launch_bounds__(256)
+pyrdown_uchar_gauss_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int srows, int scols, int drows, int dcols)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= dcols || y >= drows) return;
+    const int D = 5;
+    int tx = min(2 * x - D / 2 + D, scols - 1);
+    int ty = min(2 * y - D / 2 + D, srows - 1);
+    int cy = max(0, 2 * y - D / 2);
+    float sum = 0;
+    int count = 0;
+    for (; cy < ty; ++cy)
+        for (int cx = max(0, 2 * x - D / 2); cx < tx; ++cx) {
+            sum += src[(size_t)cy * scols + cx] * c_gauss5[(ty - cy - 1) * 5 + (tx - cx - 1)];
+            count += c_gauss5[(ty - cy - 1) * 5 + (tx - cx - 1)];
+        }
+    dst[(size_t)y * dcols + x] = (sum / (float)count);
+}
+
+__constant__ float c_gsx[9] = {0.52201f, 0.00000f, -0.52201f, 0.79451f, -0.00000f, -0.79451f, 0.52201f, 0.00000f, -0.52201f};
+__constant__ float c_gsy[9] = {0.52201f, 0.79451f, 0.52201f, 0.00000f, 0.00000f, 0.00000f, -0.52201f, -0.79451f, -0.52201f};
+
+__global__ void __launch_bounds__(256)
+derivative_kernel(const uint8_t* __restrict__ src, int16_t* __restrict__ dx, int16_t* __restrict__ dy, int rows, int cols)
+{
+    int x = threadIdx.x + blockIdx.x * blockDim.x;
+    int y = threadIdx.y + blockIdx.y * blockDim.y;
+    if (x >= cols || y >= rows) return;
+    float dxVal = 0, dyVal = 0;
+    int kernelIndex = 8;                                        // walks 8..0 over the taps actually visited (border quirk kept)
+    for (int j = max(y - 1, 0); j <= min(y + 1, rows - 1); j++)
+        for (int i = max(x - 1, 0); i <= min(x + 1, cols - 1); i++) {
+            dxVal += (float)src[(size_t)j * cols + i] * c_gsx[kernelIndex];
+            dyVal += (float)src[(size_t)j * cols + i] * c_gsy[kernelIndex];
+            --kernelIndex;
+        }
+    dx[(size_t)y * cols + x] = dxVal;
+    dy[(size_t)y * cols + x] = dyVal;
+}
+
+__global__ void __launch_bounds__(256)
+project_points_kernel(const float* __restrict__ depth, float3* __restrict__ cloud, int rows, int cols,
+                      const double invFx, const double invFy, const double cx, const double cy)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= cols || y >= rows) return;
+    size_t i = (size_t)y * cols + x;
+    float z = depth[i];
+    float3 c;
+    c.x = (float)((x - cx) * z * invFx);
+    c.y = (float)((y - cy) * z * invFy);
+    c.z = z;
+    cloud[i] = c;
+}
+
+// 16-byte correspondence record, byte-compatible with the reference's DataTerm (cuda/internal.h:90-96)
+struct DataTerm { short2 zero; short2 one; float diff; bool valid; };
+
+struct ResidualParams { RgbLevelArgs a; OdomState* st; int* partials; };
+
+// (K R K^-1, K t) from the inverse of the running estimate (RGBDOdometry.cpp:209-231), double then float.
+__device__ inline void build_warp(const OdomState* st, double fx, double fy, double cx, double cy, float* krkinv, float* kt)
+{
+    const double* T = st->resultRt;
+    double R[9], t[3];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) R[i * 3 + j] = T[j * 4 + i];          // R^T
+    for (int i = 0; i < 3; ++i) t[i] = -(R[i * 3 + 0] * T[3] + R[i * 3 + 1] * T[7] + R[i * 3 + 2] * T[11]);
+    const double K[9] = {fx, 0, cx, 0, fy, cy, 0, 0, 1};
+    const double Ki[9] = {1.0 / fx, 0, -cx / fx, 0, 1.0 / fy, -cy / fy, 0, 0, 1};
+    double KR[9];
+    for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) { double s = 0; for (int k = 0; k < 3; ++k) s += K[a * 3 + k] * R[k * 3 + b]; KR[a * 3 + b] = s; }
+    for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) { double s = 0; for (int k = 0; k < 3; ++k) s += KR[a * 3 + k] * Ki[k * 3 + b]; krkinv[a * 3 + b] = (float)s; }
+    for (int a = 0; a < 3; ++a) { double s = 0; for (int k = 0; k < 3; ++k) s += K[a * 3 + k] * t[k]; kt[a] = (float)s; }
+}
+
+__global__ void __launch_bounds__(RED_THREADS)
+residual_kernel(const ResidualParams p, int use_state_warp)
+{
+    __shared__ float s_w[12];
+    __shared__ int s_cnt[RED_THREADS / 32][2];
+    __shared__ bool s_last;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        if (use_state_warp) build_warp(p.st, p.a.Kfx, p.a.Kfy, p.a.Kcx, p.a.Kcy, s_w, s_w + 9);
+        else { for (int k = 0; k < 9; ++k) s_w[k] = p.st->krkinv[k]; for (int k = 0; k < 3; ++k) s_w[9 + k] = p.st->kt[k]; }
+    }
+    __syncthreads();
+    const float k00 = s_w[0], k01 = s_w[1], k02 = s_w[2], k10 = s_w[3], k11 = s_w[4], k12 = s_w[5], k20 = s_w[6], k21 = s_w[7], k22 = s_w[8];
+    const float3 kt = make_float3(s_w[9], s_w[10], s_w[11]);
+    const int cols = p.a.cols, rows = p.a.rows, N = cols * rows;
+    const int16_t* __restrict__ dIdx = p.a.dIdx; const int16_t* __restrict__ dIdy = p.a.dIdy;
+    const float* __restrict__ lastDepth = p.a.last_depth; const float* __restrict__ nextDepth = p.a.next_depth;
+    const uint8_t* __restrict__ lastImage = p.a.last_image; const uint8_t* __restrict__ nextImage = p.a.next_image;
+    DataTerm* __restrict__ corresImg = (DataTerm*)p.a.corres;
+    const float minScale = p.a.min_scale, maxDepthDelta = p.a.max_depth_delta;
+
+    int2 sum = {0, 0};
+    for (int k = blockIdx.x * RED_THREADS + tid; k < N; k += gridDim.x * RED_THREADS) {
+        int i = k / cols;
+        int j0 = k - (i * cols);
+        int2 value = {0, 0};
+        DataTerm corres;
+        corres.zero = make_short2(0, 0); corres.one = make_short2(0, 0); corres.diff = 0.f;
+        corres.valid = false;
+        if (j0 < cols - 5 && i < rows - 1) {
+            bool valid = true;
+            for (int u = max(i - 2, 0); u < min(i + 2, rows); u++)
+                for (int v = max(j0 - 2, 0); v < min(j0 + 2, cols); v++)
+                    valid = valid && (nextImage[(size_t)u * cols + v] > 0);
+            if (valid) {
+                short valx = dIdx[(size_t)i * cols + j0];
+                short valy = dIdy[(size_t)i * cols + j0];
+                float mTwo = (valx * valx) + (valy * valy);
+                if (mTwo >= minScale) {
+                    int y = i, x = j0;
+                    float d1 = nextDepth[(size_t)y * cols + x];
+                    if (!isnan(d1)) {
+                        float transformed_d1 = (float)(d1 * (k20 * x + k21 * y + k22) + kt.z);
+                        int u0 = __float2int_rn((d1 * (k00 * x + k01 * y + k02) + kt.x) / transformed_d1);
+                        int v0 = __float2int_rn((d1 * (k10 * x + k11 * y + k12) + kt.y) / transformed_d1);
+                        if (u0 >= 0 && v0 >= 0 && u0 < cols && v0 < rows) {
+                            float d0 = lastDepth[(size_t)v0 * cols + u0];
+                            if (d0 > 0 && fabsf(transformed_d1 - d0) <= maxDepthDelta && lastImage[(size_t)v0 * cols + u0] != 0) {
+                                corres.zero.x = u0; corres.zero.y = v0;
+                                corres.one.x = x; corres.one.y = y;
+                                corres.diff = static_cast<float>(nextImage[(size_t)y * cols + x]) - static_cast<float>(lastImage[(size_t)v0 * cols + u0]);
+                                corres.valid = true;
+                                value.x = 1;
+                                value.y = corres.diff * corres.diff;           // Q5: truncated to int per pixel
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        corresImg[k] = corres;
+        sum.x += value.x;
+        sum.y += value.y;
+    }
+    // integer reduction (order-independent): shuffle -> smem -> one partial per CTA -> last CTA totals
+    for (int o = 16; o > 0; o >>= 1) { sum.x += __shfl_down_sync(0xffffffffu, sum.x, o); sum.y += __shfl_down_sync(0xffffffffu, sum.y, o); }
+    if ((tid & 31) == 0) { s_cnt[tid >> 5][0] = sum.x; s_cnt[tid >> 5][1] = sum.y; }
+    __syncthreads();
+    if (tid == 0) {
+        int a = 0, b = 0;
+        for (int w = 0; w < RED_THREADS / 32; ++w) { a += s_cnt[w][0]; b += s_cnt[w][1]; }
+        p.partials[blockIdx.x * 2] = a; p.partials[blockIdx.x * 2 + 1] = b;
+        __threadfence();
+        unsigned int ticket = atomicInc(&p.st->blocks_done_rgb, gridDim.x - 1);
+        s_last = (ticket == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (tid == 0) {
+        int a = 0, b = 0;
+        for (int g = 0; g < (int)gridDim.x; ++g) { a += __ldcg(&p.partials[g * 2]); b += __ldcg(&p.partials[g * 2 + 1]); }
+        p.st->rgb_count = a;
+        p.st->rgb_sigma = b;
+    }
+}
+
+struct RgbStepParams { RgbLevelArgs a; OdomState* st; float* partials; float* trace; int mode; float sigma_override; };
+
+__global__ void __launch_bounds__(RED_THREADS)
+rgb_step_kernel(const RgbStepParams p)
+{
+    __shared__ float s_red[RED_THREADS / 32][32];
+    __shared__ bool s_last;
+    const int tid = threadIdx.x;
+    // Q3: sigmaVal = sqrt((float)sigma / rgbSize == 0 ? 1 : rgbSize)  (RGBDOdometry.cpp:253) -- computed like the host does
+    float sigma;
+    if (p.mode == 0) sigma = p.sigma_override;
+    else {
+        const int sg = p.st->rgb_sigma, cnt = p.st->rgb_count;
+        sigma = (float)sqrt((double)(((float)sg / cnt == 0) ? 1 : cnt));
+    }
+    const int cols = p.a.cols, rows = p.a.rows, N = cols * rows;
+    const DataTerm* __restrict__ corresImg = (const DataTerm*)p.a.corres;
+    const float3* __restrict__ cloud = (const float3*)p.a.cloud;
+    const int16_t* __restrict__ dIdx = p.a.dIdx; const int16_t* __restrict__ dIdy = p.a.dIdy;
+    const float fx = p.a.fx, fy = p.a.fy, sobelScale = p.a.sobel_scale;
+
+    float sum[NSUM];
+#pragma unroll
+    for (int k = 0; k < NSUM; ++k) sum[k] = 0.f;
+    for (int i = blockIdx.x * RED_THREADS + tid; i < N; i += gridDim.x * RED_THREADS) {
+        const DataTerm corresp = corresImg[i];
+        if (!corresp.valid) continue;
+        float w = sigma + fabsf(corresp.diff);
+        w = w > 1.19209290E-07F ? 1.0f / w : 1.0f;
+        if (sigma == -1) w = 1;
+        float row[7];
+        row[6] = -w * corresp.diff;
+        float3 cloudPoint = cloud[(size_t)corresp.zero.y * cols + corresp.zero.x];
+        float invz = 1.0 / cloudPoint.z;
+        float dI_dx_val = w * sobelScale * dIdx[(size_t)corresp.one.y * cols + corresp.one.x];
+        float dI_dy_val = w * sobelScale * dIdy[(size_t)corresp.one.y * cols + corresp.one.x];
+        float v0 = dI_dx_val * fx * invz;
+        float v1 = dI_dy_val * fy * invz;
+        float v2 = -(v0 * cloudPoint.x + v1 * cloudPoint.y) * invz;
+        row[0] = v0; row[1] = v1; row[2] = v2;
+        row[3] = -cloudPoint.z * v1 + cloudPoint.y * v2;
+        row[4] = cloudPoint.z * v0 - cloudPoint.x * v2;
+        row[5] = -cloudPoint.y * v0 + cloudPoint.x * v1;
+        accumulate_row(sum, row);
+    }
+    if (!grid_reduce29(sum, p.partials, &p.st->blocks_done, s_red, &s_last)) return;
+
+    if (tid < NSUM) p.st->sums_rgb[tid] = s_red[0][tid];
+    if (tid == 0) {
+        OdomState* st = p.st;
+        float A[36], b[6];
+        unpack_normal_equations(s_red[0], A, b);
+        if (p.trace) {
+            float* t = p.trace + (size_t)st->iter * TRACE_STRIDE;
+            for (int k = 0; k < 36; ++k) t[k] = A[k];
+            for (int k = 0; k < 6; ++k) t[36 + k] = b[k];
+            t[42] = (float)st->rgb_sigma; t[43] = (float)st->rgb_count;
+        }
+        if (p.mode != 0) {
+            double dA[36], db[6];
+            if (p.mode == 2) {                                  // RGBDOdometry.cpp:316-321
+                float Ai[36], bi[6];
+                unpack_normal_equations(st->sums_icp, Ai, bi);
+                const double w = 10;
+                for (int k = 0; k < 36; ++k) dA[k] = (double)A[k] + w * w * (double)Ai[k];
+                for (int k = 0; k < 6; ++k) db[k] = (double)b[k] + w * (double)bi[k];
+            } else {
+                for (int k = 0; k < 36; ++k) dA[k] = A[k];
+                for (int k = 0; k < 6; ++k) db[k] = b[k];
+            }
+            gauss_newton_update(dA, db, st);
+            st->iter += 1;
+        }
+    }
+}
+
+} // namespace
+
+#define KT_GRID2D(cols, rows) dim3 block(32, 8), grid(div_up(cols, 32), div_up(rows, 8))
+
+int short_depth_to_metres(const uint16_t* src, float* dst, int rows, int cols, int cut_off, cudaStream_t s)
+{ KT_GRID2D(cols, rows); short2float_kernel<<<grid, block, 0, s>>>(src, dst, rows, cols, cut_off); KT_LAUNCH_CHECK(); return 0; }
+
+int bgr_to_intensity(const uint8_t* rgb, uint8_t* dst, int rows, int cols, cudaStream_t s)
+{ KT_GRID2D(cols, rows); bgr2intensity_kernel<<<grid, block, 0, s>>>(rgb, dst, rows, cols); KT_LAUNCH_CHECK(); return 0; }
+
+int pyrdown_gauss_f(const float* src, float* dst, int srows, int scols, cudaStream_t s)
+{ int dr = srows / 2, dc = scols / 2; KT_GRID2D(dc, dr); pyrdown_gauss_f_kernel<<<grid, block, 0, s>>>(src, dst, srows, scols, dr, dc); KT_LAUNCH_CHECK(); return 0; }
+
+int pyrdown_uchar_gauss(const uint8_t* src, uint8_t* dst, int srows, int scols, cudaStream_t s)
+{ int dr = srows / 2, dc = scols / 2; KT_GRID2D(dc, dr); pyrdown_uchar_gauss_kernel<<<grid, block, 0, s>>>(src, dst, srows, scols, dr, dc); KT_LAUNCH_CHECK(); return 0; }
+
+int derivative_images(const uint8_t* src, int16_t* dx, int16_t* dy, int rows, int cols, cudaStream_t s)
+{ KT_GRID2D(cols, rows); derivative_kernel<<<grid, block, 0, s>>>(src, dx, dy, rows, cols); KT_LAUNCH_CHECK(); return 0; }
+
+int project_to_point_cloud(const float* depth, float* cloud, int rows, int cols, double fx, double fy, double cx, double cy, cudaStream_t s)
+{
+    KT_GRID2D(cols, rows);
+    // projectToPointCloud passes 1.0f / fx with fx double (maps.cu:342): a double division
+    project_points_kernel<<<grid, block, 0, s>>>(depth, (float3*)cloud, rows, cols, 1.0f / fx, 1.0f / fy, cx, cy);
+    KT_LAUNCH_CHECK();
+    return 0;
+}
+
+int rgb_residual(const RgbLevelArgs& a, OdomState* state, int* partials, int use_state_warp, cudaStream_t s)
+{
+    ResidualParams p; p.a = a; p.st = state; p.partials = partials;
+    int grid = reduce_grid_for(a.rows * a.cols);
+    residual_kernel<<<grid, RED_THREADS, 0, s>>>(p, use_state_warp);
+    KT_LAUNCH_CHECK();
+    return 0;
+}
+
+int rgb_iteration(const RgbLevelArgs& a, OdomState* state, float* partials, float* trace, int mode, float sigma_override, cudaStream_t s)
+{
+    RgbStepParams p; p.a = a; p.st = state; p.partials = partials; p.trace = trace; p.mode = mode; p.sigma_override = sigma_override;
+    int grid = reduce_grid_for(a.rows * a.cols);
+    rgb_step_kernel<<<grid, RED_THREADS, 0, s>>>(p);
+    KT_LAUNCH_CHECK();
+    return 0;
+}
+
+} // namespace kt

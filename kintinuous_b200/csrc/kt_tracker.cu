@@ -1,0 +1,580 @@
+// kintinuous_b200 -- the per-frame orchestrator behind kt_process_frame.
+//
+// Replaces (reference, src/frontend/): KintinuousTracker::{ctor, reset, processFrame, finalise, vWrapCopyUpdate,
+// mutexOutCloudBuffer} (KintinuousTracker.cpp:71-182, 262-354, 444-915, 1003-1048, 1075-1085, 1156-1208),
+// TsdfVolume (TSDFVolume.cpp:60-172), ColorVolume, and the drivers ICPOdometry::getIncrementalTransformation
+// (ICPOdometry.cpp:68-186) / RGBDOdometry::getIncrementalTransformation (RGBDOdometry.cpp:165-393).
+//
+// B200 design: everything of a frame is enqueued on ONE stream with exactly one host
+// synchronisation -- after the odometry, because the shift decision and the slice hand-off are host logic in
+// the reference too.  The reference's frame has 59 launches, 26 cudaDeviceSynchronize and 19 blocking D2H
+// copies; here: 5 pyramid launches, 1 + 19 odometry launches (solve on device), 3 fusion launches, 1 raycast
+// launch that also builds the model pyramid, one 200-byte D2H.
+#include "kt_ops.h"
+#include "../../include/kintinuous_b200.h"
+#include <vector>
+#include <cstring>
+#include <cmath>
+#include <climits>
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+
+namespace kt {
+
+// ---- error plumbing ------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+long long g_launches = 0;
+void set_error(const char* fmt, ...)
+{
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+}
+const char* last_error() { return g_err; }
+int cuda_check(cudaError_t e, const char* what, const char* file, int line)
+{
+    if (e == cudaSuccess) return 0;
+    set_error("CUDA error '%s' at %s:%d (%s)", cudaGetErrorString(e), file, line, what);
+    return KT_ERR_CUDA;
+}
+
+// ---- small host math (what the reference takes from Eigen) ---------------------------------------
+struct M3 { float m[9]; };
+struct V3 { float v[3]; };
+static M3 m3_identity() { M3 r = {{1, 0, 0, 0, 1, 0, 0, 0, 1}}; return r; }
+static M3 m3_inverse(const M3& a)      // Eigen::Matrix3f::inverse(): cofactors / determinant
+{
+    const float* m = a.m;
+    auto M = [&](int i, int j) { return m[i * 3 + j]; };
+    auto cof = [&](int i, int j) { return M((i + 1) % 3, (j + 1) % 3) * M((i + 2) % 3, (j + 2) % 3) - M((i + 1) % 3, (j + 2) % 3) * M((i + 2) % 3, (j + 1) % 3); };
+    float c00 = cof(0, 0), c10 = cof(1, 0), c20 = cof(2, 0);
+    float det = (c00 * M(0, 0) + c10 * M(1, 0)) + c20 * M(2, 0);
+    float invdet = 1.0f / det;
+    M3 r;
+    r.m[0] = c00 * invdet; r.m[1] = c10 * invdet; r.m[2] = c20 * invdet;
+    r.m[3] = cof(0, 1) * invdet; r.m[4] = cof(1, 1) * invdet; r.m[5] = cof(2, 1) * invdet;
+    r.m[6] = cof(0, 2) * invdet; r.m[7] = cof(1, 2) * invdet; r.m[8] = cof(2, 2) * invdet;
+    return r;
+}
+static Mat33 to_mat33(const float* m) { Mat33 r; r.r0 = make_float3(m[0], m[1], m[2]); r.r1 = make_float3(m[3], m[4], m[5]); r.r2 = make_float3(m[6], m[7], m[8]); return r; }
+
+struct SliceRec { int dimension; std::vector<kt_point_xyzrgb> points; float camera_t[3]; float camera_R[9]; uint64_t utime; };
+
+// what the host reads back after the odometry of a frame
+struct OdomResult { float Rcurr[9]; float tcurr[3]; int iter; int rgb_count; int rgb_sigma; };
+
+} // namespace kt
+
+using namespace kt;
+
+struct kt_ctx {
+    kt_config cfg;
+    cudaStream_t stream;
+    float size, voxel, trunc;
+    float volumeBasis[3], currentGlobalCamera[3];
+    int voxelWrap[3];
+    int global_time; uint64_t current_utime;
+    int overlap, parked;
+    std::vector<M3> rmats; std::vector<V3> tvecs;
+    std::vector<SliceRec> slices;
+    int iterations[LEVELS];
+    // device memory
+    int16_t* tsdf; uint8_t* color;
+    uint16_t* depth_raw; uint8_t* rgb;
+    uint16_t* depths_curr[LEVELS];
+    float* vmaps_g_prev[LEVELS]; float* nmaps_g_prev[LEVELS]; float* vmaps_curr[LEVELS]; float* nmaps_curr[LEVELS];
+    uint8_t* vmap_curr_color; float* depth_scaled; float* ztable;
+    OdomState* state; float* partials; int* ipartials; float* trace_dev; float* pose12_dev;
+    kt_point_xyzrgb* cloud_dev; unsigned int* counter_dev; size_t cloud_capacity; size_t cloud_count;
+    // RGB-D
+    float* lastDepth[LEVELS]; float* nextDepth[LEVELS]; uint8_t* lastImage[LEVELS]; uint8_t* nextImage[LEVELS];
+    int16_t* nextdIdx[LEVELS]; int16_t* nextdIdy[LEVELS]; float* pointClouds[LEVELS]; void* corresImg[LEVELS];
+    // pinned host staging
+    float* pose12_host; OdomResult* result_host; float* trace_host; unsigned int* counter_host;
+    int trace_iters; int shifted_last;
+    // timing
+    bool timing; cudaEvent_t ev[7]; float stage_ms[6];
+    long long launches_at_create;
+    std::vector<void*> allocs;
+};
+
+namespace {
+
+const int MAX_TRACE_ITERS = 64;
+
+template <class T> int dev_alloc(kt_ctx* c, T** p, size_t count)
+{
+    void* q = 0;
+    KT_CUDA(cudaMalloc(&q, count * sizeof(T) ? count * sizeof(T) : 1));
+    c->allocs.push_back(q);
+    *p = (T*)q;
+    return 0;
+}
+
+void vwrap_copy(const kt_ctx* c, int* w)       // KintinuousTracker::vWrapCopyUpdate (.cpp:1075-1085)
+{
+    const int V = c->cfg.vol;
+    for (int i = 0; i < 3; ++i) { w[i] = c->voxelWrap[i]; if (w[i] < 0) w[i] = V - ((-w[i]) % V); }
+}
+
+int fetch_cloud(kt_ctx* c, const int* vWrapCopy, const int* lo, const int* hi)      // TsdfVolume::fetchCloud (TSDFVolume.cpp:131-172)
+{
+    KT_CUDA(cudaMemsetAsync(c->counter_dev, 0, sizeof(unsigned int), c->stream));
+    float3 vs = make_float3(c->size, c->size, c->size);
+    int r = extract_slice(c->tsdf, vs, c->cfg.vol, c->cloud_dev, c->cloud_capacity, make_int3(vWrapCopy[0], vWrapCopy[1], vWrapCopy[2]), c->color,
+                          lo[0], hi[0], lo[1], hi[1], lo[2], hi[2], 1, make_int3(c->voxelWrap[0], c->voxelWrap[1], c->voxelWrap[2]), c->counter_dev, c->stream);
+    if (r) return r;
+    KT_CUDA(cudaMemcpyAsync(c->counter_host, c->counter_dev, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+    KT_CUDA(cudaStreamSynchronize(c->stream));
+    c->cloud_count = std::min((size_t)*c->counter_host, c->cloud_capacity);
+    return 0;
+}
+
+int push_slice(kt_ctx* c, int dimension)
+{
+    SliceRec s; s.dimension = dimension;
+    s.points.resize(c->cloud_count);
+    if (c->cloud_count) KT_CUDA(cudaMemcpy(s.points.data(), c->cloud_dev, c->cloud_count * sizeof(kt_point_xyzrgb), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 3; ++i) s.camera_t[i] = c->currentGlobalCamera[i];
+    for (int i = 0; i < 9; ++i) s.camera_R[i] = c->rmats.back().m[i];
+    s.utime = c->current_utime;
+    c->slices.push_back(std::move(s));
+    return 0;
+}
+
+int populate_rgbd(kt_ctx* c, float** destDepths, uint8_t** destImages)             // RGBDOdometry::populateRGBDData (.cpp:140-158)
+{
+    const int rows = c->cfg.rows, cols = c->cfg.cols;
+    int r;
+    if ((r = short_depth_to_metres(c->depth_raw, destDepths[0], rows, cols, (int)(6.0 * 1000), c->stream))) return r;
+    for (int i = 0; i + 1 < LEVELS; ++i) if ((r = pyrdown_gauss_f(destDepths[i], destDepths[i + 1], rows >> i, cols >> i, c->stream))) return r;
+    if ((r = bgr_to_intensity(c->rgb, destImages[0], rows, cols, c->stream))) return r;
+    for (int i = 0; i + 1 < LEVELS; ++i) if ((r = pyrdown_uchar_gauss(destImages[i], destImages[i + 1], rows >> i, cols >> i, c->stream))) return r;
+    return 0;
+}
+
+int do_integrate(kt_ctx* c, const M3& Rinv, const V3& t, const int* wrap)
+{
+    const int rows = c->cfg.rows, cols = c->cfg.cols;
+    Intr k = {c->cfg.fx, c->cfg.fy, c->cfg.cx, c->cfg.cy};
+    int r = scale_depth(c->depth_raw, c->depth_scaled, rows, cols, k, c->cfg.angle_color != 0, c->stream);
+    if (r) return r;
+    IntegrateArgs a;
+    a.depth_scaled = c->depth_scaled; a.rows = rows; a.cols = cols; a.k = k; a.volume_size = make_float3(c->size, c->size, c->size);
+    a.Rinv = to_mat33(Rinv.m); a.t = make_float3(t.v[0], t.v[1], t.v[2]); a.trunc = c->trunc;
+    a.tsdf = c->tsdf; a.color = c->color; a.vol = c->cfg.vol; a.wrap = make_int3(wrap[0], wrap[1], wrap[2]);
+    a.rgb = c->rgb; a.nmap_curr = c->nmaps_curr[0]; a.angle_color = c->cfg.angle_color != 0;
+    a.z_begin = 0; a.z_end = c->cfg.vol;
+    return integrate(a, c->ztable, c->stream);
+}
+
+int run_odometry(kt_ctx* c, const M3& Rprev, const V3& tprev, M3* Rcurr, V3* tcurr)
+{
+    const int rows = c->cfg.rows, cols = c->cfg.cols;
+    const int mode = c->cfg.odometry;
+    int r;
+    for (int k = 0; k < 9; ++k) c->pose12_host[k] = Rprev.m[k];
+    for (int k = 0; k < 3; ++k) c->pose12_host[9 + k] = tprev.v[k];
+    KT_CUDA(cudaMemcpyAsync(c->pose12_dev, c->pose12_host, 12 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    if ((r = odom_begin_frame(c->state, c->pose12_dev, c->stream))) return r;
+    const float distThres = 0.10f, angleThres = sinf(20.f * 3.14159254f / 180.f);      // ICPOdometry.h:35-36
+    Intr K = {c->cfg.fx, c->cfg.fy, c->cfg.cx, c->cfg.cy};
+    if (mode != 0) {
+        if ((r = populate_rgbd(c, c->nextDepth, c->nextImage))) return r;
+        for (int i = 0; i < LEVELS; ++i)
+            if ((r = derivative_images(c->nextImage[i], c->nextdIdx[i], c->nextdIdy[i], rows >> i, cols >> i, c->stream))) return r;
+    }
+    int total_iters = 0;
+    const double SOBEL_SCALE = 1.0 / std::pow(2.0, 3);
+    const int minimumGradientMagnitudes[4] = {12, 5, 3, 1};
+    for (int level = LEVELS - 1; level >= 0; --level) {
+        const int lr = rows >> level, lc = cols >> level;
+        Intr kl = intr_level(K, level);
+        IcpLevelArgs ia = {c->vmaps_curr[level], c->nmaps_curr[level], c->vmaps_g_prev[level], c->nmaps_g_prev[level], lr, lc, kl, distThres, angleThres};
+        RgbLevelArgs ra;
+        if (mode != 0) {
+            const int div = 1 << level;
+            // IntrDoublePrecision built from the float Intr (RGBDOdometry.cpp:70-73), per-level division in double
+            const double dfx = (double)K.fx / div, dfy = (double)K.fy / div, dcx = (double)K.cx / div, dcy = (double)K.cy / div;
+            if ((r = project_to_point_cloud(c->lastDepth[level], c->pointClouds[level], lr, lc, dfx, dfy, dcx, dcy, c->stream))) return r;
+            ra.dIdx = c->nextdIdx[level]; ra.dIdy = c->nextdIdy[level]; ra.last_depth = c->lastDepth[level]; ra.next_depth = c->nextDepth[level];
+            ra.last_image = c->lastImage[level]; ra.next_image = c->nextImage[level]; ra.corres = c->corresImg[level]; ra.cloud = c->pointClouds[level];
+            ra.rows = lr; ra.cols = lc;
+            ra.min_scale = (float)(std::pow((double)minimumGradientMagnitudes[level], 2.0) / std::pow(SOBEL_SCALE, 2.0));
+            ra.max_depth_delta = 0.07f; ra.fx = kl.fx; ra.fy = kl.fy; ra.sobel_scale = (float)SOBEL_SCALE;
+            ra.Kfx = dfx; ra.Kfy = dfy; ra.Kcx = dcx; ra.Kcy = dcy;
+        }
+        for (int iter = 0; iter < c->iterations[level]; ++iter) {
+            float* trace = (total_iters < MAX_TRACE_ITERS) ? c->trace_dev : 0;
+            if (mode == 0) {
+                if ((r = icp_iteration(ia, c->state, c->partials, trace, 1, c->stream))) return r;
+            } else {
+                if ((r = rgb_residual(ra, c->state, c->ipartials, 1, c->stream))) return r;
+                if (mode == 2 && (r = icp_iteration(ia, c->state, c->partials, 0, 0, c->stream))) return r;
+                if ((r = rgb_iteration(ra, c->state, c->partials, trace, mode == 2 ? 2 : 1, 0.f, c->stream))) return r;
+            }
+            ++total_iters;
+        }
+    }
+    c->trace_iters = std::min(total_iters, MAX_TRACE_ITERS);
+    // one 64-byte read-back of the estimate (+ the trace when someone asked for it later: it stays on the device)
+    KT_CUDA(cudaMemcpyAsync(c->result_host->Rcurr, (char*)c->state + offsetof(OdomState, Rcurr), 12 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    KT_CUDA(cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < 9; ++k) Rcurr->m[k] = c->result_host->Rcurr[k];
+    for (int k = 0; k < 3; ++k) tcurr->v[k] = c->result_host->tcurr[k];
+    if (mode != 0) {
+        for (int i = 0; i < LEVELS; ++i) { std::swap(c->lastDepth[i], c->nextDepth[i]); std::swap(c->lastImage[i], c->nextImage[i]); }   // RGBDOdometry.cpp:377-381
+        float dx = tcurr->v[0] - tprev.v[0], dy = tcurr->v[1] - tprev.v[1], dz = tcurr->v[2] - tprev.v[2];
+        if (std::sqrt(dx * dx + dy * dy + dz * dz) > 0.3) { *Rcurr = Rprev; *tcurr = tprev; }                                               // :383-387
+    }
+    return 0;
+}
+
+void mark(kt_ctx* c, int i) { if (c->timing) cudaEventRecord(c->ev[i], c->stream); }
+
+int process_frame_device(kt_ctx* c, uint64_t utime, kt_pose* out)
+{
+    const int rows = c->cfg.rows, cols = c->cfg.cols, V = c->cfg.vol;
+    const int mode = c->cfg.odometry;
+    int r;
+    c->shifted_last = 0;
+    mark(c, 0);
+    const bool use_icp_maps = (mode == 0) || (mode == 2) || c->cfg.angle_color;        // KintinuousTracker.cpp:465 (Q10)
+    if (use_icp_maps) {
+        if ((r = bilateral(c->depth_raw, c->depths_curr[0], rows, cols, c->stream))) return r;
+        for (int i = 1; i < LEVELS; ++i) if ((r = pyrdown(c->depths_curr[i - 1], c->depths_curr[i], rows >> (i - 1), cols >> (i - 1), c->stream))) return r;
+        MapsLevel ml[LEVELS];
+        Intr K = {c->cfg.fx, c->cfg.fy, c->cfg.cx, c->cfg.cy};
+        for (int i = 0; i < LEVELS; ++i) { ml[i].depth = c->depths_curr[i]; ml[i].vmap = c->vmaps_curr[i]; ml[i].nmap = c->nmaps_curr[i]; ml[i].rows = rows >> i; ml[i].cols = cols >> i; ml[i].k = intr_level(K, i); }
+        if ((r = create_maps_pyramid(ml, LEVELS, c->stream))) return r;
+    }
+    mark(c, 1);
+
+    if (c->global_time == 0) {                                                           // .cpp:481-557
+        M3 Rcam = c->rmats.back(); V3 tcam = c->tvecs.back();
+        M3 Rcam_inv = m3_inverse(Rcam);
+        int emptyVoxel[3] = {0, 0, 0};
+        if (mode != 0 && (r = populate_rgbd(c, c->lastDepth, c->lastImage))) return r;    // rgbd->firstRun
+        mark(c, 2); mark(c, 3);
+        if ((r = do_integrate(c, Rcam_inv, tcam, emptyVoxel))) return r;
+        mark(c, 4);
+        TransformLevel tl[LEVELS];
+        for (int i = 0; i < LEVELS; ++i) { tl[i].vs = c->vmaps_curr[i]; tl[i].ns = c->nmaps_curr[i]; tl[i].vd = c->vmaps_g_prev[i]; tl[i].nd = c->nmaps_g_prev[i]; tl[i].rows = rows >> i; tl[i].cols = cols >> i; }
+        if ((r = transform_maps_pyramid(tl, LEVELS, to_mat33(Rcam.m), make_float3(tcam.v[0], tcam.v[1], tcam.v[2]), c->stream))) return r;
+        mark(c, 5);
+        ++c->global_time;
+        c->current_utime = utime;
+        if (out) kt_get_pose(c, out);
+        return 0;
+    }
+
+    M3 Rprev = c->rmats.back(); V3 tprev = c->tvecs.back();
+    M3 Rcurr = Rprev; V3 tcurr = tprev;
+    if ((r = run_odometry(c, Rprev, tprev, &Rcurr, &tcurr))) return r;
+    mark(c, 2);
+    c->current_utime = utime;
+    c->rmats.push_back(Rcurr); c->tvecs.push_back(tcurr);                                // .cpp:578-579
+
+    for (int i = 0; i < 3; ++i) {                                                        // .cpp:581-596
+        float g = c->volumeBasis[i] - c->size * 0.5f;
+        g += c->voxelWrap[i] * c->voxel;
+        g += tcurr.v[i] - c->volumeBasis[i];
+        c->currentGlobalCamera[i] = g;
+    }
+    M3 Rcurr_inv = m3_inverse(Rcurr);                                                    // .cpp:627
+    float currentTranslation[3];
+    for (int i = 0; i < 3; ++i) currentTranslation[i] = c->tvecs.back().v[i] - c->volumeBasis[i];
+    const int thresh = c->parked ? INT_MAX : c->cfg.voxel_shift;                         // .cpp:636
+    int trans[3];
+    for (int i = 0; i < 3; ++i) {                                                        // .cpp:642-667
+        int f = (int)std::floor(currentTranslation[i] / c->voxel);
+        trans[i] = (f < 0) ? std::max(-thresh, f) : std::min(thresh, f);
+    }
+    int vWrapCopy[3];
+    for (int axis = 0; axis < 3; ++axis) {                                               // x :675-723, y :729-777, z :783-831
+        vwrap_copy(c, vWrapCopy);
+        const int n = trans[axis];
+        int lo[3] = {0, 0, 0}, hi[3] = {V, V, V};
+        bool cycled = false;
+        if (n >= thresh) {
+            lo[axis] = 0; hi[axis] = n + 1 + c->overlap;
+            if ((r = fetch_cloud(c, vWrapCopy, lo, hi))) return r;
+            if ((r = clear_volume(axis, 0, c->tsdf, c->color, V, c->voxelWrap[axis], c->voxelWrap[axis] + n, c->stream))) return r;
+            cycled = true;
+        } else if (n <= -thresh) {
+            if (axis < 2) { lo[axis] = V + (n - c->overlap); hi[axis] = V; }
+            else { lo[axis] = V + (n - c->overlap) - 1; hi[axis] = V - 1; }               // .cpp:805 (Q12)
+            if ((r = fetch_cloud(c, vWrapCopy, lo, hi))) return r;
+            if ((r = clear_volume(axis, 1, c->tsdf, c->color, V, c->voxelWrap[axis], c->voxelWrap[axis] + n, c->stream))) return r;
+            cycled = true;
+        }
+        if (cycled) {                                                                    // mutexOutCloudBuffer (.cpp:1156-1208)
+            int vt[3] = {0, 0, 0}; vt[axis] = n;
+            float voxelTransSize[3];
+            for (int i = 0; i < 3; ++i) voxelTransSize[i] = c->voxel * vt[i];
+            // the slice is recorded before tvecs_.back() / voxelWrap move, with the camera of this frame
+            for (int i = 0; i < 3; ++i) c->tvecs.back().v[i] -= voxelTransSize[i];
+            int dim = vt[0] > 0 ? 0 : vt[0] < 0 ? 1 : vt[1] > 0 ? 2 : vt[1] < 0 ? 3 : vt[2] > 0 ? 4 : 5;
+            if ((r = push_slice(c, dim))) return r;
+            for (int i = 0; i < 3; ++i) c->voxelWrap[i] += vt[i];
+            for (int i = 0; i < 3; ++i) tcurr.v[i] -= voxelTransSize[i];
+            ++c->shifted_last;
+        }
+    }
+    vwrap_copy(c, vWrapCopy);
+    mark(c, 3);
+
+    if ((r = do_integrate(c, Rcurr_inv, tcurr, vWrapCopy))) return r;                    // .cpp:864-876
+    mark(c, 4);
+    vwrap_copy(c, vWrapCopy);
+    RaycastArgs ra;
+    ra.k.fx = c->cfg.fx; ra.k.fy = c->cfg.fy; ra.k.cx = c->cfg.cx; ra.k.cy = c->cfg.cy;
+    ra.R = to_mat33(Rcurr.m); ra.t = make_float3(tcurr.v[0], tcurr.v[1], tcurr.v[2]); ra.trunc = c->trunc;
+    ra.volume_size = make_float3(c->size, c->size, c->size); ra.tsdf = c->tsdf; ra.color = c->color; ra.vol = V;
+    ra.wrap = make_int3(vWrapCopy[0], vWrapCopy[1], vWrapCopy[2]);
+    for (int l = 0; l < LEVELS; ++l) { ra.vmap[l] = c->vmaps_g_prev[l]; ra.nmap[l] = c->nmaps_g_prev[l]; }
+    ra.rows = rows; ra.cols = cols; ra.vmap_color = c->vmap_curr_color;
+    ra.n_levels = (mode == 0 || mode == 2) ? LEVELS : 1;                                 // .cpp:892-899
+    if ((r = raycast(ra, c->stream))) return r;
+    mark(c, 5);
+    ++c->global_time;
+    if (out) kt_get_pose(c, out);
+    return 0;
+}
+
+} // namespace
+
+// ---------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* kt_last_error(void) { return kt::last_error(); }
+
+int kt_cuda_available(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n > 0 ? 1 : 0;
+}
+
+int kt_reset(kt_ctx* c)
+{
+    if (!c) return KT_ERR_INVALID;
+    c->global_time = 0;
+    c->rmats.clear(); c->tvecs.clear();
+    c->rmats.push_back(m3_identity());
+    V3 tb = {{c->volumeBasis[0], c->volumeBasis[1], c->volumeBasis[2]}};
+    c->tvecs.push_back(tb);
+    for (int i = 0; i < 3; ++i) { c->voxelWrap[i] = 0; c->currentGlobalCamera[i] = c->volumeBasis[i] - c->size * 0.5f; }
+    c->slices.clear();
+    c->trace_iters = 0; c->shifted_last = 0; c->cloud_count = 0;
+    int r = init_volume(c->tsdf, c->color, c->cfg.vol, c->stream);
+    if (r) return r;
+    // Q7: stale y/z planes of invalid pixels start from a defined state (zeros)
+    const size_t P = (size_t)c->cfg.rows * c->cfg.cols;
+    for (int l = 0; l < LEVELS; ++l) {
+        size_t Pl = P >> (2 * l);
+        KT_CUDA(cudaMemsetAsync(c->vmaps_g_prev[l], 0, Pl * 12, c->stream)); KT_CUDA(cudaMemsetAsync(c->nmaps_g_prev[l], 0, Pl * 12, c->stream));
+        KT_CUDA(cudaMemsetAsync(c->vmaps_curr[l], 0, Pl * 12, c->stream)); KT_CUDA(cudaMemsetAsync(c->nmaps_curr[l], 0, Pl * 12, c->stream));
+    }
+    KT_CUDA(cudaMemsetAsync(c->vmap_curr_color, 0, P * 4, c->stream));
+    KT_CUDA(cudaMemsetAsync(c->state, 0, sizeof(OdomState), c->stream));
+    KT_CUDA(cudaStreamSynchronize(c->stream));
+    return KT_OK;
+}
+
+int kt_create(const kt_config* cfg, kt_ctx** out)
+{
+    if (!cfg || !out) { set_error("kt_create: null argument"); return KT_ERR_INVALID; }
+    if (cfg->rows <= 0 || cfg->cols <= 0 || cfg->vol < 32 || cfg->vol % 32 != 0 || cfg->volume_size <= 0) { set_error("kt_create: bad geometry (vol must be a multiple of 32)"); return KT_ERR_INVALID; }
+    if ((cfg->rows % 8) != 0 || (cfg->cols % 32) != 0) { set_error("kt_create: rows must be a multiple of 8 and cols of 32"); return KT_ERR_INVALID; }
+    if (cfg->odometry < 0 || cfg->odometry > 2) { set_error("kt_create: odometry must be 0, 1 or 2"); return KT_ERR_INVALID; }
+    if (!kt_cuda_available()) { set_error("kt_create: no CUDA device (this library has no CPU path)"); return KT_ERR_CUDA; }
+    KT_CUDA(cudaSetDevice(cfg->device));
+    kt_ctx* c = new kt_ctx();
+    c->cfg = *cfg;
+    c->launches_at_create = g_launches;
+    if (c->cfg.cloud_capacity <= 0) c->cfg.cloud_capacity = 3 * cfg->rows * cfg->cols;          // KintinuousTracker.cpp:77
+    c->overlap = cfg->overlap; c->parked = cfg->parked;
+    c->size = cfg->volume_size;
+    c->voxel = c->size / (float)cfg->vol;
+    float def = std::max(0.01f, c->size / 100.0f);                                              // KintinuousTracker.cpp:112
+    c->trunc = std::max(def, 2.1f * c->voxel);                                                  // TSDFVolume.cpp:96
+    for (int i = 0; i < 3; ++i) c->volumeBasis[i] = c->size * 0.5f;                             // KintinuousTracker.cpp:109
+    c->timing = false;
+    {   // iteration schedules: ICPOdometry.cpp:42-55, RGBDOdometry.cpp:76-107
+        const int icp[4] = {10, 5, 4, 0}, icpf[4] = {0, 10, 5, 0}, rgb[4] = {10, 7, 7, 7}, rgbf[4] = {0, 10, 7, 0}, ri[4] = {10, 5, 4, 0}, rif[4] = {0, 10, 7, 0};
+        const int* sel = cfg->odometry == 0 ? (cfg->fast_odometry ? icpf : icp) : cfg->odometry == 1 ? (cfg->fast_odometry ? rgbf : rgb) : (cfg->fast_odometry ? rif : ri);
+        for (int i = 0; i < 4; ++i) c->iterations[i] = sel[i];
+    }
+    int r = 0;
+#define KT_TRY(x) do { r = (x); if (r) { kt_destroy(c); return r; } } while (0)
+    r = kt::cuda_check(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "stream", __FILE__, __LINE__);
+    if (r) { delete c; return r; }
+    const size_t P = (size_t)cfg->rows * cfg->cols, V3n = (size_t)cfg->vol * cfg->vol * cfg->vol;
+    KT_TRY(dev_alloc(c, &c->tsdf, V3n)); KT_TRY(dev_alloc(c, &c->color, V3n * 4));
+    KT_TRY(dev_alloc(c, &c->depth_raw, P)); KT_TRY(dev_alloc(c, &c->rgb, P * 3));
+    for (int l = 0; l < LEVELS; ++l) {
+        size_t Pl = P >> (2 * l);
+        KT_TRY(dev_alloc(c, &c->depths_curr[l], Pl));
+        KT_TRY(dev_alloc(c, &c->vmaps_g_prev[l], Pl * 3)); KT_TRY(dev_alloc(c, &c->nmaps_g_prev[l], Pl * 3));
+        KT_TRY(dev_alloc(c, &c->vmaps_curr[l], Pl * 3)); KT_TRY(dev_alloc(c, &c->nmaps_curr[l], Pl * 3));
+        c->lastDepth[l] = c->nextDepth[l] = 0; c->lastImage[l] = c->nextImage[l] = 0; c->nextdIdx[l] = c->nextdIdy[l] = 0; c->pointClouds[l] = 0; c->corresImg[l] = 0;
+        if (cfg->odometry != 0) {
+            KT_TRY(dev_alloc(c, &c->lastDepth[l], Pl)); KT_TRY(dev_alloc(c, &c->nextDepth[l], Pl));
+            KT_TRY(dev_alloc(c, &c->lastImage[l], Pl)); KT_TRY(dev_alloc(c, &c->nextImage[l], Pl));
+            KT_TRY(dev_alloc(c, &c->nextdIdx[l], Pl)); KT_TRY(dev_alloc(c, &c->nextdIdy[l], Pl));
+            KT_TRY(dev_alloc(c, &c->pointClouds[l], Pl * 3));
+            uint8_t* ci = 0; KT_TRY(dev_alloc(c, &ci, Pl * 16)); c->corresImg[l] = ci;
+        }
+    }
+    KT_TRY(dev_alloc(c, &c->vmap_curr_color, P * 4)); KT_TRY(dev_alloc(c, &c->depth_scaled, P));
+    KT_TRY(dev_alloc(c, &c->ztable, (size_t)2 * cfg->vol));
+    KT_TRY(dev_alloc(c, &c->state, 1)); KT_TRY(dev_alloc(c, &c->partials, (size_t)MAX_PARTIALS * 32)); KT_TRY(dev_alloc(c, &c->ipartials, (size_t)MAX_PARTIALS * 2));
+    KT_TRY(dev_alloc(c, &c->trace_dev, (size_t)MAX_TRACE_ITERS * TRACE_STRIDE)); KT_TRY(dev_alloc(c, &c->pose12_dev, 12));
+    c->cloud_capacity = (size_t)c->cfg.cloud_capacity;
+    KT_TRY(dev_alloc(c, &c->cloud_dev, c->cloud_capacity)); KT_TRY(dev_alloc(c, &c->counter_dev, 1));
+    KT_TRY(kt::cuda_check(cudaMallocHost((void**)&c->pose12_host, 12 * sizeof(float)), "pinned", __FILE__, __LINE__));
+    KT_TRY(kt::cuda_check(cudaMallocHost((void**)&c->result_host, sizeof(OdomResult)), "pinned", __FILE__, __LINE__));
+    KT_TRY(kt::cuda_check(cudaMallocHost((void**)&c->trace_host, (size_t)MAX_TRACE_ITERS * TRACE_STRIDE * sizeof(float)), "pinned", __FILE__, __LINE__));
+    KT_TRY(kt::cuda_check(cudaMallocHost((void**)&c->counter_host, sizeof(unsigned int)), "pinned", __FILE__, __LINE__));
+    for (int i = 0; i < 7; ++i) KT_TRY(kt::cuda_check(cudaEventCreate(&c->ev[i]), "event", __FILE__, __LINE__));
+    for (int i = 0; i < 6; ++i) c->stage_ms[i] = 0.f;
+    KT_TRY(kt_reset(c));
+#undef KT_TRY
+    *out = c;
+    return KT_OK;
+}
+
+int kt_destroy(kt_ctx* c)
+{
+    if (!c) return KT_OK;
+    cudaSetDevice(c->cfg.device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (void* p : c->allocs) cudaFree(p);
+    if (c->pose12_host) cudaFreeHost(c->pose12_host);
+    if (c->result_host) cudaFreeHost(c->result_host);
+    if (c->trace_host) cudaFreeHost(c->trace_host);
+    if (c->counter_host) cudaFreeHost(c->counter_host);
+    for (int i = 0; i < 7; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return KT_OK;
+}
+
+int kt_process_frame_device(kt_ctx* c, const uint16_t* depth_dev, const uint8_t* rgb_dev, uint64_t utime, kt_pose* out)
+{
+    if (!c || !depth_dev || !rgb_dev) { set_error("kt_process_frame_device: null argument"); return KT_ERR_INVALID; }
+    KT_CUDA(cudaSetDevice(c->cfg.device));
+    const size_t P = (size_t)c->cfg.rows * c->cfg.cols;
+    KT_CUDA(cudaMemcpyAsync(c->depth_raw, depth_dev, P * 2, cudaMemcpyDeviceToDevice, c->stream));
+    KT_CUDA(cudaMemcpyAsync(c->rgb, rgb_dev, P * 3, cudaMemcpyDeviceToDevice, c->stream));
+    return process_frame_device(c, utime, out);
+}
+
+int kt_process_frame(kt_ctx* c, const uint16_t* depth_host, const uint8_t* rgb_host, uint64_t utime, kt_pose* out)
+{
+    if (!c || !depth_host || !rgb_host) { set_error("kt_process_frame: null argument"); return KT_ERR_INVALID; }
+    KT_CUDA(cudaSetDevice(c->cfg.device));
+    const size_t P = (size_t)c->cfg.rows * c->cfg.cols;
+    KT_CUDA(cudaMemcpyAsync(c->depth_raw, depth_host, P * 2, cudaMemcpyHostToDevice, c->stream));   // TrackerInterface.cpp:90
+    KT_CUDA(cudaMemcpyAsync(c->rgb, rgb_host, P * 3, cudaMemcpyHostToDevice, c->stream));           // TrackerInterface.cpp:91
+    return process_frame_device(c, utime, out);
+}
+
+int kt_finalise(kt_ctx* c)                                                                           // KintinuousTracker::finalise (.cpp:1003-1048)
+{
+    if (!c) return KT_ERR_INVALID;
+    KT_CUDA(cudaSetDevice(c->cfg.device));
+    int vWrapCopy[3]; vwrap_copy(c, vWrapCopy);
+    const int V = c->cfg.vol;
+    int lo[3] = {0, 0, 0}, hi[3] = {V, V, V};
+    int r = fetch_cloud(c, vWrapCopy, lo, hi);
+    if (r) return r;
+    return push_slice(c, 7);     // CloudSlice::FINAL
+}
+
+int kt_get_pose(kt_ctx* c, kt_pose* out)
+{
+    if (!c || !out) return KT_ERR_INVALID;
+    for (int i = 0; i < 9; ++i) out->R[i] = c->rmats.back().m[i];
+    for (int i = 0; i < 3; ++i) { out->t[i] = c->tvecs.back().v[i]; out->global_t[i] = c->currentGlobalCamera[i]; out->voxel_wrap[i] = c->voxelWrap[i]; }
+    out->shifted = c->shifted_last;
+    out->frame = c->global_time;
+    return KT_OK;
+}
+
+float kt_get_voxel_size(kt_ctx* c) { return c ? c->voxel : 0.f; }
+float kt_get_trunc_dist(kt_ctx* c) { return c ? c->trunc : 0.f; }
+int kt_set_overlap(kt_ctx* c, int overlap) { if (!c) return KT_ERR_INVALID; c->overlap = overlap; return KT_OK; }
+int kt_set_parked(kt_ctx* c, int parked) { if (!c) return KT_ERR_INVALID; c->parked = parked; return KT_OK; }
+int kt_num_slices(kt_ctx* c) { return c ? (int)c->slices.size() : 0; }
+
+int kt_get_slice(kt_ctx* c, int idx, kt_point_xyzrgb* points, size_t max_points, size_t* count, int* dimension, float* camera_t)
+{
+    if (!c || idx < 0 || idx >= (int)c->slices.size()) { set_error("kt_get_slice: bad index"); return KT_ERR_INVALID; }
+    const SliceRec& s = c->slices[idx];
+    if (count) *count = s.points.size();
+    if (dimension) *dimension = s.dimension;
+    if (camera_t) for (int i = 0; i < 3; ++i) camera_t[i] = s.camera_t[i];
+    size_t n = std::min(max_points, s.points.size());
+    if (points && n) std::memcpy(points, s.points.data(), n * sizeof(kt_point_xyzrgb));
+    return KT_OK;
+}
+
+int kt_get_trace(kt_ctx* c, float* dst, int max_iters, int* n_iters)
+{
+    if (!c) return KT_ERR_INVALID;
+    KT_CUDA(cudaSetDevice(c->cfg.device));
+    int n = std::min(max_iters, c->trace_iters);
+    if (n_iters) *n_iters = c->trace_iters;
+    if (dst && n > 0) {
+        KT_CUDA(cudaMemcpyAsync(c->trace_host, c->trace_dev, (size_t)n * TRACE_STRIDE * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        KT_CUDA(cudaStreamSynchronize(c->stream));
+        std::memcpy(dst, c->trace_host, (size_t)n * TRACE_STRIDE * sizeof(float));
+    }
+    return KT_OK;
+}
+
+int kt_volume_export_reference_layout(kt_ctx* c, int16_t* tsdf_host, uint8_t* color_host)
+{
+    if (!c) return KT_ERR_INVALID;
+    KT_CUDA(cudaSetDevice(c->cfg.device));
+    KT_CUDA(cudaStreamSynchronize(c->stream));
+    const size_t n = (size_t)c->cfg.vol * c->cfg.vol * c->cfg.vol;
+    if (tsdf_host) KT_CUDA(cudaMemcpy(tsdf_host, c->tsdf, n * 2, cudaMemcpyDeviceToHost));
+    if (color_host) KT_CUDA(cudaMemcpy(color_host, c->color, n * 4, cudaMemcpyDeviceToHost));
+    return KT_OK;
+}
+
+int kt_download_map(kt_ctx* c, int which, int level, void* dst)
+{
+    if (!c || !dst || level < 0 || level >= LEVELS || which < 0 || which > 5) return KT_ERR_INVALID;
+    KT_CUDA(cudaSetDevice(c->cfg.device));
+    const size_t Pl = ((size_t)c->cfg.rows * c->cfg.cols) >> (2 * level);
+    const void* src = which == 0 ? (void*)c->vmaps_curr[level] : which == 1 ? (void*)c->nmaps_curr[level] :
+                      which == 2 ? (void*)c->vmaps_g_prev[level] : which == 3 ? (void*)c->nmaps_g_prev[level] :
+                      which == 4 ? (void*)c->depths_curr[level] : (void*)c->vmap_curr_color;
+    const size_t bytes = which <= 3 ? Pl * 12 : which == 4 ? Pl * 2 : Pl * 4;
+    KT_CUDA(cudaStreamSynchronize(c->stream));
+    KT_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    return KT_OK;
+}
+
+int kt_set_stage_timing(kt_ctx* c, int enabled) { if (!c) return KT_ERR_INVALID; c->timing = enabled != 0; return KT_OK; }
+
+int kt_get_stage_ms(kt_ctx* c, float* ms6)
+{
+    if (!c || !ms6) return KT_ERR_INVALID;
+    if (!c->timing) { for (int i = 0; i < 6; ++i) ms6[i] = 0.f; return KT_OK; }
+    KT_CUDA(cudaStreamSynchronize(c->stream));
+    float total = 0.f;
+    for (int i = 0; i < 5; ++i) { float t = 0.f; if (cudaEventElapsedTime(&t, c->ev[i], c->ev[i + 1]) != cudaSuccess) { cudaGetLastError(); t = 0.f; } ms6[i] = t; total += t; }
+    ms6[5] = total;
+    return KT_OK;
+}
+
+long long kt_launch_count(kt_ctx* c) { return c ? g_launches - c->launches_at_create : g_launches; }
+
+int kt_alloc_pinned(void** ptr, size_t bytes) { KT_CUDA(cudaMallocHost(ptr, bytes)); return KT_OK; }
+int kt_free_pinned(void* ptr) { if (ptr) KT_CUDA(cudaFreeHost(ptr)); return KT_OK; }
+
+} // extern "C"

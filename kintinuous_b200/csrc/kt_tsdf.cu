@@ -1,0 +1,338 @@
+// kintinuous_b200 -- TSDF volume: initialise, clear shifted-out slabs, integrate a depth frame.
+//
+// Replaces (reference, src/frontend/cuda/tsdf_volume.cu):
+//   initVolume / initColorVolume                         :452-479, :57-86
+//   clearVolume{X,Y,Z}[Back][c] (12 wrappers, 6 kernels) :88-448
+//   scaleDepth                                           :491-538
+//   tsdf23 / integrateTsdfVolume                         :541-674
+// Volume layout: two planes in HBM, exactly the reference's encoding so that
+// kt_volume_export_reference_layout is a plain copy: tsdf short[V^3] (value * 32767, round toward zero)
+// and colour uchar4[V^3] = {r, g, b, weight}; x fastest; cyclic ("shifting") addressing
+//   storage(x,y,z) = ((x+wx)%V) + ((y+wy)%V)*V + ((z+wz)%V)*V^2        (tsdf_volume.cu:612)
+// B200 re-layout of the WORK, not of the bytes: threads are mapped to STORAGE coordinates (the
+// reference maps them to logical coordinates, so after a shift every warp straddles sector
+// boundaries); a warp always owns one aligned 64-B tsdf segment + one aligned 128-B colour line per z,
+// the z axis is split into slabs (grid.z) for 8x more CTAs than the reference's 1 024, whole columns
+// and z-ranges outside the view frustum are skipped analytically (about 95 % of a centred 6 m cube),
+// and slab clears / init use 128-bit stores.
+// Exactness: the reference advances v_x, v_y, v_g_z, z_scaled by repeated float additions along z
+// (:565-574); rounding of those running sums decides which depth pixel a voxel reads, so the same
+// sequence of additions is replayed here (the z tables once per launch, v_x / v_y per thread).
+// Roofline: HBM; algorithmic bytes = 12 B per updated voxel + image-side gathers.
+#include "kt_ops.h"
+
+namespace kt {
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// fills
+__global__ void __launch_bounds__(256) fill_zero_u4(uint4* __restrict__ p, size_t n16)
+{
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) p[i] = z;
+}
+
+// Clear `count` consecutive storage planes [p0, p0+count) (mod V) along `axis` in both volumes.
+// Work item = 8 consecutive x voxels (16 B of tsdf, 32 B of colour) for the y / z axes.
+__global__ void __launch_bounds__(256)
+clear_planes_yz_kernel(int16_t* __restrict__ tsdf, uint8_t* __restrict__ color, int V, int axis, int p0, int count)
+{
+    const int xg = V / 8;                                   // groups of 8 voxels per row
+    const size_t total = (size_t)count * V * xg;
+    const uint4 z4 = make_uint4(0, 0, 0, 0);
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        int g = (int)(idx % xg);
+        size_t r = idx / xg;
+        int other = (int)(r % V);
+        int i = (int)(r / V);
+        int plane = p0 + i; if (plane >= V) plane -= V;
+        int sy = axis == 1 ? plane : other;
+        int sz = axis == 1 ? other : plane;
+        size_t base = ((size_t)sz * V + sy) * V + (size_t)g * 8;
+        *reinterpret_cast<uint4*>(tsdf + base) = z4;
+        uint4* c = reinterpret_cast<uint4*>(color + base * 4);
+        c[0] = z4; c[1] = z4;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+clear_planes_x_kernel(int16_t* __restrict__ tsdf, uchar4* __restrict__ color, int V, int p0, int count)
+{
+    const size_t total = (size_t)count * V * V;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        int i = (int)(idx % count);
+        size_t r = idx / count;                              // r = sz * V + sy
+        int sx = p0 + i; if (sx >= V) sx -= V;
+        size_t a = r * V + sx;
+        tsdf[a] = 0;
+        color[a] = make_uchar4(0, 0, 0, 0);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+scale_depth_kernel(const uint16_t* __restrict__ depth, float* __restrict__ scaled, int rows, int cols, const Intr intr, bool angleColor)
+{
+    int x = threadIdx.x + blockIdx.x * blockDim.x;
+    int y = threadIdx.y + blockIdx.y * blockDim.y;
+    if (x >= cols || y >= rows) return;
+    int Dp = depth[(size_t)y * cols + x];
+    float xl = (x - intr.cx) / intr.fx;
+    float yl = (y - intr.cy) / intr.fy;
+    float lambda = sqrtf(xl * xl + yl * yl + 1);
+    if (angleColor) {
+        int STEP = 1, ky = 7, kx = 7;
+        int ty = min(y - ky / 2 + ky, rows - 1);
+        int tx = min(x - kx / 2 + kx, cols - 1);
+        int count = 0;
+        for (int cy = max(y - ky / 2, 0); cy < ty; cy += STEP)
+            for (int cx = max(x - kx / 2, 0); cx < tx; cx += STEP)
+                if (abs(Dp - depth[(size_t)cy * cols + cx]) > 200 || Dp == 0) count++;
+        if (count > 5) scaled[(size_t)y * cols + x] = -Dp * lambda / 1000.f;
+        else scaled[(size_t)y * cols + x] = Dp * lambda / 1000.f;
+    } else {
+        scaled[(size_t)y * cols + x] = Dp * lambda / 1000.f;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// z tables: v_g_z(z) and z_scaled(z) as the reference's running sums produce them (tsdf_volume.cu:555,563,570-571)
+__global__ void ztable_kernel(float* __restrict__ table, int V, float cell_z, float t_z)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    float v_g_z = (0 + 0.5f) * cell_z - t_z;
+    float z_scaled = 0;
+    for (int z = 0; z < V; ++z) {
+        table[z] = v_g_z;
+        table[V + z] = z_scaled;
+        v_g_z += cell_z;
+        z_scaled += cell_z;
+    }
+}
+
+struct IntegrateParams {
+    const float* depth_scaled; int rows, cols; Intr k; float3 cell; Mat33 Rinv; float3 t; float trunc;
+    int16_t* tsdf; uchar4* color; int V; int3 wrap; const uint8_t* rgb; const float* nmap; bool angle_color;
+    const float* ztable; int zchunk;
+    int z_begin, z_end;        // storage-z range owned here; volume pointers are indexed with (sz - z_begin)
+};
+
+#define KT_MAX_WEIGHT 128          // Tsdf::MAX_WEIGHT (tsdf_volume.cu:486)
+#define KT_RGB_VIEW_ANGLE_WEIGHT 0.75f
+
+__global__ void __launch_bounds__(256)
+integrate_kernel(const IntegrateParams p)
+{
+    const int V = p.V;
+    const int sx = blockIdx.x * 32 + threadIdx.x;          // STORAGE x, y
+    const int sy = blockIdx.y * 8 + threadIdx.y;
+    if (sx >= V || sy >= V) return;
+    int x = sx - p.wrap.x; if (x < 0) x += V;             // logical voxel
+    int y = sy - p.wrap.y; if (y < 0) y += V;
+    const int z0 = blockIdx.z * p.zchunk;
+    const int z1 = min(z0 + p.zchunk, V);
+
+    const float3 cell_size = p.cell;
+    const Intr intr = p.k;
+    const Mat33 Rcurr_inv = p.Rinv;
+    const float3 tcurr = p.t;
+    const float tranc_dist = p.trunc;
+    const int cols = p.cols, rows = p.rows;
+
+    float v_g_x = (x + 0.5f) * cell_size.x - tcurr.x;
+    float v_g_y = (y + 0.5f) * cell_size.y - tcurr.y;
+    float v_g_z = (0 + 0.5f) * cell_size.z - tcurr.z;
+
+    float v_g_part_norm = v_g_x * v_g_x + v_g_y * v_g_y;
+
+    float v_x = (Rcurr_inv.r0.x * v_g_x + Rcurr_inv.r0.y * v_g_y + Rcurr_inv.r0.z * v_g_z) * intr.fx;
+    float v_y = (Rcurr_inv.r1.x * v_g_x + Rcurr_inv.r1.y * v_g_y + Rcurr_inv.r1.z * v_g_z) * intr.fy;
+    float v_z = (Rcurr_inv.r2.x * v_g_x + Rcurr_inv.r2.y * v_g_y + Rcurr_inv.r2.z * v_g_z);
+
+    float Rcurr_inv_0_z_scaled = Rcurr_inv.r0.z * cell_size.z * intr.fx;
+    float Rcurr_inv_1_z_scaled = Rcurr_inv.r1.z * cell_size.z * intr.fy;
+
+    float tranc_dist_inv = 1.0f / tranc_dist;
+
+    // ---- conservative frustum interval of this column (not part of the reference; it only removes voxels the
+    // exact tests below would reject): with q(z) = q0 + z*dq, q = (fx*p_x, fy*p_y, p_z) in the camera frame, a voxel
+    // can be accepted only if p_z > 0 and -0.5 <= u < cols-0.5, -0.5 <= v < rows-0.5.  Margin: 2 voxels + 1 pixel.
+    int zlo = z0, zhi = z1;
+    {
+        const float dqx = Rcurr_inv_0_z_scaled, dqy = Rcurr_inv_1_z_scaled, dqz = Rcurr_inv.r2.z * cell_size.z;
+        float lo = -1e30f, hi = 1e30f;
+        // each constraint: a + b*z >= 0
+        const float ca[5] = { v_z,
+                              v_x + (intr.cx + 1.5f) * v_z,
+                              -(v_x + (intr.cx - cols - 0.5f) * v_z),
+                              v_y + (intr.cy + 1.5f) * v_z,
+                              -(v_y + (intr.cy - rows - 0.5f) * v_z) };
+        const float cb[5] = { dqz,
+                              dqx + (intr.cx + 1.5f) * dqz,
+                              -(dqx + (intr.cx - cols - 0.5f) * dqz),
+                              dqy + (intr.cy + 1.5f) * dqz,
+                              -(dqy + (intr.cy - rows - 0.5f) * dqz) };
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+            const float a = ca[c], b = cb[c];
+            const float eps = 1e-3f * (fabsf(a) + fabsf(b) * V) + 1e-6f;      // float-rounding slack
+            if (fabsf(b) * V <= eps) { if (a < -eps) { lo = 1e30f; hi = -1e30f; } }
+            else {
+                float zc = -(a + eps) / b;                     // boundary moved outward by eps (either sign of b)
+                if (b > 0) lo = fmaxf(lo, zc); else hi = fminf(hi, zc);
+            }
+        }
+        if (lo > hi) return;
+        zlo = max(z0, (int)floorf(fmaxf(lo, -4.f)) - 2);
+        zhi = min(z1, (int)ceilf(fminf(hi, (float)V + 4.f)) + 3);
+        if (zlo >= zhi) return;
+    }
+
+    // replay the running sums up to zlo (exactly the additions the reference performs)
+    for (int z = 0; z < zlo; ++z) {
+        v_x += Rcurr_inv_0_z_scaled;
+        v_y += Rcurr_inv_1_z_scaled;
+    }
+
+    const float* __restrict__ zt = p.ztable;
+    const float* __restrict__ depthScaled = p.depth_scaled;
+    const float* __restrict__ nmap_curr = p.nmap;
+    const uchar3* __restrict__ colors = reinterpret_cast<const uchar3*>(p.rgb);
+    const size_t P = (size_t)rows * cols;
+    const size_t plane = (size_t)V * V;
+    const size_t col_off = (size_t)sy * V + sx;
+
+    for (int z = zlo; z < zhi; ++z, v_x += Rcurr_inv_0_z_scaled, v_y += Rcurr_inv_1_z_scaled) {
+        v_g_z = zt[z];
+        const float z_scaled = zt[V + z];
+        float inv_z = 1.0f / (v_z + Rcurr_inv.r2.z * z_scaled);
+        if (inv_z < 0) continue;
+
+        int2 coo = { __float2int_rn(v_x * inv_z + intr.cx), __float2int_rn(v_y * inv_z + intr.cy) };
+        if (coo.x >= 0 && coo.y >= 0 && coo.x < cols && coo.y < rows) {
+            int sz = z + p.wrap.z; if (sz >= V) sz -= V;
+            if (sz < p.z_begin || sz >= p.z_end) continue;             // not this GPU's slab
+            const size_t pix = (size_t)coo.y * cols + coo.x;
+            float Dp_scaled = depthScaled[pix];
+            bool no_color = false;
+            if (Dp_scaled < 0.0) { Dp_scaled = -Dp_scaled; no_color = true; }
+            float sdf = Dp_scaled - sqrtf(v_g_z * v_g_z + v_g_part_norm);
+            if (Dp_scaled != 0 && sdf >= -tranc_dist) {
+                float3 ncurr;
+                ncurr.x = nmap_curr[pix];
+                ncurr.z = nmap_curr[pix + 2 * P];
+                if (ncurr.z < 0) ncurr.z = -ncurr.z;
+
+                float tsdf = fmin(1.0f, sdf * tranc_dist_inv);
+
+                const size_t a = (size_t)(sz - p.z_begin) * plane + col_off;
+                int16_t* pos = p.tsdf + a;
+                float tsdf_prev = unpack_tsdf(*pos);
+                uchar4* ptrColor = p.color + a;
+                uchar4 c = *ptrColor;
+                float weight_prev = c.w;
+                const float Wrk = 1;
+                *pos = pack_tsdf((tsdf_prev * weight_prev + Wrk * tsdf) / (weight_prev + Wrk));
+                c.w = min(weight_prev + Wrk, (float)KT_MAX_WEIGHT);
+
+                if ((!isnan(ncurr.x) && !no_color) || (c.x == 0 && c.y == 0 && c.z == 0)) {
+                    const float Wrkc = (p.angle_color ? min(1.0f, ncurr.z / KT_RGB_VIEW_ANGLE_WEIGHT) : 1.0f) * 2.0f;
+                    uchar3 rgb = colors[pix];
+                    float new_x = (c.x * weight_prev + Wrkc * rgb.x) / (weight_prev + Wrkc);
+                    float new_y = (c.y * weight_prev + Wrkc * rgb.y) / (weight_prev + Wrkc);
+                    float new_z = (c.z * weight_prev + Wrkc * rgb.z) / (weight_prev + Wrkc);
+                    c.x = min(255, max(0, __float2int_rn(new_x)));
+                    c.y = min(255, max(0, __float2int_rn(new_y)));
+                    c.z = min(255, max(0, __float2int_rn(new_z)));
+                }
+                *ptrColor = c;
+            }
+        }
+    }
+}
+
+int fill_zero(void* p, size_t bytes, cudaStream_t s)
+{
+    size_t n16 = bytes / 16;
+    int grid = (int)((n16 + 255) / 256 < 148 * 16 ? (n16 + 255) / 256 : 148 * 16);
+    if (grid < 1) grid = 1;
+    fill_zero_u4<<<grid, 256, 0, s>>>((uint4*)p, n16);
+    KT_LAUNCH_CHECK();
+    return 0;
+}
+
+// storage index of logical plane 0 for a signed wrap (tsdf_volume.cu:134, :254, :359)
+int wrap_base(int current, int V)
+{
+    int b = current > 0 ? current % V : V - ((-current) % V);
+    return b % V;
+}
+
+} // namespace
+
+int init_volume(int16_t* tsdf, uint8_t* color, int vol, cudaStream_t s)
+{
+    size_t n = (size_t)vol * vol * vol;
+    int r = fill_zero(tsdf, n * 2, s); if (r) return r;
+    return fill_zero(color, n * 4, s);
+}
+
+// Semantics of the 12 reference wrappers, n = delta - current:
+//   forward (n > 0): storage planes base .. base+n   (n+1 planes)
+//   back    (n < 0): storage planes base-|n| .. base (|n|+1 planes)
+//   X variants only reach round_up_16(|n|) planes from the start of the range (the launch is that wide),
+//   which drops the last plane exactly when |n| is a multiple of 16.
+int clear_volume(int axis, int back, int16_t* tsdf, uint8_t* color, int vol, int current, int delta, cudaStream_t s)
+{
+    const int V = vol;
+    const int n = delta - current;
+    const int an = n < 0 ? -n : n;
+    const int base = wrap_base(current, V);
+    int p0 = back ? ((base - an) % V + V) % V : base;
+    int count = an + 1;
+    if (axis == 0) {
+        int reach = (an % 16 != 0) ? (an + 16 - an % 16) : an;
+        if (count > reach) count = reach;
+    }
+    if (count <= 0) return 0;
+    if (count > V) count = V;
+    if (axis == 0) {
+        size_t total = (size_t)count * V * V;
+        int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+        clear_planes_x_kernel<<<grid, 256, 0, s>>>(tsdf, (uchar4*)color, V, p0, count);
+    } else {
+        size_t total = (size_t)count * V * (V / 8);
+        int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+        clear_planes_yz_kernel<<<grid, 256, 0, s>>>(tsdf, color, V, axis, p0, count);
+    }
+    KT_LAUNCH_CHECK();
+    return 0;
+}
+
+int scale_depth(const uint16_t* depth, float* scaled, int rows, int cols, const Intr& k, bool angle_color, cudaStream_t s)
+{
+    dim3 block(32, 8), grid(div_up(cols, 32), div_up(rows, 8));
+    scale_depth_kernel<<<grid, block, 0, s>>>(depth, scaled, rows, cols, k, angle_color);
+    KT_LAUNCH_CHECK();
+    return 0;
+}
+
+int integrate(const IntegrateArgs& a, float* ztable_dev, cudaStream_t s)
+{
+    const int V = a.vol;
+    float3 cell = make_float3(a.volume_size.x / V, a.volume_size.y / V, a.volume_size.z / V);   // host division, tsdf_volume.cu:659-661
+    ztable_kernel<<<1, 32, 0, s>>>(ztable_dev, V, cell.z, a.t.z);
+    KT_LAUNCH_CHECK();
+    IntegrateParams p;
+    p.depth_scaled = a.depth_scaled; p.rows = a.rows; p.cols = a.cols; p.k = a.k; p.cell = cell; p.Rinv = a.Rinv; p.t = a.t; p.trunc = a.trunc;
+    p.tsdf = a.tsdf; p.color = (uchar4*)a.color; p.V = V; p.wrap = a.wrap; p.rgb = a.rgb; p.nmap = a.nmap_curr; p.angle_color = a.angle_color;
+    p.ztable = ztable_dev; p.zchunk = V >= 64 ? V / 8 : V;
+    p.z_begin = a.z_begin; p.z_end = a.z_end;
+    dim3 block(32, 8), grid(div_up(V, 32), div_up(V, 8), div_up(V, p.zchunk));
+    integrate_kernel<<<grid, block, 0, s>>>(p);
+    KT_LAUNCH_CHECK();
+    return 0;
+}
+
+} // namespace kt
