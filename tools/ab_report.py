@@ -56,6 +56,7 @@ def main():
     ap.add_argument("--frames", type=int, default=12)
     ap.add_argument("--odometry", type=int, default=0)
     ap.add_argument("--skip-ops", action="store_true")
+    ap.add_argument("--voxel-shift", type=int, default=14)
     args = ap.parse_args()
     V = args.vol
     dev = torch.device("cuda:0")
@@ -170,7 +171,7 @@ def main():
                     cleared=int(((xb == 0) & (tb != 0)).sum().item()))
 
     # ---------------- trackers over the sequence ----------------
-    cfg = kb.Config.default(rows=rows, cols=cols, vol=V, odometry=args.odometry)
+    cfg = kb.Config.default(rows=rows, cols=cols, vol=V, odometry=args.odometry, voxel_shift=args.voxel_shift)
     mine = kb.Tracker(cfg)
     rt = ref.tracker(refbind.TrackerConfig.from_kt(cfg))
     poses = []
@@ -207,7 +208,11 @@ def main():
     pa, _, _ = mine.get_slice(mine.num_slices() - 1); pb, _, _ = rt.get_slice(rt.num_slices() - 1)
     rec("finalise", slices_mine=mine.num_slices(), slices_ref=rt.num_slices(), n_mine=len(pa), n_ref=len(pb))
     os.makedirs("gpurun_out", exist_ok=True)
-    with open(f"gpurun_out/ab_report_{V}_odo{args.odometry}.json", "w") as f:
+    for i in range(min(mine.num_slices(), rt.num_slices())):
+        qa, da, _ = mine.get_slice(i); qb, db, _ = rt.get_slice(i)
+        ca_, cb_ = canon(qa), canon(qb)
+        rec(f"slice_{i}", dim=(da, db), n=(len(qa), len(qb)), equal=bool(ca_.shape == cb_.shape and (ca_ == cb_).all()))
+    with open(f"gpurun_out/ab_report_{V}_odo{args.odometry}_s{args.voxel_shift}.json", "w") as f:
         json.dump(REPORT, f, indent=1, default=str)
 
 
