@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""bench.py -- frames/s of the dense tracking-and-fusion hot path on B200 (BASELINE.json metric).
+
+Workload (N=1): BASELINE.json configs[1] -- synthetic 640x480 RGB-D stream into a 512^3 TSDF volume (6 m), ICP-only
+tracker {10,5,4} iterations, volume shifting on (-t 14, overlap 2).  A "step" is ONE frame through
+KintinuousTracker::processFrame's replacement (kt_process_frame*): pyramid -> 19 ICP iterations -> shift test ->
+integrate -> raycast + model pyramid.
+
+  value : frames/s with the RGB-D frames already resident in HBM (kt_process_frame_device), whole job (all ranks).
+  e2e   : frames/s through the public C ABI with HOST (pinned) buffers: H2D of depth + rgb and D2H of the pose are
+          inside the timed region (kt_process_frame).
+  roofline / stages : CUDA-event stage timers of the tracker (on its own stream), algorithmic bytes from DESIGN.md section 4.
+  cpu_baseline : the CPU oracle ("port") on a bounded sample of the same workload, on this box's host cores.
+  --impl reference : the reference's OWN CUDA kernels (oracle/_ref/libkt_ref_512.so, compiled from /root/reference with
+          two mechanical patches), driven by the restated host loop with the reference's launch / sync pattern.
+          The reference has no CPU implementation of this path; if the library is missing, the CPU oracle port is timed.
+Timing: W>=3 warm-up frames, exactly K timed frames between barrier + cuda synchronize, max over ranks, CUDA clocks sampled
+with nvidia-smi during the timed region.  Inputs: 96 distinct frames (147 MB) cycled, i.e. larger than the 126 MB L2.
+Multi-GPU (torchrun): rank r tracks its own stream into its own volume (independent sessions, no data-path collective):
+weak scaling.  The z-slab single-stream mode of BASELINE configs[3] is selected with --mode zslab.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ROWS, COLS, VOL, SIZE = 480, 640, 512, 6.0
+N_INPUT_FRAMES = int(os.environ.get("KT_BENCH_FRAMES", "96"))
+P_LEVELS = [ROWS * COLS >> (2 * l) for l in range(4)]
+ICP_ITERS = [10, 5, 4, 0]
+
+
+def _render_one(k):
+    from kintinuous_b200 import synth
+    return synth.render(k, COLS, ROWS)
+
+
+def make_stream(n, offset=0):
+    """n frames of the synthetic trajectory, played forward then backward (ping-pong) so any number of steps is continuous."""
+    ks = [offset + i for i in range(n)]
+    try:
+        from concurrent.futures import ProcessPoolExecutor
+        with ProcessPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as ex:
+            frames = list(ex.map(_render_one, ks, chunksize=2))
+    except Exception:
+        frames = [_render_one(k) for k in ks]
+    return frames
+
+
+def pingpong(i, n):
+    period = 2 * (n - 1)
+    j = i % period
+    return j if j < n else period - j
+
+
+class ClockSampler:
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index), "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def dist_setup(n_gpus):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl" if not os.environ.get("KT_BENCH_GLOO") else "gloo")
+    return world, rank, local
+
+
+def barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+
+
+def max_over_ranks(x, world, device):
+    if world == 1:
+        return x
+    import torch, torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def cpu_baseline_leg(frames, n_sample):
+    """CPU oracle port on a bounded sample (rank 0 only)."""
+    from oracle import refbind
+    import kintinuous_b200 as kb
+    o = refbind.CpuOracle()
+    cores = o.lib.ktoracle_hardware_threads() or (os.cpu_count() or 1)
+    o.lib.ktoracle_set_threads(cores)
+    cfg = kb.Config.default(rows=ROWS, cols=COLS, vol=VOL, odometry=0)
+    t = o.tracker(refbind.TrackerConfig.from_kt(cfg))
+    t.process(frames[0][0], frames[0][1], 0)          # first frame (no odometry) is not timed
+    t0 = time.time()
+    for k in range(1, 1 + n_sample):
+        t.process(frames[k][0], frames[k][1], k)
+    dt = time.time() - t0
+    t.close()
+    return {"value": n_sample / dt, "unit": "frames/s", "cores": int(cores), "kind": "port",
+            "sample": f"{n_sample} frames of the same 640x480 -> 512^3 ICP workload, oracle/kt_oracle_cpu.cpp on {cores} std::threads ({dt:.1f} s)"}
+
+
+def run_reference(args, world, rank, local):
+    """--impl reference: the reference's own CUDA kernels behind the restated host loop (rank 0 only)."""
+    if rank != 0:
+        return
+    from oracle import refbind
+    import kintinuous_b200 as kb
+    cfg = kb.Config.default(rows=ROWS, cols=COLS, vol=VOL, odometry=0)
+    n_frames = min(N_INPUT_FRAMES, max(8, args.steps + args.warmup + 1))
+    frames = make_stream(n_frames)
+    line = {"metric": "frames/s 640x480 into 512^3 TSDF (ICP-only tracker)", "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": "synthetic 640x480 RGB-D stream, 512^3 volume (6 m), ICP-only tracker {10,5,4}, shifting on", "frames_cycled": n_frames}}
+    use_cuda = False
+    try:
+        import torch
+        use_cuda = torch.cuda.is_available() and refbind.RefCuda.available(VOL)
+    except Exception:
+        use_cuda = False
+    if use_cuda:
+        import torch
+        torch.cuda.set_device(0)
+        ref = refbind.RefCuda(VOL)
+        t = ref.tracker(refbind.TrackerConfig.from_kt(cfg))
+        sync = torch.cuda.synchronize
+        kind, cores = "reference", 1
+        sample = "every step: the reference's own CUDA kernels (oracle/_ref/libkt_ref_512.so = /root/reference src/frontend/cuda/*.cu recompiled for sm_100) on cuda:0, original launch shapes and 26 syncs/frame, restated host loop on 1 host thread, blocking H2D from pageable memory"
+    else:
+        o = refbind.CpuOracle()
+        cores = o.lib.ktoracle_hardware_threads() or 1
+        o.lib.ktoracle_set_threads(cores)
+        t = o.tracker(refbind.TrackerConfig.from_kt(cfg))
+        sync = lambda: None
+        kind = "port"
+        sample = f"oracle/_ref unavailable: CPU oracle port on {cores} threads"
+        args.steps = min(args.steps, 8); args.warmup = min(args.warmup, 1)
+        line["steps"], line["warmup"] = args.steps, args.warmup
+    i = 0
+    for _ in range(args.warmup + 1):
+        d, c = frames[pingpong(i, n_frames)]; t.process(d, c, i); i += 1
+    sync(); t0 = time.perf_counter()
+    for _ in range(args.steps):
+        d, c = frames[pingpong(i, n_frames)]; t.process(d, c, i); i += 1
+    sync(); dt = time.perf_counter() - t0
+    v = args.steps / dt
+    line.update({"value": v, "ms_per_step": 1e3 * dt / args.steps,
+                 "cpu_baseline": {"value": v, "unit": "frames/s", "cores": int(cores), "kind": kind, "sample": sample},
+                 "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mode", default="streams", choices=["streams", "zslab"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=6)
+    args = ap.parse_args()
+    world, rank, local = dist_setup(args.gpus)
+    if args.impl == "reference":
+        run_reference(args, world, rank, local)
+        return
+
+    import torch
+    import kintinuous_b200 as kb
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- kintinuous_b200 has no CPU path (use --impl reference for the CPU/legacy arm)")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    warmup = max(3, args.warmup)
+
+    frames = make_stream(N_INPUT_FRAMES, offset=0)
+    n = len(frames)
+    # resident inputs (value) and pinned host inputs (e2e)
+    dev_depth = [torch.from_numpy(f[0].view(np.int16)).to(device) for f in frames]
+    dev_rgb = [torch.from_numpy(f[1]).to(device) for f in frames]
+    pin_depth = [torch.from_numpy(f[0].view(np.int16)).pin_memory() for f in frames]
+    pin_rgb = [torch.from_numpy(f[1]).pin_memory() for f in frames]
+    cfg = kb.Config.default(rows=ROWS, cols=COLS, vol=VOL, odometry=0, device=local)
+
+    def run(tracker, use_host, steps, start):
+        i = start
+        for _ in range(steps):
+            j = pingpong(i, n)
+            if use_host:
+                tracker.process_frame(pin_depth[j].data_ptr(), pin_rgb[j].data_ptr(), i)
+            else:
+                tracker.process_frame_device(dev_depth[j], dev_rgb[j], i)
+            i += 1
+        return i
+
+    results = {}
+    clocks = None
+    for leg in ("device", "host"):
+        trk = kb.Tracker(cfg)
+        i = run(trk, leg == "host", warmup + 1, 0)
+        torch.cuda.synchronize(); barrier(world)
+        sampler = ClockSampler(local)
+        if leg == "device" and rank == 0:
+            sampler.start()
+        l0 = trk.launch_count()
+        ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        i = run(trk, leg == "host", args.steps, i)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        l1 = trk.launch_count()
+        barrier(world)
+        if leg == "device" and rank == 0:
+            clocks = sampler.stop()
+        dt = max_over_ranks(dt, world, device)
+        results[leg] = {"dt": dt, "launches": l1 - l0}
+        if leg == "device":
+            # stage timers (CUDA events on the tracker's stream) over a few extra frames, outside the timed region
+            trk.set_stage_timing(True)
+            acc = np.zeros(6)
+            m = 0
+            for _ in range(16):
+                j = pingpong(i, n); p = trk.process_frame_device(dev_depth[j], dev_rgb[j], i); i += 1
+                ms = np.array(trk.stage_ms())
+                if p.shifted == 0:
+                    acc += ms; m += 1
+            results["stages_ms"] = (acc / max(1, m)).tolist()
+        trk.close()
+
+    if rank != 0:
+        return
+    peak, peak_src = measured_peak()
+    st = results["stages_ms"]
+    names = ["pyramid", "odometry", "shift", "integrate", "raycast"]
+    icp_bytes = sum(48 * P_LEVELS[l] * ICP_ITERS[l] for l in range(4))
+    alg_bytes = {"pyramid": 4 * P_LEVELS[0] + sum(2 * P_LEVELS[l] + 2 * P_LEVELS[l + 1] for l in range(3)) + sum(2 * P_LEVELS[l] + 24 * P_LEVELS[l] for l in range(4)),
+                 "odometry": icp_bytes, "integrate": None, "raycast": None}
+    stages = {nm: {"ms": st[k]} for k, nm in enumerate(names)}
+    for nm in ("pyramid", "odometry"):
+        stages[nm]["alg_bytes"] = alg_bytes[nm]
+        stages[nm]["gbs"] = alg_bytes[nm] / (st[names.index(nm)] * 1e-3) / 1e9 if st[names.index(nm)] > 0 else None
+    dom = max(names, key=lambda nm: st[names.index(nm)])
+    # dominant kernel = the ICP reduction (19 launches per frame): per-launch figures
+    icp_launches = sum(ICP_ITERS)
+    ach = icp_bytes / icp_launches / (st[1] * 1e-3 / icp_launches) / 1e9 if st[1] > 0 else None
+    roofline = {"kernel": "icp_kernel (19 launches/frame, Gauss-Newton solve fused in the tail)", "bound": "hbm",
+                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None, "traffic": None,
+                "peak_source": peak_src, "bytes_per_launch_avg": icp_bytes / icp_launches, "avg_launch_ms": st[1] / icp_launches,
+                "note": "latency-bound by design at 640x480 (maps are L2 resident); see DESIGN.md section 4", "dominant_stage": dom}
+    dt = results["device"]["dt"]
+    value = world * args.steps / dt
+    e2e_v = world * args.steps / results["host"]["dt"]
+    line = {"metric": "frames/s 640x480 into 512^3 TSDF (ICP-only tracker)", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
+            "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "synthetic 640x480 RGB-D stream, 512^3 volume (6 m), ICP-only tracker {10,5,4}, shifting on (-t 14)", "parallelism": f"{world} independent streams",
+                       "l2": f"inputs larger than L2: {n} frames x 1.54 MB = {n * 1.536:.0f} MB cycled (ping-pong)"},
+            "e2e": {"value": e2e_v, "unit": "frames/s", "h2d_bytes_per_step": ROWS * COLS * 5, "d2h_bytes_per_step": 48},
+            "gpu_launches": int(results["device"]["launches"]), "clocks": clocks, "roofline": roofline, "stages": stages}
+    if not args.no_cpu_baseline:
+        try:
+            line["cpu_baseline"] = cpu_baseline_leg(frames, args.cpu_sample)
+        except Exception as e:  # the oracle is a checker, its absence must not hide the GPU number
+            line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": 0, "kind": "port", "sample": f"unavailable: {e}"}
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -3,7 +3,7 @@
 The reference ships no data (its sample log is a download, README.md:166-170), so the workload is an
 analytic scene rendered exactly: the interior of an axis-aligned 5 x 3 x 5 m room centred on the
 first camera, a sphere (r = 0.5 m) and a 1 m cube standing on the floor, textured with a smooth
-procedural pattern (non-zero image gradients everywhere, which the photometric odometry needs).
+procedural pattern plus a 7.85 cm checker (edges strong enough for the photometric odometry's gradient test).
 
 Camera: fx = fy = 528.01442863461716, cx = 320, cy = 267 (reference default,
 MainController.cpp:222-227), scaled with the resolution.  Trajectory of frame k (camera -> world):
@@ -42,8 +42,11 @@ def pose(k: int):
 
 def _texture(p):
     out = np.empty(p.shape[:-1] + (3,), dtype=np.float64)
+    # 7.85 cm checker cells give the photometric odometry edges above its gradient threshold
+    # (RGBDOdometry.cpp:109-113: |grad|^2 >= (12*8)^2 at level 0); the smooth term keeps every pixel distinct.
+    sq = np.sign(np.sin(40.0 * p[..., 0] + 0.3)) * np.sign(np.sin(40.0 * p[..., 1] + 0.7)) * np.sign(np.sin(40.0 * p[..., 2] + 1.1))
     for c, ph in enumerate((0.0, 2.1, 4.2)):
-        out[..., c] = 128.0 + 100.0 * np.sin(7.0 * p[..., 0] + ph) * np.sin(5.0 * p[..., 1] + 0.5 * ph) * np.sin(6.0 * p[..., 2] - ph)
+        out[..., c] = 128.0 + 55.0 * np.sin(7.0 * p[..., 0] + ph) * np.sin(5.0 * p[..., 1] + 0.5 * ph) * np.sin(6.0 * p[..., 2] - ph) + 60.0 * sq
     return np.clip(np.rint(out), 0, 255).astype(np.uint8)
 
 

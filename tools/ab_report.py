@@ -193,7 +193,9 @@ def main():
         tra, trb = mine.trace(), rt.trace()
         if k in (1, 2) and len(tra) and len(tra) == len(trb):
             rel = np.abs(tra[:, :42] - trb[:, :42]).max(1) / np.abs(trb[:, :42]).max(1)
-            rec(f"trace_frame{k}", iters=len(tra), max_rel=float(rel.max()), inliers_first=(float(tra[0, 43]), float(trb[0, 43])), inliers_last=(float(tra[-1, 43]), float(trb[-1, 43])))
+            bad = np.flatnonzero(rel > 1e-4)
+            rec(f"trace_frame{k}", iters=len(tra), max_rel=float(rel.max()), first_bad_iter=(int(bad[0]) if len(bad) else -1),
+                counts_at_bad=((float(tra[bad[0], 43]), float(trb[bad[0], 43])) if len(bad) else None), inliers_first=(float(tra[0, 43]), float(trb[0, 43])), inliers_last=(float(tra[-1, 43]), float(trb[-1, 43])))
     rec("poses", max_dt=max(p["dt"] for p in poses), max_drot=max(p["drot"] for p in poses), last=poses[-1],
         err_gt_mine=max(p["err_gt_mine"] for p in poses), err_gt_ref=max(p["err_gt_ref"] for p in poses))
     REPORT["pose_list"] = poses
