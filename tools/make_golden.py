@@ -79,22 +79,23 @@ def main():
     cap = 400000
     ob = torch.zeros(cap * 32, dtype=torch.uint8, device="cuda")
     real = (14, 3, 250 - V)
-    for name, box in {"zminus": (0, V, 0, V, V - 17, V - 1), "xplus": (0, 120, 0, V, 0, V)}.items():
+    for name, box in {"zslab": (0, V, 0, V, 225, 242), "xplus": (0, 120, 0, V, 0, V), "yslab": (0, V, 180, 197, 0, V)}.items():
         n = ref.extract(ts, vs, ob, cap, wrap, cs, box, 1, real)
         pts = ob.cpu().numpy().view(refbind.POINT_DTYPE)[:n]
         arr = np.ascontiguousarray(pts).view(np.uint64).reshape(n, 4)
         g[f"extract_{name}"] = arr[np.lexsort(arr.T[::-1])] if n else arr
+    # clear: sentinel-filled volumes, record which storage planes along the axis end up zero
+    sent_t = torch.full((V ** 3,), 7, dtype=torch.int16, device="cuda"); sent_c = torch.full((V ** 3 * 4,), 9, dtype=torch.uint8, device="cuda")
     for axis in range(3):
-        for back, (cur, n) in ((0, (14, 14)), (1, (-3, -14)), (0, (40, 16)), (1, (5, -16))):
-            x, y = ts.clone(), cs.clone()
+        for back, (cur, n) in ((0, (14, 14)), (1, (-3, -14)), (0, (40, 16)), (1, (5, -16)), (0, (250, 14)), (1, (3, -14)), (0, (-20, 1)), (1, (0, -2))):
+            x, y = sent_t.clone(), sent_c.clone()
             ref.clear(axis, back, x, y, cur, cur + n); torch.cuda.synchronize()
-            # which storage planes along `axis` were touched: compare a plane probe (voxels that were non-zero)
-            w = y.cpu().numpy().reshape(V, V, V, 4)[..., 3]
-            w0 = col[..., 3]
-            changed = (w != w0)
-            ax = {0: (0, 1), 1: (0, 2), 2: (1, 2)}[axis]          # array dims are (z, y, x)
-            planes = np.flatnonzero(changed.any(axis=ax))
-            g[f"clear_a{axis}_b{back}_c{cur}_n{n}"] = planes.astype(np.int32)
+            zt = (x.view(V, V, V) == 0); zc = (y.view(V, V, V, 4) == 0).all(-1)
+            assert bool((zt == zc).all())
+            ax = {0: (0, 1), 1: (0, 2), 2: (1, 2)}[axis]          # tensor dims are (z, y, x)
+            full = zt.all(dim=ax[1]).all(dim=ax[0]); part = zt.any(dim=ax[1]).any(dim=ax[0])
+            assert bool((full == part).all())                     # planes are cleared completely or not at all
+            g[f"clear_a{axis}_b{back}_c{cur}_n{n}"] = torch.nonzero(full).flatten().cpu().numpy().astype(np.int32)
     g["params"] = np.array([rows, cols, V, SIZE, trunc, ang], np.float64)
     np.savez_compressed(os.path.join(OUT, "ops_160x120.npz"), **g)
 
