@@ -33,6 +33,50 @@ struct IcpParams {
     int mode;              // 0 reduce only, 1 reduce + solve (ICP-only odometry)
 };
 
+// One pixel of ICPReduction::search + getProducts (cuda/reduce.cu:211-316): accumulates its 29 products into sum.
+__device__ __forceinline__ void icp_pixel(int i, int N, int cols, int rows,
+                                          const float* __restrict__ vmap_curr, const float* __restrict__ nmap_curr,
+                                          const float* __restrict__ vmap_g_prev, const float* __restrict__ nmap_g_prev,
+                                          const Intr& intr, const Mat33& Rcurr, const float3& tcurr, const Mat33& Rprev_inv, const float3& tprev,
+                                          float dist_thres, float angle_thres, float (&sum)[NSUM])
+{
+    float3 vcurr;
+    vcurr.x = __ldg(&vmap_curr[i]);
+    if (isnan(vcurr.x)) return;                          // Q16: the reference rejects these through NaN propagation
+    vcurr.y = __ldg(&vmap_curr[i + N]);
+    vcurr.z = __ldg(&vmap_curr[i + 2 * N]);
+
+    float3 vcurr_g = add3(mul33(Rcurr, vcurr), tcurr);
+    float3 vcurr_cp = mul33(Rprev_inv, sub3(vcurr_g, tprev));
+
+    int2 ukr;
+    ukr.x = __float2int_rn(vcurr_cp.x * intr.fx / vcurr_cp.z + intr.cx);
+    ukr.y = __float2int_rn(vcurr_cp.y * intr.fy / vcurr_cp.z + intr.cy);
+    if (ukr.x < 0 || ukr.y < 0 || ukr.x >= cols || ukr.y >= rows || vcurr_cp.z < 0) return;
+
+    const int j = ukr.y * cols + ukr.x;
+    float3 vprev_g, nprev_g, ncurr;
+    vprev_g.x = __ldg(&vmap_g_prev[j]);
+    nprev_g.x = __ldg(&nmap_g_prev[j]);
+    ncurr.x = __ldg(&nmap_curr[i]);
+    if (isnan(vprev_g.x) || isnan(nprev_g.x) || isnan(ncurr.x)) return;
+    vprev_g.y = __ldg(&vmap_g_prev[j + N]); vprev_g.z = __ldg(&vmap_g_prev[j + 2 * N]);
+    nprev_g.y = __ldg(&nmap_g_prev[j + N]); nprev_g.z = __ldg(&nmap_g_prev[j + 2 * N]);
+    ncurr.y = __ldg(&nmap_curr[i + N]); ncurr.z = __ldg(&nmap_curr[i + 2 * N]);
+
+    float3 ncurr_g = mul33(Rcurr, ncurr);
+    float dist = norm3(sub3(vprev_g, vcurr_g));
+    float sine = norm3(cross3(ncurr_g, nprev_g));
+    if (!(sine < angle_thres && dist <= dist_thres)) return;
+
+    float3 s_cp = mul33(Rprev_inv, sub3(vcurr_g, tprev));
+    float3 d_cp = mul33(Rprev_inv, sub3(vprev_g, tprev));
+    float3 n_cp = mul33(Rprev_inv, nprev_g);
+    float3 sxn = cross3(s_cp, n_cp);
+    float row[7] = {n_cp.x, n_cp.y, n_cp.z, sxn.x, sxn.y, sxn.z, dot3(n_cp, sub3(s_cp, d_cp))};
+    accumulate_row(sum, row);
+}
+
 __global__ void __launch_bounds__(ICP_THREADS)
 icp_kernel(const IcpParams p)
 {
@@ -60,43 +104,9 @@ icp_kernel(const IcpParams p)
 #pragma unroll
     for (int k = 0; k < NSUM; ++k) sum[k] = 0.f;
 
-    for (int i = blockIdx.x * ICP_THREADS + tid; i < N; i += gridDim.x * ICP_THREADS) {
-        float3 vcurr;
-        vcurr.x = vmap_curr[i];
-        if (isnan(vcurr.x)) continue;                       // Q16: the reference rejects these through NaN propagation
-        vcurr.y = vmap_curr[i + N];
-        vcurr.z = vmap_curr[i + 2 * N];
-
-        float3 vcurr_g = add3(mul33(Rcurr, vcurr), tcurr);
-        float3 vcurr_cp = mul33(Rprev_inv, sub3(vcurr_g, tprev));
-
-        int2 ukr;
-        ukr.x = __float2int_rn(vcurr_cp.x * intr.fx / vcurr_cp.z + intr.cx);
-        ukr.y = __float2int_rn(vcurr_cp.y * intr.fy / vcurr_cp.z + intr.cy);
-        if (ukr.x < 0 || ukr.y < 0 || ukr.x >= cols || ukr.y >= rows || vcurr_cp.z < 0) continue;
-
-        const int j = ukr.y * cols + ukr.x;
-        float3 vprev_g, nprev_g, ncurr;
-        vprev_g.x = __ldg(&vmap_g_prev[j]);
-        nprev_g.x = __ldg(&nmap_g_prev[j]);
-        ncurr.x = nmap_curr[i];
-        if (isnan(vprev_g.x) || isnan(nprev_g.x) || isnan(ncurr.x)) continue;
-        vprev_g.y = __ldg(&vmap_g_prev[j + N]); vprev_g.z = __ldg(&vmap_g_prev[j + 2 * N]);
-        nprev_g.y = __ldg(&nmap_g_prev[j + N]); nprev_g.z = __ldg(&nmap_g_prev[j + 2 * N]);
-        ncurr.y = nmap_curr[i + N]; ncurr.z = nmap_curr[i + 2 * N];
-
-        float3 ncurr_g = mul33(Rcurr, ncurr);
-        float dist = norm3(sub3(vprev_g, vcurr_g));
-        float sine = norm3(cross3(ncurr_g, nprev_g));
-        if (!(sine < p.a.angle_thres && dist <= p.a.dist_thres)) continue;
-
-        float3 s_cp = mul33(Rprev_inv, sub3(vcurr_g, tprev));
-        float3 d_cp = mul33(Rprev_inv, sub3(vprev_g, tprev));
-        float3 n_cp = mul33(Rprev_inv, nprev_g);
-        float3 sxn = cross3(s_cp, n_cp);
-        float row[7] = {n_cp.x, n_cp.y, n_cp.z, sxn.x, sxn.y, sxn.z, dot3(n_cp, sub3(s_cp, d_cp))};
-        accumulate_row(sum, row);
-    }
+    for (int i = blockIdx.x * ICP_THREADS + tid; i < N; i += gridDim.x * ICP_THREADS)
+        icp_pixel(i, N, cols, rows, vmap_curr, nmap_curr, vmap_g_prev, nmap_g_prev, intr, Rcurr, tcurr, Rprev_inv, tprev,
+                  p.a.dist_thres, p.a.angle_thres, sum);
 
     if (!grid_reduce29(sum, p.partials, &p.st->blocks_done, s_red, &s_last)) return;
 
@@ -119,6 +129,130 @@ icp_kernel(const IcpParams p)
             gauss_newton_update(dA, db, st);
             st->iter += 1;
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Whole-frame ICP: all levels and iterations in ONE cooperative launch (one CTA per SM).  Per iteration: every CTA reduces
+// its pixels to a 29-float partial, ONE grid barrier, then EVERY CTA sums the per-CTA partials in the same fixed order and
+// performs the same FP64 solve redundantly, so that no second barrier / broadcast of the pose is needed (the result is
+// bit-identical in all CTAs because the instruction sequence and inputs are identical).
+enum { FRAME_THREADS = 512 };
+
+struct IcpFrameParams {
+    IcpLevelArgs lv[LEVELS];
+    int iters[LEVELS];
+    float pose12[12];          // Rprev (9), tprev (3)
+    OdomState* st;
+    float* partials;           // [2][32][grid]  (double-buffered by iteration parity; component-major)
+    float* trace;
+    unsigned int* bar;         // monotonically increasing arrival counter
+    unsigned int bar_base;     // value of the counter when this launch starts
+};
+
+__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int target)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(bar, 1u);
+        while ((int)(*((volatile unsigned int*)bar) - target) < 0) { }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(FRAME_THREADS, 1)
+icp_frame_kernel(const IcpFrameParams p)
+{
+    __shared__ float s_Rp[9], s_tp[3], s_Rpi[9], s_R[9], s_t[3];
+    __shared__ double s_Rt[16];
+    __shared__ float s_red[FRAME_THREADS / 32][32];
+    __shared__ float s_sum[32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int G = gridDim.x;
+    if (tid == 0) {
+        for (int k = 0; k < 9; ++k) { s_Rp[k] = p.pose12[k]; s_R[k] = p.pose12[k]; }
+        for (int k = 0; k < 3; ++k) { s_tp[k] = p.pose12[9 + k]; s_t[k] = p.pose12[9 + k]; }
+        mat3f_inverse(s_Rp, s_Rpi);                                    // Rprev.inverse(), ICPOdometry.cpp:81
+        for (int k = 0; k < 16; ++k) s_Rt[k] = (k % 5 == 0) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    Mat33 Rprev_inv; float3 tprev;
+    Rprev_inv.r0 = make_float3(s_Rpi[0], s_Rpi[1], s_Rpi[2]); Rprev_inv.r1 = make_float3(s_Rpi[3], s_Rpi[4], s_Rpi[5]); Rprev_inv.r2 = make_float3(s_Rpi[6], s_Rpi[7], s_Rpi[8]);
+    tprev = make_float3(s_tp[0], s_tp[1], s_tp[2]);
+
+    int it = 0;
+    unsigned int target = p.bar_base;
+    for (int level = LEVELS - 1; level >= 0; --level) {
+        const IcpLevelArgs& a = p.lv[level];
+        const int cols = a.cols, rows = a.rows, N = cols * rows;
+        const float* __restrict__ vmap_curr = a.vmap_curr;
+        const float* __restrict__ nmap_curr = a.nmap_curr;
+        const float* __restrict__ vmap_g_prev = a.vmap_g_prev;
+        const float* __restrict__ nmap_g_prev = a.nmap_g_prev;
+        const Intr intr = a.k;
+        const float dist_thres = a.dist_thres, angle_thres = a.angle_thres;
+        for (int iter = 0; iter < p.iters[level]; ++iter, ++it) {
+            Mat33 Rcurr; float3 tcurr;
+            Rcurr.r0 = make_float3(s_R[0], s_R[1], s_R[2]); Rcurr.r1 = make_float3(s_R[3], s_R[4], s_R[5]); Rcurr.r2 = make_float3(s_R[6], s_R[7], s_R[8]);
+            tcurr = make_float3(s_t[0], s_t[1], s_t[2]);
+            float sum[NSUM];
+#pragma unroll
+            for (int k = 0; k < NSUM; ++k) sum[k] = 0.f;
+            for (int i = blockIdx.x * FRAME_THREADS + tid; i < N; i += G * FRAME_THREADS)
+                icp_pixel(i, N, cols, rows, vmap_curr, nmap_curr, vmap_g_prev, nmap_g_prev, intr, Rcurr, tcurr, Rprev_inv, tprev, dist_thres, angle_thres, sum);
+            // CTA reduction
+#pragma unroll
+            for (int k = 0; k < NSUM; ++k) {
+                float v = warp_sum(sum[k]);
+                if (lane == 0) s_red[wid][k] = v;
+            }
+            __syncthreads();
+            float* part = p.partials + (size_t)(it & 1) * 32 * G;
+            if (tid < NSUM) {
+                float v = 0.f;
+#pragma unroll
+                for (int w = 0; w < FRAME_THREADS / 32; ++w) v += s_red[w][tid];
+                part[(size_t)tid * G + blockIdx.x] = v;
+            }
+            target += (unsigned int)G;
+            grid_barrier(p.bar, target);
+            // every CTA: fixed-order total of the G partials of each component (16 lanes per component)
+            {
+                const int comp = tid >> 4, sub = tid & 15;
+                float v = 0.f;
+                if (comp < NSUM)
+                    for (int b = sub; b < G; b += 16) v += __ldcg(&part[(size_t)comp * G + b]);
+                v += __shfl_xor_sync(0xffffffffu, v, 8);
+                v += __shfl_xor_sync(0xffffffffu, v, 4);
+                v += __shfl_xor_sync(0xffffffffu, v, 2);
+                v += __shfl_xor_sync(0xffffffffu, v, 1);
+                if (sub == 0 && comp < NSUM) s_sum[comp] = v;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                float A[36], b[6];
+                unpack_normal_equations(s_sum, A, b);
+                if (p.trace && blockIdx.x == 0 && it < 64) {
+                    float* t = p.trace + (size_t)it * TRACE_STRIDE;
+                    for (int k = 0; k < 36; ++k) t[k] = A[k];
+                    for (int k = 0; k < 6; ++k) t[36 + k] = b[k];
+                    t[42] = s_sum[27]; t[43] = s_sum[28];
+                }
+                double dA[36], db[6];
+#pragma unroll
+                for (int k = 0; k < 36; ++k) dA[k] = A[k];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) db[k] = b[k];
+                gauss_newton_update_p(dA, db, s_Rt, s_Rp, s_tp, s_R, s_t);
+            }
+            __syncthreads();
+        }
+    }
+    if (blockIdx.x == 0 && tid < 12) {
+        if (tid < 9) p.st->Rcurr[tid] = s_R[tid]; else p.st->tcurr[tid - 9] = s_t[tid - 9];
+        if (tid == 0) p.st->iter = it;
     }
 }
 
@@ -170,6 +304,27 @@ int odom_begin_frame(OdomState* state, const float* pose12_dev, cudaStream_t s)
 {
     odom_begin_kernel<<<1, 32, 0, s>>>(state, pose12_dev);
     KT_LAUNCH_CHECK();
+    return 0;
+}
+
+
+// Whole-frame ICP (ICP-only odometry).  pose12 = Rprev (9) + tprev (3) on the host; the result lands in state->Rcurr/tcurr.
+// bar_dev: one unsigned int, zeroed once at allocation; *bar_count (host) tracks its value across launches.
+int icp_frame(const IcpLevelArgs* levels, const int* iters, const float* pose12_host, OdomState* state, float* partials,
+              float* trace, unsigned int* bar_dev, unsigned int* bar_count, cudaStream_t s)
+{
+    IcpFrameParams p;
+    int total = 0;
+    for (int l = 0; l < LEVELS; ++l) { p.lv[l] = levels[l]; p.iters[l] = iters[l]; total += iters[l]; }
+    for (int k = 0; k < 12; ++k) p.pose12[k] = pose12_host[k];
+    p.st = state; p.partials = partials; p.trace = trace; p.bar = bar_dev; p.bar_base = *bar_count;
+    int grid = sm_count();
+    if (grid * 32 * 2 > MAX_PARTIALS * 32) grid = MAX_PARTIALS / 2;
+    void* args[] = {&p};
+    cudaError_t e = cudaLaunchCooperativeKernel((const void*)icp_frame_kernel, dim3(grid), dim3(FRAME_THREADS), args, 0, s);
+    ++g_launches;
+    if (e != cudaSuccess) return cuda_check(e, "cudaLaunchCooperativeKernel(icp_frame_kernel)", __FILE__, __LINE__);
+    *bar_count += (unsigned int)(grid * total);
     return 0;
 }
 

@@ -55,6 +55,9 @@ struct IcpLevelArgs {
 //   mode 1: reduce + LDLT solve + pose update on device (ICP-only odometry)
 int icp_iteration(const IcpLevelArgs& a, OdomState* state, float* partials, float* trace, int mode, cudaStream_t s);
 
+int icp_frame(const IcpLevelArgs* levels, const int* iters, const float* pose12_host, OdomState* state, float* partials,
+              float* trace, unsigned int* bar_dev, unsigned int* bar_count, cudaStream_t s);
+
 struct RgbLevelArgs {
     const int16_t* dIdx; const int16_t* dIdy; const float* last_depth; const float* next_depth;
     const uint8_t* last_image; const uint8_t* next_image; void* corres; const float* cloud;

@@ -158,40 +158,62 @@ __device__ __forceinline__ void cast_ray(const RayParams& p, int x, int y, bool&
     float tsdf = rc.readTsdf(g.x, g.y, g.z);
 
     const float max_time = 3 * (p.volume_size.x + p.volume_size.y + p.volume_size.z);
-    for (; time_curr < max_time; time_curr += time_step) {
-        float tsdf_prev = tsdf;
-        int3 gn = rc.getVoxel(add3(ray_start, scale3(ray_dir, (time_curr + time_step))));
-        if (!rc.checkInds(gn)) break;
-        tsdf = rc.readTsdf(gn.x, gn.y, gn.z);
-        if (tsdf_prev < 0.f && tsdf > 0.f) break;
-        if (tsdf_prev > 0.f && tsdf < 0.f) {
-            float Ftdt = rc.interpolateTrilineary(add3(ray_start, scale3(ray_dir, (time_curr + time_step))));
-            if (isnan(Ftdt)) break;
-            float Ft = rc.interpolateTrilineary(add3(ray_start, scale3(ray_dir, time_curr)));
-            if (isnan(Ft)) break;
-
-            float Ts = time_curr - time_step * Ft / (Ftdt - Ft);
-            float3 vetex_found = add3(ray_start, scale3(ray_dir, Ts));
-            vtx = vetex_found; v_ok = true;
-
-            int3 gc = rc.getVoxel(add3(ray_start, scale3(ray_dir, time_curr)));
-            col = rc.interpolateColorHeat(vetex_found); c_ok = true;
-
-            if (gc.x > 1 && gc.y > 1 && gc.z > 1 && gc.x < p.V - 2 && gc.y < p.V - 2 && gc.z < p.V - 2) {
-                float3 t, n;
-                t = vetex_found; t.x += p.cell_size.x; float Fx1 = rc.interpolateTrilineary(t);
-                t = vetex_found; t.x -= p.cell_size.x; float Fx2 = rc.interpolateTrilineary(t);
-                n.x = (Fx1 - Fx2);
-                t = vetex_found; t.y += p.cell_size.y; float Fy1 = rc.interpolateTrilineary(t);
-                t = vetex_found; t.y -= p.cell_size.y; float Fy2 = rc.interpolateTrilineary(t);
-                n.y = (Fy1 - Fy2);
-                t = vetex_found; t.z += p.cell_size.z; float Fz1 = rc.interpolateTrilineary(t);
-                t = vetex_found; t.z -= p.cell_size.z; float Fz2 = rc.interpolateTrilineary(t);
-                n.z = (Fz1 - Fz2);
-                nrm = normalized3(n); n_ok = true;
-            }
-            break;
+    // The march (ray_caster.cu:345-425) is evaluated strictly in order, but the nearest-voxel reads of the next RS steps are
+    // issued together: a step only needs the previous TSDF value to DECIDE, not to ADDRESS, so RS dependent L2 round trips
+    // become one.  time_curr advances by the same sequence of float additions as the reference's for-loop.
+    enum { RS = 4 };
+    bool done = false;
+    while (!done && time_curr < max_time) {
+        float tq[RS]; bool inb[RS]; short raw[RS];
+        float t = time_curr;
+#pragma unroll
+        for (int s = 0; s < RS; ++s) {
+            tq[s] = t;
+            int3 gn = rc.getVoxel(add3(ray_start, scale3(ray_dir, (t + time_step))));
+            inb[s] = rc.checkInds(gn);
+            raw[s] = inb[s] ? __ldg(&p.volume[rc.addr(gn.x, gn.y, gn.z)]) : (short)0;
+            t += time_step;
         }
+#pragma unroll
+        for (int s = 0; s < RS; ++s) {
+            if (done) break;
+            const float tc = tq[s];
+            if (!(tc < max_time)) { done = true; break; }
+            float tsdf_prev = tsdf;
+            if (!inb[s]) { done = true; break; }
+            tsdf = unpack_tsdf(raw[s]);
+            if (tsdf_prev < 0.f && tsdf > 0.f) { done = true; break; }
+            if (tsdf_prev > 0.f && tsdf < 0.f) {
+                done = true;
+                float Ftdt = rc.interpolateTrilineary(add3(ray_start, scale3(ray_dir, (tc + time_step))));
+                if (isnan(Ftdt)) break;
+                float Ft = rc.interpolateTrilineary(add3(ray_start, scale3(ray_dir, tc)));
+                if (isnan(Ft)) break;
+
+                float Ts = tc - time_step * Ft / (Ftdt - Ft);
+                float3 vetex_found = add3(ray_start, scale3(ray_dir, Ts));
+                vtx = vetex_found; v_ok = true;
+
+                int3 gc = rc.getVoxel(add3(ray_start, scale3(ray_dir, tc)));
+                col = rc.interpolateColorHeat(vetex_found); c_ok = true;
+
+                if (gc.x > 1 && gc.y > 1 && gc.z > 1 && gc.x < p.V - 2 && gc.y < p.V - 2 && gc.z < p.V - 2) {
+                    float3 tt, n;
+                    tt = vetex_found; tt.x += p.cell_size.x; float Fx1 = rc.interpolateTrilineary(tt);
+                    tt = vetex_found; tt.x -= p.cell_size.x; float Fx2 = rc.interpolateTrilineary(tt);
+                    n.x = (Fx1 - Fx2);
+                    tt = vetex_found; tt.y += p.cell_size.y; float Fy1 = rc.interpolateTrilineary(tt);
+                    tt = vetex_found; tt.y -= p.cell_size.y; float Fy2 = rc.interpolateTrilineary(tt);
+                    n.y = (Fy1 - Fy2);
+                    tt = vetex_found; tt.z += p.cell_size.z; float Fz1 = rc.interpolateTrilineary(tt);
+                    tt = vetex_found; tt.z -= p.cell_size.z; float Fz2 = rc.interpolateTrilineary(tt);
+                    n.z = (Fz1 - Fz2);
+                    nrm = normalized3(n); n_ok = true;
+                }
+                break;
+            }
+        }
+        time_curr = t;
     }
 }
 

@@ -28,37 +28,57 @@ __device__ __forceinline__ void unpack_normal_equations(const float* sums, float
         }
 }
 
-// LDL^T with diagonal pivoting (largest |d| first), as Eigen::LDLT does; double precision.
-__device__ inline void ldlt6_solve(const double* Ain, const double* b, double* x)
+// x = A^-1 b for the symmetric positive (semi-)definite 6x6 normal matrix, LDL^T in FP64, fully unrolled so that the
+// whole factorisation lives in registers (a local-memory version with pivot swaps costs ~18 us of dependent latency on one
+// thread; this one ~1 us).  Eigen::LDLT pivots on the largest diagonal entry; for an SPD matrix both orders are backward
+// stable and the solutions agree to ~cond(A) * 1e-16, far below the float pose they are rounded to.  A vanishing pivot
+// (degenerate geometry, e.g. no inliers) contributes 0 to the solution, which is what Eigen's solve does with its tolerance.
+__device__ __forceinline__ void ldlt6_solve(const double* Ain, const double* bin, double* x)
 {
-    const int n = 6;
-    double a[36];
-    int perm[6];
-    for (int i = 0; i < 36; ++i) a[i] = Ain[i];
-    for (int i = 0; i < n; ++i) perm[i] = i;
-    for (int k = 0; k < n; ++k) {
-        int piv = k; double best = fabs(a[k * n + k]);
-        for (int i = k + 1; i < n; ++i) { double v = fabs(a[i * n + i]); if (v > best) { best = v; piv = i; } }
-        if (piv != k) {
-            for (int j = 0; j < n; ++j) { double t = a[k * n + j]; a[k * n + j] = a[piv * n + j]; a[piv * n + j] = t; }
-            for (int i = 0; i < n; ++i) { double t = a[i * n + k]; a[i * n + k] = a[i * n + piv]; a[i * n + piv] = t; }
-            int t = perm[k]; perm[k] = perm[piv]; perm[piv] = t;
-        }
-        double d = a[k * n + k];
-        if (d == 0.0) continue;
-        for (int i = k + 1; i < n; ++i) a[i * n + k] /= d;
-        for (int i = k + 1; i < n; ++i)
-            for (int j = k + 1; j <= i; ++j) {
-                a[i * n + j] -= a[i * n + k] * d * a[j * n + k];
-                a[j * n + i] = a[i * n + j];
-            }
+    double a[6][6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j < 6; ++j) a[i][j] = Ain[i * 6 + j];
+    double dinv[6];
+    double scale = 0.0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) scale = fmax(scale, fabs(a[i][i]));
+    const double tiny = scale * 1e-30 + DBL_MIN;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        const double d = a[k][k];
+        const double inv = (fabs(d) > tiny) ? 1.0 / d : 0.0;
+        dinv[k] = inv;
+        double col[6], l[6];
+#pragma unroll
+        for (int i = k + 1; i < 6; ++i) { col[i] = a[i][k]; l[i] = col[i] * inv; }      // L(i,k) = A(i,k) / d_k
+#pragma unroll
+        for (int i = k + 1; i < 6; ++i)
+#pragma unroll
+            for (int j = k + 1; j <= i; ++j) a[i][j] -= l[i] * col[j];                    // A(i,j) -= L(i,k) d_k L(j,k)
+#pragma unroll
+        for (int i = k + 1; i < 6; ++i) a[i][k] = l[i];
     }
     double y[6];
-    for (int i = 0; i < n; ++i) y[i] = b[perm[i]];
-    for (int i = 0; i < n; ++i) for (int j = 0; j < i; ++j) y[i] -= a[i * n + j] * y[j];
-    for (int i = 0; i < n; ++i) { double d = a[i * n + i]; y[i] = (fabs(d) > DBL_MIN) ? y[i] / d : 0.0; }
-    for (int i = n - 1; i >= 0; --i) for (int j = i + 1; j < n; ++j) y[i] -= a[j * n + i] * y[j];
-    for (int i = 0; i < n; ++i) x[perm[i]] = y[i];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        double v = bin[i];
+#pragma unroll
+        for (int j = 0; j < i; ++j) v -= a[i][j] * y[j];
+        y[i] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) y[i] *= dinv[i];
+#pragma unroll
+    for (int i = 5; i >= 0; --i) {
+        double v = y[i];
+#pragma unroll
+        for (int j = i + 1; j < 6; ++j) v -= a[j][i] * y[j];
+        y[i] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) x[i] = y[i];
 }
 
 // cv::Rodrigues, rotation vector -> matrix, double (OpenCV 2.4.9 semantics)
@@ -107,33 +127,50 @@ __device__ __forceinline__ float dot3_rn(float a0, float a1, float a2, float b0,
     return __fadd_rn(__fadd_rn(__fmul_rn(a0, b0), __fmul_rn(a1, b1)), __fmul_rn(a2, b2));
 }
 
-// Solve for the increment and update st->resultRt / Rcurr / tcurr.  A, b in double.
-__device__ inline void gauss_newton_update(const double* dA, const double* db, OdomState* st)
+// Solve for the increment and update resultRt (4x4 double) and the float pose (Rcurr, tcurr) given (Rprev, tprev).
+__device__ __forceinline__ void gauss_newton_update_p(const double* dA, const double* db, double* resultRt,
+                                                      const float* Rp, const float* tprev, float* Rcurr, float* tcurr)
 {
     double x[6];
     ldlt6_solve(dA, db, x);
     double R[9];
     rodrigues(x + 3, R);
-    double cur[16] = {R[0], R[1], R[2], x[0], R[3], R[4], R[5], x[1], R[6], R[7], R[8], x[2], 0, 0, 0, 1};
+    const double cur[16] = {R[0], R[1], R[2], x[0], R[3], R[4], R[5], x[1], R[6], R[7], R[8], x[2], 0, 0, 0, 1};
     double res[16];
+#pragma unroll
     for (int i = 0; i < 4; ++i)
+#pragma unroll
         for (int j = 0; j < 4; ++j) {
             double s = 0;
-            for (int k = 0; k < 4; ++k) s += cur[i * 4 + k] * st->resultRt[k * 4 + j];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) s += cur[i * 4 + k] * resultRt[k * 4 + j];
             res[i * 4 + j] = s;
         }
-    for (int k = 0; k < 16; ++k) st->resultRt[k] = res[k];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) resultRt[k] = res[k];
     // float part (Eigen::Isometry3f): inverse of [rot|tr] is [rot^T | -rot^T tr]; then Rprev * that.
     float rot[9], tr[3];
-    for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) rot[i * 3 + j] = (float)res[i * 4 + j]; tr[i] = (float)res[i * 4 + 3]; }
-    float tinv[3];
-    for (int i = 0; i < 3; ++i) tinv[i] = -dot3_rn(rot[0 * 3 + i], rot[1 * 3 + i], rot[2 * 3 + i], tr[0], tr[1], tr[2]);
-    const float* Rp = st->Rprev;
+#pragma unroll
     for (int i = 0; i < 3; ++i) {
-        for (int j = 0; j < 3; ++j)   // (Rprev * rot^T)(i,j) = sum_k Rprev(i,k) * rot(j,k)
-            st->Rcurr[i * 3 + j] = dot3_rn(Rp[i * 3 + 0], Rp[i * 3 + 1], Rp[i * 3 + 2], rot[j * 3 + 0], rot[j * 3 + 1], rot[j * 3 + 2]);
-        st->tcurr[i] = __fadd_rn(dot3_rn(Rp[i * 3 + 0], Rp[i * 3 + 1], Rp[i * 3 + 2], tinv[0], tinv[1], tinv[2]), st->tprev[i]);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) rot[i * 3 + j] = (float)res[i * 4 + j];
+        tr[i] = (float)res[i * 4 + 3];
     }
+    float tinv[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) tinv[i] = -dot3_rn(rot[0 * 3 + i], rot[1 * 3 + i], rot[2 * 3 + i], tr[0], tr[1], tr[2]);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j)   // (Rprev * rot^T)(i,j) = sum_k Rprev(i,k) * rot(j,k)
+            Rcurr[i * 3 + j] = dot3_rn(Rp[i * 3 + 0], Rp[i * 3 + 1], Rp[i * 3 + 2], rot[j * 3 + 0], rot[j * 3 + 1], rot[j * 3 + 2]);
+        tcurr[i] = __fadd_rn(dot3_rn(Rp[i * 3 + 0], Rp[i * 3 + 1], Rp[i * 3 + 2], tinv[0], tinv[1], tinv[2]), tprev[i]);
+    }
+}
+
+__device__ __forceinline__ void gauss_newton_update(const double* dA, const double* db, OdomState* st)
+{
+    gauss_newton_update_p(dA, db, st->resultRt, st->Rprev, st->tprev, st->Rcurr, st->tcurr);
 }
 
 } // namespace kt

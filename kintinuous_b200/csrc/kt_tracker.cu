@@ -83,7 +83,7 @@ struct kt_ctx {
     uint16_t* depths_curr[LEVELS];
     float* vmaps_g_prev[LEVELS]; float* nmaps_g_prev[LEVELS]; float* vmaps_curr[LEVELS]; float* nmaps_curr[LEVELS];
     uint8_t* vmap_curr_color; float* depth_scaled; float* ztable;
-    OdomState* state; float* partials; int* ipartials; float* trace_dev; float* pose12_dev;
+    OdomState* state; float* partials; int* ipartials; float* trace_dev; float* pose12_dev; unsigned int* bar_dev; unsigned int bar_count;
     kt_point_xyzrgb* cloud_dev; unsigned int* counter_dev; size_t cloud_capacity; size_t cloud_count;
     // RGB-D
     float* lastDepth[LEVELS]; float* nextDepth[LEVELS]; uint8_t* lastImage[LEVELS]; uint8_t* nextImage[LEVELS];
@@ -174,8 +174,6 @@ int run_odometry(kt_ctx* c, const M3& Rprev, const V3& tprev, M3* Rcurr, V3* tcu
     int r;
     for (int k = 0; k < 9; ++k) c->pose12_host[k] = Rprev.m[k];
     for (int k = 0; k < 3; ++k) c->pose12_host[9 + k] = tprev.v[k];
-    KT_CUDA(cudaMemcpyAsync(c->pose12_dev, c->pose12_host, 12 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    if ((r = odom_begin_frame(c->state, c->pose12_dev, c->stream))) return r;
     const float distThres = 0.10f, angleThres = sinf(20.f * 3.14159254f / 180.f);      // ICPOdometry.h:35-36
     Intr K = {c->cfg.fx, c->cfg.fy, c->cfg.cx, c->cfg.cy};
     if (mode != 0) {
@@ -184,9 +182,23 @@ int run_odometry(kt_ctx* c, const M3& Rprev, const V3& tprev, M3* Rcurr, V3* tcu
             if ((r = derivative_images(c->nextImage[i], c->nextdIdx[i], c->nextdIdy[i], rows >> i, cols >> i, c->stream))) return r;
     }
     int total_iters = 0;
+    if (mode == 0) {
+        // ICP-only: the whole coarse-to-fine loop is ONE cooperative launch (kt_icp.cu, icp_frame_kernel)
+        IcpLevelArgs la[LEVELS];
+        for (int level = 0; level < LEVELS; ++level) {
+            IcpLevelArgs ia = {c->vmaps_curr[level], c->nmaps_curr[level], c->vmaps_g_prev[level], c->nmaps_g_prev[level], rows >> level, cols >> level,
+                               intr_level(K, level), distThres, angleThres};
+            la[level] = ia;
+            total_iters += c->iterations[level];
+        }
+        if ((r = icp_frame(la, c->iterations, c->pose12_host, c->state, c->partials, c->trace_dev, c->bar_dev, &c->bar_count, c->stream))) return r;
+    } else {
+    KT_CUDA(cudaMemcpyAsync(c->pose12_dev, c->pose12_host, 12 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    if ((r = odom_begin_frame(c->state, c->pose12_dev, c->stream))) return r;
+    }
     const double SOBEL_SCALE = 1.0 / std::pow(2.0, 3);
     const int minimumGradientMagnitudes[4] = {12, 5, 3, 1};
-    for (int level = LEVELS - 1; level >= 0; --level) {
+    for (int level = LEVELS - 1; level >= 0 && mode != 0; --level) {
         const int lr = rows >> level, lc = cols >> level;
         Intr kl = intr_level(K, level);
         IcpLevelArgs ia = {c->vmaps_curr[level], c->nmaps_curr[level], c->vmaps_g_prev[level], c->nmaps_g_prev[level], lr, lc, kl, distThres, angleThres};
@@ -428,7 +440,8 @@ int kt_create(const kt_config* cfg, kt_ctx** out)
     }
     KT_TRY(dev_alloc(c, &c->vmap_curr_color, P * 4)); KT_TRY(dev_alloc(c, &c->depth_scaled, P));
     KT_TRY(dev_alloc(c, &c->ztable, (size_t)2 * cfg->vol));
-    KT_TRY(dev_alloc(c, &c->state, 1)); KT_TRY(dev_alloc(c, &c->partials, (size_t)MAX_PARTIALS * 32)); KT_TRY(dev_alloc(c, &c->ipartials, (size_t)MAX_PARTIALS * 2));
+    KT_TRY(dev_alloc(c, &c->state, 1)); KT_TRY(dev_alloc(c, &c->partials, (size_t)MAX_PARTIALS * 32));
+    KT_TRY(dev_alloc(c, &c->bar_dev, 1)); KT_TRY(kt::cuda_check(cudaMemset(c->bar_dev, 0, sizeof(unsigned int)), "memset", __FILE__, __LINE__)); c->bar_count = 0; KT_TRY(dev_alloc(c, &c->ipartials, (size_t)MAX_PARTIALS * 2));
     KT_TRY(dev_alloc(c, &c->trace_dev, (size_t)MAX_TRACE_ITERS * TRACE_STRIDE)); KT_TRY(dev_alloc(c, &c->pose12_dev, 12));
     c->cloud_capacity = (size_t)c->cfg.cloud_capacity;
     KT_TRY(dev_alloc(c, &c->cloud_dev, c->cloud_capacity)); KT_TRY(dev_alloc(c, &c->counter_dev, 1));

@@ -203,51 +203,83 @@ integrate_kernel(const IntegrateParams p)
     const size_t plane = (size_t)V * V;
     const size_t col_off = (size_t)sy * V + sx;
 
-    for (int z = zlo; z < zhi; ++z, v_x += Rcurr_inv_0_z_scaled, v_y += Rcurr_inv_1_z_scaled) {
-        v_g_z = zt[z];
-        const float z_scaled = zt[V + z];
-        float inv_z = 1.0f / (v_z + Rcurr_inv.r2.z * z_scaled);
-        if (inv_z < 0) continue;
-
-        int2 coo = { __float2int_rn(v_x * inv_z + intr.cx), __float2int_rn(v_y * inv_z + intr.cy) };
-        if (coo.x >= 0 && coo.y >= 0 && coo.x < cols && coo.y < rows) {
-            int sz = z + p.wrap.z; if (sz >= V) sz -= V;
-            if (sz < p.z_begin || sz >= p.z_end) continue;             // not this GPU's slab
-            const size_t pix = (size_t)coo.y * cols + coo.x;
-            float Dp_scaled = depthScaled[pix];
-            bool no_color = false;
-            if (Dp_scaled < 0.0) { Dp_scaled = -Dp_scaled; no_color = true; }
-            float sdf = Dp_scaled - sqrtf(v_g_z * v_g_z + v_g_part_norm);
-            if (Dp_scaled != 0 && sdf >= -tranc_dist) {
-                float3 ncurr;
-                ncurr.x = nmap_curr[pix];
-                ncurr.z = nmap_curr[pix + 2 * P];
-                if (ncurr.z < 0) ncurr.z = -ncurr.z;
-
-                float tsdf = fmin(1.0f, sdf * tranc_dist_inv);
-
-                const size_t a = (size_t)(sz - p.z_begin) * plane + col_off;
-                int16_t* pos = p.tsdf + a;
-                float tsdf_prev = unpack_tsdf(*pos);
-                uchar4* ptrColor = p.color + a;
-                uchar4 c = *ptrColor;
-                float weight_prev = c.w;
-                const float Wrk = 1;
-                *pos = pack_tsdf((tsdf_prev * weight_prev + Wrk * tsdf) / (weight_prev + Wrk));
-                c.w = min(weight_prev + Wrk, (float)KT_MAX_WEIGHT);
-
-                if ((!isnan(ncurr.x) && !no_color) || (c.x == 0 && c.y == 0 && c.z == 0)) {
-                    const float Wrkc = (p.angle_color ? min(1.0f, ncurr.z / KT_RGB_VIEW_ANGLE_WEIGHT) : 1.0f) * 2.0f;
-                    uchar3 rgb = colors[pix];
-                    float new_x = (c.x * weight_prev + Wrkc * rgb.x) / (weight_prev + Wrkc);
-                    float new_y = (c.y * weight_prev + Wrkc * rgb.y) / (weight_prev + Wrkc);
-                    float new_z = (c.z * weight_prev + Wrkc * rgb.z) / (weight_prev + Wrkc);
-                    c.x = min(255, max(0, __float2int_rn(new_x)));
-                    c.y = min(255, max(0, __float2int_rn(new_y)));
-                    c.z = min(255, max(0, __float2int_rn(new_z)));
+    // The z loop is processed in batches of ZU voxels in three phases (project + depth gather / sdf test + volume loads /
+    // blend + stores) so that ZU independent memory round trips are in flight per thread; the per-voxel arithmetic and the
+    // running sums are exactly the reference's (storage addresses of different z never alias, which the compiler cannot know).
+    enum { ZU = 4 };
+    for (int zb = zlo; zb < zhi; zb += ZU) {
+        float vgz[ZU], Dp[ZU];
+        size_t pix[ZU], addr[ZU];
+        bool ok[ZU];
+#pragma unroll
+        for (int u = 0; u < ZU; ++u) {
+            const int z = zb + u;
+            ok[u] = false;
+            if (z < zhi) {
+                vgz[u] = zt[z];
+                const float z_scaled = zt[V + z];
+                float inv_z = 1.0f / (v_z + Rcurr_inv.r2.z * z_scaled);
+                if (!(inv_z < 0)) {
+                    int2 coo = { __float2int_rn(v_x * inv_z + intr.cx), __float2int_rn(v_y * inv_z + intr.cy) };
+                    if (coo.x >= 0 && coo.y >= 0 && coo.x < cols && coo.y < rows) {
+                        int sz = z + p.wrap.z; if (sz >= V) sz -= V;
+                        if (sz >= p.z_begin && sz < p.z_end) {             // this GPU's slab
+                            ok[u] = true;
+                            pix[u] = (size_t)coo.y * cols + coo.x;
+                            addr[u] = (size_t)(sz - p.z_begin) * plane + col_off;
+                            Dp[u] = depthScaled[pix[u]];
+                        }
+                    }
                 }
-                *ptrColor = c;
+                v_x += Rcurr_inv_0_z_scaled;
+                v_y += Rcurr_inv_1_z_scaled;
             }
+        }
+        bool upd[ZU], nocol[ZU];
+        float tsdf_new[ZU], nx[ZU], nz[ZU];
+        int16_t tprev[ZU]; uchar4 cprev[ZU]; uchar3 rgbv[ZU];
+#pragma unroll
+        for (int u = 0; u < ZU; ++u) {
+            upd[u] = false;
+            if (ok[u]) {
+                float Dp_scaled = Dp[u];
+                bool no_color = false;
+                if (Dp_scaled < 0.0) { Dp_scaled = -Dp_scaled; no_color = true; }
+                float sdf = Dp_scaled - sqrtf(vgz[u] * vgz[u] + v_g_part_norm);
+                if (Dp_scaled != 0 && sdf >= -tranc_dist) {
+                    upd[u] = true; nocol[u] = no_color;
+                    tsdf_new[u] = fmin(1.0f, sdf * tranc_dist_inv);
+                    tprev[u] = p.tsdf[addr[u]];
+                    cprev[u] = p.color[addr[u]];
+                    nx[u] = nmap_curr[pix[u]];
+                    nz[u] = nmap_curr[pix[u] + 2 * P];
+                    rgbv[u] = colors[pix[u]];
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < ZU; ++u) {
+            if (!upd[u]) continue;
+            float3 ncurr; ncurr.x = nx[u]; ncurr.z = nz[u];
+            if (ncurr.z < 0) ncurr.z = -ncurr.z;
+            float tsdf = tsdf_new[u];
+            float tsdf_prev = unpack_tsdf(tprev[u]);
+            uchar4 c = cprev[u];
+            float weight_prev = c.w;
+            const float Wrk = 1;
+            p.tsdf[addr[u]] = pack_tsdf((tsdf_prev * weight_prev + Wrk * tsdf) / (weight_prev + Wrk));
+            c.w = min(weight_prev + Wrk, (float)KT_MAX_WEIGHT);
+            if ((!isnan(ncurr.x) && !nocol[u]) || (c.x == 0 && c.y == 0 && c.z == 0)) {
+                const float Wrkc = (p.angle_color ? min(1.0f, ncurr.z / KT_RGB_VIEW_ANGLE_WEIGHT) : 1.0f) * 2.0f;
+                uchar3 rgb = rgbv[u];
+                float new_x = (c.x * weight_prev + Wrkc * rgb.x) / (weight_prev + Wrkc);
+                float new_y = (c.y * weight_prev + Wrkc * rgb.y) / (weight_prev + Wrkc);
+                float new_z = (c.z * weight_prev + Wrkc * rgb.z) / (weight_prev + Wrkc);
+                c.x = min(255, max(0, __float2int_rn(new_x)));
+                c.y = min(255, max(0, __float2int_rn(new_y)));
+                c.z = min(255, max(0, __float2int_rn(new_z)));
+            }
+            p.color[addr[u]] = c;
         }
     }
 }
