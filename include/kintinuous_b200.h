@@ -119,6 +119,8 @@ KT_API int kt_get_stage_ms(kt_ctx* ctx, float* ms6);
 KT_API int kt_set_stage_timing(kt_ctx* ctx, int enabled);
 /* number of kernels this library launched since kt_create (for bench.py's gpu_launches) */
 KT_API long long kt_launch_count(kt_ctx* ctx);
+/* debug: 64 x 5 clock64() stamps of the last whole-frame ICP launch (recorded only while stage timing is enabled) */
+KT_API int kt_debug_icp_profile(kt_ctx* ctx, long long* out320);
 KT_API int kt_alloc_pinned(void** ptr, size_t bytes);
 KT_API int kt_free_pinned(void* ptr);
 

@@ -148,6 +148,7 @@ struct IcpFrameParams {
     float* trace;
     unsigned int* bar;         // monotonically increasing arrival counter
     unsigned int bar_base;     // value of the counter when this launch starts
+    long long* prof;           // optional: 5 clock64() stamps per iteration from CTA 0 (debug)
 };
 
 __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int target)
@@ -197,6 +198,8 @@ icp_frame_kernel(const IcpFrameParams p)
             Mat33 Rcurr; float3 tcurr;
             Rcurr.r0 = make_float3(s_R[0], s_R[1], s_R[2]); Rcurr.r1 = make_float3(s_R[3], s_R[4], s_R[5]); Rcurr.r2 = make_float3(s_R[6], s_R[7], s_R[8]);
             tcurr = make_float3(s_t[0], s_t[1], s_t[2]);
+            const bool prof = (p.prof != 0) && blockIdx.x == 0 && tid == 0 && it < 64;
+            if (prof) p.prof[it * 5 + 0] = clock64();
             float sum[NSUM];
 #pragma unroll
             for (int k = 0; k < NSUM; ++k) sum[k] = 0.f;
@@ -217,7 +220,9 @@ icp_frame_kernel(const IcpFrameParams p)
                 part[(size_t)tid * G + blockIdx.x] = v;
             }
             target += (unsigned int)G;
+            if (prof) p.prof[it * 5 + 1] = clock64();
             grid_barrier(p.bar, target);
+            if (prof) p.prof[it * 5 + 2] = clock64();
             // every CTA: fixed-order total of the G partials of each component (16 lanes per component)
             {
                 const int comp = tid >> 4, sub = tid & 15;
@@ -231,6 +236,7 @@ icp_frame_kernel(const IcpFrameParams p)
                 if (sub == 0 && comp < NSUM) s_sum[comp] = v;
             }
             __syncthreads();
+            if (prof) p.prof[it * 5 + 3] = clock64();
             if (tid == 0) {
                 float A[36], b[6];
                 unpack_normal_equations(s_sum, A, b);
@@ -246,6 +252,7 @@ icp_frame_kernel(const IcpFrameParams p)
 #pragma unroll
                 for (int k = 0; k < 6; ++k) db[k] = b[k];
                 gauss_newton_update_p(dA, db, s_Rt, s_Rp, s_tp, s_R, s_t);
+                if (prof) p.prof[it * 5 + 4] = clock64();
             }
             __syncthreads();
         }
@@ -311,9 +318,10 @@ int odom_begin_frame(OdomState* state, const float* pose12_dev, cudaStream_t s)
 // Whole-frame ICP (ICP-only odometry).  pose12 = Rprev (9) + tprev (3) on the host; the result lands in state->Rcurr/tcurr.
 // bar_dev: one unsigned int, zeroed once at allocation; *bar_count (host) tracks its value across launches.
 int icp_frame(const IcpLevelArgs* levels, const int* iters, const float* pose12_host, OdomState* state, float* partials,
-              float* trace, unsigned int* bar_dev, unsigned int* bar_count, cudaStream_t s)
+              float* trace, unsigned int* bar_dev, unsigned int* bar_count, long long* prof_dev, cudaStream_t s)
 {
     IcpFrameParams p;
+    p.prof = prof_dev;
     int total = 0;
     for (int l = 0; l < LEVELS; ++l) { p.lv[l] = levels[l]; p.iters[l] = iters[l]; total += iters[l]; }
     for (int k = 0; k < 12; ++k) p.pose12[k] = pose12_host[k];

@@ -56,7 +56,7 @@ struct IcpLevelArgs {
 int icp_iteration(const IcpLevelArgs& a, OdomState* state, float* partials, float* trace, int mode, cudaStream_t s);
 
 int icp_frame(const IcpLevelArgs* levels, const int* iters, const float* pose12_host, OdomState* state, float* partials,
-              float* trace, unsigned int* bar_dev, unsigned int* bar_count, cudaStream_t s);
+              float* trace, unsigned int* bar_dev, unsigned int* bar_count, long long* prof_dev, cudaStream_t s);
 
 struct RgbLevelArgs {
     const int16_t* dIdx; const int16_t* dIdy; const float* last_depth; const float* next_depth;

@@ -83,7 +83,7 @@ struct kt_ctx {
     uint16_t* depths_curr[LEVELS];
     float* vmaps_g_prev[LEVELS]; float* nmaps_g_prev[LEVELS]; float* vmaps_curr[LEVELS]; float* nmaps_curr[LEVELS];
     uint8_t* vmap_curr_color; float* depth_scaled; float* ztable;
-    OdomState* state; float* partials; int* ipartials; float* trace_dev; float* pose12_dev; unsigned int* bar_dev; unsigned int bar_count;
+    OdomState* state; float* partials; int* ipartials; float* trace_dev; float* pose12_dev; unsigned int* bar_dev; unsigned int bar_count; long long* prof_dev;
     kt_point_xyzrgb* cloud_dev; unsigned int* counter_dev; size_t cloud_capacity; size_t cloud_count;
     // RGB-D
     float* lastDepth[LEVELS]; float* nextDepth[LEVELS]; uint8_t* lastImage[LEVELS]; uint8_t* nextImage[LEVELS];
@@ -191,7 +191,7 @@ int run_odometry(kt_ctx* c, const M3& Rprev, const V3& tprev, M3* Rcurr, V3* tcu
             la[level] = ia;
             total_iters += c->iterations[level];
         }
-        if ((r = icp_frame(la, c->iterations, c->pose12_host, c->state, c->partials, c->trace_dev, c->bar_dev, &c->bar_count, c->stream))) return r;
+        if ((r = icp_frame(la, c->iterations, c->pose12_host, c->state, c->partials, c->trace_dev, c->bar_dev, &c->bar_count, c->timing ? c->prof_dev : 0, c->stream))) return r;
     } else {
     KT_CUDA(cudaMemcpyAsync(c->pose12_dev, c->pose12_host, 12 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     if ((r = odom_begin_frame(c->state, c->pose12_dev, c->stream))) return r;
@@ -441,7 +441,8 @@ int kt_create(const kt_config* cfg, kt_ctx** out)
     KT_TRY(dev_alloc(c, &c->vmap_curr_color, P * 4)); KT_TRY(dev_alloc(c, &c->depth_scaled, P));
     KT_TRY(dev_alloc(c, &c->ztable, (size_t)2 * cfg->vol));
     KT_TRY(dev_alloc(c, &c->state, 1)); KT_TRY(dev_alloc(c, &c->partials, (size_t)MAX_PARTIALS * 32));
-    KT_TRY(dev_alloc(c, &c->bar_dev, 1)); KT_TRY(kt::cuda_check(cudaMemset(c->bar_dev, 0, sizeof(unsigned int)), "memset", __FILE__, __LINE__)); c->bar_count = 0; KT_TRY(dev_alloc(c, &c->ipartials, (size_t)MAX_PARTIALS * 2));
+    KT_TRY(dev_alloc(c, &c->bar_dev, 1)); KT_TRY(kt::cuda_check(cudaMemset(c->bar_dev, 0, sizeof(unsigned int)), "memset", __FILE__, __LINE__)); c->bar_count = 0;
+    KT_TRY(dev_alloc(c, &c->prof_dev, 64 * 5)); KT_TRY(dev_alloc(c, &c->ipartials, (size_t)MAX_PARTIALS * 2));
     KT_TRY(dev_alloc(c, &c->trace_dev, (size_t)MAX_TRACE_ITERS * TRACE_STRIDE)); KT_TRY(dev_alloc(c, &c->pose12_dev, 12));
     c->cloud_capacity = (size_t)c->cfg.cloud_capacity;
     KT_TRY(dev_alloc(c, &c->cloud_dev, c->cloud_capacity)); KT_TRY(dev_alloc(c, &c->counter_dev, 1));
@@ -582,6 +583,14 @@ int kt_get_stage_ms(kt_ctx* c, float* ms6)
     float total = 0.f;
     for (int i = 0; i < 5; ++i) { float t = 0.f; if (cudaEventElapsedTime(&t, c->ev[i], c->ev[i + 1]) != cudaSuccess) { cudaGetLastError(); t = 0.f; } ms6[i] = t; total += t; }
     ms6[5] = total;
+    return KT_OK;
+}
+
+int kt_debug_icp_profile(kt_ctx* c, long long* out320)
+{
+    if (!c || !out320) return KT_ERR_INVALID;
+    KT_CUDA(cudaStreamSynchronize(c->stream));
+    KT_CUDA(cudaMemcpy(out320, c->prof_dev, 64 * 5 * sizeof(long long), cudaMemcpyDeviceToHost));
     return KT_OK;
 }
 
