@@ -137,7 +137,7 @@ icp_kernel(const IcpParams p)
 // its pixels to a 29-float partial, ONE grid barrier, then EVERY CTA sums the per-CTA partials in the same fixed order and
 // performs the same FP64 solve redundantly, so that no second barrier / broadcast of the pose is needed (the result is
 // bit-identical in all CTAs because the instruction sequence and inputs are identical).
-enum { FRAME_THREADS = 512 };
+enum { FRAME_THREADS = 512, STAGE_MAX_K = 8 };
 
 struct IcpFrameParams {
     IcpLevelArgs lv[LEVELS];
@@ -149,6 +149,7 @@ struct IcpFrameParams {
     unsigned int* bar;         // monotonically increasing arrival counter
     unsigned int bar_base;     // value of the counter when this launch starts
     long long* prof;           // optional: 5 clock64() stamps per iteration from CTA 0 (debug)
+    int stage_k;               // chunks of FRAME_THREADS pixels per CTA that fit the shared-memory stage (0 = no staging)
 };
 
 __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int target)
@@ -163,13 +164,96 @@ __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int tar
     __syncthreads();
 }
 
+// ---- TMA (bulk async copy engine) helpers: global -> shared 1-D bulk copies completing on an mbarrier ----
+__device__ __forceinline__ unsigned int smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned int bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, unsigned int bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned int parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "KT_WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra KT_WAIT_DONE;\n"
+        "bra KT_WAIT_LOOP;\n"
+        "KT_WAIT_DONE:\n"
+        "}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// 32 per-lane values -> lane l holds the warp total of value l (31 shuffles instead of 32 x 5; fixed tree)
+__device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane)
+{
+#pragma unroll
+    for (int step = 16; step >= 1; step >>= 1) {
+        const bool upper = (lane & step) != 0;
+#pragma unroll
+        for (int j = 0; j < step; ++j) {
+            const float send = upper ? v[j] : v[j + step];
+            const float keep = upper ? v[j + step] : v[j];
+            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, step);
+        }
+    }
+    return v[0];
+}
+
+// one pixel whose current vertex / normal were staged in shared memory
+__device__ __forceinline__ void icp_pixel_staged(const float3& vcurr, const float3& ncurr, int N, int cols, int rows,
+                                                 const float* __restrict__ vmap_g_prev, const float* __restrict__ nmap_g_prev,
+                                                 const Intr& intr, const Mat33& Rcurr, const float3& tcurr, const Mat33& Rprev_inv, const float3& tprev,
+                                                 float dist_thres, float angle_thres, float (&sum)[32])
+{
+    if (isnan(vcurr.x)) return;
+    float3 vcurr_g = add3(mul33(Rcurr, vcurr), tcurr);
+    float3 vcurr_cp = mul33(Rprev_inv, sub3(vcurr_g, tprev));
+    int2 ukr;
+    ukr.x = __float2int_rn(vcurr_cp.x * intr.fx / vcurr_cp.z + intr.cx);
+    ukr.y = __float2int_rn(vcurr_cp.y * intr.fy / vcurr_cp.z + intr.cy);
+    if (ukr.x < 0 || ukr.y < 0 || ukr.x >= cols || ukr.y >= rows || vcurr_cp.z < 0) return;
+    const int j = ukr.y * cols + ukr.x;
+    float3 vprev_g, nprev_g;
+    vprev_g.x = __ldg(&vmap_g_prev[j]); vprev_g.y = __ldg(&vmap_g_prev[j + N]); vprev_g.z = __ldg(&vmap_g_prev[j + 2 * N]);
+    nprev_g.x = __ldg(&nmap_g_prev[j]); nprev_g.y = __ldg(&nmap_g_prev[j + N]); nprev_g.z = __ldg(&nmap_g_prev[j + 2 * N]);
+    if (isnan(vprev_g.x) || isnan(nprev_g.x) || isnan(ncurr.x)) return;
+    float3 ncurr_g = mul33(Rcurr, ncurr);
+    float dist = norm3(sub3(vprev_g, vcurr_g));
+    float sine = norm3(cross3(ncurr_g, nprev_g));
+    if (!(sine < angle_thres && dist <= dist_thres)) return;
+    float3 s_cp = mul33(Rprev_inv, sub3(vcurr_g, tprev));
+    float3 d_cp = mul33(Rprev_inv, sub3(vprev_g, tprev));
+    float3 n_cp = mul33(Rprev_inv, nprev_g);
+    float3 sxn = cross3(s_cp, n_cp);
+    const float row[7] = {n_cp.x, n_cp.y, n_cp.z, sxn.x, sxn.y, sxn.z, dot3(n_cp, sub3(s_cp, d_cp))};
+    int k = 0;
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int b = a; b < 7; ++b) sum[k++] += row[a] * row[b];
+    sum[27] += row[6] * row[6];
+    sum[28] += 1.f;
+}
+
 __global__ void __launch_bounds__(FRAME_THREADS, 1)
 icp_frame_kernel(const IcpFrameParams p)
 {
+    extern __shared__ __align__(128) float s_stage[];               // [6 planes][stage_k][FRAME_THREADS]
     __shared__ float s_Rp[9], s_tp[3], s_Rpi[9], s_R[9], s_t[3];
     __shared__ double s_Rt[16];
     __shared__ float s_red[FRAME_THREADS / 32][32];
     __shared__ float s_sum[32];
+    __shared__ __align__(8) unsigned long long s_mbar;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int G = gridDim.x;
     if (tid == 0) {
@@ -177,6 +261,7 @@ icp_frame_kernel(const IcpFrameParams p)
         for (int k = 0; k < 3; ++k) { s_tp[k] = p.pose12[9 + k]; s_t[k] = p.pose12[9 + k]; }
         mat3f_inverse(s_Rp, s_Rpi);                                    // Rprev.inverse(), ICPOdometry.cpp:81
         for (int k = 0; k < 16; ++k) s_Rt[k] = (k % 5 == 0) ? 1.0 : 0.0;
+        mbar_init(&s_mbar, 1);
     }
     __syncthreads();
     Mat33 Rprev_inv; float3 tprev;
@@ -185,7 +270,9 @@ icp_frame_kernel(const IcpFrameParams p)
 
     int it = 0;
     unsigned int target = p.bar_base;
+    unsigned int stage_parity = 0;
     for (int level = LEVELS - 1; level >= 0; --level) {
+        if (p.iters[level] == 0) continue;
         const IcpLevelArgs& a = p.lv[level];
         const int cols = a.cols, rows = a.rows, N = cols * rows;
         const float* __restrict__ vmap_curr = a.vmap_curr;
@@ -194,22 +281,66 @@ icp_frame_kernel(const IcpFrameParams p)
         const float* __restrict__ nmap_g_prev = a.nmap_g_prev;
         const Intr intr = a.k;
         const float dist_thres = a.dist_thres, angle_thres = a.angle_thres;
+        // pixels of this CTA: chunk k covers [ (k*G + blockIdx.x) * FRAME_THREADS, +FRAME_THREADS )
+        const int n_chunks = (N + G * FRAME_THREADS - 1) / (G * FRAME_THREADS);
+        const bool staged = (p.stage_k > 0) && (n_chunks <= p.stage_k);
+        if (staged) {
+            // The current vertex / normal maps do not change during the level's iterations: ONE bulk copy per plane and chunk
+            // (2 KB each, 16-byte aligned) brings them into shared memory through the TMA engine; every iteration then reads
+            // its 24 streamed bytes per pixel from shared memory instead of L2.
+            __syncthreads();                                         // previous level's readers are done with the stage
+            if (tid == 0) {
+                unsigned int total = 0;
+                for (int k = 0; k < n_chunks; ++k) {
+                    const int i0 = (k * G + blockIdx.x) * FRAME_THREADS;
+                    if (i0 < N) total += (unsigned int)(min(FRAME_THREADS, N - i0) * 4) * 6u;
+                }
+                if (total) mbar_expect_tx(&s_mbar, total);
+                for (int k = 0; k < n_chunks; ++k) {
+                    const int i0 = (k * G + blockIdx.x) * FRAME_THREADS;
+                    if (i0 >= N) continue;
+                    const unsigned int bytes = (unsigned int)(min(FRAME_THREADS, N - i0) * 4);
+#pragma unroll
+                    for (int pl = 0; pl < 3; ++pl) {
+                        tma_bulk_g2s(&s_stage[((pl) * p.stage_k + k) * FRAME_THREADS], vmap_curr + (size_t)pl * N + i0, bytes, &s_mbar);
+                        tma_bulk_g2s(&s_stage[((3 + pl) * p.stage_k + k) * FRAME_THREADS], nmap_curr + (size_t)pl * N + i0, bytes, &s_mbar);
+                    }
+                }
+                if (total == 0) mbar_expect_tx(&s_mbar, 0);          // complete the phase for CTAs without pixels at this level
+            }
+            mbar_wait(&s_mbar, stage_parity);
+            stage_parity ^= 1u;
+        }
         for (int iter = 0; iter < p.iters[level]; ++iter, ++it) {
             Mat33 Rcurr; float3 tcurr;
             Rcurr.r0 = make_float3(s_R[0], s_R[1], s_R[2]); Rcurr.r1 = make_float3(s_R[3], s_R[4], s_R[5]); Rcurr.r2 = make_float3(s_R[6], s_R[7], s_R[8]);
             tcurr = make_float3(s_t[0], s_t[1], s_t[2]);
             const bool prof = (p.prof != 0) && blockIdx.x == 0 && tid == 0 && it < 64;
             if (prof) p.prof[it * 5 + 0] = clock64();
-            float sum[NSUM];
+            float sum[32];
 #pragma unroll
-            for (int k = 0; k < NSUM; ++k) sum[k] = 0.f;
-            for (int i = blockIdx.x * FRAME_THREADS + tid; i < N; i += G * FRAME_THREADS)
-                icp_pixel(i, N, cols, rows, vmap_curr, nmap_curr, vmap_g_prev, nmap_g_prev, intr, Rcurr, tcurr, Rprev_inv, tprev, dist_thres, angle_thres, sum);
-            // CTA reduction
-#pragma unroll
-            for (int k = 0; k < NSUM; ++k) {
-                float v = warp_sum(sum[k]);
-                if (lane == 0) s_red[wid][k] = v;
+            for (int k = 0; k < 32; ++k) sum[k] = 0.f;
+            if (staged) {
+                for (int k = 0; k < n_chunks; ++k) {
+                    const int i = (k * G + blockIdx.x) * FRAME_THREADS + tid;
+                    if (i < N) {
+                        const int o = k * FRAME_THREADS + tid, ps = p.stage_k * FRAME_THREADS;
+                        const float3 vc = make_float3(s_stage[o], s_stage[ps + o], s_stage[2 * ps + o]);
+                        const float3 nc = make_float3(s_stage[3 * ps + o], s_stage[4 * ps + o], s_stage[5 * ps + o]);
+                        icp_pixel_staged(vc, nc, N, cols, rows, vmap_g_prev, nmap_g_prev, intr, Rcurr, tcurr, Rprev_inv, tprev, dist_thres, angle_thres, sum);
+                    }
+                }
+            } else {
+                for (int i = blockIdx.x * FRAME_THREADS + tid; i < N; i += G * FRAME_THREADS) {
+                    const float3 vc = make_float3(__ldg(&vmap_curr[i]), __ldg(&vmap_curr[i + N]), __ldg(&vmap_curr[i + 2 * N]));
+                    const float3 nc = make_float3(__ldg(&nmap_curr[i]), __ldg(&nmap_curr[i + N]), __ldg(&nmap_curr[i + 2 * N]));
+                    icp_pixel_staged(vc, nc, N, cols, rows, vmap_g_prev, nmap_g_prev, intr, Rcurr, tcurr, Rprev_inv, tprev, dist_thres, angle_thres, sum);
+                }
+            }
+            // CTA reduction: warp transpose-sum (lane l ends with component l), then a fixed-order sum over the 16 warps
+            {
+                const float v = warp_transpose_sum(sum, lane);
+                s_red[wid][lane] = v;
             }
             __syncthreads();
             float* part = p.partials + (size_t)(it & 1) * 32 * G;
@@ -223,12 +354,19 @@ icp_frame_kernel(const IcpFrameParams p)
             if (prof) p.prof[it * 5 + 1] = clock64();
             grid_barrier(p.bar, target);
             if (prof) p.prof[it * 5 + 2] = clock64();
-            // every CTA: fixed-order total of the G partials of each component (16 lanes per component)
+            // every CTA: fixed-order total of the G partials of each component (16 lanes per component, loads issued together)
             {
                 const int comp = tid >> 4, sub = tid & 15;
+                float x[10];
+#pragma unroll
+                for (int q = 0; q < 10; ++q) {
+                    const int b = sub + 16 * q;
+                    x[q] = (comp < NSUM && b < G) ? __ldcg(&part[(size_t)comp * G + b]) : 0.f;
+                }
                 float v = 0.f;
-                if (comp < NSUM)
-                    for (int b = sub; b < G; b += 16) v += __ldcg(&part[(size_t)comp * G + b]);
+#pragma unroll
+                for (int q = 0; q < 10; ++q) v += x[q];
+                for (int b = sub + 160; b < G; b += 16) v += (comp < NSUM) ? __ldcg(&part[(size_t)comp * G + b]) : 0.f;
                 v += __shfl_xor_sync(0xffffffffu, v, 8);
                 v += __shfl_xor_sync(0xffffffffu, v, 4);
                 v += __shfl_xor_sync(0xffffffffu, v, 2);
@@ -238,19 +376,26 @@ icp_frame_kernel(const IcpFrameParams p)
             __syncthreads();
             if (prof) p.prof[it * 5 + 3] = clock64();
             if (tid == 0) {
-                float A[36], b[6];
-                unpack_normal_equations(s_sum, A, b);
+                // unpack 27 sums -> symmetric A (row-major) and b, constant indices only (registers, no local memory)
+                double dA[36], db[6];
+                {
+                    int shift = 0;
+#pragma unroll
+                    for (int i = 0; i < 6; ++i)
+#pragma unroll
+                        for (int j = i; j < 7; ++j) {
+                            const double value = (double)s_sum[shift++];
+                            if (j == 6) db[i] = value; else { dA[j * 6 + i] = value; dA[i * 6 + j] = value; }
+                        }
+                }
                 if (p.trace && blockIdx.x == 0 && it < 64) {
                     float* t = p.trace + (size_t)it * TRACE_STRIDE;
-                    for (int k = 0; k < 36; ++k) t[k] = A[k];
-                    for (int k = 0; k < 6; ++k) t[36 + k] = b[k];
+#pragma unroll
+                    for (int k = 0; k < 36; ++k) t[k] = (float)dA[k];
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) t[36 + k] = (float)db[k];
                     t[42] = s_sum[27]; t[43] = s_sum[28];
                 }
-                double dA[36], db[6];
-#pragma unroll
-                for (int k = 0; k < 36; ++k) dA[k] = A[k];
-#pragma unroll
-                for (int k = 0; k < 6; ++k) db[k] = b[k];
                 gauss_newton_update_p(dA, db, s_Rt, s_Rp, s_tp, s_R, s_t);
                 if (prof) p.prof[it * 5 + 4] = clock64();
             }
@@ -328,8 +473,21 @@ int icp_frame(const IcpLevelArgs* levels, const int* iters, const float* pose12_
     p.st = state; p.partials = partials; p.trace = trace; p.bar = bar_dev; p.bar_base = *bar_count;
     int grid = sm_count();
     if (grid * 32 * 2 > MAX_PARTIALS * 32) grid = MAX_PARTIALS / 2;
+    // shared-memory stage for the current maps: 6 planes x stage_k chunks x 2 KB, sized for the largest level in use
+    int need_k = 0;
+    for (int l = 0; l < LEVELS; ++l)
+        if (iters[l] > 0) { int k = div_up(levels[l].rows * levels[l].cols, grid * FRAME_THREADS); if (k > need_k) need_k = k; }
+    static int smem_optin = -1;
+    if (smem_optin < 0) {
+        int dev = 0; cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        if (smem_optin > 0) cudaFuncSetAttribute((const void*)icp_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - 4096);
+    }
+    const size_t stage_bytes = (size_t)6 * need_k * FRAME_THREADS * sizeof(float);
+    const bool can_stage = need_k > 0 && need_k <= STAGE_MAX_K && smem_optin > 0 && stage_bytes <= (size_t)(smem_optin - 4096);
+    p.stage_k = can_stage ? need_k : 0;
     void* args[] = {&p};
-    cudaError_t e = cudaLaunchCooperativeKernel((const void*)icp_frame_kernel, dim3(grid), dim3(FRAME_THREADS), args, 0, s);
+    cudaError_t e = cudaLaunchCooperativeKernel((const void*)icp_frame_kernel, dim3(grid), dim3(FRAME_THREADS), args, can_stage ? stage_bytes : 0, s);
     ++g_launches;
     if (e != cudaSuccess) return cuda_check(e, "cudaLaunchCooperativeKernel(icp_frame_kernel)", __FILE__, __LINE__);
     *bar_count += (unsigned int)(grid * total);

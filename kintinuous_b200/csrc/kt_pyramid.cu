@@ -41,6 +41,27 @@ bilateral_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst, i
 
     const int D = BIL_R * 2 + 1;
     const int value = tile[threadIdx.y + BIL_R][threadIdx.x + BIL_R];
+    // interior CTAs (every pixel has its full 13x13 window): same taps in the same order, bounds and the spatial term known at
+    // compile time (about 40 % fewer instructions per tap)
+    if (x0 >= BIL_R && y0 >= BIL_R && x0 + BIL_TX - 1 + BIL_R + 1 <= cols - 1 && y0 + BIL_TY - 1 + BIL_R + 1 <= rows - 1) {
+        float sum1 = 0, sum2 = 0;
+#pragma unroll
+        for (int dy = -BIL_R; dy <= BIL_R; ++dy) {
+            const int* trow = tile[threadIdx.y + BIL_R + dy];
+#pragma unroll
+            for (int dx = -BIL_R; dx <= BIL_R; ++dx) {
+                int tmp = trow[threadIdx.x + BIL_R + dx];
+                float space2 = dx * dx + dy * dy;
+                float color2 = (value - tmp) * (value - tmp);
+                float weight = __expf(-(space2 * sigma_space2_inv_half + color2 * sigma_color2_inv_half));
+                sum1 += tmp * weight;
+                sum2 += weight;
+            }
+        }
+        int res = __float2int_rn(sum1 / sum2);
+        dst[(size_t)y * cols + x] = (uint16_t)max(0, min(res, 32767));
+        return;
+    }
     const int tx = min(x - D / 2 + D, cols - 1);      // exclusive, and clipped to cols-1: Q1
     const int ty = min(y - D / 2 + D, rows - 1);
     float sum1 = 0, sum2 = 0;

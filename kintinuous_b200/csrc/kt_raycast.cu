@@ -23,16 +23,24 @@ struct RayParams {
     int z_begin;            // storage-z offset of the local slab (0 on a single GPU)
 };
 
+// POW2: V is a power of two (cyclic wrap by mask, plane / row offsets by shift); IdxT: 32-bit voxel index when V^3 <= 2^31.
+template <bool POW2, typename IdxT>
 struct Caster {
     const RayParams& p;
-    __device__ __forceinline__ Caster(const RayParams& p_) : p(p_) {}
+    int shift;
+    __device__ __forceinline__ Caster(const RayParams& p_) : p(p_) { shift = POW2 ? (31 - __clz(p_.V)) : 0; }
 
-    __device__ __forceinline__ size_t addr(int x, int y, int z) const
+    __device__ __forceinline__ IdxT addr(int x, int y, int z) const
     {
+        if (POW2) {
+            const int m = p.V - 1;
+            const unsigned int sx = (x + p.wrap.x) & m, sy = (y + p.wrap.y) & m, sz = (z + p.wrap.z) & m;
+            return ((((IdxT)sz << shift) | sy) << shift) | sx;
+        }
         int sx = x + p.wrap.x; if (sx >= p.V) sx -= p.V;
         int sy = y + p.wrap.y; if (sy >= p.V) sy -= p.V;
         int sz = z + p.wrap.z; if (sz >= p.V) sz -= p.V;
-        return ((size_t)sz * p.V + sy) * p.V + sx;
+        return ((IdxT)sz * p.V + sy) * p.V + sx;
     }
     __device__ __forceinline__ float readTsdf(int x, int y, int z) const { return unpack_tsdf(__ldg(&p.volume[addr(x, y, z)])); }
     __device__ __forceinline__ uchar4 readColor(int x, int y, int z) const { return __ldg(&p.color_volume[addr(x, y, z)]); }
@@ -46,7 +54,7 @@ struct Caster {
     }
     __device__ __forceinline__ bool checkInds(const int3& g) const
     {
-        return (g.x >= 0 && g.y >= 0 && g.z >= 0 && g.x < p.V && g.y < p.V && g.z < p.V);
+        return ((unsigned)g.x < (unsigned)p.V && (unsigned)g.y < (unsigned)p.V && (unsigned)g.z < (unsigned)p.V);
     }
 
     // trilinear weights and base voxel of a point; false if the base voxel is outside [1, V-2]
@@ -127,11 +135,12 @@ __device__ __forceinline__ float getMaxTime(const float3& volume_max, const floa
 enum { RC_X = 32, RC_Y = 8 };
 
 // One ray.  Returns validity of vertex / normal; outputs by reference.
+template <bool POW2, typename IdxT>
 __device__ __forceinline__ void cast_ray(const RayParams& p, int x, int y, bool& v_ok, float3& vtx, bool& n_ok, float3& nrm,
                                          bool& c_ok, uchar4& col)
 {
     v_ok = false; n_ok = false; c_ok = false;
-    Caster rc(p);
+    Caster<POW2, IdxT> rc(p);
     float3 ray_start = p.tcurr;
     float3 ray_next_c;
     ray_next_c.x = (x - p.intr.cx) / p.intr.fx;
@@ -155,7 +164,8 @@ __device__ __forceinline__ void cast_ray(const RayParams& p, int x, int y, bool&
     g.x = max(0, min(g.x, p.V - 1));
     g.y = max(0, min(g.y, p.V - 1));
     g.z = max(0, min(g.z, p.V - 1));
-    float tsdf = rc.readTsdf(g.x, g.y, g.z);
+    // the march only needs the SIGN of the TSDF, and sign(short / 32767) == sign(short) (no underflow: |1/32767| is normal)
+    int tsdf = __ldg(&p.volume[rc.addr(g.x, g.y, g.z)]);
 
     const float max_time = 3 * (p.volume_size.x + p.volume_size.y + p.volume_size.z);
     // The march (ray_caster.cu:345-425) is evaluated strictly in order, but the nearest-voxel reads of the next RS steps are
@@ -179,11 +189,11 @@ __device__ __forceinline__ void cast_ray(const RayParams& p, int x, int y, bool&
             if (done) break;
             const float tc = tq[s];
             if (!(tc < max_time)) { done = true; break; }
-            float tsdf_prev = tsdf;
+            const int tsdf_prev = tsdf;
             if (!inb[s]) { done = true; break; }
-            tsdf = unpack_tsdf(raw[s]);
-            if (tsdf_prev < 0.f && tsdf > 0.f) { done = true; break; }
-            if (tsdf_prev > 0.f && tsdf < 0.f) {
+            tsdf = raw[s];
+            if (tsdf_prev < 0 && tsdf > 0) { done = true; break; }
+            if (tsdf_prev > 0 && tsdf < 0) {
                 done = true;
                 float Ftdt = rc.interpolateTrilineary(add3(ray_start, scale3(ray_dir, (tc + time_step))));
                 if (isnan(Ftdt)) break;
@@ -236,6 +246,7 @@ __device__ __forceinline__ bool resize_tile(const float* in, int W, int H, int o
     return true;
 }
 
+template <bool POW2, typename IdxT>
 __global__ void __launch_bounds__(RC_X * RC_Y)
 raycast_kernel(const RayParams p)
 {
@@ -253,7 +264,7 @@ raycast_kernel(const RayParams p)
     float3 vtx = make_float3(nan, nan, nan), nrm = make_float3(nan, nan, nan);
     uchar4 col;
     if (inside) {
-        cast_ray(p, x, y, v_ok, vtx, n_ok, nrm, c_ok, col);
+        cast_ray<POW2, IdxT>(p, x, y, v_ok, vtx, n_ok, nrm, c_ok, col);
         const size_t P = (size_t)p.rows * p.cols, i = (size_t)y * p.cols + x;
         // like the reference: x planes are always written (NaN = no surface), y/z only on success
         if (v_ok) { p.vmap[0][i] = vtx.x; p.vmap[0][i + P] = vtx.y; p.vmap[0][i + 2 * P] = vtx.z; }
@@ -341,7 +352,12 @@ int raycast(const RaycastArgs& a, cudaStream_t s)
     // the in-tile pyramid needs every level's tile to be whole
     if (p.n_levels > 1 && ((a.cols % RC_X) != 0 || (a.rows % RC_Y) != 0)) { set_error("raycast: fused pyramid needs cols %% 32 == 0 and rows %% 8 == 0"); return -1; }
     dim3 block(RC_X, RC_Y), grid(div_up(a.cols, RC_X), div_up(a.rows, RC_Y));
-    raycast_kernel<<<grid, block, 0, s>>>(p);
+    const bool pow2 = (a.vol & (a.vol - 1)) == 0;
+    const bool idx32 = (size_t)a.vol * a.vol * a.vol <= ((size_t)1 << 31);
+    if (pow2 && idx32) raycast_kernel<true, unsigned int><<<grid, block, 0, s>>>(p);
+    else if (pow2) raycast_kernel<true, size_t><<<grid, block, 0, s>>>(p);
+    else if (idx32) raycast_kernel<false, unsigned int><<<grid, block, 0, s>>>(p);
+    else raycast_kernel<false, size_t><<<grid, block, 0, s>>>(p);
     KT_LAUNCH_CHECK();
     return 0;
 }

@@ -121,6 +121,7 @@ struct IntegrateParams {
 #define KT_MAX_WEIGHT 128          // Tsdf::MAX_WEIGHT (tsdf_volume.cu:486)
 #define KT_RGB_VIEW_ANGLE_WEIGHT 0.75f
 
+template <typename IdxT>
 __global__ void __launch_bounds__(256)
 integrate_kernel(const IntegrateParams p)
 {
@@ -161,6 +162,17 @@ integrate_kernel(const IntegrateParams p)
     int zlo = z0, zhi = z1;
     {
         const float dqx = Rcurr_inv_0_z_scaled, dqy = Rcurr_inv_1_z_scaled, dqz = Rcurr_inv.r2.z * cell_size.z;
+        {   // cheap reject (most threads): every constraint is linear in z, so if both ends of [z0-3, z1+3] violate the same
+            // one (with the slack used below) the whole chunk of this column is outside the view frustum
+            const float za = (float)(z0 - 3), zb = (float)(z1 + 3);
+            const float ax = v_x + za * dqx, ay = v_y + za * dqy, az = v_z + za * dqz;
+            const float bx = v_x + zb * dqx, by = v_y + zb * dqy, bz = v_z + zb * dqz;
+            const float kx0 = intr.cx + 1.5f, kx1 = intr.cx - cols - 0.5f, ky0 = intr.cy + 1.5f, ky1 = intr.cy - rows - 0.5f;
+            const float sl = 2e-3f * (fabsf(v_x) + fabsf(v_y) + (fabsf(v_z) + fabsf(dqz) * V) * (fabsf(kx1) + fabsf(ky1) + fabsf(kx0) + fabsf(ky0)) + (fabsf(dqx) + fabsf(dqy)) * V) + 1e-5f;
+            if ((az < -sl && bz < -sl) ||
+                (ax + kx0 * az < -sl && bx + kx0 * bz < -sl) || (ax + kx1 * az > sl && bx + kx1 * bz > sl) ||
+                (ay + ky0 * az < -sl && by + ky0 * bz < -sl) || (ay + ky1 * az > sl && by + ky1 * bz > sl)) return;
+        }
         float lo = -1e30f, hi = 1e30f;
         // each constraint: a + b*z >= 0
         const float ca[5] = { v_z,
@@ -199,9 +211,9 @@ integrate_kernel(const IntegrateParams p)
     const float* __restrict__ depthScaled = p.depth_scaled;
     const float* __restrict__ nmap_curr = p.nmap;
     const uchar3* __restrict__ colors = reinterpret_cast<const uchar3*>(p.rgb);
-    const size_t P = (size_t)rows * cols;
-    const size_t plane = (size_t)V * V;
-    const size_t col_off = (size_t)sy * V + sx;
+    const IdxT P = (IdxT)rows * cols;
+    const IdxT plane = (IdxT)V * V;
+    const IdxT col_off = (IdxT)sy * V + sx;
 
     // The z loop is processed in batches of ZU voxels in three phases (project + depth gather / sdf test + volume loads /
     // blend + stores) so that ZU independent memory round trips are in flight per thread; the per-voxel arithmetic and the
@@ -209,7 +221,7 @@ integrate_kernel(const IntegrateParams p)
     enum { ZU = 4 };
     for (int zb = zlo; zb < zhi; zb += ZU) {
         float vgz[ZU], Dp[ZU];
-        size_t pix[ZU], addr[ZU];
+        IdxT pix[ZU], addr[ZU];
         bool ok[ZU];
 #pragma unroll
         for (int u = 0; u < ZU; ++u) {
@@ -225,8 +237,8 @@ integrate_kernel(const IntegrateParams p)
                         int sz = z + p.wrap.z; if (sz >= V) sz -= V;
                         if (sz >= p.z_begin && sz < p.z_end) {             // this GPU's slab
                             ok[u] = true;
-                            pix[u] = (size_t)coo.y * cols + coo.x;
-                            addr[u] = (size_t)(sz - p.z_begin) * plane + col_off;
+                            pix[u] = (IdxT)coo.y * cols + coo.x;
+                            addr[u] = (IdxT)(sz - p.z_begin) * plane + col_off;
                             Dp[u] = depthScaled[pix[u]];
                         }
                     }
@@ -362,7 +374,8 @@ int integrate(const IntegrateArgs& a, float* ztable_dev, cudaStream_t s)
     p.ztable = ztable_dev; p.zchunk = V >= 64 ? V / 8 : V;
     p.z_begin = a.z_begin; p.z_end = a.z_end;
     dim3 block(32, 8), grid(div_up(V, 32), div_up(V, 8), div_up(V, p.zchunk));
-    integrate_kernel<<<grid, block, 0, s>>>(p);
+    if ((size_t)(a.z_end - a.z_begin) * V * V <= ((size_t)1 << 31)) integrate_kernel<unsigned int><<<grid, block, 0, s>>>(p);
+    else integrate_kernel<size_t><<<grid, block, 0, s>>>(p);
     KT_LAUNCH_CHECK();
     return 0;
 }
