@@ -51,11 +51,13 @@ bilateral_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst, i
 #pragma unroll
             for (int dx = -BIL_R; dx <= BIL_R; ++dx) {
                 int tmp = trow[threadIdx.x + BIL_R + dx];
-                float space2 = dx * dx + dy * dy;
-                float color2 = (value - tmp) * (value - tmp);
-                float weight = __expf(-(space2 * sigma_space2_inv_half + color2 * sigma_color2_inv_half));
-                sum1 += tmp * weight;
-                sum2 += weight;
+                const float space2 = (float)(dx * dx + dy * dy);
+                const float color2 = (float)((value - tmp) * (value - tmp));
+                // same contraction as the general loop below compiles to (checked in SASS): fma(space2, k_s, color2 * k_c)
+                const float e = __fmaf_rn(space2, sigma_space2_inv_half, __fmul_rn(color2, sigma_color2_inv_half));
+                float weight = __expf(-e);
+                sum1 = __fmaf_rn((float)tmp, weight, sum1);
+                sum2 = __fadd_rn(sum2, weight);
             }
         }
         int res = __float2int_rn(sum1 / sum2);
@@ -94,6 +96,27 @@ pyrdown_gauss_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ ds
     int y_ma = min(srows, 2 * y - D / 2 + D) - 2 * y;
     float sum = 0, wall = 0;
     const float weights[3] = {0.375f, 0.25f, 0.0625f};
+    if (x_mi == -2 && y_mi == -2 && x_ma == 3 && y_ma == 3) {
+        // interior: the 25 loads are issued together; same taps in the same order (all products of these dyadic weights with
+        // a 16-bit integer are exact in float, so the accumulation is bit-identical to the general loop)
+        int vals[25];
+#pragma unroll
+        for (int yi = -2; yi <= 2; ++yi)
+#pragma unroll
+            for (int xi = -2; xi <= 2; ++xi) vals[(yi + 2) * 5 + xi + 2] = src[(size_t)(2 * y + yi) * scols + 2 * x + xi];
+#pragma unroll
+        for (int yi = -2; yi <= 2; ++yi)
+#pragma unroll
+            for (int xi = -2; xi <= 2; ++xi) {
+                const int val = vals[(yi + 2) * 5 + xi + 2];
+                if (abs(val - center) < 3 * sigma_color) {
+                    sum += val * weights[xi < 0 ? -xi : xi] * weights[yi < 0 ? -yi : yi];
+                    wall += weights[xi < 0 ? -xi : xi] * weights[yi < 0 ? -yi : yi];
+                }
+            }
+        dst[(size_t)y * dcols + x] = (uint16_t)static_cast<int>(sum / wall);
+        return;
+    }
     for (int yi = y_mi; yi < y_ma; ++yi)
         for (int xi = x_mi; xi < x_ma; ++xi) {
             int val = src[(size_t)(2 * y + yi) * scols + 2 * x + xi];

@@ -11,6 +11,7 @@
 // order; the volume is read through the read-only path with cyclic addressing by compare-subtract.
 // Bound: L2 / latency (scattered 2-byte reads, about 60-100 per ray); DESIGN.md section 3.5.
 #include "kt_ops.h"
+#include <cstdlib>
 
 namespace kt {
 
@@ -135,7 +136,7 @@ __device__ __forceinline__ float getMaxTime(const float3& volume_max, const floa
 enum { RC_X = 32, RC_Y = 8 };
 
 // One ray.  Returns validity of vertex / normal; outputs by reference.
-template <bool POW2, typename IdxT>
+template <bool POW2, typename IdxT, int RS>
 __device__ __forceinline__ void cast_ray(const RayParams& p, int x, int y, bool& v_ok, float3& vtx, bool& n_ok, float3& nrm,
                                          bool& c_ok, uchar4& col)
 {
@@ -171,7 +172,6 @@ __device__ __forceinline__ void cast_ray(const RayParams& p, int x, int y, bool&
     // The march (ray_caster.cu:345-425) is evaluated strictly in order, but the nearest-voxel reads of the next RS steps are
     // issued together: a step only needs the previous TSDF value to DECIDE, not to ADDRESS, so RS dependent L2 round trips
     // become one.  time_curr advances by the same sequence of float additions as the reference's for-loop.
-    enum { RS = 4 };
     bool done = false;
     while (!done && time_curr < max_time) {
         float tq[RS]; bool inb[RS]; short raw[RS];
@@ -246,8 +246,8 @@ __device__ __forceinline__ bool resize_tile(const float* in, int W, int H, int o
     return true;
 }
 
-template <bool POW2, typename IdxT>
-__global__ void __launch_bounds__(RC_X * RC_Y)
+template <bool POW2, typename IdxT, int RS, int MINB>
+__global__ void __launch_bounds__(RC_X * RC_Y, MINB)
 raycast_kernel(const RayParams p)
 {
     // level-0 tile, then levels 1..3 (each [v|n][3 planes][H][W])
@@ -264,7 +264,7 @@ raycast_kernel(const RayParams p)
     float3 vtx = make_float3(nan, nan, nan), nrm = make_float3(nan, nan, nan);
     uchar4 col;
     if (inside) {
-        cast_ray<POW2, IdxT>(p, x, y, v_ok, vtx, n_ok, nrm, c_ok, col);
+        cast_ray<POW2, IdxT, RS>(p, x, y, v_ok, vtx, n_ok, nrm, c_ok, col);
         const size_t P = (size_t)p.rows * p.cols, i = (size_t)y * p.cols + x;
         // like the reference: x planes are always written (NaN = no surface), y/z only on success
         if (v_ok) { p.vmap[0][i] = vtx.x; p.vmap[0][i + P] = vtx.y; p.vmap[0][i + 2 * P] = vtx.z; }
@@ -354,10 +354,16 @@ int raycast(const RaycastArgs& a, cudaStream_t s)
     dim3 block(RC_X, RC_Y), grid(div_up(a.cols, RC_X), div_up(a.rows, RC_Y));
     const bool pow2 = (a.vol & (a.vol - 1)) == 0;
     const bool idx32 = (size_t)a.vol * a.vol * a.vol <= ((size_t)1 << 31);
-    if (pow2 && idx32) raycast_kernel<true, unsigned int><<<grid, block, 0, s>>>(p);
-    else if (pow2) raycast_kernel<true, size_t><<<grid, block, 0, s>>>(p);
-    else if (idx32) raycast_kernel<false, unsigned int><<<grid, block, 0, s>>>(p);
-    else raycast_kernel<false, size_t><<<grid, block, 0, s>>>(p);
+    static int variant = -1;                 // tuning knob (KT_RC_VARIANT): 0 = RS 4, 1 = RS 8, 2 = RS 8 with 5 CTAs/SM
+    if (variant < 0) { const char* e = getenv("KT_RC_VARIANT"); variant = e ? atoi(e) : 1; }
+    if (pow2 && idx32) {
+        if (variant == 0) raycast_kernel<true, unsigned int, 4, 4><<<grid, block, 0, s>>>(p);
+        else if (variant == 2) raycast_kernel<true, unsigned int, 8, 5><<<grid, block, 0, s>>>(p);
+        else raycast_kernel<true, unsigned int, 8, 4><<<grid, block, 0, s>>>(p);
+    }
+    else if (pow2) raycast_kernel<true, size_t, 8, 4><<<grid, block, 0, s>>>(p);
+    else if (idx32) raycast_kernel<false, unsigned int, 8, 4><<<grid, block, 0, s>>>(p);
+    else raycast_kernel<false, size_t, 8, 4><<<grid, block, 0, s>>>(p);
     KT_LAUNCH_CHECK();
     return 0;
 }

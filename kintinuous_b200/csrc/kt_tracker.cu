@@ -68,7 +68,8 @@ using namespace kt;
 
 struct kt_ctx {
     kt_config cfg;
-    cudaStream_t stream;
+    cudaStream_t stream, stream2;          // stream2: pose-independent side work (scaleDepth) overlapped with the pyramid / ICP
+    cudaEvent_t ev_input, ev_scaled;
     float size, voxel, trunc;
     float volumeBasis[3], currentGlobalCamera[3];
     int voxelWrap[3];
@@ -156,8 +157,7 @@ int do_integrate(kt_ctx* c, const M3& Rinv, const V3& t, const int* wrap)
 {
     const int rows = c->cfg.rows, cols = c->cfg.cols;
     Intr k = {c->cfg.fx, c->cfg.fy, c->cfg.cx, c->cfg.cy};
-    int r = scale_depth(c->depth_raw, c->depth_scaled, rows, cols, k, c->cfg.angle_color != 0, c->stream);
-    if (r) return r;
+    KT_CUDA(cudaStreamWaitEvent(c->stream, c->ev_scaled, 0));       // scaleDepth ran on stream2 since the frame arrived
     IntegrateArgs a;
     a.depth_scaled = c->depth_scaled; a.rows = rows; a.cols = cols; a.k = k; a.volume_size = make_float3(c->size, c->size, c->size);
     a.Rinv = to_mat33(Rinv.m); a.t = make_float3(t.v[0], t.v[1], t.v[2]); a.trunc = c->trunc;
@@ -249,6 +249,13 @@ int process_frame_device(kt_ctx* c, uint64_t utime, kt_pose* out)
     const int mode = c->cfg.odometry;
     int r;
     c->shifted_last = 0;
+    {   // fork: scaleDepth (tsdf_volume.cu:491-538) only needs the raw depth; it overlaps the pyramid on a second stream
+        Intr k0 = {c->cfg.fx, c->cfg.fy, c->cfg.cx, c->cfg.cy};
+        KT_CUDA(cudaEventRecord(c->ev_input, c->stream));
+        KT_CUDA(cudaStreamWaitEvent(c->stream2, c->ev_input, 0));
+        if ((r = scale_depth(c->depth_raw, c->depth_scaled, rows, cols, k0, c->cfg.angle_color != 0, c->stream2))) return r;
+        KT_CUDA(cudaEventRecord(c->ev_scaled, c->stream2));
+    }
     mark(c, 0);
     const bool use_icp_maps = (mode == 0) || (mode == 2) || c->cfg.angle_color;        // KintinuousTracker.cpp:465 (Q10)
     if (use_icp_maps) {
@@ -421,6 +428,9 @@ int kt_create(const kt_config* cfg, kt_ctx** out)
 #define KT_TRY(x) do { r = (x); if (r) { kt_destroy(c); return r; } } while (0)
     r = kt::cuda_check(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "stream", __FILE__, __LINE__);
     if (r) { delete c; return r; }
+    KT_TRY(kt::cuda_check(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking), "stream2", __FILE__, __LINE__));
+    KT_TRY(kt::cuda_check(cudaEventCreateWithFlags(&c->ev_input, cudaEventDisableTiming), "event", __FILE__, __LINE__));
+    KT_TRY(kt::cuda_check(cudaEventCreateWithFlags(&c->ev_scaled, cudaEventDisableTiming), "event", __FILE__, __LINE__));
     const size_t P = (size_t)cfg->rows * cfg->cols, V3n = (size_t)cfg->vol * cfg->vol * cfg->vol;
     KT_TRY(dev_alloc(c, &c->tsdf, V3n)); KT_TRY(dev_alloc(c, &c->color, V3n * 4));
     KT_TRY(dev_alloc(c, &c->depth_raw, P)); KT_TRY(dev_alloc(c, &c->rgb, P * 3));
@@ -469,6 +479,9 @@ int kt_destroy(kt_ctx* c)
     if (c->trace_host) cudaFreeHost(c->trace_host);
     if (c->counter_host) cudaFreeHost(c->counter_host);
     for (int i = 0; i < 7; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
+    if (c->ev_input) cudaEventDestroy(c->ev_input);
+    if (c->ev_scaled) cudaEventDestroy(c->ev_scaled);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return KT_OK;

@@ -122,7 +122,7 @@ struct IntegrateParams {
 #define KT_RGB_VIEW_ANGLE_WEIGHT 0.75f
 
 template <typename IdxT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 integrate_kernel(const IntegrateParams p)
 {
     const int V = p.V;
@@ -218,7 +218,7 @@ integrate_kernel(const IntegrateParams p)
     // The z loop is processed in batches of ZU voxels in three phases (project + depth gather / sdf test + volume loads /
     // blend + stores) so that ZU independent memory round trips are in flight per thread; the per-voxel arithmetic and the
     // running sums are exactly the reference's (storage addresses of different z never alias, which the compiler cannot know).
-    enum { ZU = 4 };
+    enum { ZU = 2 };
     for (int zb = zlo; zb < zhi; zb += ZU) {
         float vgz[ZU], Dp[ZU];
         IdxT pix[ZU], addr[ZU];
