@@ -55,7 +55,8 @@ def test_tracker_vs_golden_reference_cuda(built, frames, name, kw, nframes):
         for i in range(len(gs)):
             pts, dim, _ = trk.get_slice(i)
             assert dim == gs[i][0]
-            assert abs(len(pts) - gs[i][1]) <= max(5, 0.01 * gs[i][1])
+            # the reference's count of a full-volume extraction can be a few points short (its publication race)
+            assert abs(len(pts) - gs[i][1]) <= max(5, 0.01 * gs[i][1]), (i, len(pts), gs[i])
     trk.close()
 
 
