@@ -205,7 +205,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default="streams", choices=["streams", "zslab"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample", type=int, default=6)
+    ap.add_argument("--cpu-sample", type=int, default=48)
     args = ap.parse_args()
     world, rank, local = dist_setup(args.gpus)
     if args.impl == "reference":

@@ -6,6 +6,21 @@
 namespace kt {
 
 static const int LEVELS = 4;                 // ICPOdometry.h:52 / RGBDOdometry.h:96
+static const int MAX_GPUS = 8;
+
+// How a kernel reaches any voxel of the (possibly z-slab sharded) volume: rank g owns the storage planes
+// [g * slab_z, (g + 1) * slab_z); tsdf[g] / color[g] point at the first voxel of that slab -- local memory for g == rank,
+// CUDA-IPC mapped peer memory (NVLink P2P) otherwise.  Single GPU: world = 1, slab_z = V.
+struct VolumeView {
+    int16_t* tsdf[MAX_GPUS]; uint8_t* color[MAX_GPUS];
+    int world, rank, slab_z, slab_shift;
+};
+inline VolumeView single_volume(int16_t* tsdf, uint8_t* color, int V)
+{
+    VolumeView v; for (int g = 0; g < MAX_GPUS; ++g) { v.tsdf[g] = tsdf; v.color[g] = color; }
+    v.world = 1; v.rank = 0; v.slab_z = V; v.slab_shift = 0; int t = V; while (t > 1) { t >>= 1; ++v.slab_shift; }
+    return v;
+}
 
 // ---- pyramid (kt_pyramid.cu) ----
 int bilateral(const uint16_t* src, uint16_t* dst, int rows, int cols, cudaStream_t s);
@@ -72,8 +87,11 @@ int odom_begin_frame(OdomState* state, const float* pose12_dev, cudaStream_t s);
 int reduce_grid_for(int n_items);
 
 // ---- volume (kt_tsdf.cu, kt_raycast.cu, kt_extract.cu) ----
-int init_volume(int16_t* tsdf, uint8_t* color, int vol, cudaStream_t s);
+int init_volume(int16_t* tsdf, uint8_t* color, int vol, cudaStream_t s);                  // whole volume
+int init_slab(int16_t* tsdf_local, uint8_t* color_local, int vol, int slab_z, cudaStream_t s);
 int clear_volume(int axis, int back, int16_t* tsdf, uint8_t* color, int vol, int current_wrap, int delta_wrap, cudaStream_t s);
+// sharded: tsdf_local / color_local are this rank's slab (storage planes [z_begin, z_end))
+int clear_volume_slab(int axis, int back, int16_t* tsdf_local, uint8_t* color_local, int vol, int z_begin, int z_end, int current_wrap, int delta_wrap, cudaStream_t s);
 int scale_depth(const uint16_t* depth, float* scaled, int rows, int cols, const Intr& k, bool angle_color, cudaStream_t s);
 struct IntegrateArgs {
     const float* depth_scaled; int rows, cols; Intr k; float3 volume_size; Mat33 Rinv; float3 t; float trunc;
@@ -84,10 +102,22 @@ int integrate(const IntegrateArgs& a, float* ztable_dev /* 2*vol floats */, cuda
 struct RaycastArgs {
     Intr k; Mat33 R; float3 t; float trunc; float3 volume_size; const int16_t* tsdf; const uint8_t* color; int vol; int3 wrap;
     float* vmap[LEVELS]; float* nmap[LEVELS]; int rows, cols; uint8_t* vmap_color; int n_levels;   // n_levels>1: fused model pyramid
+    // multi-GPU (world > 1): rays read any slab through vv, this rank casts the tile rows [tile_row_begin, tile_row_end) and stores
+    // its results into EVERY rank's model maps (P2P stores = the all-gather, fused into the kernel epilogue)
+    int multi; VolumeView vv; int tile_row_begin, tile_row_end;
+    float* peer_vmap[MAX_GPUS][LEVELS]; float* peer_nmap[MAX_GPUS][LEVELS]; uint8_t* peer_vcol[MAX_GPUS];
 };
 int raycast(const RaycastArgs& a, cudaStream_t s);
 int extract_slice(const int16_t* tsdf, const float3& volume_size, int vol, void* out, size_t capacity, const int3& wrap,
                   const uint8_t* color, int minX, int maxX, int minY, int maxY, int minZ, int maxZ, int subsample,
                   const int3& real_wrap, unsigned int* counter_dev, cudaStream_t s);
+// sharded: only voxels whose storage plane lies in this rank's slab emit points; neighbours are read through vv (P2P at slab edges)
+int extract_slice_mg(const VolumeView& vv, const float3& volume_size, int vol, void* out, size_t capacity, const int3& wrap,
+                     int minX, int maxX, int minY, int maxY, int minZ, int maxZ, int subsample,
+                     const int3& real_wrap, unsigned int* counter_dev, cudaStream_t s);
+// cross-GPU barrier: every rank writes `epoch` into slot [rank] of every peer's flag array, then waits until all slots of its own
+// array reach `epoch` (bounded spin: returns through *error_dev != 0 instead of hanging the GPU if a peer never arrives)
+int xgpu_barrier(unsigned int* const* peer_flags_dev /* [world] device array of pointers */, unsigned int* my_flags, int rank, int world,
+                 unsigned int epoch, int* error_dev, cudaStream_t s);
 
 } // namespace kt

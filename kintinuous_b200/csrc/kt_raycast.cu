@@ -22,10 +22,13 @@ struct RayParams {
     const int16_t* volume; const uchar4* color_volume; int V; int3 wrap;
     float* vmap[LEVELS]; float* nmap[LEVELS]; uchar4* vmap_color; int rows, cols; int n_levels;
     int z_begin;            // storage-z offset of the local slab (0 on a single GPU)
+    // multi-GPU
+    VolumeView vv; int tile_row_begin; int n_out;
+    float* peer_vmap[MAX_GPUS][LEVELS]; float* peer_nmap[MAX_GPUS][LEVELS]; uchar4* peer_vcol[MAX_GPUS];
 };
 
 // POW2: V is a power of two (cyclic wrap by mask, plane / row offsets by shift); IdxT: 32-bit voxel index when V^3 <= 2^31.
-template <bool POW2, typename IdxT>
+template <bool POW2, typename IdxT, bool MG = false>
 struct Caster {
     const RayParams& p;
     int shift;
@@ -43,8 +46,28 @@ struct Caster {
         int sz = z + p.wrap.z; if (sz >= p.V) sz -= p.V;
         return ((IdxT)sz * p.V + sy) * p.V + sx;
     }
-    __device__ __forceinline__ float readTsdf(int x, int y, int z) const { return unpack_tsdf(__ldg(&p.volume[addr(x, y, z)])); }
-    __device__ __forceinline__ uchar4 readColor(int x, int y, int z) const { return __ldg(&p.color_volume[addr(x, y, z)]); }
+    // sharded volume: slab owner = storage z >> slab_shift; the pointer table holds local or NVLink-peer (CUDA IPC) addresses
+    __device__ __forceinline__ short rawTsdf(int x, int y, int z) const
+    {
+        if (MG) {
+            const int m = p.V - 1;
+            const unsigned int sx = (x + p.wrap.x) & m, sy = (y + p.wrap.y) & m, sz = (z + p.wrap.z) & m;
+            const unsigned int lz = sz & (p.vv.slab_z - 1);
+            return __ldg(p.vv.tsdf[sz >> p.vv.slab_shift] + ((((size_t)lz << shift) | sy) << shift | sx));
+        }
+        return __ldg(&p.volume[addr(x, y, z)]);
+    }
+    __device__ __forceinline__ float readTsdf(int x, int y, int z) const { return unpack_tsdf(rawTsdf(x, y, z)); }
+    __device__ __forceinline__ uchar4 readColor(int x, int y, int z) const
+    {
+        if (MG) {
+            const int m = p.V - 1;
+            const unsigned int sx = (x + p.wrap.x) & m, sy = (y + p.wrap.y) & m, sz = (z + p.wrap.z) & m;
+            const unsigned int lz = sz & (p.vv.slab_z - 1);
+            return __ldg(reinterpret_cast<const uchar4*>(p.vv.color[sz >> p.vv.slab_shift]) + ((((size_t)lz << shift) | sy) << shift | sx));
+        }
+        return __ldg(&p.color_volume[addr(x, y, z)]);
+    }
 
     __device__ __forceinline__ int3 getVoxel(float3 point) const
     {
@@ -136,12 +159,12 @@ __device__ __forceinline__ float getMaxTime(const float3& volume_max, const floa
 enum { RC_X = 32, RC_Y = 8 };
 
 // One ray.  Returns validity of vertex / normal; outputs by reference.
-template <bool POW2, typename IdxT, int RS>
+template <bool POW2, typename IdxT, int RS, bool MG>
 __device__ __forceinline__ void cast_ray(const RayParams& p, int x, int y, bool& v_ok, float3& vtx, bool& n_ok, float3& nrm,
                                          bool& c_ok, uchar4& col)
 {
     v_ok = false; n_ok = false; c_ok = false;
-    Caster<POW2, IdxT> rc(p);
+    Caster<POW2, IdxT, MG> rc(p);
     float3 ray_start = p.tcurr;
     float3 ray_next_c;
     ray_next_c.x = (x - p.intr.cx) / p.intr.fx;
@@ -166,7 +189,7 @@ __device__ __forceinline__ void cast_ray(const RayParams& p, int x, int y, bool&
     g.y = max(0, min(g.y, p.V - 1));
     g.z = max(0, min(g.z, p.V - 1));
     // the march only needs the SIGN of the TSDF, and sign(short / 32767) == sign(short) (no underflow: |1/32767| is normal)
-    int tsdf = __ldg(&p.volume[rc.addr(g.x, g.y, g.z)]);
+    int tsdf = rc.rawTsdf(g.x, g.y, g.z);
 
     const float max_time = 3 * (p.volume_size.x + p.volume_size.y + p.volume_size.z);
     // The march (ray_caster.cu:345-425) is evaluated strictly in order, but the nearest-voxel reads of the next RS steps are
@@ -181,7 +204,7 @@ __device__ __forceinline__ void cast_ray(const RayParams& p, int x, int y, bool&
             tq[s] = t;
             int3 gn = rc.getVoxel(add3(ray_start, scale3(ray_dir, (t + time_step))));
             inb[s] = rc.checkInds(gn);
-            raw[s] = inb[s] ? __ldg(&p.volume[rc.addr(gn.x, gn.y, gn.z)]) : (short)0;
+            raw[s] = inb[s] ? rc.rawTsdf(gn.x, gn.y, gn.z) : (short)0;
             t += time_step;
         }
 #pragma unroll
@@ -246,7 +269,22 @@ __device__ __forceinline__ bool resize_tile(const float* in, int W, int H, int o
     return true;
 }
 
-template <bool POW2, typename IdxT, int RS, int MINB>
+// store one pyramid-level sample into the model maps of every destination (1 locally; all ranks when sharded: the
+// all-gather of the predicted surface is these P2P stores)
+template <bool MG>
+__device__ __forceinline__ void store_maps(const RayParams& p, int level, size_t i, size_t P, bool okv, const float3& v, bool okn, const float3& n)
+{
+    const float nan = qnan();
+    const int n_out = MG ? p.n_out : 1;
+    for (int g = 0; g < n_out; ++g) {
+        float* vm = MG ? p.peer_vmap[g][level] : p.vmap[level];
+        float* nm = MG ? p.peer_nmap[g][level] : p.nmap[level];
+        if (okv) { vm[i] = v.x; vm[i + P] = v.y; vm[i + 2 * P] = v.z; } else vm[i] = nan;
+        if (okn) { nm[i] = n.x; nm[i + P] = n.y; nm[i + 2 * P] = n.z; } else nm[i] = nan;
+    }
+}
+
+template <bool POW2, typename IdxT, int RS, int MINB, bool MG>
 __global__ void __launch_bounds__(RC_X * RC_Y, MINB)
 raycast_kernel(const RayParams p)
 {
@@ -255,8 +293,9 @@ raycast_kernel(const RayParams p)
     __shared__ float s1[2][3][RC_Y / 2][RC_X / 2];
     __shared__ float s2[2][3][RC_Y / 4][RC_X / 4];
 
+    const int tile_y = blockIdx.y + (MG ? p.tile_row_begin : 0);
     const int x = threadIdx.x + blockIdx.x * RC_X;
-    const int y = threadIdx.y + blockIdx.y * RC_Y;
+    const int y = threadIdx.y + tile_y * RC_Y;
     const float nan = qnan();
     const bool inside = (x < p.cols && y < p.rows);
 
@@ -264,14 +303,11 @@ raycast_kernel(const RayParams p)
     float3 vtx = make_float3(nan, nan, nan), nrm = make_float3(nan, nan, nan);
     uchar4 col;
     if (inside) {
-        cast_ray<POW2, IdxT, RS>(p, x, y, v_ok, vtx, n_ok, nrm, c_ok, col);
+        cast_ray<POW2, IdxT, RS, MG>(p, x, y, v_ok, vtx, n_ok, nrm, c_ok, col);
         const size_t P = (size_t)p.rows * p.cols, i = (size_t)y * p.cols + x;
         // like the reference: x planes are always written (NaN = no surface), y/z only on success
-        if (v_ok) { p.vmap[0][i] = vtx.x; p.vmap[0][i + P] = vtx.y; p.vmap[0][i + 2 * P] = vtx.z; }
-        else p.vmap[0][i] = nan;
-        if (n_ok) { p.nmap[0][i] = nrm.x; p.nmap[0][i + P] = nrm.y; p.nmap[0][i + 2 * P] = nrm.z; }
-        else p.nmap[0][i] = nan;
-        if (c_ok) p.vmap_color[i] = col;
+        store_maps<MG>(p, 0, i, P, v_ok, vtx, n_ok, nrm);
+        if (c_ok) { if (MG) { for (int g = 0; g < p.n_out; ++g) p.peer_vcol[g][i] = col; } else p.vmap_color[i] = col; }
     }
     if (p.n_levels <= 1) return;
 
@@ -285,7 +321,7 @@ raycast_kernel(const RayParams p)
         const int rows1 = p.rows >> 1, cols1 = p.cols >> 1;
         if (threadIdx.x < W && threadIdx.y < H) {
             const int ox = threadIdx.x, oy = threadIdx.y;
-            const int gx = blockIdx.x * W + ox, gy = blockIdx.y * H + oy;
+            const int gx = blockIdx.x * W + ox, gy = tile_y * H + oy;
             float3 v, n;
             bool okv = resize_tile<false>(&s0[0][0][0][0], RC_X, RC_Y, ox, oy, v);
             bool okn = resize_tile<true>(&s0[1][0][0][0], RC_X, RC_Y, ox, oy, n);
@@ -293,8 +329,7 @@ raycast_kernel(const RayParams p)
             s1[1][0][oy][ox] = okn ? n.x : nan; s1[1][1][oy][ox] = n.y; s1[1][2][oy][ox] = n.z;
             if (gx < cols1 && gy < rows1) {
                 const size_t P = (size_t)rows1 * cols1, i = (size_t)gy * cols1 + gx;
-                if (okv) { p.vmap[1][i] = v.x; p.vmap[1][i + P] = v.y; p.vmap[1][i + 2 * P] = v.z; } else p.vmap[1][i] = nan;
-                if (okn) { p.nmap[1][i] = n.x; p.nmap[1][i + P] = n.y; p.nmap[1][i + 2 * P] = n.z; } else p.nmap[1][i] = nan;
+                store_maps<MG>(p, 1, i, P, okv, v, okn, n);
             }
         }
     }
@@ -305,7 +340,7 @@ raycast_kernel(const RayParams p)
         const int rows2 = p.rows >> 2, cols2 = p.cols >> 2;
         if (threadIdx.x < W && threadIdx.y < H) {
             const int ox = threadIdx.x, oy = threadIdx.y;
-            const int gx = blockIdx.x * W + ox, gy = blockIdx.y * H + oy;
+            const int gx = blockIdx.x * W + ox, gy = tile_y * H + oy;
             float3 v, n;
             bool okv = resize_tile<false>(&s1[0][0][0][0], RC_X / 2, RC_Y / 2, ox, oy, v);
             bool okn = resize_tile<true>(&s1[1][0][0][0], RC_X / 2, RC_Y / 2, ox, oy, n);
@@ -313,8 +348,7 @@ raycast_kernel(const RayParams p)
             s2[1][0][oy][ox] = okn ? n.x : nan; s2[1][1][oy][ox] = n.y; s2[1][2][oy][ox] = n.z;
             if (gx < cols2 && gy < rows2) {
                 const size_t P = (size_t)rows2 * cols2, i = (size_t)gy * cols2 + gx;
-                if (okv) { p.vmap[2][i] = v.x; p.vmap[2][i + P] = v.y; p.vmap[2][i + 2 * P] = v.z; } else p.vmap[2][i] = nan;
-                if (okn) { p.nmap[2][i] = n.x; p.nmap[2][i + P] = n.y; p.nmap[2][i + 2 * P] = n.z; } else p.nmap[2][i] = nan;
+                store_maps<MG>(p, 2, i, P, okv, v, okn, n);
             }
         }
     }
@@ -325,14 +359,13 @@ raycast_kernel(const RayParams p)
         const int rows3 = p.rows >> 3, cols3 = p.cols >> 3;
         if (threadIdx.x < W && threadIdx.y < H) {
             const int ox = threadIdx.x, oy = threadIdx.y;
-            const int gx = blockIdx.x * W + ox, gy = blockIdx.y * H + oy;
+            const int gx = blockIdx.x * W + ox, gy = tile_y * H + oy;
             float3 v, n;
             bool okv = resize_tile<false>(&s2[0][0][0][0], RC_X / 4, RC_Y / 4, ox, oy, v);
             bool okn = resize_tile<true>(&s2[1][0][0][0], RC_X / 4, RC_Y / 4, ox, oy, n);
             if (gx < cols3 && gy < rows3) {
                 const size_t P = (size_t)rows3 * cols3, i = (size_t)gy * cols3 + gx;
-                if (okv) { p.vmap[3][i] = v.x; p.vmap[3][i + P] = v.y; p.vmap[3][i + 2 * P] = v.z; } else p.vmap[3][i] = nan;
-                if (okn) { p.nmap[3][i] = n.x; p.nmap[3][i + P] = n.y; p.nmap[3][i + 2 * P] = n.z; } else p.nmap[3][i] = nan;
+                store_maps<MG>(p, 3, i, P, okv, v, okn, n);
             }
         }
     }
@@ -348,7 +381,7 @@ int raycast(const RaycastArgs& a, cudaStream_t s)
     p.volume = a.tsdf; p.color_volume = (const uchar4*)a.color; p.V = a.vol; p.wrap = a.wrap;
     for (int l = 0; l < LEVELS; ++l) { p.vmap[l] = a.vmap[l]; p.nmap[l] = a.nmap[l]; }
     p.vmap_color = (uchar4*)a.vmap_color; p.rows = a.rows; p.cols = a.cols;
-    p.n_levels = a.n_levels; p.z_begin = 0;
+    p.n_levels = a.n_levels; p.z_begin = 0; p.tile_row_begin = 0; p.n_out = 1;
     // the in-tile pyramid needs every level's tile to be whole
     if (p.n_levels > 1 && ((a.cols % RC_X) != 0 || (a.rows % RC_Y) != 0)) { set_error("raycast: fused pyramid needs cols %% 32 == 0 and rows %% 8 == 0"); return -1; }
     dim3 block(RC_X, RC_Y), grid(div_up(a.cols, RC_X), div_up(a.rows, RC_Y));
@@ -356,14 +389,21 @@ int raycast(const RaycastArgs& a, cudaStream_t s)
     const bool idx32 = (size_t)a.vol * a.vol * a.vol <= ((size_t)1 << 31);
     static int variant = -1;                 // tuning knob (KT_RC_VARIANT): 0 = RS 4, 1 = RS 8, 2 = RS 8 with 5 CTAs/SM
     if (variant < 0) { const char* e = getenv("KT_RC_VARIANT"); variant = e ? atoi(e) : 1; }
-    if (pow2 && idx32) {
-        if (variant == 0) raycast_kernel<true, unsigned int, 4, 4><<<grid, block, 0, s>>>(p);
-        else if (variant == 2) raycast_kernel<true, unsigned int, 8, 5><<<grid, block, 0, s>>>(p);
-        else raycast_kernel<true, unsigned int, 8, 4><<<grid, block, 0, s>>>(p);
+    if (a.multi) {
+        if (!pow2 || (a.vv.slab_z & (a.vv.slab_z - 1))) { set_error("raycast: the sharded volume needs power-of-two V and slab"); return -1; }
+        p.vv = a.vv; p.tile_row_begin = a.tile_row_begin; p.n_out = a.vv.world;
+        for (int g = 0; g < MAX_GPUS; ++g) { for (int l = 0; l < LEVELS; ++l) { p.peer_vmap[g][l] = a.peer_vmap[g][l]; p.peer_nmap[g][l] = a.peer_nmap[g][l]; } p.peer_vcol[g] = (uchar4*)a.peer_vcol[g]; }
+        grid.y = a.tile_row_end - a.tile_row_begin;
+        if (grid.y > 0) raycast_kernel<true, size_t, 8, 4, true><<<grid, block, 0, s>>>(p);
     }
-    else if (pow2) raycast_kernel<true, size_t, 8, 4><<<grid, block, 0, s>>>(p);
-    else if (idx32) raycast_kernel<false, unsigned int, 8, 4><<<grid, block, 0, s>>>(p);
-    else raycast_kernel<false, size_t, 8, 4><<<grid, block, 0, s>>>(p);
+    else if (pow2 && idx32) {
+        if (variant == 0) raycast_kernel<true, unsigned int, 4, 4, false><<<grid, block, 0, s>>>(p);
+        else if (variant == 2) raycast_kernel<true, unsigned int, 8, 5, false><<<grid, block, 0, s>>>(p);
+        else raycast_kernel<true, unsigned int, 8, 4, false><<<grid, block, 0, s>>>(p);
+    }
+    else if (pow2) raycast_kernel<true, size_t, 8, 4, false><<<grid, block, 0, s>>>(p);
+    else if (idx32) raycast_kernel<false, unsigned int, 8, 4, false><<<grid, block, 0, s>>>(p);
+    else raycast_kernel<false, size_t, 8, 4, false><<<grid, block, 0, s>>>(p);
     KT_LAUNCH_CHECK();
     return 0;
 }
