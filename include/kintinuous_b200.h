@@ -118,6 +118,15 @@ KT_API int kt_download_map(kt_ctx* ctx, int which, int level, void* dst_host);
 KT_API int kt_get_stage_ms(kt_ctx* ctx, float* ms6);
 KT_API int kt_set_stage_timing(kt_ctx* ctx, int enabled);
 /* number of kernels this library launched since kt_create (for bench.py's gpu_launches) */
+/* ---- z-slab sharding of ONE volume over `world` GPUs, one process per GPU (no counterpart in the reference) ----
+ * Every rank creates its context with kt_config.rank / world, exports the CUDA-IPC handle (64 bytes) of its shared arena
+ * (volume slab, model maps, barrier flags), the host exchanges the handles (torch.distributed / MPI / anything) and every rank
+ * calls kt_mgpu_connect with all `world` handles in rank order.  After that kt_process_frame must be called by all ranks with
+ * the same frame; results (poses, model maps) are bit-identical on every rank and to the single-GPU run.  With world > 1,
+ * kt_volume_export_reference_layout and the slices cover this rank's storage planes [rank*vol/world, (rank+1)*vol/world). */
+KT_API int kt_mgpu_arena_handle(kt_ctx* ctx, void* handle64);
+KT_API int kt_mgpu_connect(kt_ctx* ctx, const void* handles /* world x 64 bytes */, int world);
+KT_API int kt_mgpu_info(kt_ctx* ctx, int* info5);
 KT_API long long kt_launch_count(kt_ctx* ctx);
 /* debug: 64 x 5 clock64() stamps of the last whole-frame ICP launch (recorded only while stage timing is enabled) */
 KT_API int kt_debug_icp_profile(kt_ctx* ctx, long long* out320);

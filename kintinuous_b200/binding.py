@@ -189,6 +189,29 @@ class Tracker:
     def launch_count(self):
         return int(self.lib.kt_launch_count(self.h))
 
+    # ---- z-slab sharding (one process per GPU) ----
+    def mgpu_arena_handle(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        _check(self.lib.kt_mgpu_arena_handle(self.h, buf))
+        return buf.raw
+
+    def mgpu_connect(self, handles):
+        blob = b"".join(handles)
+        assert len(blob) == 64 * len(handles)
+        _check(self.lib.kt_mgpu_connect(self.h, C.c_char_p(blob), len(handles)))
+
+    def mgpu_info(self):
+        info = (C.c_int * 5)()
+        _check(self.lib.kt_mgpu_info(self.h, info))
+        return dict(world=info[0], rank=info[1], slab_planes=info[2], first_plane=info[3], arena_mb=info[4])
+
+    def export_slab(self):
+        """This rank's storage planes of both volume planes (the whole volume when world == 1)."""
+        i = self.mgpu_info(); V = self.cfg.vol
+        t = np.empty((i["slab_planes"], V, V), dtype=np.int16); c = np.empty((i["slab_planes"], V, V, 4), dtype=np.uint8)
+        _check(self.lib.kt_volume_export_reference_layout(self.h, _ptr(t), _ptr(c)))
+        return t, c
+
 
 class _Ops:
     """Operator API: one function per free function of the reference's cuda/internal.h:299-536.

@@ -19,6 +19,7 @@ namespace {
 
 struct ExtractParams {
     const int16_t* tsdf; const uchar4* color; int V; int3 wrap; int3 real_wrap; float3 cell;
+    VolumeView vv; int multi; int z_begin, z_end;          // sharded volume: emit only for voxels of the local slab
     int minX, maxX, minY, maxY, minZ, maxZ, subsample;
     uint4* out; unsigned int capacity; unsigned int* counter;
 };
@@ -31,6 +32,15 @@ __device__ __forceinline__ size_t vox_addr(const ExtractParams& p, int x, int y,
 
 __device__ __forceinline__ float fetch(const ExtractParams& p, int x, int y, int z, int& weight, uchar4& c)
 {
+    if (p.multi) {
+        const int sx = (x + p.wrap.x) % p.V, sy = (y + p.wrap.y) % p.V, sz = (z + p.wrap.z) % p.V;
+        const int owner = sz >> p.vv.slab_shift, lz = sz & (p.vv.slab_z - 1);
+        const size_t a = ((size_t)lz * p.V + sy) * p.V + sx;
+        float tsdf = unpack_tsdf(__ldg(p.vv.tsdf[owner] + a));
+        c = __ldg(reinterpret_cast<const uchar4*>(p.vv.color[owner]) + a);
+        weight = c.w;
+        return tsdf;
+    }
     size_t a = vox_addr(p, x, y, z);
     float tsdf = unpack_tsdf(__ldg(&p.tsdf[a]));
     c = __ldg(&p.color[a]);
@@ -68,7 +78,9 @@ extract_kernel(const ExtractParams p)
             const size_t r = idx / nx;
             const int y = p.minY + (int)(r % ny);
             const int z = p.minZ + (int)(r / ny);
-            if (x < p.V && y < p.V && x % p.subsample == 0 && y % p.subsample == 0 && (z - p.minZ) % p.subsample == 0) {
+            bool mine = true;
+            if (p.multi) { const int sz = (z + p.wrap.z) % p.V; mine = (sz >= p.z_begin && sz < p.z_end); }
+            if (mine && x < p.V && y < p.V && x % p.subsample == 0 && y % p.subsample == 0 && (z - p.minZ) % p.subsample == 0) {
                 uchar4 c;
                 float F = fetch(p, x, y, z, W, c);
                 if (W != 0 && F != 1.f) {
@@ -139,9 +151,29 @@ int extract_slice(const int16_t* tsdf, const float3& volume_size, int vol, void*
     if (maxX <= minX || maxY <= minY || maxZ <= minZ) return 0;
     ExtractParams p;
     p.tsdf = tsdf; p.color = (const uchar4*)color; p.V = vol; p.wrap = wrap; p.real_wrap = real_wrap;
+    p.multi = 0; p.z_begin = 0; p.z_end = vol;
     p.cell = make_float3(volume_size.x / vol, volume_size.y / vol, volume_size.z / vol);
     p.minX = minX; p.maxX = maxX; p.minY = minY; p.maxY = maxY; p.minZ = minZ; p.maxZ = maxZ; p.subsample = subsample < 1 ? 1 : subsample;
     p.out = (uint4*)out; p.capacity = (unsigned int)capacity; p.counter = counter_dev;
+    size_t total = (size_t)(maxX - minX) * (maxY - minY) * (maxZ - minZ);
+    size_t blocks = (total + 255) / 256;
+    int grid = (int)(blocks < (size_t)148 * 16 ? blocks : (size_t)148 * 16);
+    extract_kernel<<<grid, 256, 0, s>>>(p);
+    KT_LAUNCH_CHECK();
+    return 0;
+}
+
+int extract_slice_mg(const VolumeView& vv, const float3& volume_size, int vol, void* out, size_t capacity, const int3& wrap,
+                     int minX, int maxX, int minY, int maxY, int minZ, int maxZ, int subsample,
+                     const int3& real_wrap, unsigned int* counter_dev, cudaStream_t s)
+{
+    if (maxX <= minX || maxY <= minY || maxZ <= minZ) return 0;
+    ExtractParams p;
+    p.tsdf = vv.tsdf[vv.rank]; p.color = (const uchar4*)vv.color[vv.rank]; p.V = vol; p.wrap = wrap; p.real_wrap = real_wrap;
+    p.cell = make_float3(volume_size.x / vol, volume_size.y / vol, volume_size.z / vol);
+    p.minX = minX; p.maxX = maxX; p.minY = minY; p.maxY = maxY; p.minZ = minZ; p.maxZ = maxZ; p.subsample = subsample < 1 ? 1 : subsample;
+    p.out = (uint4*)out; p.capacity = (unsigned int)capacity; p.counter = counter_dev;
+    p.vv = vv; p.multi = 1; p.z_begin = vv.rank * vv.slab_z; p.z_end = p.z_begin + vv.slab_z;
     size_t total = (size_t)(maxX - minX) * (maxY - minY) * (maxZ - minZ);
     size_t blocks = (total + 255) / 256;
     int grid = (int)(blocks < (size_t)148 * 16 ? blocks : (size_t)148 * 16);

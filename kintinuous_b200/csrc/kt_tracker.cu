@@ -96,6 +96,13 @@ struct kt_ctx {
     bool timing; cudaEvent_t ev[7]; float stage_ms[6];
     long long launches_at_create;
     std::vector<void*> allocs;
+    // z-slab sharding over `world` GPUs (one process per GPU; peers' arenas are mapped through CUDA IPC)
+    int world, rank, slab_z, z_begin, z_end;
+    uint8_t* arena; size_t arena_bytes;
+    size_t off_tsdf, off_color, off_vmap[LEVELS], off_nmap[LEVELS], off_vcol, off_flags;
+    uint8_t* peer_arena[MAX_GPUS]; bool connected;
+    unsigned int** peer_flags_dev; unsigned int epoch; int* mg_error_dev; int* mg_error_host;
+    VolumeView vv;
 };
 
 namespace {
@@ -121,8 +128,11 @@ int fetch_cloud(kt_ctx* c, const int* vWrapCopy, const int* lo, const int* hi)  
 {
     KT_CUDA(cudaMemsetAsync(c->counter_dev, 0, sizeof(unsigned int), c->stream));
     float3 vs = make_float3(c->size, c->size, c->size);
-    int r = extract_slice(c->tsdf, vs, c->cfg.vol, c->cloud_dev, c->cloud_capacity, make_int3(vWrapCopy[0], vWrapCopy[1], vWrapCopy[2]), c->color,
-                          lo[0], hi[0], lo[1], hi[1], lo[2], hi[2], 1, make_int3(c->voxelWrap[0], c->voxelWrap[1], c->voxelWrap[2]), c->counter_dev, c->stream);
+    int r = c->world > 1
+        ? extract_slice_mg(c->vv, vs, c->cfg.vol, c->cloud_dev, c->cloud_capacity, make_int3(vWrapCopy[0], vWrapCopy[1], vWrapCopy[2]),
+                           lo[0], hi[0], lo[1], hi[1], lo[2], hi[2], 1, make_int3(c->voxelWrap[0], c->voxelWrap[1], c->voxelWrap[2]), c->counter_dev, c->stream)
+        : extract_slice(c->tsdf, vs, c->cfg.vol, c->cloud_dev, c->cloud_capacity, make_int3(vWrapCopy[0], vWrapCopy[1], vWrapCopy[2]), c->color,
+                        lo[0], hi[0], lo[1], hi[1], lo[2], hi[2], 1, make_int3(c->voxelWrap[0], c->voxelWrap[1], c->voxelWrap[2]), c->counter_dev, c->stream);
     if (r) return r;
     KT_CUDA(cudaMemcpyAsync(c->counter_host, c->counter_dev, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
     KT_CUDA(cudaStreamSynchronize(c->stream));
@@ -163,7 +173,7 @@ int do_integrate(kt_ctx* c, const M3& Rinv, const V3& t, const int* wrap)
     a.Rinv = to_mat33(Rinv.m); a.t = make_float3(t.v[0], t.v[1], t.v[2]); a.trunc = c->trunc;
     a.tsdf = c->tsdf; a.color = c->color; a.vol = c->cfg.vol; a.wrap = make_int3(wrap[0], wrap[1], wrap[2]);
     a.rgb = c->rgb; a.nmap_curr = c->nmaps_curr[0]; a.angle_color = c->cfg.angle_color != 0;
-    a.z_begin = 0; a.z_end = c->cfg.vol;
+    a.z_begin = c->z_begin; a.z_end = c->z_end;
     return integrate(a, c->ztable, c->stream);
 }
 
@@ -230,7 +240,9 @@ int run_odometry(kt_ctx* c, const M3& Rprev, const V3& tprev, M3* Rcurr, V3* tcu
     c->trace_iters = std::min(total_iters, MAX_TRACE_ITERS);
     // one 64-byte read-back of the estimate (+ the trace when someone asked for it later: it stays on the device)
     KT_CUDA(cudaMemcpyAsync(c->result_host->Rcurr, (char*)c->state + offsetof(OdomState, Rcurr), 12 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    if (c->world > 1) KT_CUDA(cudaMemcpyAsync(c->mg_error_host, c->mg_error_dev, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     KT_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->world > 1 && *c->mg_error_host) { set_error("cross-GPU barrier timed out waiting for rank %d", *c->mg_error_host - 1); return KT_ERR_STATE; }
     for (int k = 0; k < 9; ++k) Rcurr->m[k] = c->result_host->Rcurr[k];
     for (int k = 0; k < 3; ++k) tcurr->v[k] = c->result_host->tcurr[k];
     if (mode != 0) {
@@ -239,6 +251,14 @@ int run_odometry(kt_ctx* c, const M3& Rprev, const V3& tprev, M3* Rcurr, V3* tcu
         if (std::sqrt(dx * dx + dy * dy + dz * dz) > 0.3) { *Rcurr = Rprev; *tcurr = tprev; }                                               // :383-387
     }
     return 0;
+}
+
+int mg_barrier(kt_ctx* c)
+{
+    if (c->world <= 1) return 0;
+    if (!c->connected) { set_error("multi-GPU context used before kt_mgpu_connect"); return KT_ERR_STATE; }
+    ++c->epoch;
+    return xgpu_barrier(c->peer_flags_dev, (unsigned int*)(c->arena + c->off_flags), c->rank, c->world, c->epoch, c->mg_error_dev, c->stream);
 }
 
 void mark(kt_ctx* c, int i) { if (c->timing) cudaEventRecord(c->ev[i], c->stream); }
@@ -317,13 +337,15 @@ int process_frame_device(kt_ctx* c, uint64_t utime, kt_pose* out)
         if (n >= thresh) {
             lo[axis] = 0; hi[axis] = n + 1 + c->overlap;
             if ((r = fetch_cloud(c, vWrapCopy, lo, hi))) return r;
-            if ((r = clear_volume(axis, 0, c->tsdf, c->color, V, c->voxelWrap[axis], c->voxelWrap[axis] + n, c->stream))) return r;
+            if ((r = mg_barrier(c))) return r;                          // peers may still read my boundary plane for their extraction
+            if ((r = clear_volume_slab(axis, 0, c->tsdf, c->color, V, c->z_begin, c->z_end, c->voxelWrap[axis], c->voxelWrap[axis] + n, c->stream))) return r;
             cycled = true;
         } else if (n <= -thresh) {
             if (axis < 2) { lo[axis] = V + (n - c->overlap); hi[axis] = V; }
             else { lo[axis] = V + (n - c->overlap) - 1; hi[axis] = V - 1; }               // .cpp:805 (Q12)
             if ((r = fetch_cloud(c, vWrapCopy, lo, hi))) return r;
-            if ((r = clear_volume(axis, 1, c->tsdf, c->color, V, c->voxelWrap[axis], c->voxelWrap[axis] + n, c->stream))) return r;
+            if ((r = mg_barrier(c))) return r;
+            if ((r = clear_volume_slab(axis, 1, c->tsdf, c->color, V, c->z_begin, c->z_end, c->voxelWrap[axis], c->voxelWrap[axis] + n, c->stream))) return r;
             cycled = true;
         }
         if (cycled) {                                                                    // mutexOutCloudBuffer (.cpp:1156-1208)
@@ -343,6 +365,7 @@ int process_frame_device(kt_ctx* c, uint64_t utime, kt_pose* out)
     mark(c, 3);
 
     if ((r = do_integrate(c, Rcurr_inv, tcurr, vWrapCopy))) return r;                    // .cpp:864-876
+    if ((r = mg_barrier(c))) return r;                                                   // every slab holds this frame before any ray reads it
     mark(c, 4);
     vwrap_copy(c, vWrapCopy);
     RaycastArgs ra;
@@ -353,7 +376,19 @@ int process_frame_device(kt_ctx* c, uint64_t utime, kt_pose* out)
     for (int l = 0; l < LEVELS; ++l) { ra.vmap[l] = c->vmaps_g_prev[l]; ra.nmap[l] = c->nmaps_g_prev[l]; }
     ra.rows = rows; ra.cols = cols; ra.vmap_color = c->vmap_curr_color;
     ra.n_levels = (mode == 0 || mode == 2) ? LEVELS : 1;                                 // .cpp:892-899
+    ra.multi = c->world > 1 ? 1 : 0;
+    if (ra.multi) {
+        ra.n_levels = LEVELS;
+        ra.vv = c->vv;
+        const int tiles_y = rows / 8;
+        ra.tile_row_begin = c->rank * tiles_y / c->world; ra.tile_row_end = (c->rank + 1) * tiles_y / c->world;
+        for (int g = 0; g < c->world; ++g) {
+            for (int l = 0; l < LEVELS; ++l) { ra.peer_vmap[g][l] = (float*)(c->peer_arena[g] + c->off_vmap[l]); ra.peer_nmap[g][l] = (float*)(c->peer_arena[g] + c->off_nmap[l]); }
+            ra.peer_vcol[g] = c->peer_arena[g] + c->off_vcol;
+        }
+    }
     if ((r = raycast(ra, c->stream))) return r;
+    if ((r = mg_barrier(c))) return r;                                                   // all tiles of the predicted surface have landed everywhere
     mark(c, 5);
     ++c->global_time;
     if (out) kt_get_pose(c, out);
@@ -385,7 +420,7 @@ int kt_reset(kt_ctx* c)
     for (int i = 0; i < 3; ++i) { c->voxelWrap[i] = 0; c->currentGlobalCamera[i] = c->volumeBasis[i] - c->size * 0.5f; }
     c->slices.clear();
     c->trace_iters = 0; c->shifted_last = 0; c->cloud_count = 0;
-    int r = init_volume(c->tsdf, c->color, c->cfg.vol, c->stream);
+    int r = init_slab(c->tsdf, c->color, c->cfg.vol, c->slab_z, c->stream);
     if (r) return r;
     // Q7: stale y/z planes of invalid pixels start from a defined state (zeros)
     const size_t P = (size_t)c->cfg.rows * c->cfg.cols;
@@ -406,6 +441,11 @@ int kt_create(const kt_config* cfg, kt_ctx** out)
     if (cfg->rows <= 0 || cfg->cols <= 0 || cfg->vol < 32 || cfg->vol % 32 != 0 || cfg->volume_size <= 0) { set_error("kt_create: bad geometry (vol must be a multiple of 32)"); return KT_ERR_INVALID; }
     if ((cfg->rows % 8) != 0 || (cfg->cols % 32) != 0) { set_error("kt_create: rows must be a multiple of 8 and cols of 32"); return KT_ERR_INVALID; }
     if (cfg->odometry < 0 || cfg->odometry > 2) { set_error("kt_create: odometry must be 0, 1 or 2"); return KT_ERR_INVALID; }
+    if (cfg->world > 1) {
+        const int w = cfg->world;
+        if (w > MAX_GPUS || (w & (w - 1)) || cfg->rank < 0 || cfg->rank >= w || (cfg->vol & (cfg->vol - 1)) || cfg->vol / w < 2) {
+            set_error("kt_create: z-slab sharding needs world in {2,4,8}, 0 <= rank < world and a power-of-two vol"); return KT_ERR_INVALID; }
+    }
     if (!kt_cuda_available()) { set_error("kt_create: no CUDA device (this library has no CPU path)"); return KT_ERR_CUDA; }
     KT_CUDA(cudaSetDevice(cfg->device));
     kt_ctx* c = new kt_ctx();
@@ -431,13 +471,36 @@ int kt_create(const kt_config* cfg, kt_ctx** out)
     KT_TRY(kt::cuda_check(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking), "stream2", __FILE__, __LINE__));
     KT_TRY(kt::cuda_check(cudaEventCreateWithFlags(&c->ev_input, cudaEventDisableTiming), "event", __FILE__, __LINE__));
     KT_TRY(kt::cuda_check(cudaEventCreateWithFlags(&c->ev_scaled, cudaEventDisableTiming), "event", __FILE__, __LINE__));
-    const size_t P = (size_t)cfg->rows * cfg->cols, V3n = (size_t)cfg->vol * cfg->vol * cfg->vol;
-    KT_TRY(dev_alloc(c, &c->tsdf, V3n)); KT_TRY(dev_alloc(c, &c->color, V3n * 4));
+    const size_t P = (size_t)cfg->rows * cfg->cols;
+    {   // shared arena: local volume slab, model maps, raycast colour, barrier flags -- one allocation, one IPC handle
+        c->world = cfg->world > 1 ? cfg->world : 1; c->rank = cfg->world > 1 ? cfg->rank : 0;
+        c->slab_z = cfg->vol / c->world; c->z_begin = c->rank * c->slab_z; c->z_end = c->z_begin + c->slab_z;
+        auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+        size_t off = 0;
+        const size_t slab_vox = (size_t)cfg->vol * cfg->vol * c->slab_z;
+        c->off_tsdf = off; off = al(off + slab_vox * 2);
+        c->off_color = off; off = al(off + slab_vox * 4);
+        for (int l = 0; l < LEVELS; ++l) { size_t Pl = P >> (2 * l); c->off_vmap[l] = off; off = al(off + Pl * 12); c->off_nmap[l] = off; off = al(off + Pl * 12); }
+        c->off_vcol = off; off = al(off + P * 4);
+        c->off_flags = off; off = al(off + 256);
+        c->arena_bytes = off;
+        KT_TRY(dev_alloc(c, &c->arena, off));
+        KT_TRY(kt::cuda_check(cudaMemset(c->arena + c->off_flags, 0, 256), "memset", __FILE__, __LINE__));
+        c->tsdf = (int16_t*)(c->arena + c->off_tsdf); c->color = c->arena + c->off_color;
+        for (int g = 0; g < MAX_GPUS; ++g) c->peer_arena[g] = c->arena;
+        c->connected = (c->world == 1);
+        c->epoch = 0;
+        c->vv = single_volume(c->tsdf, c->color, cfg->vol);
+        c->vv.world = c->world; c->vv.rank = c->rank; c->vv.slab_z = c->slab_z; c->vv.slab_shift = 0; { int t = c->slab_z; while (t > 1) { t >>= 1; ++c->vv.slab_shift; } }
+        KT_TRY(dev_alloc(c, &c->peer_flags_dev, (size_t)MAX_GPUS)); KT_TRY(dev_alloc(c, &c->mg_error_dev, 1));
+        KT_TRY(kt::cuda_check(cudaMemset(c->mg_error_dev, 0, sizeof(int)), "memset", __FILE__, __LINE__));
+        KT_TRY(kt::cuda_check(cudaMallocHost((void**)&c->mg_error_host, sizeof(int)), "pinned", __FILE__, __LINE__)); *c->mg_error_host = 0;
+    }
     KT_TRY(dev_alloc(c, &c->depth_raw, P)); KT_TRY(dev_alloc(c, &c->rgb, P * 3));
     for (int l = 0; l < LEVELS; ++l) {
         size_t Pl = P >> (2 * l);
         KT_TRY(dev_alloc(c, &c->depths_curr[l], Pl));
-        KT_TRY(dev_alloc(c, &c->vmaps_g_prev[l], Pl * 3)); KT_TRY(dev_alloc(c, &c->nmaps_g_prev[l], Pl * 3));
+        c->vmaps_g_prev[l] = (float*)(c->arena + c->off_vmap[l]); c->nmaps_g_prev[l] = (float*)(c->arena + c->off_nmap[l]);
         KT_TRY(dev_alloc(c, &c->vmaps_curr[l], Pl * 3)); KT_TRY(dev_alloc(c, &c->nmaps_curr[l], Pl * 3));
         c->lastDepth[l] = c->nextDepth[l] = 0; c->lastImage[l] = c->nextImage[l] = 0; c->nextdIdx[l] = c->nextdIdy[l] = 0; c->pointClouds[l] = 0; c->corresImg[l] = 0;
         if (cfg->odometry != 0) {
@@ -448,7 +511,7 @@ int kt_create(const kt_config* cfg, kt_ctx** out)
             uint8_t* ci = 0; KT_TRY(dev_alloc(c, &ci, Pl * 16)); c->corresImg[l] = ci;
         }
     }
-    KT_TRY(dev_alloc(c, &c->vmap_curr_color, P * 4)); KT_TRY(dev_alloc(c, &c->depth_scaled, P));
+    c->vmap_curr_color = c->arena + c->off_vcol; KT_TRY(dev_alloc(c, &c->depth_scaled, P));
     KT_TRY(dev_alloc(c, &c->ztable, (size_t)2 * cfg->vol));
     KT_TRY(dev_alloc(c, &c->state, 1)); KT_TRY(dev_alloc(c, &c->partials, (size_t)MAX_PARTIALS * 32));
     KT_TRY(dev_alloc(c, &c->bar_dev, 1)); KT_TRY(kt::cuda_check(cudaMemset(c->bar_dev, 0, sizeof(unsigned int)), "memset", __FILE__, __LINE__)); c->bar_count = 0;
@@ -473,6 +536,8 @@ int kt_destroy(kt_ctx* c)
     if (!c) return KT_OK;
     cudaSetDevice(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    for (int g = 0; g < MAX_GPUS; ++g) if (c->peer_arena[g] && c->peer_arena[g] != c->arena) cudaIpcCloseMemHandle(c->peer_arena[g]);
+    if (c->mg_error_host) cudaFreeHost(c->mg_error_host);
     for (void* p : c->allocs) cudaFree(p);
     if (c->pose12_host) cudaFreeHost(c->pose12_host);
     if (c->result_host) cudaFreeHost(c->result_host);
@@ -566,7 +631,7 @@ int kt_volume_export_reference_layout(kt_ctx* c, int16_t* tsdf_host, uint8_t* co
     if (!c) return KT_ERR_INVALID;
     KT_CUDA(cudaSetDevice(c->cfg.device));
     KT_CUDA(cudaStreamSynchronize(c->stream));
-    const size_t n = (size_t)c->cfg.vol * c->cfg.vol * c->cfg.vol;
+    const size_t n = (size_t)c->cfg.vol * c->cfg.vol * c->slab_z;       // sharded: this rank's slab (storage planes [rank*V/world, ...))
     if (tsdf_host) KT_CUDA(cudaMemcpy(tsdf_host, c->tsdf, n * 2, cudaMemcpyDeviceToHost));
     if (color_host) KT_CUDA(cudaMemcpy(color_host, c->color, n * 4, cudaMemcpyDeviceToHost));
     return KT_OK;
@@ -604,6 +669,47 @@ int kt_debug_icp_profile(kt_ctx* c, long long* out320)
     if (!c || !out320) return KT_ERR_INVALID;
     KT_CUDA(cudaStreamSynchronize(c->stream));
     KT_CUDA(cudaMemcpy(out320, c->prof_dev, 64 * 5 * sizeof(long long), cudaMemcpyDeviceToHost));
+    return KT_OK;
+}
+
+int kt_mgpu_arena_handle(kt_ctx* c, void* handle64)
+{
+    if (!c || !handle64) return KT_ERR_INVALID;
+    KT_CUDA(cudaSetDevice(c->cfg.device));
+    cudaIpcMemHandle_t h;
+    KT_CUDA(cudaIpcGetMemHandle(&h, c->arena));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    std::memcpy(handle64, &h, 64);
+    return KT_OK;
+}
+
+int kt_mgpu_connect(kt_ctx* c, const void* handles, int n)
+{
+    if (!c || !handles || n != c->world) { set_error("kt_mgpu_connect: need exactly world handles"); return KT_ERR_INVALID; }
+    KT_CUDA(cudaSetDevice(c->cfg.device));
+    unsigned int* flags_host[MAX_GPUS];
+    for (int g = 0; g < c->world; ++g) {
+        if (g == c->rank) c->peer_arena[g] = c->arena;
+        else {
+            cudaIpcMemHandle_t h; std::memcpy(&h, (const char*)handles + (size_t)g * 64, 64);
+            void* p = 0;
+            KT_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+            c->peer_arena[g] = (uint8_t*)p;
+        }
+        c->vv.tsdf[g] = (int16_t*)(c->peer_arena[g] + c->off_tsdf);
+        c->vv.color[g] = c->peer_arena[g] + c->off_color;
+        flags_host[g] = (unsigned int*)(c->peer_arena[g] + c->off_flags);
+    }
+    for (int g = c->world; g < MAX_GPUS; ++g) flags_host[g] = flags_host[0];
+    KT_CUDA(cudaMemcpy(c->peer_flags_dev, flags_host, sizeof(flags_host), cudaMemcpyHostToDevice));
+    c->connected = true;
+    return KT_OK;
+}
+
+int kt_mgpu_info(kt_ctx* c, int* info5)       // world, rank, slab planes, first storage plane, arena bytes (MB)
+{
+    if (!c || !info5) return KT_ERR_INVALID;
+    info5[0] = c->world; info5[1] = c->rank; info5[2] = c->slab_z; info5[3] = c->z_begin; info5[4] = (int)(c->arena_bytes >> 20);
     return KT_OK;
 }
 

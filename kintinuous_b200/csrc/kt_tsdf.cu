@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(256) fill_zero_u4(uint4* __restrict__ p, size_
 // Clear `count` consecutive storage planes [p0, p0+count) (mod V) along `axis` in both volumes.
 // Work item = 8 consecutive x voxels (16 B of tsdf, 32 B of colour) for the y / z axes.
 __global__ void __launch_bounds__(256)
-clear_planes_yz_kernel(int16_t* __restrict__ tsdf, uint8_t* __restrict__ color, int V, int axis, int p0, int count)
+clear_planes_yz_kernel(int16_t* __restrict__ tsdf, uint8_t* __restrict__ color, int V, int axis, int p0, int count, int zb, int ze)
 {
     const int xg = V / 8;                                   // groups of 8 voxels per row
     const size_t total = (size_t)count * V * xg;
@@ -49,7 +49,8 @@ clear_planes_yz_kernel(int16_t* __restrict__ tsdf, uint8_t* __restrict__ color, 
         int plane = p0 + i; if (plane >= V) plane -= V;
         int sy = axis == 1 ? plane : other;
         int sz = axis == 1 ? other : plane;
-        size_t base = ((size_t)sz * V + sy) * V + (size_t)g * 8;
+        if (sz < zb || sz >= ze) continue;                    // not this rank's slab
+        size_t base = ((size_t)(sz - zb) * V + sy) * V + (size_t)g * 8;
         *reinterpret_cast<uint4*>(tsdf + base) = z4;
         uint4* c = reinterpret_cast<uint4*>(color + base * 4);
         c[0] = z4; c[1] = z4;
@@ -57,14 +58,16 @@ clear_planes_yz_kernel(int16_t* __restrict__ tsdf, uint8_t* __restrict__ color, 
 }
 
 __global__ void __launch_bounds__(256)
-clear_planes_x_kernel(int16_t* __restrict__ tsdf, uchar4* __restrict__ color, int V, int p0, int count)
+clear_planes_x_kernel(int16_t* __restrict__ tsdf, uchar4* __restrict__ color, int V, int p0, int count, int zb, int ze)
 {
     const size_t total = (size_t)count * V * V;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         int i = (int)(idx % count);
         size_t r = idx / count;                              // r = sz * V + sy
         int sx = p0 + i; if (sx >= V) sx -= V;
-        size_t a = r * V + sx;
+        const int sz = (int)(r / V);
+        if (sz < zb || sz >= ze) continue;
+        size_t a = (r - (size_t)zb * V) * V + sx;
         tsdf[a] = 0;
         color[a] = make_uchar4(0, 0, 0, 0);
     }
@@ -329,6 +332,18 @@ int init_volume(int16_t* tsdf, uint8_t* color, int vol, cudaStream_t s)
 //   which drops the last plane exactly when |n| is a multiple of 16.
 int clear_volume(int axis, int back, int16_t* tsdf, uint8_t* color, int vol, int current, int delta, cudaStream_t s)
 {
+    return clear_volume_slab(axis, back, tsdf, color, vol, 0, vol, current, delta, s);
+}
+
+int init_slab(int16_t* tsdf_local, uint8_t* color_local, int vol, int slab_z, cudaStream_t s)
+{
+    size_t n = (size_t)vol * vol * slab_z;
+    int r = fill_zero(tsdf_local, n * 2, s); if (r) return r;
+    return fill_zero(color_local, n * 4, s);
+}
+
+int clear_volume_slab(int axis, int back, int16_t* tsdf, uint8_t* color, int vol, int zb, int ze, int current, int delta, cudaStream_t s)
+{
     const int V = vol;
     const int n = delta - current;
     const int an = n < 0 ? -n : n;
@@ -344,11 +359,11 @@ int clear_volume(int axis, int back, int16_t* tsdf, uint8_t* color, int vol, int
     if (axis == 0) {
         size_t total = (size_t)count * V * V;
         int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-        clear_planes_x_kernel<<<grid, 256, 0, s>>>(tsdf, (uchar4*)color, V, p0, count);
+        clear_planes_x_kernel<<<grid, 256, 0, s>>>(tsdf, (uchar4*)color, V, p0, count, zb, ze);
     } else {
         size_t total = (size_t)count * V * (V / 8);
         int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-        clear_planes_yz_kernel<<<grid, 256, 0, s>>>(tsdf, color, V, axis, p0, count);
+        clear_planes_yz_kernel<<<grid, 256, 0, s>>>(tsdf, color, V, axis, p0, count, zb, ze);
     }
     KT_LAUNCH_CHECK();
     return 0;
@@ -376,6 +391,33 @@ int integrate(const IntegrateArgs& a, float* ztable_dev, cudaStream_t s)
     dim3 block(32, 8), grid(div_up(V, 32), div_up(V, 8), div_up(V, p.zchunk));
     if ((size_t)(a.z_end - a.z_begin) * V * V <= ((size_t)1 << 31)) integrate_kernel<unsigned int><<<grid, block, 0, s>>>(p);
     else integrate_kernel<size_t><<<grid, block, 0, s>>>(p);
+    KT_LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Cross-GPU barrier over NVLink peer memory (one process per GPU, flag arrays exchanged through CUDA IPC).
+namespace {
+__global__ void xgpu_barrier_kernel(unsigned int* const* peer_flags, volatile unsigned int* my_flags, int rank, int world, unsigned int epoch, int* error)
+{
+    const int t = threadIdx.x;
+    if (t < world) {
+        __threadfence_system();                                  // everything this GPU wrote before (local slab, P2P stores) is visible first
+        volatile unsigned int* dst = peer_flags[t] + rank;
+        *dst = epoch;
+        __threadfence_system();
+        const long long t0 = clock64();
+        while ((int)(my_flags[t] - epoch) < 0) {
+            if (clock64() - t0 > 4000000000LL) { *error = 1 + t; break; }   // ~2 s at 2 GHz: report instead of hanging the GPU
+        }
+        __threadfence_system();
+    }
+}
+}
+
+int xgpu_barrier(unsigned int* const* peer_flags_dev, unsigned int* my_flags, int rank, int world, unsigned int epoch, int* error_dev, cudaStream_t s)
+{
+    xgpu_barrier_kernel<<<1, 32, 0, s>>>(peer_flags_dev, my_flags, rank, world, epoch, error_dev);
     KT_LAUNCH_CHECK();
     return 0;
 }

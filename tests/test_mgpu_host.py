@@ -1,0 +1,58 @@
+"""Host-side logic of the z-slab mode on CPU: partitions cover everything exactly once, and the control-plane exchange works
+with world_size 2 over gloo (the data path itself needs GPUs: tools/mgpu_check.py under torchrun)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+from conftest import ROOT
+
+
+def test_partitions_cover_exactly_once():
+    from kintinuous_b200 import mgpu
+    for vol in (256, 512, 1024):
+        for world in (1, 2, 4, 8):
+            owned = np.zeros(vol, int)
+            for r in range(world):
+                a, b = mgpu.slab_range(r, world, vol)
+                owned[a:b] += 1
+                assert all(mgpu.owner_of_plane(z, world, vol) == r for z in (a, b - 1))
+            assert (owned == 1).all()
+    for rows in (480, 960, 120):
+        for world in (1, 2, 4, 8):
+            cover = np.zeros(rows // 8, int)
+            for r in range(world):
+                a, b = mgpu.tile_rows(r, world, rows)
+                cover[a:b] += 1
+            assert (cover == 1).all()
+
+
+WORKER = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import torch.distributed as dist
+from kintinuous_b200 import mgpu
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+handle = bytes([rank]) * 64                      # stands in for the 64-byte cudaIpcMemHandle_t
+got = mgpu.exchange(handle)
+assert len(got) == world and all(got[r] == bytes([r]) * 64 for r in range(world)), got
+a, b = mgpu.slab_range(rank, world, 512)
+import torch
+t = torch.tensor([b - a], dtype=torch.int64)
+dist.all_reduce(t)
+assert int(t.item()) == 512
+dist.barrier()
+print("rank", rank, "ok")
+'''
+
+
+def test_control_plane_world2_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29533",
+                          str(script), ROOT], capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("ok") == 2
