@@ -307,7 +307,7 @@ def main():
     streams = 1 if zslab else world          # z-slab: all ranks work on ONE stream (strong scaling)
     value = streams * args.steps / dt
     e2e_v = streams * args.steps / results["host"]["dt"]
-    line = {"metric": "frames/s 640x480 into 512^3 TSDF (ICP-only tracker)", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
+    line = {"metric": f"frames/s 640x480 into {args.vol}^3 TSDF ({'ICP-only' if args.odometry == 0 else 'ICP+RGB-D'} tracker)", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
             "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong" if zslab else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "synthetic 640x480 RGB-D stream, 512^3 volume (6 m), ICP-only tracker {10,5,4}, shifting on (-t 14)", "parallelism": (f"one stream, volume z-slab sharded over {world} GPUs (P2P raycast, replicated ICP)" if zslab else f"{world} independent streams"), "vol": args.vol, "odometry": args.odometry,
                        "l2": f"inputs larger than L2: {n} frames x 1.54 MB = {n * 1.536:.0f} MB cycled (ping-pong)"},
