@@ -90,7 +90,9 @@ __device__ inline void rodrigues(const double* r, double* R)
         for (int k = 0; k < 9; ++k) R[k] = (k % 4 == 0) ? 1.0 : 0.0;
         return;
     }
-    double c = cos(theta), s = sin(theta), c1 = 1.0 - c;
+    double s, c;
+    sincos(theta, &s, &c);
+    const double c1 = 1.0 - c;
     double itheta = 1.0 / theta;
     rx *= itheta; ry *= itheta; rz *= itheta;
     const double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
