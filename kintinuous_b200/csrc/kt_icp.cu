@@ -331,11 +331,13 @@ icp_frame_kernel(const IcpFrameParams p)
             }
             __syncthreads();
             // Exchange: every CTA publishes its 29 partial sums as 8-byte {value, tag} words (one store each, so value and tag can
-            // never be seen torn) and every CTA then polls all G x 29 words until they carry this iteration's tag.  Data and flag
-            // travel together: no atomic counter, no __threadfence, one L2 round trip.  Buffers alternate with the iteration
-            // parity, which is enough because a CTA cannot publish iteration it+2 before every CTA has published it+1, i.e. has
-            // finished reading iteration it.
-            unsigned long long* part = reinterpret_cast<unsigned long long*>(p.partials) + (size_t)(it & 1) * 32 * G;
+            // never be seen torn) followed by a 4-byte "ready" tag.  Warp 0 of every CTA polls the G ready tags (a few hundred
+            // bytes per round), then all threads read the data words and check their tags (a word whose tag is not there yet is
+            // simply re-read).  Data and flag travel together, so there is no atomic counter and no __threadfence.  Buffers
+            // alternate with the iteration parity, which is enough because a CTA cannot publish iteration it+2 before every CTA
+            // has published it+1, i.e. has finished reading iteration it.
+            unsigned long long* part = reinterpret_cast<unsigned long long*>(p.partials) + (size_t)(it & 1) * 33 * G;
+            volatile unsigned int* ready = reinterpret_cast<volatile unsigned int*>(part + (size_t)32 * G);
             const unsigned int tag = p.bar_base + (unsigned int)it + 1u;
             if (tid < NSUM) {
                 float v = 0.f;
@@ -344,7 +346,13 @@ icp_frame_kernel(const IcpFrameParams p)
                 const unsigned long long word = ((unsigned long long)tag << 32) | (unsigned long long)__float_as_uint(v);
                 *reinterpret_cast<volatile unsigned long long*>(&part[(size_t)tid * G + blockIdx.x]) = word;
             }
+            __syncwarp();
+            if (tid == 0) ready[blockIdx.x] = tag;
             if (prof) p.prof[it * 5 + 1] = clock64();
+            if (wid == 0) {
+                for (int b = lane; b < G; b += 32) while (ready[b] != tag) { }
+            }
+            __syncthreads();
             if (prof) p.prof[it * 5 + 2] = clock64();
             // every CTA: fixed-order total of the G partials of each component (16 lanes per component, polls issued together)
             {
