@@ -357,27 +357,26 @@ icp_frame_kernel(const IcpFrameParams p)
             // every CTA: fixed-order total of the G partials of each component (16 lanes per component, polls issued together)
             {
                 const int comp = tid >> 4, sub = tid & 15;
-                float x[10];
+                unsigned long long e[10];
 #pragma unroll
-                for (int q = 0; q < 10; ++q) {
+                for (int q = 0; q < 10; ++q) {                          // all loads in flight together (L2, bypassing L1)
                     const int b = sub + 16 * q;
-                    x[q] = 0.f;
-                    if (comp < NSUM && b < G) {
-                        const volatile unsigned long long* src = reinterpret_cast<const volatile unsigned long long*>(&part[(size_t)comp * G + b]);
-                        unsigned long long e = *src;
-                        while ((unsigned int)(e >> 32) != tag) e = *src;
-                        x[q] = __uint_as_float((unsigned int)e);
-                    }
+                    e[q] = (comp < NSUM && b < G) ? __ldcg(&part[(size_t)comp * G + b]) : ((unsigned long long)tag << 32);
                 }
                 float v = 0.f;
 #pragma unroll
-                for (int q = 0; q < 10; ++q) v += x[q];
+                for (int q = 0; q < 10; ++q) {
+                    const int b = sub + 16 * q;
+                    while ((unsigned int)(e[q] >> 32) != tag)               // rare: the ready tag overtook this data word
+                        e[q] = *reinterpret_cast<const volatile unsigned long long*>(&part[(size_t)comp * G + b]);
+                    v += __uint_as_float((unsigned int)e[q]);
+                }
                 for (int b = sub + 160; b < G; b += 16) {
                     if (comp < NSUM) {
                         const volatile unsigned long long* src = reinterpret_cast<const volatile unsigned long long*>(&part[(size_t)comp * G + b]);
-                        unsigned long long e = *src;
-                        while ((unsigned int)(e >> 32) != tag) e = *src;
-                        v += __uint_as_float((unsigned int)e);
+                        unsigned long long w = *src;
+                        while ((unsigned int)(w >> 32) != tag) w = *src;
+                        v += __uint_as_float((unsigned int)w);
                     }
                 }
                 v += __shfl_xor_sync(0xffffffffu, v, 8);
