@@ -144,13 +144,25 @@ struct IcpFrameParams {
     int iters[LEVELS];
     float pose12[12];          // Rprev (9), tprev (3)
     OdomState* st;
-    float* partials;           // [2][32][grid] 8-byte {value, tag} words (double-buffered by iteration parity; component-major)
+    float* partials;           // [2][32][grid]  (double-buffered by iteration parity; component-major)
     float* trace;
     unsigned int* bar;         // monotonically increasing arrival counter
-    unsigned int bar_base;     // tag base: iterations published by earlier launches
+    unsigned int bar_base;     // value of the counter when this launch starts
     long long* prof;           // optional: 5 clock64() stamps per iteration from CTA 0 (debug)
     int stage_k;               // chunks of FRAME_THREADS pixels per CTA that fit the shared-memory stage (0 = no staging)
 };
+
+__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int target)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(bar, 1u);
+        while ((int)(*((volatile unsigned int*)bar) - target) < 0) { }
+        __threadfence();
+    }
+    __syncthreads();
+}
 
 // ---- TMA (bulk async copy engine) helpers: global -> shared 1-D bulk copies completing on an mbarrier ----
 __device__ __forceinline__ unsigned int smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
@@ -257,6 +269,7 @@ icp_frame_kernel(const IcpFrameParams p)
     tprev = make_float3(s_tp[0], s_tp[1], s_tp[2]);
 
     int it = 0;
+    unsigned int target = p.bar_base;
     unsigned int stage_parity = 0;
     for (int level = LEVELS - 1; level >= 0; --level) {
         if (p.iters[level] == 0) continue;
@@ -330,55 +343,30 @@ icp_frame_kernel(const IcpFrameParams p)
                 s_red[wid][lane] = v;
             }
             __syncthreads();
-            // Exchange: every CTA publishes its 29 partial sums as 8-byte {value, tag} words (one store each, so value and tag can
-            // never be seen torn) followed by a 4-byte "ready" tag.  Warp 0 of every CTA polls the G ready tags (a few hundred
-            // bytes per round), then all threads read the data words and check their tags (a word whose tag is not there yet is
-            // simply re-read).  Data and flag travel together, so there is no atomic counter and no __threadfence.  Buffers
-            // alternate with the iteration parity, which is enough because a CTA cannot publish iteration it+2 before every CTA
-            // has published it+1, i.e. has finished reading iteration it.
-            unsigned long long* part = reinterpret_cast<unsigned long long*>(p.partials) + (size_t)(it & 1) * 33 * G;
-            volatile unsigned int* ready = reinterpret_cast<volatile unsigned int*>(part + (size_t)32 * G);
-            const unsigned int tag = p.bar_base + (unsigned int)it + 1u;
+            float* part = p.partials + (size_t)(it & 1) * 32 * G;
             if (tid < NSUM) {
                 float v = 0.f;
 #pragma unroll
                 for (int w = 0; w < FRAME_THREADS / 32; ++w) v += s_red[w][tid];
-                const unsigned long long word = ((unsigned long long)tag << 32) | (unsigned long long)__float_as_uint(v);
-                *reinterpret_cast<volatile unsigned long long*>(&part[(size_t)tid * G + blockIdx.x]) = word;
+                part[(size_t)tid * G + blockIdx.x] = v;
             }
-            __syncwarp();
-            if (tid == 0) ready[blockIdx.x] = tag;
+            target += (unsigned int)G;
             if (prof) p.prof[it * 5 + 1] = clock64();
-            if (wid == 0) {
-                for (int b = lane; b < G; b += 32) while (ready[b] != tag) { }
-            }
-            __syncthreads();
+            grid_barrier(p.bar, target);
             if (prof) p.prof[it * 5 + 2] = clock64();
-            // every CTA: fixed-order total of the G partials of each component (16 lanes per component, polls issued together)
+            // every CTA: fixed-order total of the G partials of each component (16 lanes per component, loads issued together)
             {
                 const int comp = tid >> 4, sub = tid & 15;
-                unsigned long long e[10];
-#pragma unroll
-                for (int q = 0; q < 10; ++q) {                          // all loads in flight together (L2, bypassing L1)
-                    const int b = sub + 16 * q;
-                    e[q] = (comp < NSUM && b < G) ? __ldcg(&part[(size_t)comp * G + b]) : ((unsigned long long)tag << 32);
-                }
-                float v = 0.f;
+                float x[10];
 #pragma unroll
                 for (int q = 0; q < 10; ++q) {
                     const int b = sub + 16 * q;
-                    while ((unsigned int)(e[q] >> 32) != tag)               // rare: the ready tag overtook this data word
-                        e[q] = *reinterpret_cast<const volatile unsigned long long*>(&part[(size_t)comp * G + b]);
-                    v += __uint_as_float((unsigned int)e[q]);
+                    x[q] = (comp < NSUM && b < G) ? __ldcg(&part[(size_t)comp * G + b]) : 0.f;
                 }
-                for (int b = sub + 160; b < G; b += 16) {
-                    if (comp < NSUM) {
-                        const volatile unsigned long long* src = reinterpret_cast<const volatile unsigned long long*>(&part[(size_t)comp * G + b]);
-                        unsigned long long w = *src;
-                        while ((unsigned int)(w >> 32) != tag) w = *src;
-                        v += __uint_as_float((unsigned int)w);
-                    }
-                }
+                float v = 0.f;
+#pragma unroll
+                for (int q = 0; q < 10; ++q) v += x[q];
+                for (int b = sub + 160; b < G; b += 16) v += (comp < NSUM) ? __ldcg(&part[(size_t)comp * G + b]) : 0.f;
                 v += __shfl_xor_sync(0xffffffffu, v, 8);
                 v += __shfl_xor_sync(0xffffffffu, v, 4);
                 v += __shfl_xor_sync(0xffffffffu, v, 2);
@@ -484,7 +472,7 @@ int icp_frame(const IcpLevelArgs* levels, const int* iters, const float* pose12_
     for (int k = 0; k < 12; ++k) p.pose12[k] = pose12_host[k];
     p.st = state; p.partials = partials; p.trace = trace; p.bar = bar_dev; p.bar_base = *bar_count;
     int grid = sm_count();
-    if (grid * 32 * 2 * 2 > MAX_PARTIALS * 32) grid = MAX_PARTIALS / 4;          // 8-byte words, two buffers
+    if (grid * 32 * 2 > MAX_PARTIALS * 32) grid = MAX_PARTIALS / 2;
     // shared-memory stage for the current maps: 6 planes x stage_k chunks x 2 KB, sized for the largest level in use
     int need_k = 0;
     for (int l = 0; l < LEVELS; ++l)
@@ -502,7 +490,7 @@ int icp_frame(const IcpLevelArgs* levels, const int* iters, const float* pose12_
     cudaError_t e = cudaLaunchCooperativeKernel((const void*)icp_frame_kernel, dim3(grid), dim3(FRAME_THREADS), args, can_stage ? stage_bytes : 0, s);
     ++g_launches;
     if (e != cudaSuccess) return cuda_check(e, "cudaLaunchCooperativeKernel(icp_frame_kernel)", __FILE__, __LINE__);
-    *bar_count += (unsigned int)total;
+    *bar_count += (unsigned int)(grid * total);
     return 0;
 }
 
