@@ -48,6 +48,14 @@ __device__ __forceinline__ float fetch(const ExtractParams& p, int x, int y, int
     return tsdf;
 }
 
+// (V * |Fn| + Vn * |F|) * d_inv with the contraction the reference build has (extract.cu:155, checked in its SASS:
+// FMUL V*|Fn|; FFMA |F|*Vn + that; FMUL by the reciprocal).  Left to the compiler, the choice of which product is fused
+// changes with unrelated edits and moves the point by 1 ulp.
+__device__ __forceinline__ float interp(float V, float Vn, float F, float Fn, float d_inv)
+{
+    return __fmul_rn(__fmaf_rn(fabsf(F), Vn, __fmul_rn(V, fabsf(Fn))), d_inv);
+}
+
 __device__ __forceinline__ void store_point(const ExtractParams& p, unsigned int slot, float x, float y, float z, uchar4 ncol, int W)
 {
     if (slot >= p.capacity) return;
@@ -94,7 +102,7 @@ extract_kernel(const ExtractParams p)
                                 float4 q; q.y = Vc.y; q.z = Vc.z;
                                 float Vnx = Vc.x + p.cell.x;
                                 float d_inv = 1.f / (fabs(F) + fabs(Fn));
-                                q.x = (Vc.x * fabs(Fn) + Vnx * fabs(F)) * d_inv;
+                                q.x = interp(Vc.x, Vnx, F, Fn, d_inv);
                                 pts[local_count] = q; cols[local_count] = cn; ++local_count;
                             }
                     }
@@ -106,7 +114,7 @@ extract_kernel(const ExtractParams p)
                                 float4 q; q.x = Vc.x; q.z = Vc.z;
                                 float Vny = Vc.y + p.cell.y;
                                 float d_inv = 1.f / (fabs(F) + fabs(Fn));
-                                q.y = (Vc.y * fabs(Fn) + Vny * fabs(F)) * d_inv;
+                                q.y = interp(Vc.y, Vny, F, Fn, d_inv);
                                 pts[local_count] = q; cols[local_count] = cn; ++local_count;
                             }
                     }
@@ -118,7 +126,7 @@ extract_kernel(const ExtractParams p)
                                 float4 q; q.x = Vc.x; q.y = Vc.y;
                                 float Vnz = Vc.z + p.cell.z;
                                 float d_inv = 1.f / (fabs(F) + fabs(Fn));
-                                q.z = (Vc.z * fabs(Fn) + Vnz * fabs(F)) * d_inv;
+                                q.z = interp(Vc.z, Vnz, F, Fn, d_inv);
                                 pts[local_count] = q; cols[local_count] = cn; ++local_count;
                             }
                     }
