@@ -240,6 +240,8 @@ def main():
             j = pingpong(i, n)
             if use_host:
                 tracker.process_frame(pin_depth[j].data_ptr(), pin_rgb[j].data_ptr(), i)
+                jn = pingpong(i + 1, n)                      # public-API hint: overlap the next frame's H2D with this frame's fusion
+                tracker.prefetch_frame(pin_depth[jn].data_ptr(), pin_rgb[jn].data_ptr())
             else:
                 tracker.process_frame_device(dev_depth[j], dev_rgb[j], i)
             i += 1

@@ -122,6 +122,10 @@ class Tracker:
         _check(self.lib.kt_process_frame(self.h, _ptr(depth), _ptr(rgb), C.c_uint64(utime), C.byref(p)))
         return p
 
+    def prefetch_frame(self, depth, rgb):
+        """Hint: start the H2D copy of the next frame now (kt_prefetch_frame)."""
+        _check(self.lib.kt_prefetch_frame(self.h, _ptr(depth), _ptr(rgb)))
+
     def process_frame_device(self, depth_dev, rgb_dev, utime: int = 0) -> Pose:
         p = Pose()
         _check(self.lib.kt_process_frame_device(self.h, _ptr(depth_dev), _ptr(rgb_dev), C.c_uint64(utime), C.byref(p)))

@@ -81,6 +81,9 @@ struct kt_ctx {
     // device memory
     int16_t* tsdf; uint8_t* color;
     uint16_t* depth_raw; uint8_t* rgb;
+    // double-buffered inputs: kt_prefetch_frame fills the spare set on a copy stream while the previous frame is still being fused
+    uint16_t* depth_alt; uint8_t* rgb_alt; const void* pf_depth; const void* pf_rgb; bool pf_valid;
+    cudaStream_t stream_copy; cudaEvent_t ev_prefetch, ev_done[2]; int last_parity;
     uint16_t* depths_curr[LEVELS];
     float* vmaps_g_prev[LEVELS]; float* nmaps_g_prev[LEVELS]; float* vmaps_curr[LEVELS]; float* nmaps_curr[LEVELS];
     uint8_t* vmap_curr_color; float* depth_scaled; float* ztable;
@@ -497,6 +500,11 @@ int kt_create(const kt_config* cfg, kt_ctx** out)
         KT_TRY(kt::cuda_check(cudaMallocHost((void**)&c->mg_error_host, sizeof(int)), "pinned", __FILE__, __LINE__)); *c->mg_error_host = 0;
     }
     KT_TRY(dev_alloc(c, &c->depth_raw, P)); KT_TRY(dev_alloc(c, &c->rgb, P * 3));
+    KT_TRY(dev_alloc(c, &c->depth_alt, P)); KT_TRY(dev_alloc(c, &c->rgb_alt, P * 3)); c->pf_valid = false; c->pf_depth = c->pf_rgb = 0;
+    KT_TRY(kt::cuda_check(cudaStreamCreateWithFlags(&c->stream_copy, cudaStreamNonBlocking), "stream_copy", __FILE__, __LINE__));
+    KT_TRY(kt::cuda_check(cudaEventCreateWithFlags(&c->ev_prefetch, cudaEventDisableTiming), "event", __FILE__, __LINE__));
+    for (int i = 0; i < 2; ++i) KT_TRY(kt::cuda_check(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming), "event", __FILE__, __LINE__));
+    c->last_parity = 0;
     for (int l = 0; l < LEVELS; ++l) {
         size_t Pl = P >> (2 * l);
         KT_TRY(dev_alloc(c, &c->depths_curr[l], Pl));
@@ -546,6 +554,9 @@ int kt_destroy(kt_ctx* c)
     if (c->counter_host) cudaFreeHost(c->counter_host);
     for (int i = 0; i < 7; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
+    if (c->stream_copy) { cudaStreamSynchronize(c->stream_copy); cudaStreamDestroy(c->stream_copy); }
+    if (c->ev_prefetch) cudaEventDestroy(c->ev_prefetch);
+    for (int i = 0; i < 2; ++i) if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
     if (c->ev_input) cudaEventDestroy(c->ev_input);
     if (c->ev_scaled) cudaEventDestroy(c->ev_scaled);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -568,9 +579,34 @@ int kt_process_frame(kt_ctx* c, const uint16_t* depth_host, const uint8_t* rgb_h
     if (!c || !depth_host || !rgb_host) { set_error("kt_process_frame: null argument"); return KT_ERR_INVALID; }
     KT_CUDA(cudaSetDevice(c->cfg.device));
     const size_t P = (size_t)c->cfg.rows * c->cfg.cols;
-    KT_CUDA(cudaMemcpyAsync(c->depth_raw, depth_host, P * 2, cudaMemcpyHostToDevice, c->stream));   // TrackerInterface.cpp:90
-    KT_CUDA(cudaMemcpyAsync(c->rgb, rgb_host, P * 3, cudaMemcpyHostToDevice, c->stream));           // TrackerInterface.cpp:91
-    return process_frame_device(c, utime, out);
+    if (c->pf_valid && c->pf_depth == depth_host && c->pf_rgb == rgb_host) {
+        // the frame was prefetched into the spare input set: swap the sets and make the compute stream wait for the copy
+        std::swap(c->depth_raw, c->depth_alt); std::swap(c->rgb, c->rgb_alt);
+        KT_CUDA(cudaStreamWaitEvent(c->stream, c->ev_prefetch, 0));
+        c->pf_valid = false;
+    } else {
+        KT_CUDA(cudaMemcpyAsync(c->depth_raw, depth_host, P * 2, cudaMemcpyHostToDevice, c->stream));   // TrackerInterface.cpp:90
+        KT_CUDA(cudaMemcpyAsync(c->rgb, rgb_host, P * 3, cudaMemcpyHostToDevice, c->stream));           // TrackerInterface.cpp:91
+    }
+    int r = process_frame_device(c, utime, out);
+    c->last_parity ^= 1;
+    cudaEventRecord(c->ev_done[c->last_parity], c->stream);      // completion of this frame's last kernel
+    return r;
+}
+
+int kt_prefetch_frame(kt_ctx* c, const uint16_t* depth_host, const uint8_t* rgb_host)
+{
+    if (!c || !depth_host || !rgb_host) { set_error("kt_prefetch_frame: null argument"); return KT_ERR_INVALID; }
+    KT_CUDA(cudaSetDevice(c->cfg.device));
+    const size_t P = (size_t)c->cfg.rows * c->cfg.cols;
+    // the spare input set was read by the frame BEFORE the last one; wait for that frame's completion event only, so the copy
+    // overlaps the last frame's integrate / ray-cast
+    KT_CUDA(cudaStreamWaitEvent(c->stream_copy, c->ev_done[c->last_parity ^ 1], 0));
+    KT_CUDA(cudaMemcpyAsync(c->depth_alt, depth_host, P * 2, cudaMemcpyHostToDevice, c->stream_copy));
+    KT_CUDA(cudaMemcpyAsync(c->rgb_alt, rgb_host, P * 3, cudaMemcpyHostToDevice, c->stream_copy));
+    KT_CUDA(cudaEventRecord(c->ev_prefetch, c->stream_copy));
+    c->pf_depth = depth_host; c->pf_rgb = rgb_host; c->pf_valid = true;
+    return KT_OK;
 }
 
 int kt_finalise(kt_ctx* c)                                                                           // KintinuousTracker::finalise (.cpp:1003-1048)

@@ -154,3 +154,21 @@ def test_full_size_properties_512(built, frames):
         ops.clear_volume(2, 0, ts, cs, V, wrap[2], wrap[2] + 500)                                # logical z planes [0, 500]
         assert ops.extract_slice(ts, vs, V, out, cap, wrap, cs, (0, V, 0, V, 0, 499), 1, (0, 0, 0)) == 0
     assert results[0] == results[1]                                                              # cyclic offset changes storage, not content
+
+
+def test_prefetch_hint_does_not_change_results(built, frames):
+    """kt_prefetch_frame only moves the H2D copy earlier (double-buffered inputs on a copy stream)."""
+    import torch
+    import kintinuous_b200 as kb
+    pd = [torch.from_numpy(f[0].view(np.int16)).pin_memory() for f in frames[:6]]
+    pc = [torch.from_numpy(f[1]).pin_memory() for f in frames[:6]]
+    a = kb.Tracker(kb.Config.default(vol=256)); b = kb.Tracker(kb.Config.default(vol=256))
+    for k in range(6):
+        pa = a.process_frame(frames[k][0], frames[k][1], k)
+        pb = b.process_frame(pd[k].data_ptr(), pc[k].data_ptr(), k)
+        if k + 1 < 6:
+            b.prefetch_frame(pd[k + 1].data_ptr(), pc[k + 1].data_ptr())
+        assert list(pa.t) == list(pb.t) and list(pa.R) == list(pb.R)
+    ta, ca = a.export_volume(); tb, cb = b.export_volume()
+    assert (ta == tb).all() and (ca == cb).all()
+    a.close(); b.close()
