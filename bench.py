@@ -154,22 +154,22 @@ def run_reference(args, world, rank, local):
         return
     from oracle import refbind
     import kintinuous_b200 as kb
-    cfg = kb.Config.default(rows=ROWS, cols=COLS, vol=VOL, odometry=0)
+    cfg = kb.Config.default(rows=ROWS, cols=COLS, vol=args.vol, odometry=args.odometry)
     n_frames = min(N_INPUT_FRAMES, max(8, args.steps + args.warmup + 1))
     frames = make_stream(n_frames)
-    line = {"metric": "frames/s 640x480 into 512^3 TSDF (ICP-only tracker)", "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+    line = {"metric": f"frames/s 640x480 into {args.vol}^3 TSDF ({'ICP-only' if args.odometry == 0 else 'ICP+RGB-D'} tracker)", "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
             "config": {"workload": "synthetic 640x480 RGB-D stream, 512^3 volume (6 m), ICP-only tracker {10,5,4}, shifting on", "frames_cycled": n_frames}}
     use_cuda = False
     try:
         import torch
-        use_cuda = torch.cuda.is_available() and refbind.RefCuda.available(VOL)
+        use_cuda = torch.cuda.is_available() and refbind.RefCuda.available(args.vol)
     except Exception:
         use_cuda = False
     if use_cuda:
         import torch
         torch.cuda.set_device(0)
-        ref = refbind.RefCuda(VOL)
+        ref = refbind.RefCuda(args.vol)
         t = ref.tracker(refbind.TrackerConfig.from_kt(cfg))
         sync = torch.cuda.synchronize
         kind, cores = "reference", 1
