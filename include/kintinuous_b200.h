@@ -122,6 +122,8 @@ KT_API int kt_download_map(kt_ctx* ctx, int which, int level, void* dst_host);
 /* Stage timers (CUDA events) of the last frame, milliseconds: pyramid, odometry, shift, integrate, raycast, total. */
 KT_API int kt_get_stage_ms(kt_ctx* ctx, float* ms6);
 KT_API int kt_set_stage_timing(kt_ctx* ctx, int enabled);
+/* CUDA-event duration of the last whole-frame ICP launch (icp_frame_kernel), ms; 0 unless stage timing is on and odometry == 0 */
+KT_API float kt_get_icp_kernel_ms(kt_ctx* ctx);
 /* number of kernels this library launched since kt_create (for bench.py's gpu_launches) */
 /* ---- z-slab sharding of ONE volume over `world` GPUs, one process per GPU (no counterpart in the reference) ----
  * Every rank creates its context with kt_config.rank / world, exports the CUDA-IPC handle (64 bytes) of its shared arena

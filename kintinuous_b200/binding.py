@@ -31,6 +31,7 @@ def load():
     lib.kt_get_voxel_size.restype = C.c_float
     lib.kt_get_trunc_dist.restype = C.c_float
     lib.kt_launch_count.restype = C.c_longlong
+    lib.kt_get_icp_kernel_ms.restype = C.c_float
     _LIB = lib
     return lib
 
@@ -192,6 +193,9 @@ class Tracker:
 
     def launch_count(self):
         return int(self.lib.kt_launch_count(self.h))
+
+    def icp_kernel_ms(self):
+        return float(self.lib.kt_get_icp_kernel_ms(self.h))
 
     # ---- z-slab sharding (one process per GPU) ----
     def mgpu_arena_handle(self) -> bytes:

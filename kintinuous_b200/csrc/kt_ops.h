@@ -81,6 +81,8 @@ struct RgbLevelArgs {
 // use_state_warp 1: (K R K^-1, K t) rebuilt on the device from state->resultRt; 0: taken from state->krkinv / kt
 int rgb_residual(const RgbLevelArgs& a, OdomState* state, int* partials, int use_state_warp, cudaStream_t s);
 // mode 0: reduce only; 1: solve RGB-only; 2: solve A_rgb + 100 A_icp (RGBDOdometry.cpp:316-321)
+int rgbd_frame(const IcpLevelArgs* icp_levels, const RgbLevelArgs* rgb_levels, const int* iters, int with_icp, const float* pose12_host, OdomState* state,
+               float* partials, float* trace, unsigned int* bar_dev, unsigned int* bar_count, cudaStream_t s);
 int rgb_iteration(const RgbLevelArgs& a, OdomState* state, float* partials, float* trace, int mode, float sigma_override, cudaStream_t s);
 // pose12_dev: Rprev (9) + tprev (3) in device memory
 int odom_begin_frame(OdomState* state, const float* pose12_dev, cudaStream_t s);

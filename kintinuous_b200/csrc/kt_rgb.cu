@@ -18,6 +18,7 @@
 #include "kt_ops.h"
 #include "kt_solve.cuh"
 #include "kt_reduce.cuh"
+#include "kt_frame.cuh"
 
 namespace kt {
 
@@ -133,9 +134,8 @@ struct DataTerm { short2 zero; short2 one; float diff; bool valid; };
 struct ResidualParams { RgbLevelArgs a; OdomState* st; int* partials; };
 
 // (K R K^-1, K t) from the inverse of the running estimate (RGBDOdometry.cpp:209-231), double then float.
-__device__ inline void build_warp(const OdomState* st, double fx, double fy, double cx, double cy, float* krkinv, float* kt)
+__device__ inline void build_warp_T(const double* T, double fx, double fy, double cx, double cy, float* krkinv, float* kt)
 {
-    const double* T = st->resultRt;
     double R[9], t[3];
     for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) R[i * 3 + j] = T[j * 4 + i];          // R^T
     for (int i = 0; i < 3; ++i) t[i] = -(R[i * 3 + 0] * T[3] + R[i * 3 + 1] * T[7] + R[i * 3 + 2] * T[11]);
@@ -145,6 +145,11 @@ __device__ inline void build_warp(const OdomState* st, double fx, double fy, dou
     for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) { double s = 0; for (int k = 0; k < 3; ++k) s += K[a * 3 + k] * R[k * 3 + b]; KR[a * 3 + b] = s; }
     for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) { double s = 0; for (int k = 0; k < 3; ++k) s += KR[a * 3 + k] * Ki[k * 3 + b]; krkinv[a * 3 + b] = (float)s; }
     for (int a = 0; a < 3; ++a) { double s = 0; for (int k = 0; k < 3; ++k) s += K[a * 3 + k] * t[k]; kt[a] = (float)s; }
+}
+
+__device__ inline void build_warp(const OdomState* st, double fx, double fy, double cx, double cy, float* krkinv, float* kt)
+{
+    build_warp_T(st->resultRt, fx, fy, cx, cy, krkinv, kt);
 }
 
 __global__ void __launch_bounds__(RED_THREADS)
@@ -310,6 +315,296 @@ rgb_step_kernel(const RgbStepParams p)
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Whole-frame RGB-D odometry (-r) and combined ICP + RGB-D (-ri): all levels and iterations in ONE cooperative launch,
+// the photometric twin of icp_frame_kernel (kt_icp.cu).  Per level, once: the pose-independent part of the residual test
+// (4x4 neighbourhood of the next image, gradient magnitude, depth validity: reduce.cu:709-733) and the pixel's depth /
+// gradients / intensity are staged per thread in shared memory.  Per iteration:
+//   pass A  correspondence + photometric residual per pixel (reduce.cu:735-764), kept in REGISTERS for pass B (the
+//           reference writes and re-reads a 16-byte DataTerm image); with -ri the point-to-plane sums of the same
+//           pixels are accumulated in the same pass;          -> grid barrier 1: count, sigma^2 (+ 29 ICP sums)
+//   pass B  Jacobian rows with the robust weight 1/(sigma + |diff|) (reduce.cu:443-480); the last-frame point is
+//           rebuilt from its depth (maps.cu:311-329 arithmetic) instead of reading a float3 cloud
+//                                                               -> grid barrier 2: 29 sums, FP64 solve in every CTA.
+struct RgbdFrameParams {
+    IcpLevelArgs icp[LEVELS];
+    RgbLevelArgs rgb[LEVELS];
+    int iters[LEVELS];
+    float pose12[12];
+    OdomState* st;
+    float* partials;           // [2][64][grid]
+    float* trace;
+    unsigned int* bar; unsigned int bar_base;
+    int stage_k;               // chunks of FRAME_THREADS pixels per CTA (<= RGBD_MAX_K)
+    int with_icp;
+};
+
+enum { RGBD_MAX_K = 5 };
+
+template <bool WITH_ICP>
+__global__ void __launch_bounds__(FRAME_THREADS, 1)
+rgbd_frame_kernel(const RgbdFrameParams p)
+{
+    extern __shared__ __align__(128) float s_dyn[];
+    // dynamic smem: [ICP stage: 6 x K x 512 floats (WITH_ICP)] [d1: K x 512 floats] [grad: K x 512 x short2] [meta: K x 512 x uint]
+    __shared__ float s_Rp[9], s_tp[3], s_Rpi[9], s_R[9], s_t[3], s_w[12];
+    __shared__ double s_Rt[16];
+    __shared__ float s_red[FRAME_THREADS / 32][32];
+    __shared__ float s_sum[32], s_sum_icp[32];
+    __shared__ int s_cnt[FRAME_THREADS / 32][2];
+    __shared__ int s_tot[2];
+    __shared__ __align__(8) unsigned long long s_mbar;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int G = gridDim.x, K = p.stage_k;
+    float* s_stage = s_dyn;
+    float* s_d1 = s_dyn + (WITH_ICP ? (size_t)6 * K * FRAME_THREADS : 0);
+    short2* s_grad = reinterpret_cast<short2*>(s_d1 + (size_t)K * FRAME_THREADS);
+    unsigned int* s_meta = reinterpret_cast<unsigned int*>(s_grad + (size_t)K * FRAME_THREADS);       // bit 0: precheck, bits 8..15: I_next
+
+    if (tid == 0) {
+        for (int k = 0; k < 9; ++k) { s_Rp[k] = p.pose12[k]; s_R[k] = p.pose12[k]; }
+        for (int k = 0; k < 3; ++k) { s_tp[k] = p.pose12[9 + k]; s_t[k] = p.pose12[9 + k]; }
+        mat3f_inverse(s_Rp, s_Rpi);
+        for (int k = 0; k < 16; ++k) s_Rt[k] = (k % 5 == 0) ? 1.0 : 0.0;
+        mbar_init(&s_mbar, 1);
+    }
+    __syncthreads();
+    Mat33 Rprev_inv; float3 tprev;
+    Rprev_inv.r0 = make_float3(s_Rpi[0], s_Rpi[1], s_Rpi[2]); Rprev_inv.r1 = make_float3(s_Rpi[3], s_Rpi[4], s_Rpi[5]); Rprev_inv.r2 = make_float3(s_Rpi[6], s_Rpi[7], s_Rpi[8]);
+    tprev = make_float3(s_tp[0], s_tp[1], s_tp[2]);
+
+    int it = 0;
+    unsigned int target = p.bar_base;
+    unsigned int stage_parity = 0;
+    for (int level = LEVELS - 1; level >= 0; --level) {
+        if (p.iters[level] == 0) continue;
+        const RgbLevelArgs& a = p.rgb[level];
+        const int cols = a.cols, rows = a.rows, N = cols * rows;
+        const int n_chunks = (N + G * FRAME_THREADS - 1) / (G * FRAME_THREADS);
+        const float* __restrict__ lastDepth = a.last_depth;
+        const uint8_t* __restrict__ lastImage = a.last_image;
+        const float maxDepthDelta = a.max_depth_delta, fx = a.fx, fy = a.fy, sobelScale = a.sobel_scale;
+        const double invFx = 1.0f / a.Kfx, invFy = 1.0f / a.Kfy, dcx = a.Kcx, dcy = a.Kcy;      // projectToPointCloud (maps.cu:342)
+        // ---- per-level staging ----
+        __syncthreads();
+        if (WITH_ICP && tid == 0) {
+            const IcpLevelArgs& ia = p.icp[level];
+            unsigned int total = 0;
+            for (int k = 0; k < n_chunks; ++k) { const int i0 = (k * G + blockIdx.x) * FRAME_THREADS; if (i0 < N) total += (unsigned int)(min(FRAME_THREADS, N - i0) * 4) * 6u; }
+            mbar_expect_tx(&s_mbar, total);
+            for (int k = 0; k < n_chunks; ++k) {
+                const int i0 = (k * G + blockIdx.x) * FRAME_THREADS;
+                if (i0 >= N) continue;
+                const unsigned int bytes = (unsigned int)(min(FRAME_THREADS, N - i0) * 4);
+#pragma unroll
+                for (int pl = 0; pl < 3; ++pl) {
+                    tma_bulk_g2s(&s_stage[((pl) * K + k) * FRAME_THREADS], ia.vmap_curr + (size_t)pl * N + i0, bytes, &s_mbar);
+                    tma_bulk_g2s(&s_stage[((3 + pl) * K + k) * FRAME_THREADS], ia.nmap_curr + (size_t)pl * N + i0, bytes, &s_mbar);
+                }
+            }
+        }
+        for (int k = 0; k < n_chunks; ++k) {
+            const int idx = (k * G + blockIdx.x) * FRAME_THREADS + tid;
+            const int o = k * FRAME_THREADS + tid;
+            unsigned int meta = 0; float d1 = 0.f; short2 gr = make_short2(0, 0);
+            if (idx < N) {
+                const int i = idx / cols, j0 = idx - i * cols;
+                if (j0 < cols - 5 && i < rows - 1) {
+                    bool valid = true;
+                    for (int u = max(i - 2, 0); u < min(i + 2, rows); u++)
+                        for (int v = max(j0 - 2, 0); v < min(j0 + 2, cols); v++)
+                            valid = valid && (a.next_image[(size_t)u * cols + v] > 0);
+                    if (valid) {
+                        gr.x = a.dIdx[idx]; gr.y = a.dIdy[idx];
+                        float mTwo = (gr.x * gr.x) + (gr.y * gr.y);
+                        if (mTwo >= a.min_scale) {
+                            d1 = a.next_depth[idx];
+                            if (!isnan(d1)) meta = 1u | ((unsigned int)a.next_image[idx] << 8);
+                        }
+                    }
+                }
+            }
+            s_meta[o] = meta; s_d1[o] = d1; s_grad[o] = gr;
+        }
+        if (WITH_ICP) { mbar_wait(&s_mbar, stage_parity); stage_parity ^= 1u; }
+        __syncthreads();
+
+        for (int iter = 0; iter < p.iters[level]; ++iter, ++it) {
+            // warp of this iteration from the running estimate (RGBDOdometry.cpp:209-231)
+            if (tid == 0) build_warp_T(s_Rt, a.Kfx, a.Kfy, a.Kcx, a.Kcy, s_w, s_w + 9);
+            __syncthreads();
+            const float k00 = s_w[0], k01 = s_w[1], k02 = s_w[2], k10 = s_w[3], k11 = s_w[4], k12 = s_w[5], k20 = s_w[6], k21 = s_w[7], k22 = s_w[8];
+            const float3 kt = make_float3(s_w[9], s_w[10], s_w[11]);
+            Mat33 Rcurr; float3 tcurr;
+            Rcurr.r0 = make_float3(s_R[0], s_R[1], s_R[2]); Rcurr.r1 = make_float3(s_R[3], s_R[4], s_R[5]); Rcurr.r2 = make_float3(s_R[6], s_R[7], s_R[8]);
+            tcurr = make_float3(s_t[0], s_t[1], s_t[2]);
+
+            // ---------------- pass A ----------------
+            float sum[32];
+#pragma unroll
+            for (int k = 0; k < 32; ++k) sum[k] = 0.f;
+            int cnt = 0, sig = 0;
+            int cu0[RGBD_MAX_K], cv0[RGBD_MAX_K]; float cdiff[RGBD_MAX_K], cd0[RGBD_MAX_K]; bool cval[RGBD_MAX_K];
+#pragma unroll
+            for (int k = 0; k < RGBD_MAX_K; ++k) {
+                cval[k] = false; cu0[k] = 0; cv0[k] = 0; cdiff[k] = 0.f; cd0[k] = 0.f;
+                if (k < n_chunks) {
+                    const int idx = (k * G + blockIdx.x) * FRAME_THREADS + tid;
+                    const int o = k * FRAME_THREADS + tid;
+                    if (idx < N) {
+                        const unsigned int meta = s_meta[o];
+                        if (meta & 1u) {
+                            const int y = idx / cols, x = idx - y * cols;
+                            const float d1 = s_d1[o];
+                            float transformed_d1 = (float)(d1 * (k20 * x + k21 * y + k22) + kt.z);
+                            int u0 = __float2int_rn((d1 * (k00 * x + k01 * y + k02) + kt.x) / transformed_d1);
+                            int v0 = __float2int_rn((d1 * (k10 * x + k11 * y + k12) + kt.y) / transformed_d1);
+                            if (u0 >= 0 && v0 >= 0 && u0 < cols && v0 < rows) {
+                                float d0 = __ldg(&lastDepth[(size_t)v0 * cols + u0]);
+                                const unsigned int il = __ldg(&lastImage[(size_t)v0 * cols + u0]);
+                                if (d0 > 0 && fabsf(transformed_d1 - d0) <= maxDepthDelta && il != 0) {
+                                    const float diff = static_cast<float>((meta >> 8) & 0xffu) - static_cast<float>(il);
+                                    cval[k] = true; cu0[k] = u0; cv0[k] = v0; cdiff[k] = diff; cd0[k] = d0;
+                                    cnt += 1; sig += (int)(diff * diff);
+                                }
+                            }
+                        }
+                        if (WITH_ICP) {
+                            const IcpLevelArgs& ia = p.icp[level];
+                            const int ps = K * FRAME_THREADS;
+                            const float3 vc = make_float3(s_stage[o], s_stage[ps + o], s_stage[2 * ps + o]);
+                            const float3 nc = make_float3(s_stage[3 * ps + o], s_stage[4 * ps + o], s_stage[5 * ps + o]);
+                            icp_pixel_staged(vc, nc, N, cols, rows, ia.vmap_g_prev, ia.nmap_g_prev, ia.k, Rcurr, tcurr, Rprev_inv, tprev, ia.dist_thres, ia.angle_thres, sum);
+                        }
+                    }
+                }
+            }
+            // reduce pass A: ints (count, sigma) and, with ICP, the 29 float sums
+            for (int o = 16; o > 0; o >>= 1) { cnt += __shfl_down_sync(0xffffffffu, cnt, o); sig += __shfl_down_sync(0xffffffffu, sig, o); }
+            if (lane == 0) { s_cnt[wid][0] = cnt; s_cnt[wid][1] = sig; }
+            if (WITH_ICP) { const float v = warp_transpose_sum(sum, lane); s_red[wid][lane] = v; }
+            __syncthreads();
+            float* partA = p.partials + (size_t)(it & 1) * 64 * G;             // rows 0..31: ICP floats, 32..33: count / sigma (as int bits)
+            if (WITH_ICP && tid < NSUM) {
+                float v = 0.f;
+#pragma unroll
+                for (int w = 0; w < FRAME_THREADS / 32; ++w) v += s_red[w][tid];
+                partA[(size_t)tid * G + blockIdx.x] = v;
+            }
+            if (tid == 32) { int c = 0; for (int w = 0; w < FRAME_THREADS / 32; ++w) c += s_cnt[w][0]; partA[(size_t)32 * G + blockIdx.x] = __int_as_float(c); }
+            if (tid == 33) { int c = 0; for (int w = 0; w < FRAME_THREADS / 32; ++w) c += s_cnt[w][1]; partA[(size_t)33 * G + blockIdx.x] = __int_as_float(c); }
+            target += (unsigned int)G;
+            grid_barrier(p.bar, target);
+            {
+                const int comp = tid >> 4, sub = tid & 15;
+                if (comp < 32) {
+                    float v = 0.f;
+                    if (WITH_ICP && comp < NSUM) for (int b = sub; b < G; b += 16) v += __ldcg(&partA[(size_t)comp * G + b]);
+                    v += __shfl_xor_sync(0xffffffffu, v, 8); v += __shfl_xor_sync(0xffffffffu, v, 4);
+                    v += __shfl_xor_sync(0xffffffffu, v, 2); v += __shfl_xor_sync(0xffffffffu, v, 1);
+                    if (sub == 0) s_sum_icp[comp] = v;
+                }
+                if (wid == 0) {       // integer totals (order-independent)
+                    int c = 0, g2 = 0;
+                    for (int b = lane; b < G; b += 32) { c += __float_as_int(__ldcg(&partA[(size_t)32 * G + b])); g2 += __float_as_int(__ldcg(&partA[(size_t)33 * G + b])); }
+                    for (int o = 16; o > 0; o >>= 1) { c += __shfl_down_sync(0xffffffffu, c, o); g2 += __shfl_down_sync(0xffffffffu, g2, o); }
+                    if (lane == 0) { s_tot[0] = c; s_tot[1] = g2; }
+                }
+            }
+            __syncthreads();
+            // Q3: sigmaVal = sqrt((float)sigma / rgbSize == 0 ? 1 : rgbSize)   (RGBDOdometry.cpp:253)
+            const int rgb_count = s_tot[0], rgb_sigma = s_tot[1];
+            const float sigma = (float)sqrt((double)(((float)rgb_sigma / rgb_count == 0) ? 1 : rgb_count));
+
+            // ---------------- pass B ----------------
+#pragma unroll
+            for (int k = 0; k < 32; ++k) sum[k] = 0.f;
+#pragma unroll
+            for (int k = 0; k < RGBD_MAX_K; ++k) {
+                if (k < n_chunks && cval[k]) {
+                    const int o = k * FRAME_THREADS + tid;
+                    const float diff = cdiff[k];
+                    float w = sigma + fabsf(diff);
+                    w = w > 1.19209290E-07F ? 1.0f / w : 1.0f;
+                    if (sigma == -1) w = 1;
+                    float row[7];
+                    row[6] = -w * diff;
+                    const float z = cd0[k];
+                    float3 cloudPoint;
+                    cloudPoint.x = (float)((cu0[k] - dcx) * z * invFx);
+                    cloudPoint.y = (float)((cv0[k] - dcy) * z * invFy);
+                    cloudPoint.z = z;
+                    float invz = 1.0 / cloudPoint.z;
+                    const short2 gr = s_grad[o];
+                    float dI_dx_val = w * sobelScale * gr.x;
+                    float dI_dy_val = w * sobelScale * gr.y;
+                    float v0 = dI_dx_val * fx * invz;
+                    float v1 = dI_dy_val * fy * invz;
+                    float v2 = -(v0 * cloudPoint.x + v1 * cloudPoint.y) * invz;
+                    row[0] = v0; row[1] = v1; row[2] = v2;
+                    row[3] = -cloudPoint.z * v1 + cloudPoint.y * v2;
+                    row[4] = cloudPoint.z * v0 - cloudPoint.x * v2;
+                    row[5] = -cloudPoint.y * v0 + cloudPoint.x * v1;
+                    int q = 0;
+#pragma unroll
+                    for (int aa = 0; aa < 6; ++aa)
+#pragma unroll
+                        for (int bb = aa; bb < 7; ++bb) sum[q++] += row[aa] * row[bb];
+                    sum[27] += row[6] * row[6];
+                    sum[28] += 1.f;
+                }
+            }
+            { const float v = warp_transpose_sum(sum, lane); s_red[wid][lane] = v; }
+            __syncthreads();
+            float* partB = partA + (size_t)34 * G;
+            if (tid < NSUM) {
+                float v = 0.f;
+#pragma unroll
+                for (int w = 0; w < FRAME_THREADS / 32; ++w) v += s_red[w][tid];
+                partB[(size_t)tid * G + blockIdx.x] = v;
+            }
+            target += (unsigned int)G;
+            grid_barrier(p.bar, target);
+            {
+                const int comp = tid >> 4, sub = tid & 15;
+                float v = 0.f;
+                if (comp < NSUM) for (int b = sub; b < G; b += 16) v += __ldcg(&partB[(size_t)comp * G + b]);
+                v += __shfl_xor_sync(0xffffffffu, v, 8); v += __shfl_xor_sync(0xffffffffu, v, 4);
+                v += __shfl_xor_sync(0xffffffffu, v, 2); v += __shfl_xor_sync(0xffffffffu, v, 1);
+                if (sub == 0 && comp < NSUM) s_sum[comp] = v;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                float A[36], b[6];
+                unpack_normal_equations(s_sum, A, b);
+                if (p.trace && blockIdx.x == 0 && it < 64) {
+                    float* t = p.trace + (size_t)it * TRACE_STRIDE;
+                    for (int k = 0; k < 36; ++k) t[k] = A[k];
+                    for (int k = 0; k < 6; ++k) t[36 + k] = b[k];
+                    t[42] = (float)rgb_sigma; t[43] = (float)rgb_count;
+                }
+                double dA[36], db[6];
+                if (WITH_ICP) {                                         // RGBDOdometry.cpp:316-321
+                    float Ai[36], bi[6];
+                    unpack_normal_equations(s_sum_icp, Ai, bi);
+                    const double w = 10;
+                    for (int k = 0; k < 36; ++k) dA[k] = (double)A[k] + w * w * (double)Ai[k];
+                    for (int k = 0; k < 6; ++k) db[k] = (double)b[k] + w * (double)bi[k];
+                } else {
+                    for (int k = 0; k < 36; ++k) dA[k] = A[k];
+                    for (int k = 0; k < 6; ++k) db[k] = b[k];
+                }
+                gauss_newton_update_p(dA, db, s_Rt, s_Rp, s_tp, s_R, s_t);
+            }
+            __syncthreads();
+        }
+    }
+    if (blockIdx.x == 0 && tid < 12) {
+        if (tid < 9) p.st->Rcurr[tid] = s_R[tid]; else p.st->tcurr[tid - 9] = s_t[tid - 9];
+        if (tid == 0) p.st->iter = it;
+    }
+}
+
 } // namespace
 
 #define KT_GRID2D(cols, rows) dim3 block(32, 8), grid(div_up(cols, 32), div_up(rows, 8))
@@ -353,6 +648,45 @@ int rgb_iteration(const RgbLevelArgs& a, OdomState* state, float* partials, floa
     int grid = reduce_grid_for(a.rows * a.cols);
     rgb_step_kernel<<<grid, RED_THREADS, 0, s>>>(p);
     KT_LAUNCH_CHECK();
+    return 0;
+}
+
+
+// Whole-frame RGB-D / ICP+RGB-D odometry.  Returns 1 (and launches nothing) when the image does not fit the shared-memory stage,
+// in which case the caller falls back to the per-iteration kernels above.
+int rgbd_frame(const IcpLevelArgs* icp_levels, const RgbLevelArgs* rgb_levels, const int* iters, int with_icp, const float* pose12_host, OdomState* state,
+               float* partials, float* trace, unsigned int* bar_dev, unsigned int* bar_count, cudaStream_t s)
+{
+    RgbdFrameParams p;
+    int total = 0;
+    for (int l = 0; l < LEVELS; ++l) { p.icp[l] = icp_levels[l]; p.rgb[l] = rgb_levels[l]; p.iters[l] = iters[l]; total += iters[l]; }
+    for (int k = 0; k < 12; ++k) p.pose12[k] = pose12_host[k];
+    p.st = state; p.partials = partials; p.trace = trace; p.bar = bar_dev; p.bar_base = *bar_count; p.with_icp = with_icp;
+    int dev = 0, sms = 0, smem_optin = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    int grid = sms > 0 ? sms : 148;
+    if (grid * 64 * 2 > MAX_PARTIALS * 32) grid = MAX_PARTIALS * 32 / 128;
+    int need_k = 0;
+    for (int l = 0; l < LEVELS; ++l)
+        if (iters[l] > 0) { int k = div_up(rgb_levels[l].rows * rgb_levels[l].cols, grid * FRAME_THREADS); if (k > need_k) need_k = k; }
+    if (need_k > RGBD_MAX_K) return 1;
+    const size_t bytes = (size_t)need_k * FRAME_THREADS * ((with_icp ? 6 * 4 : 0) + 12);
+    if (smem_optin <= 0 || bytes > (size_t)(smem_optin - 8192)) return 1;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute((const void*)rgbd_frame_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - 8192);
+        cudaFuncSetAttribute((const void*)rgbd_frame_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - 8192);
+        configured = true;
+    }
+    p.stage_k = need_k;
+    void* args[] = {&p};
+    cudaError_t e = with_icp ? cudaLaunchCooperativeKernel((const void*)rgbd_frame_kernel<true>, dim3(grid), dim3(FRAME_THREADS), args, bytes, s)
+                             : cudaLaunchCooperativeKernel((const void*)rgbd_frame_kernel<false>, dim3(grid), dim3(FRAME_THREADS), args, bytes, s);
+    ++g_launches;
+    if (e != cudaSuccess) return cuda_check(e, "cudaLaunchCooperativeKernel(rgbd_frame_kernel)", __FILE__, __LINE__);
+    *bar_count += (unsigned int)(grid * total * 2);
     return 0;
 }
 

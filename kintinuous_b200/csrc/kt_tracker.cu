@@ -96,7 +96,7 @@ struct kt_ctx {
     float* pose12_host; OdomResult* result_host; float* trace_host; unsigned int* counter_host;
     int trace_iters; int shifted_last;
     // timing
-    bool timing; cudaEvent_t ev[7]; float stage_ms[6];
+    bool timing; cudaEvent_t ev[7]; float stage_ms[6]; cudaEvent_t ev_icp[2];
     long long launches_at_create;
     std::vector<void*> allocs;
     // z-slab sharding over `world` GPUs (one process per GPU; peers' arenas are mapped through CUDA IPC)
@@ -204,14 +204,39 @@ int run_odometry(kt_ctx* c, const M3& Rprev, const V3& tprev, M3* Rcurr, V3* tcu
             la[level] = ia;
             total_iters += c->iterations[level];
         }
+        if (c->timing) cudaEventRecord(c->ev_icp[0], c->stream);
         if ((r = icp_frame(la, c->iterations, c->pose12_host, c->state, c->partials, c->trace_dev, c->bar_dev, &c->bar_count, c->timing ? c->prof_dev : 0, c->stream))) return r;
-    } else {
-    KT_CUDA(cudaMemcpyAsync(c->pose12_dev, c->pose12_host, 12 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    if ((r = odom_begin_frame(c->state, c->pose12_dev, c->stream))) return r;
+        if (c->timing) cudaEventRecord(c->ev_icp[1], c->stream);
     }
     const double SOBEL_SCALE = 1.0 / std::pow(2.0, 3);
     const int minimumGradientMagnitudes[4] = {12, 5, 3, 1};
-    for (int level = LEVELS - 1; level >= 0 && mode != 0; --level) {
+    bool per_iteration_path = (mode != 0);
+    if (mode != 0) {
+        // whole-frame RGB-D / ICP+RGB-D kernel (kt_rgb.cu, rgbd_frame_kernel): ONE cooperative launch for all levels and iterations
+        IcpLevelArgs la[LEVELS]; RgbLevelArgs ra4[LEVELS];
+        for (int level = 0; level < LEVELS; ++level) {
+            const int lr = rows >> level, lc = cols >> level;
+            Intr kl = intr_level(K, level);
+            IcpLevelArgs ia = {c->vmaps_curr[level], c->nmaps_curr[level], c->vmaps_g_prev[level], c->nmaps_g_prev[level], lr, lc, kl, distThres, angleThres};
+            la[level] = ia;
+            const int div = 1 << level;
+            RgbLevelArgs& ra = ra4[level];
+            ra.dIdx = c->nextdIdx[level]; ra.dIdy = c->nextdIdy[level]; ra.last_depth = c->lastDepth[level]; ra.next_depth = c->nextDepth[level];
+            ra.last_image = c->lastImage[level]; ra.next_image = c->nextImage[level]; ra.corres = c->corresImg[level]; ra.cloud = c->pointClouds[level];
+            ra.rows = lr; ra.cols = lc;
+            ra.min_scale = (float)(std::pow((double)minimumGradientMagnitudes[level], 2.0) / std::pow(SOBEL_SCALE, 2.0));
+            ra.max_depth_delta = 0.07f; ra.fx = kl.fx; ra.fy = kl.fy; ra.sobel_scale = (float)SOBEL_SCALE;
+            ra.Kfx = (double)K.fx / div; ra.Kfy = (double)K.fy / div; ra.Kcx = (double)K.cx / div; ra.Kcy = (double)K.cy / div;
+        }
+        r = rgbd_frame(la, ra4, c->iterations, mode == 2 ? 1 : 0, c->pose12_host, c->state, c->partials, c->trace_dev, c->bar_dev, &c->bar_count, c->stream);
+        if (r < 0) return r;
+        if (r == 0) { per_iteration_path = false; for (int level = 0; level < LEVELS; ++level) total_iters += c->iterations[level]; }
+        else {       // image too large for the shared-memory stage: per-iteration kernels
+            KT_CUDA(cudaMemcpyAsync(c->pose12_dev, c->pose12_host, 12 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+            if ((r = odom_begin_frame(c->state, c->pose12_dev, c->stream))) return r;
+        }
+    }
+    for (int level = LEVELS - 1; level >= 0 && per_iteration_path; --level) {
         const int lr = rows >> level, lc = cols >> level;
         Intr kl = intr_level(K, level);
         IcpLevelArgs ia = {c->vmaps_curr[level], c->nmaps_curr[level], c->vmaps_g_prev[level], c->nmaps_g_prev[level], lr, lc, kl, distThres, angleThres};
@@ -533,6 +558,7 @@ int kt_create(const kt_config* cfg, kt_ctx** out)
     KT_TRY(kt::cuda_check(cudaMallocHost((void**)&c->trace_host, (size_t)MAX_TRACE_ITERS * TRACE_STRIDE * sizeof(float)), "pinned", __FILE__, __LINE__));
     KT_TRY(kt::cuda_check(cudaMallocHost((void**)&c->counter_host, sizeof(unsigned int)), "pinned", __FILE__, __LINE__));
     for (int i = 0; i < 7; ++i) KT_TRY(kt::cuda_check(cudaEventCreate(&c->ev[i]), "event", __FILE__, __LINE__));
+    for (int i = 0; i < 2; ++i) KT_TRY(kt::cuda_check(cudaEventCreate(&c->ev_icp[i]), "event", __FILE__, __LINE__));
     for (int i = 0; i < 6; ++i) c->stage_ms[i] = 0.f;
     KT_TRY(kt_reset(c));
 #undef KT_TRY
@@ -553,6 +579,7 @@ int kt_destroy(kt_ctx* c)
     if (c->trace_host) cudaFreeHost(c->trace_host);
     if (c->counter_host) cudaFreeHost(c->counter_host);
     for (int i = 0; i < 7; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (int i = 0; i < 2; ++i) if (c->ev_icp[i]) cudaEventDestroy(c->ev_icp[i]);
     if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
     if (c->stream_copy) { cudaStreamSynchronize(c->stream_copy); cudaStreamDestroy(c->stream_copy); }
     if (c->ev_prefetch) cudaEventDestroy(c->ev_prefetch);
@@ -748,6 +775,15 @@ int kt_mgpu_info(kt_ctx* c, int* info5)       // world, rank, slab planes, first
     if (!c || !info5) return KT_ERR_INVALID;
     info5[0] = c->world; info5[1] = c->rank; info5[2] = c->slab_z; info5[3] = c->z_begin; info5[4] = (int)(c->arena_bytes >> 20);
     return KT_OK;
+}
+
+float kt_get_icp_kernel_ms(kt_ctx* c)
+{
+    if (!c || !c->timing) return 0.f;
+    cudaStreamSynchronize(c->stream);
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, c->ev_icp[0], c->ev_icp[1]) != cudaSuccess) { cudaGetLastError(); return 0.f; }
+    return t;
 }
 
 long long kt_launch_count(kt_ctx* c) { return c ? g_launches - c->launches_at_create : g_launches; }
