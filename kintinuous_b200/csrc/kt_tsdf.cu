@@ -118,6 +118,7 @@ struct IntegrateParams {
     const float* depth_scaled; int rows, cols; Intr k; float3 cell; Mat33 Rinv; float3 t; float trunc;
     int16_t* tsdf; uchar4* color; int V; int3 wrap; const uint8_t* rgb; const float* nmap; bool angle_color;
     const float* ztable; int zchunk;
+    int lz_lo, lz_hi;          // LOGICAL z range walked by this launch (a slab is one or two such ranges)
     int z_begin, z_end;        // storage-z range owned here; volume pointers are indexed with (sz - z_begin)
 };
 
@@ -134,8 +135,8 @@ integrate_kernel(const IntegrateParams p)
     if (sx >= V || sy >= V) return;
     int x = sx - p.wrap.x; if (x < 0) x += V;             // logical voxel
     int y = sy - p.wrap.y; if (y < 0) y += V;
-    const int z0 = blockIdx.z * p.zchunk;
-    const int z1 = min(z0 + p.zchunk, V);
+    const int z0 = p.lz_lo + blockIdx.z * p.zchunk;
+    const int z1 = min(z0 + p.zchunk, p.lz_hi);
 
     const float3 cell_size = p.cell;
     const Intr intr = p.k;
@@ -388,10 +389,23 @@ int integrate(const IntegrateArgs& a, float* ztable_dev, cudaStream_t s)
     p.tsdf = a.tsdf; p.color = (uchar4*)a.color; p.V = V; p.wrap = a.wrap; p.rgb = a.rgb; p.nmap = a.nmap_curr; p.angle_color = a.angle_color;
     p.ztable = ztable_dev; p.zchunk = V >= 64 ? V / 8 : V;
     p.z_begin = a.z_begin; p.z_end = a.z_end;
-    dim3 block(32, 8), grid(div_up(V, 32), div_up(V, 8), div_up(V, p.zchunk));
-    if ((size_t)(a.z_end - a.z_begin) * V * V <= ((size_t)1 << 31)) integrate_kernel<unsigned int><<<grid, block, 0, s>>>(p);
-    else integrate_kernel<size_t><<<grid, block, 0, s>>>(p);
-    KT_LAUNCH_CHECK();
+    // logical z ranges of the owned storage planes [z_begin, z_end): storage = (logical + wrap.z) mod V
+    const int slab = a.z_end - a.z_begin;
+    int lo[2], hi[2], n = 0;
+    if (slab >= V) { lo[0] = 0; hi[0] = V; n = 1; }
+    else {
+        const int ls = ((a.z_begin - a.wrap.z) % V + V) % V;
+        lo[0] = ls; hi[0] = ls + slab < V ? ls + slab : V; n = 1;
+        if (ls + slab > V) { lo[1] = 0; hi[1] = ls + slab - V; n = 2; }
+    }
+    const bool idx32 = (size_t)slab * V * V <= ((size_t)1 << 31);
+    for (int i = 0; i < n; ++i) {
+        p.lz_lo = lo[i]; p.lz_hi = hi[i];
+        dim3 block(32, 8), grid(div_up(V, 32), div_up(V, 8), div_up(hi[i] - lo[i], p.zchunk));
+        if (idx32) integrate_kernel<unsigned int><<<grid, block, 0, s>>>(p);
+        else integrate_kernel<size_t><<<grid, block, 0, s>>>(p);
+        KT_LAUNCH_CHECK();
+    }
     return 0;
 }
 
