@@ -36,6 +36,8 @@ ROWS, COLS, VOL, SIZE = 480, 640, 512, 6.0
 N_INPUT_FRAMES = int(os.environ.get("KT_BENCH_FRAMES", "96"))
 P_LEVELS = [ROWS * COLS >> (2 * l) for l in range(4)]
 ICP_ITERS = [10, 5, 4, 0]
+TRACKER_NAMES = {0: "ICP-only tracker", 1: "RGB-D-only tracker (-r)", 2: "ICP+RGB-D tracker (-ri)"}
+METRIC_TAGS = {0: "ICP-only", 1: "RGB-D-only", 2: "ICP+RGB-D"}
 
 
 def _render_one(k):
@@ -168,9 +170,9 @@ def run_reference(args, world, rank, local):
     cfg = kb.Config.default(rows=ROWS, cols=COLS, vol=args.vol, odometry=args.odometry)
     n_frames = min(N_INPUT_FRAMES, max(8, args.steps + args.warmup + 1))
     frames = make_stream(n_frames)
-    line = {"metric": f"frames/s 640x480 into {args.vol}^3 TSDF ({'ICP-only' if args.odometry == 0 else 'ICP+RGB-D'} tracker)", "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+    line = {"metric": f"frames/s 640x480 into {args.vol}^3 TSDF ({METRIC_TAGS[args.odometry]} tracker)", "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": {"workload": "synthetic 640x480 RGB-D stream, 512^3 volume (6 m), ICP-only tracker {10,5,4}, shifting on", "frames_cycled": n_frames}}
+            "config": {"workload": f"synthetic 640x480 RGB-D stream, {args.vol}^3 volume (6 m), {TRACKER_NAMES[args.odometry]} {{10,5,4}}, shifting on (-t 14)", "frames_cycled": n_frames}}
     use_cuda = False
     try:
         import torch
@@ -271,18 +273,22 @@ def main():
         if leg == "device" and rank == 0:
             sampler.start()
         l0 = trk.launch_count()
-        ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
+        trk.span_mark(0)                                    # CUDA events on the tracker's own stream (torch events would not see it)
         i = run(trk, leg == "host", args.steps, i)
+        trk.span_mark(1)
+        dt = trk.span_elapsed_ms() * 1e-3                   # synchronises on the closing event
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
+        wall = time.perf_counter() - t0
         l1 = trk.launch_count()
         barrier(world)
         if leg == "device" and rank == 0:
             clocks = sampler.stop()
+        if dt <= 0:
+            raise RuntimeError("device stopwatch failed")
         dt = max_over_ranks(dt, world, device)
-        results[leg] = {"dt": dt, "launches": l1 - l0}
+        results[leg] = {"dt": dt, "wall": max_over_ranks(wall, world, device), "launches": l1 - l0}
         if leg == "device":
             # stage timers (CUDA events on the tracker's stream) over a few extra frames, outside the timed region
             trk.set_stage_timing(True)
@@ -303,7 +309,14 @@ def main():
     peak, peak_src = measured_peak()
     st = results["stages_ms"]
     names = ["pyramid", "odometry", "shift", "integrate", "raycast"]
-    icp_bytes = sum(48 * P_LEVELS[l] * ICP_ITERS[l] for l in range(4))
+    # algorithmic bytes per pixel and Gauss-Newton iteration: ICP 48 B (two float3 current maps + two float3
+    # model maps), photometric 14 B (last/next depth 4+4, last/next intensity 1+1, next gradients 2+2)
+    per_px = {0: 48, 1: 14, 2: 62}[args.odometry]
+    icp_bytes = sum(per_px * P_LEVELS[l] * ICP_ITERS[l] for l in range(4))
+    tracker_name = TRACKER_NAMES[args.odometry]
+    kernel_name = ("icp_frame_kernel (1 cooperative launch per frame = 19 Gauss-Newton iterations, TMA-staged current maps, FP64 solve on device)"
+                   if args.odometry == 0 else
+                   "rgbd_frame_kernel (1 cooperative launch per frame = 19 iterations of photometric" + (" + point-to-plane" if args.odometry == 2 else "") + " Gauss-Newton, FP64 solve on device)")
     alg_bytes = {"pyramid": 4 * P_LEVELS[0] + sum(2 * P_LEVELS[l] + 2 * P_LEVELS[l + 1] for l in range(3)) + sum(2 * P_LEVELS[l] + 24 * P_LEVELS[l] for l in range(4)),
                  "odometry": icp_bytes, "integrate": None, "raycast": None}
     stages = {nm: {"ms": st[k]} for k, nm in enumerate(names)}
@@ -318,7 +331,7 @@ def main():
     traffic = None
     try:                                                      # dram__bytes_read.sum + dram__bytes_write.sum of the committed ncu capture
         import csv
-        rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "r1_ncu_full_v4_icp_frame_kernel.csv"))))
+        rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "r1_ncu_full_v4_icp_frame_kernel.csv" if args.odometry == 0 else "r1_ncu_full_v9_rgbd_frame_kernel.csv"))))
         H, U, Vv = rows[0], rows[1], rows[2]
         def val(name):
             i = H.index(name); x = float(Vv[i]); u = U[i].lower()
@@ -326,18 +339,18 @@ def main():
         traffic = val("dram__bytes_read.sum") + val("dram__bytes_write.sum")
     except Exception:
         traffic = None
-    roofline = {"kernel": "icp_frame_kernel (1 cooperative launch per frame = 19 Gauss-Newton iterations, TMA-staged current maps, FP64 solve on device)", "bound": "hbm",
+    roofline = {"kernel": kernel_name, "bound": "hbm",
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None, "traffic": traffic,
                 "peak_source": peak_src, "bytes_per_launch": icp_bytes, "avg_launch_ms": icp_ms,
-                "note": "algorithmic bytes / CUDA-event time; the kernel is latency-bound by design at 640x480 (19 sequential reduce+solve steps, maps L2-resident: ncu DRAM traffic is 19 MB per launch); see DESIGN.md section 4 and profiles/r1_ncu_summary.md",
+                "note": "algorithmic bytes / CUDA-event time of that launch; the kernel is latency-bound by design at 640x480 (19 sequential reduce+solve steps separated by grid barriers, inputs L2-resident so DRAM traffic is far below the algorithmic bytes); see DESIGN.md section 4 and profiles/r1_ncu_summary.md",
                 "dominant_stage": dom}
     dt = results["device"]["dt"]
     streams = 1 if zslab else world          # z-slab: all ranks work on ONE stream (strong scaling)
     value = streams * args.steps / dt
     e2e_v = streams * args.steps / results["host"]["dt"]
-    line = {"metric": f"frames/s 640x480 into {args.vol}^3 TSDF ({'ICP-only' if args.odometry == 0 else 'ICP+RGB-D'} tracker)", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
-            "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong" if zslab else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "synthetic 640x480 RGB-D stream, 512^3 volume (6 m), ICP-only tracker {10,5,4}, shifting on (-t 14)", "parallelism": (f"one stream, volume z-slab sharded over {world} GPUs (P2P raycast, replicated ICP)" if zslab else f"{world} independent streams"), "vol": args.vol, "odometry": args.odometry,
+    line = {"metric": f"frames/s 640x480 into {args.vol}^3 TSDF ({METRIC_TAGS[args.odometry]} tracker)", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
+            "ms_per_step": 1e3 * dt / args.steps, "wall_ms_per_step": 1e3 * results["device"]["wall"] / args.steps, "timing": "CUDA events on the tracker stream, max over ranks", "higher_is_better": True, "scaling": "strong" if zslab else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"synthetic 640x480 RGB-D stream, {args.vol}^3 volume (6 m), {tracker_name} {{10,5,4}}, shifting on (-t 14)", "parallelism": (f"one stream, volume z-slab sharded over {world} GPUs (P2P raycast, replicated ICP)" if zslab else f"{world} independent streams"), "vol": args.vol, "odometry": args.odometry,
                        "l2": f"inputs larger than L2: {n} frames x 1.54 MB = {n * 1.536:.0f} MB cycled (ping-pong)"},
             "e2e": {"value": e2e_v, "unit": "frames/s", "h2d_bytes_per_step": ROWS * COLS * 5, "d2h_bytes_per_step": 48},
             "gpu_launches": int(results["device"]["launches"]), "clocks": clocks, "roofline": roofline, "stages": stages}

@@ -124,7 +124,10 @@ KT_API int kt_get_stage_ms(kt_ctx* ctx, float* ms6);
 KT_API int kt_set_stage_timing(kt_ctx* ctx, int enabled);
 /* CUDA-event duration of the last whole-frame ICP launch (icp_frame_kernel), ms; 0 unless stage timing is on and odometry == 0 */
 KT_API float kt_get_icp_kernel_ms(kt_ctx* ctx);
-/* number of kernels this library launched since kt_create (for bench.py's gpu_launches) */
+/* Device-side stopwatch on the tracker's own stream: mark(0) ... frames ... mark(1), then the CUDA-event time between the two
+ * marks (ms, synchronises on mark 1; < 0 on error).  bench.py times its region with this, not with the host clock. */
+KT_API int kt_span_mark(kt_ctx* ctx, int which);
+KT_API float kt_span_elapsed_ms(kt_ctx* ctx);
 /* ---- z-slab sharding of ONE volume over `world` GPUs, one process per GPU (no counterpart in the reference) ----
  * Every rank creates its context with kt_config.rank / world, exports the CUDA-IPC handle (64 bytes) of its shared arena
  * (volume slab, model maps, barrier flags), the host exchanges the handles (torch.distributed / MPI / anything) and every rank

@@ -32,6 +32,7 @@ def load():
     lib.kt_get_trunc_dist.restype = C.c_float
     lib.kt_launch_count.restype = C.c_longlong
     lib.kt_get_icp_kernel_ms.restype = C.c_float
+    lib.kt_span_elapsed_ms.restype = C.c_float
     _LIB = lib
     return lib
 
@@ -193,6 +194,12 @@ class Tracker:
 
     def launch_count(self):
         return int(self.lib.kt_launch_count(self.h))
+
+    def span_mark(self, which):
+        _check(self.lib.kt_span_mark(self.h, int(which)))
+
+    def span_elapsed_ms(self):
+        return float(self.lib.kt_span_elapsed_ms(self.h))
 
     def icp_kernel_ms(self):
         return float(self.lib.kt_get_icp_kernel_ms(self.h))

@@ -101,5 +101,47 @@ __device__ __forceinline__ void icp_pixel_staged(const float3& vcurr, const floa
     sum[28] += 1.f;
 }
 
+// The same pixel split in two so that the model-map gathers of several pixels can be in flight together (the per-iteration time of
+// the whole-frame kernel is the latency of these dependent L2 loads, not their bandwidth):
+//   icp_pixel_project  current vertex -> index of the model pixel it projects to, or -1      (reduce.cu:222-240)
+//   icp_pixel_finish   tests + row products from the six gathered floats                     (reduce.cu:241-316)
+// Expression order is the one of icp_pixel_staged, so the sums are bit-identical.
+__device__ __forceinline__ int icp_pixel_project(const float3& vcurr, int cols, int rows, const Intr& intr,
+                                                 const Mat33& Rcurr, const float3& tcurr, const Mat33& Rprev_inv, const float3& tprev)
+{
+    if (isnan(vcurr.x)) return -1;
+    float3 vcurr_g = add3(mul33(Rcurr, vcurr), tcurr);
+    float3 vcurr_cp = mul33(Rprev_inv, sub3(vcurr_g, tprev));
+    int2 ukr;
+    ukr.x = __float2int_rn(vcurr_cp.x * intr.fx / vcurr_cp.z + intr.cx);
+    ukr.y = __float2int_rn(vcurr_cp.y * intr.fy / vcurr_cp.z + intr.cy);
+    if (ukr.x < 0 || ukr.y < 0 || ukr.x >= cols || ukr.y >= rows || vcurr_cp.z < 0) return -1;
+    return ukr.y * cols + ukr.x;
+}
+
+__device__ __forceinline__ void icp_pixel_finish(const float3& vcurr, const float3& ncurr, const float3& vprev_g, const float3& nprev_g,
+                                                 const Mat33& Rcurr, const float3& tcurr, const Mat33& Rprev_inv, const float3& tprev,
+                                                 float dist_thres, float angle_thres, float (&sum)[32])
+{
+    if (isnan(vprev_g.x) || isnan(nprev_g.x) || isnan(ncurr.x)) return;
+    float3 vcurr_g = add3(mul33(Rcurr, vcurr), tcurr);
+    float3 ncurr_g = mul33(Rcurr, ncurr);
+    float dist = norm3(sub3(vprev_g, vcurr_g));
+    float sine = norm3(cross3(ncurr_g, nprev_g));
+    if (!(sine < angle_thres && dist <= dist_thres)) return;
+    float3 s_cp = mul33(Rprev_inv, sub3(vcurr_g, tprev));
+    float3 d_cp = mul33(Rprev_inv, sub3(vprev_g, tprev));
+    float3 n_cp = mul33(Rprev_inv, nprev_g);
+    float3 sxn = cross3(s_cp, n_cp);
+    const float row[7] = {n_cp.x, n_cp.y, n_cp.z, sxn.x, sxn.y, sxn.z, dot3(n_cp, sub3(s_cp, d_cp))};
+    int k = 0;
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int b = a; b < 7; ++b) sum[k++] += row[a] * row[b];
+    sum[27] += row[6] * row[6];
+    sum[28] += 1.f;
+}
+
 
 } // namespace kt

@@ -138,6 +138,8 @@ icp_kernel(const IcpParams p)
 // its pixels to a 29-float partial, ONE grid barrier, then EVERY CTA sums the per-CTA partials in the same fixed order and
 // performs the same FP64 solve redundantly, so that no second barrier / broadcast of the pose is needed (the result is
 // bit-identical in all CTAs because the instruction sequence and inputs are identical).
+enum { ICP_BATCH = 5 };          // pixels per thread whose model-map gathers are issued together (640x480 level 0 has 5 chunks)
+
 struct IcpFrameParams {
     IcpLevelArgs lv[LEVELS];
     int iters[LEVELS];
@@ -227,13 +229,34 @@ icp_frame_kernel(const IcpFrameParams p)
 #pragma unroll
             for (int k = 0; k < 32; ++k) sum[k] = 0.f;
             if (staged) {
-                for (int k = 0; k < n_chunks; ++k) {
-                    const int i = (k * G + blockIdx.x) * FRAME_THREADS + tid;
-                    if (i < N) {
-                        const int o = k * FRAME_THREADS + tid, ps = p.stage_k * FRAME_THREADS;
-                        const float3 vc = make_float3(s_stage[o], s_stage[ps + o], s_stage[2 * ps + o]);
-                        const float3 nc = make_float3(s_stage[3 * ps + o], s_stage[4 * ps + o], s_stage[5 * ps + o]);
-                        icp_pixel_staged(vc, nc, N, cols, rows, vmap_g_prev, nmap_g_prev, intr, Rcurr, tcurr, Rprev_inv, tprev, dist_thres, angle_thres, sum);
+                // batches of ICP_BATCH pixels per thread: project all, gather all (independent loads in flight together), finish all
+                const int ps = p.stage_k * FRAME_THREADS;
+                for (int k0 = 0; k0 < n_chunks; k0 += ICP_BATCH) {
+                    int j[ICP_BATCH]; float g[ICP_BATCH][6];
+#pragma unroll
+                    for (int b = 0; b < ICP_BATCH; ++b) {
+                        const int k = k0 + b, i = (k * G + blockIdx.x) * FRAME_THREADS + tid;
+                        j[b] = -1;
+                        if (k < n_chunks && i < N) {
+                            const int o = k * FRAME_THREADS + tid;
+                            j[b] = icp_pixel_project(make_float3(s_stage[o], s_stage[ps + o], s_stage[2 * ps + o]), cols, rows, intr, Rcurr, tcurr, Rprev_inv, tprev);
+                        }
+                    }
+#pragma unroll
+                    for (int b = 0; b < ICP_BATCH; ++b) {
+                        const int jj = j[b] < 0 ? 0 : j[b];
+                        g[b][0] = __ldg(&vmap_g_prev[jj]); g[b][1] = __ldg(&vmap_g_prev[jj + N]); g[b][2] = __ldg(&vmap_g_prev[jj + 2 * N]);
+                        g[b][3] = __ldg(&nmap_g_prev[jj]); g[b][4] = __ldg(&nmap_g_prev[jj + N]); g[b][5] = __ldg(&nmap_g_prev[jj + 2 * N]);
+                    }
+#pragma unroll
+                    for (int b = 0; b < ICP_BATCH; ++b) {
+                        if (j[b] >= 0) {
+                            const int o = (k0 + b) * FRAME_THREADS + tid;
+                            icp_pixel_finish(make_float3(s_stage[o], s_stage[ps + o], s_stage[2 * ps + o]),
+                                             make_float3(s_stage[3 * ps + o], s_stage[4 * ps + o], s_stage[5 * ps + o]),
+                                             make_float3(g[b][0], g[b][1], g[b][2]), make_float3(g[b][3], g[b][4], g[b][5]),
+                                             Rcurr, tcurr, Rprev_inv, tprev, dist_thres, angle_thres, sum);
+                        }
                     }
                 }
             } else {

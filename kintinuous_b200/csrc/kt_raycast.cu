@@ -386,7 +386,8 @@ int raycast(const RaycastArgs& a, cudaStream_t s)
     if (p.n_levels > 1 && ((a.cols % RC_X) != 0 || (a.rows % RC_Y) != 0)) { set_error("raycast: fused pyramid needs cols %% 32 == 0 and rows %% 8 == 0"); return -1; }
     dim3 block(RC_X, RC_Y), grid(div_up(a.cols, RC_X), div_up(a.rows, RC_Y));
     const bool pow2 = (a.vol & (a.vol - 1)) == 0;
-    const bool idx32 = (size_t)a.vol * a.vol * a.vol <= ((size_t)1 << 31);
+    static const bool force64 = getenv("KT_FORCE_IDX64") != nullptr;     // test hook, see kt_tsdf.cu
+    const bool idx32 = !force64 && (size_t)a.vol * a.vol * a.vol <= ((size_t)1 << 31);
     static int variant = -1;                 // tuning knob (KT_RC_VARIANT): 0 = RS 4, 1 = RS 8, 2 = RS 8 with 5 CTAs/SM
     if (variant < 0) { const char* e = getenv("KT_RC_VARIANT"); variant = e ? atoi(e) : 1; }
     if (a.multi) {

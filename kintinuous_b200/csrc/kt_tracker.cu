@@ -96,7 +96,7 @@ struct kt_ctx {
     float* pose12_host; OdomResult* result_host; float* trace_host; unsigned int* counter_host;
     int trace_iters; int shifted_last;
     // timing
-    bool timing; cudaEvent_t ev[7]; float stage_ms[6]; cudaEvent_t ev_icp[2];
+    bool timing; cudaEvent_t ev[7]; float stage_ms[6]; cudaEvent_t ev_icp[2]; cudaEvent_t ev_span[2];
     long long launches_at_create;
     std::vector<void*> allocs;
     // z-slab sharding over `world` GPUs (one process per GPU; peers' arenas are mapped through CUDA IPC)
@@ -559,6 +559,7 @@ int kt_create(const kt_config* cfg, kt_ctx** out)
     KT_TRY(kt::cuda_check(cudaMallocHost((void**)&c->counter_host, sizeof(unsigned int)), "pinned", __FILE__, __LINE__));
     for (int i = 0; i < 7; ++i) KT_TRY(kt::cuda_check(cudaEventCreate(&c->ev[i]), "event", __FILE__, __LINE__));
     for (int i = 0; i < 2; ++i) KT_TRY(kt::cuda_check(cudaEventCreate(&c->ev_icp[i]), "event", __FILE__, __LINE__));
+    for (int i = 0; i < 2; ++i) KT_TRY(kt::cuda_check(cudaEventCreate(&c->ev_span[i]), "event", __FILE__, __LINE__));
     for (int i = 0; i < 6; ++i) c->stage_ms[i] = 0.f;
     KT_TRY(kt_reset(c));
 #undef KT_TRY
@@ -580,6 +581,7 @@ int kt_destroy(kt_ctx* c)
     if (c->counter_host) cudaFreeHost(c->counter_host);
     for (int i = 0; i < 7; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (int i = 0; i < 2; ++i) if (c->ev_icp[i]) cudaEventDestroy(c->ev_icp[i]);
+    for (int i = 0; i < 2; ++i) if (c->ev_span[i]) cudaEventDestroy(c->ev_span[i]);
     if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
     if (c->stream_copy) { cudaStreamSynchronize(c->stream_copy); cudaStreamDestroy(c->stream_copy); }
     if (c->ev_prefetch) cudaEventDestroy(c->ev_prefetch);
@@ -783,6 +785,22 @@ float kt_get_icp_kernel_ms(kt_ctx* c)
     cudaStreamSynchronize(c->stream);
     float t = 0.f;
     if (cudaEventElapsedTime(&t, c->ev_icp[0], c->ev_icp[1]) != cudaSuccess) { cudaGetLastError(); return 0.f; }
+    return t;
+}
+
+int kt_span_mark(kt_ctx* c, int which)
+{
+    if (!c || which < 0 || which > 1) return KT_ERR_INVALID;
+    KT_CUDA(cudaSetDevice(c->cfg.device));
+    KT_CUDA(cudaEventRecord(c->ev_span[which], c->stream));
+    return KT_OK;
+}
+
+float kt_span_elapsed_ms(kt_ctx* c)
+{
+    if (!c || cudaSetDevice(c->cfg.device) != cudaSuccess) return -1.f;
+    float t = 0.f;
+    if (cudaEventSynchronize(c->ev_span[1]) != cudaSuccess || cudaEventElapsedTime(&t, c->ev_span[0], c->ev_span[1]) != cudaSuccess) { cudaGetLastError(); return -1.f; }
     return t;
 }
 

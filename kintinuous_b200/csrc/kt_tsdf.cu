@@ -398,7 +398,9 @@ int integrate(const IntegrateArgs& a, float* ztable_dev, cudaStream_t s)
         lo[0] = ls; hi[0] = ls + slab < V ? ls + slab : V; n = 1;
         if (ls + slab > V) { lo[1] = 0; hi[1] = ls + slab - V; n = 2; }
     }
-    const bool idx32 = (size_t)slab * V * V <= ((size_t)1 << 31);
+    // KT_FORCE_IDX64 (test hook): take the 64-bit index path the 2048^3 volume needs on a volume small enough to check against the reference
+    static const bool force64 = getenv("KT_FORCE_IDX64") != nullptr;
+    const bool idx32 = !force64 && (size_t)slab * V * V <= ((size_t)1 << 31);
     for (int i = 0; i < n; ++i) {
         p.lz_lo = lo[i]; p.lz_hi = hi[i];
         dim3 block(32, 8), grid(div_up(V, 32), div_up(V, 8), div_up(hi[i] - lo[i], p.zchunk));

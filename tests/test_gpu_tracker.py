@@ -172,3 +172,70 @@ def test_prefetch_hint_does_not_change_results(built, frames):
     ta, ca = a.export_volume(); tb, cb = b.export_volume()
     assert (ta == tb).all() and (ca == cb).all()
     a.close(); b.close()
+
+
+_IDX64_SCRIPT = r"""
+import hashlib, sys
+import numpy as np
+import kintinuous_b200 as kb
+from kintinuous_b200 import synth
+trk = kb.Tracker(kb.Config.default(vol=256, odometry=0, voxel_shift=2))
+h = hashlib.sha256()
+for k in range(8):
+    d, c = synth.render(k)
+    p = trk.process_frame(d, c, k)
+    R, t, gc, w = p.as_tuple()
+    h.update(np.ascontiguousarray(R).tobytes()); h.update(np.ascontiguousarray(t).tobytes()); h.update(np.ascontiguousarray(w).tobytes())
+ts, cs = trk.export_volume()
+h.update(ts.tobytes()); h.update(cs.tobytes())
+for w_ in (2, 3, 5):
+    h.update(np.ascontiguousarray(trk.download_map(w_, 0)).tobytes())
+print("HASH", h.hexdigest())
+"""
+
+
+def test_64bit_index_paths_are_bit_identical(built):
+    """The 2048^3 volume (BASELINE config 5) needs 64-bit voxel indices in integrate and raycast; the reference cannot run there
+    (its int index overflows).  KT_FORCE_IDX64 selects those template instances on a 256^3 volume, where the result
+    must be bit-identical to the 32-bit instances that the golden tests pin against the reference."""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    out = {}
+    for tag, extra in (("idx32", {}), ("idx64", {"KT_FORCE_IDX64": "1"})):
+        env = dict(os.environ, PYTHONPATH=ROOT, **extra)
+        r = subprocess.run([sys.executable, "-c", _IDX64_SCRIPT], env=env, capture_output=True, text=True, timeout=600, cwd=ROOT)
+        assert r.returncode == 0, r.stderr[-2000:]
+        out[tag] = [l for l in r.stdout.splitlines() if l.startswith("HASH")][0]
+    assert out["idx32"] == out["idx64"]
+
+
+def test_config5_1280x960_into_2048(built):
+    """BASELINE config 5 on one GPU: 1280x960 frames into a 2048^3 volume (51.5 GB, 2.9 mm voxels).  No reference exists at this size,
+    so the check is against the synthetic scene's ground truth: the tracked pose follows the generator's trajectory and the model
+    depth map raycast out of the volume reproduces the input depth to about a voxel."""
+    import torch
+    import kintinuous_b200 as kb
+    from kintinuous_b200 import synth
+    free, _ = torch.cuda.mem_get_info()
+    if free < 70e9:
+        pytest.skip("needs 70 GB of free device memory")
+    rows, cols, V = 960, 1280, 2048
+    trk = kb.Tracker(kb.Config.default(rows=rows, cols=cols, vol=V, odometry=0))
+    voxel = 6.0 / V
+    for k in range(4):
+        d, c = synth.render(k, cols, rows)
+        p = trk.process_frame(d, c, k)
+        R, t, gc, w = p.as_tuple()
+        Rg, tg = synth.pose(k)
+        assert np.abs(t - (tg + 3.0)).max() < 2e-3, (k, t, tg)
+        assert rot_angle(R, Rg.astype(np.float32)) < 1e-3, k
+    vm = trk.download_map(2, 0).reshape(3, rows, cols)                # model vertex map (volume frame) raycast at the last pose
+    zc = (vm - t.reshape(3, 1, 1))                                    # rotate into the camera: z_cam = R^T (v - t)
+    z = np.einsum("i,ihw->hw", R[:, 2].astype(np.float64), zc.astype(np.float64))
+    ok = np.isfinite(vm[0]) & (d > 0)
+    assert ok.mean() > 0.9
+    err = np.abs(z[ok] - d[ok] / 1000.0)
+    assert np.median(err) < 1.0 * voxel, np.median(err)
+    assert np.quantile(err, 0.95) < 4 * voxel
+    trk.close()
