@@ -150,7 +150,7 @@ struct IcpFrameParams {
     unsigned int* bar;         // monotonically increasing arrival counter
     unsigned int bar_base;     // value of the counter when this launch starts
     long long* prof;           // optional: 5 clock64() stamps per iteration from CTA 0 (debug)
-    int stage_k;               // chunks of FRAME_THREADS pixels per CTA that fit the shared-memory stage (0 = no staging)
+    int stage_k;               // passes of FRAME_THREADS pixels per CTA that fit the shared-memory stage (0 = no staging)
 };
 
 __global__ void __launch_bounds__(FRAME_THREADS, 1)
@@ -189,32 +189,28 @@ icp_frame_kernel(const IcpFrameParams p)
         const float* __restrict__ nmap_g_prev = a.nmap_g_prev;
         const Intr intr = a.k;
         const float dist_thres = a.dist_thres, angle_thres = a.angle_thres;
-        // pixels of this CTA: chunk k covers [ (k*G + blockIdx.x) * FRAME_THREADS, +FRAME_THREADS )
-        const int n_chunks = (N + G * FRAME_THREADS - 1) / (G * FRAME_THREADS);
-        const bool staged = (p.stage_k > 0) && (n_chunks <= p.stage_k);
+        // pixels of this CTA: ONE contiguous range of q = ceil(N / G) pixels (rounded up to the 16-byte TMA granule), so that every SM
+        // gets the same share (chunks of FRAME_THREADS pixels dealt round-robin left 8 CTAs with a fifth pass at 640x480)
+        const int q = (((N + G - 1) / G) + 3) & ~3;
+        const int i_begin = min(N, (int)blockIdx.x * q), cnt = min(N, i_begin + q) - i_begin;
+        const int n_pass = (q + FRAME_THREADS - 1) / FRAME_THREADS;
+        const int ps = p.stage_k * FRAME_THREADS;                    // floats per staged plane
+        const bool staged = (p.stage_k > 0) && (n_pass <= p.stage_k) && ((N & 3) == 0);
         if (staged) {
-            // The current vertex / normal maps do not change during the level's iterations: ONE bulk copy per plane and chunk
-            // (2 KB each, 16-byte aligned) brings them into shared memory through the TMA engine; every iteration then reads
-            // its 24 streamed bytes per pixel from shared memory instead of L2.
+            // The current vertex / normal maps do not change during the level's iterations: ONE bulk copy per plane (<= 16 KB,
+            // 16-byte aligned) brings the CTA's range into shared memory through the TMA engine; every iteration then reads its
+            // 24 streamed bytes per pixel from shared memory instead of L2.
             __syncthreads();                                         // previous level's readers are done with the stage
             if (tid == 0) {
-                unsigned int total = 0;
-                for (int k = 0; k < n_chunks; ++k) {
-                    const int i0 = (k * G + blockIdx.x) * FRAME_THREADS;
-                    if (i0 < N) total += (unsigned int)(min(FRAME_THREADS, N - i0) * 4) * 6u;
-                }
-                if (total) mbar_expect_tx(&s_mbar, total);
-                for (int k = 0; k < n_chunks; ++k) {
-                    const int i0 = (k * G + blockIdx.x) * FRAME_THREADS;
-                    if (i0 >= N) continue;
-                    const unsigned int bytes = (unsigned int)(min(FRAME_THREADS, N - i0) * 4);
+                const unsigned int bytes = (unsigned int)cnt * 4u;
+                mbar_expect_tx(&s_mbar, bytes * 6u);                 // 0 completes the phase for CTAs without pixels at this level
+                if (bytes) {
 #pragma unroll
                     for (int pl = 0; pl < 3; ++pl) {
-                        tma_bulk_g2s(&s_stage[((pl) * p.stage_k + k) * FRAME_THREADS], vmap_curr + (size_t)pl * N + i0, bytes, &s_mbar);
-                        tma_bulk_g2s(&s_stage[((3 + pl) * p.stage_k + k) * FRAME_THREADS], nmap_curr + (size_t)pl * N + i0, bytes, &s_mbar);
+                        tma_bulk_g2s(&s_stage[pl * ps], vmap_curr + (size_t)pl * N + i_begin, bytes, &s_mbar);
+                        tma_bulk_g2s(&s_stage[(3 + pl) * ps], nmap_curr + (size_t)pl * N + i_begin, bytes, &s_mbar);
                     }
                 }
-                if (total == 0) mbar_expect_tx(&s_mbar, 0);          // complete the phase for CTAs without pixels at this level
             }
             mbar_wait(&s_mbar, stage_parity);
             stage_parity ^= 1u;
@@ -230,17 +226,14 @@ icp_frame_kernel(const IcpFrameParams p)
             for (int k = 0; k < 32; ++k) sum[k] = 0.f;
             if (staged) {
                 // batches of ICP_BATCH pixels per thread: project all, gather all (independent loads in flight together), finish all
-                const int ps = p.stage_k * FRAME_THREADS;
-                for (int k0 = 0; k0 < n_chunks; k0 += ICP_BATCH) {
+                for (int k0 = 0; k0 < n_pass; k0 += ICP_BATCH) {
                     int j[ICP_BATCH]; float g[ICP_BATCH][6];
 #pragma unroll
                     for (int b = 0; b < ICP_BATCH; ++b) {
-                        const int k = k0 + b, i = (k * G + blockIdx.x) * FRAME_THREADS + tid;
+                        const int o = (k0 + b) * FRAME_THREADS + tid;
                         j[b] = -1;
-                        if (k < n_chunks && i < N) {
-                            const int o = k * FRAME_THREADS + tid;
+                        if (o < cnt)
                             j[b] = icp_pixel_project(make_float3(s_stage[o], s_stage[ps + o], s_stage[2 * ps + o]), cols, rows, intr, Rcurr, tcurr, Rprev_inv, tprev);
-                        }
                     }
 #pragma unroll
                     for (int b = 0; b < ICP_BATCH; ++b) {
@@ -402,10 +395,10 @@ int icp_frame(const IcpLevelArgs* levels, const int* iters, const float* pose12_
     p.st = state; p.partials = partials; p.trace = trace; p.bar = bar_dev; p.bar_base = *bar_count;
     int grid = sm_count();
     if (grid * 32 * 2 > MAX_PARTIALS * 32) grid = MAX_PARTIALS / 2;
-    // shared-memory stage for the current maps: 6 planes x stage_k chunks x 2 KB, sized for the largest level in use
+    // shared-memory stage for the current maps: 6 planes x stage_k x 2 KB (one contiguous pixel range per CTA), sized for the largest level in use
     int need_k = 0;
     for (int l = 0; l < LEVELS; ++l)
-        if (iters[l] > 0) { int k = div_up(levels[l].rows * levels[l].cols, grid * FRAME_THREADS); if (k > need_k) need_k = k; }
+        if (iters[l] > 0) { int q = (div_up(levels[l].rows * levels[l].cols, grid) + 3) & ~3; int k = div_up(q, FRAME_THREADS); if (k > need_k) need_k = k; }
     static int smem_optin = -1;
     if (smem_optin < 0) {
         int dev = 0; cudaGetDevice(&dev);

@@ -11,8 +11,8 @@
 // CTA (169 taps/pixel come from smem, not L1); vertex and normal maps of ALL pyramid levels are
 // produced by ONE launch straight from the depth pyramid (the vertex map is never re-read to make
 // normals); per-pixel arithmetic keeps the reference's expression order (see kt_common.cuh).
-// Roofline: HBM-bound streaming except the bilateral filter, which is MUFU(ex2)-bound
-// (169 __expf per pixel); algorithmic bytes: DESIGN.md section 4.
+// Roofline: HBM-bound streaming except the bilateral filter, which is instruction-issue / MUFU(ex2)-bound
+// (169 __expf per pixel, 9 instructions per tap); algorithmic bytes: DESIGN.md section 4.
 #include "kt_ops.h"
 
 namespace kt {
@@ -24,53 +24,85 @@ const float SIGMA_SPACE = 4.5f;      // px   (bilateral_pyrdown.cu:57)
 
 enum { BIL_TX = 32, BIL_TY = 16, BIL_R = 6, BIL_W = BIL_TX + 2 * BIL_R, BIL_H = BIL_TY + 2 * BIL_R };
 
+// One pixel's 13x13 window from the float tile, taps in the reference's order (rows, then columns).  PRED: window clipped to
+// [dx_lo, dx_hi) x [dy_lo, dy_hi) (image borders, Q1); otherwise the full window, everything known at compile time.
+// The depth tile is held as float so that a tap needs ONE special-function-unit op (ex2) instead of three: the reference's
+// (float)tmp and (float)((value - tmp)^2) int->float conversions run on the same 16-lane unit as ex2 and were the bound.
+// Exactness: depths < 2^16 are exact in float, so is their difference; RN(diff * diff) equals the int->float conversion of the
+// exact integer square as long as the square does not overflow int32 (|diff| <= 46340, checked per CTA by the caller).
+template <bool PRED>
+__device__ __forceinline__ float bilateral_window(const float (*tile)[BIL_W + 1], int ly, int lx, float value, float ks, float kc,
+                                                  int dx_lo, int dx_hi, int dy_lo, int dy_hi)
+{
+    float sum1 = 0, sum2 = 0;
+    // clipped taps contribute weight * 0: fma(tmp, 0, sum1) == sum1 and sum2 + 0 == sum2 exactly, so masking is bit-identical to
+    // skipping them and keeps the unrolled window free of branches
+    float mx[2 * BIL_R + 1];
+    if (PRED) {
+#pragma unroll
+        for (int dx = -BIL_R; dx <= BIL_R; ++dx) mx[dx + BIL_R] = (dx >= dx_lo && dx < dx_hi) ? 1.f : 0.f;
+    }
+#pragma unroll
+    for (int dy = -BIL_R; dy <= BIL_R; ++dy) {
+        const float* trow = tile[ly + BIL_R + dy];
+        const float my = (!PRED || (dy >= dy_lo && dy < dy_hi)) ? 1.f : 0.f;
+#pragma unroll
+        for (int dx = -BIL_R; dx <= BIL_R; ++dx) {
+            const float tmp = trow[lx + BIL_R + dx];
+            const float space2 = (float)(dx * dx + dy * dy);
+            const float diff = __fsub_rn(value, tmp);
+            const float color2 = __fmul_rn(diff, diff);
+            // the contraction the reference's loop compiles to (checked in SASS): fma(space2, k_s, color2 * k_c)
+            const float e = __fmaf_rn(space2, ks, __fmul_rn(color2, kc));
+            float weight = __expf(-e);
+            if (PRED) weight = __fmul_rn(weight, __fmul_rn(mx[dx + BIL_R], my));
+            sum1 = __fmaf_rn(tmp, weight, sum1);
+            sum2 = __fadd_rn(sum2, weight);
+        }
+    }
+    return sum1 / sum2;
+}
+
 __global__ void __launch_bounds__(BIL_TX * BIL_TY)
 bilateral_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst, int rows, int cols,
                  float sigma_space2_inv_half, float sigma_color2_inv_half)
 {
-    __shared__ int tile[BIL_H][BIL_W + 1];
+    __shared__ float tile[BIL_H][BIL_W + 1];
     const int x0 = blockIdx.x * BIL_TX, y0 = blockIdx.y * BIL_TY;
+    int big = 0;
     for (int i = threadIdx.y * BIL_TX + threadIdx.x; i < BIL_H * BIL_W; i += BIL_TX * BIL_TY) {
         int ty = i / BIL_W, tx = i - ty * BIL_W;
         int gx = x0 + tx - BIL_R, gy = y0 + ty - BIL_R;
-        tile[ty][tx] = (gx >= 0 && gx < cols && gy >= 0 && gy < rows) ? (int)src[(size_t)gy * cols + gx] : 0;
+        const int v = (gx >= 0 && gx < cols && gy >= 0 && gy < rows) ? (int)src[(size_t)gy * cols + gx] : 0;
+        tile[ty][tx] = (float)v;
+        big |= (v > 46340);
     }
-    __syncthreads();
+    const int any_big = __syncthreads_or(big);
     const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
     if (x >= cols || y >= rows) return;
 
     const int D = BIL_R * 2 + 1;
-    const int value = tile[threadIdx.y + BIL_R][threadIdx.x + BIL_R];
-    // interior CTAs (every pixel has its full 13x13 window): same taps in the same order, bounds and the spatial term known at
-    // compile time (about 40 % fewer instructions per tap)
-    if (x0 >= BIL_R && y0 >= BIL_R && x0 + BIL_TX - 1 + BIL_R + 1 <= cols - 1 && y0 + BIL_TY - 1 + BIL_R + 1 <= rows - 1) {
-        float sum1 = 0, sum2 = 0;
-#pragma unroll
-        for (int dy = -BIL_R; dy <= BIL_R; ++dy) {
-            const int* trow = tile[threadIdx.y + BIL_R + dy];
-#pragma unroll
-            for (int dx = -BIL_R; dx <= BIL_R; ++dx) {
-                int tmp = trow[threadIdx.x + BIL_R + dx];
-                const float space2 = (float)(dx * dx + dy * dy);
-                const float color2 = (float)((value - tmp) * (value - tmp));
-                // same contraction as the general loop below compiles to (checked in SASS): fma(space2, k_s, color2 * k_c)
-                const float e = __fmaf_rn(space2, sigma_space2_inv_half, __fmul_rn(color2, sigma_color2_inv_half));
-                float weight = __expf(-e);
-                sum1 = __fmaf_rn((float)tmp, weight, sum1);
-                sum2 = __fadd_rn(sum2, weight);
-            }
-        }
-        int res = __float2int_rn(sum1 / sum2);
+    const float value_f = tile[threadIdx.y + BIL_R][threadIdx.x + BIL_R];
+    if (!any_big) {
+        float q;
+        if (x0 >= BIL_R && y0 >= BIL_R && x0 + BIL_TX - 1 + BIL_R + 1 <= cols - 1 && y0 + BIL_TY - 1 + BIL_R + 1 <= rows - 1)
+            q = bilateral_window<false>(tile, threadIdx.y, threadIdx.x, value_f, sigma_space2_inv_half, sigma_color2_inv_half, 0, 0, 0, 0);
+        else   // window [max(x-6,0), min(x+7, cols-1)) x [max(y-6,0), min(y+7, rows-1)), exclusive and clipped to cols-1 / rows-1: Q1
+            q = bilateral_window<true>(tile, threadIdx.y, threadIdx.x, value_f, sigma_space2_inv_half, sigma_color2_inv_half,
+                                       max(-BIL_R, -x), min(BIL_R + 1, cols - 1 - x), max(-BIL_R, -y), min(BIL_R + 1, rows - 1 - y));
+        int res = __float2int_rn(q);
         dst[(size_t)y * cols + x] = (uint16_t)max(0, min(res, 32767));
         return;
     }
-    const int tx = min(x - D / 2 + D, cols - 1);      // exclusive, and clipped to cols-1: Q1
+    // a depth above 46 340 mm in the tile: (value - tmp)^2 can overflow int32 in the reference; keep its integer arithmetic
+    const int value = (int)value_f;
+    const int tx = min(x - D / 2 + D, cols - 1);
     const int ty = min(y - D / 2 + D, rows - 1);
     float sum1 = 0, sum2 = 0;
     for (int cy = max(y - D / 2, 0); cy < ty; ++cy) {
-        const int* trow = tile[cy - y0 + BIL_R];
+        const float* trow = tile[cy - y0 + BIL_R];
         for (int cx = max(x - D / 2, 0); cx < tx; ++cx) {
-            int tmp = trow[cx - x0 + BIL_R];
+            int tmp = (int)trow[cx - x0 + BIL_R];
             float space2 = (x - cx) * (x - cx) + (y - cy) * (y - cy);
             float color2 = (value - tmp) * (value - tmp);
             float weight = __expf(-(space2 * sigma_space2_inv_half + color2 * sigma_color2_inv_half));

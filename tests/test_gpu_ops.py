@@ -82,8 +82,16 @@ def test_bilateral_full_resolution_vs_reference(env):
     if e["ref"] is None:
         pytest.skip("oracle/_ref not present")
     from kintinuous_b200 import synth
-    for k in (0, 7):
-        d, _ = synth.render(k)
+    rng = np.random.default_rng(20260922)
+    inputs = [synth.render(k)[0] for k in (0, 7)]
+    noisy = inputs[0].astype(np.int64) + rng.integers(-40, 41, inputs[0].shape)          # sensor-like noise: weights far from 0 and 1
+    noisy[rng.random(noisy.shape) < 0.05] = 0                                              # holes
+    inputs.append(np.clip(noisy, 0, 65535).astype(np.uint16))
+    far = inputs[0].copy()                                                                 # depths whose squared difference overflows
+    far[100:140, 200:300] = 65535; far[300:330, 10:50] = 50000; far[0:8, 600:640] = 47000  # int32 in the reference (kept bit-exact)
+    inputs.append(far)
+    inputs.append(rng.integers(0, 65536, inputs[0].shape).astype(np.uint16))              # white noise over the whole u16 range
+    for d in inputs:
         dd = dev(e, d.view(np.int16))
         a = zeros(e, (480, 640), t.int16); b = zeros(e, (480, 640), t.int16)
         e["ops"].bilateral(dd, a, 480, 640); e["ref"].bilateral(dd, b, 480, 640)
