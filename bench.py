@@ -220,6 +220,7 @@ def main():
     ap.add_argument("--mode", default="streams", choices=["streams", "zslab"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=48)
+    ap.add_argument("--no-prefetch", action="store_true", help="do not give the kt_prefetch_frame hint (A/B)")
     ap.add_argument("--vol", type=int, default=VOL)
     ap.add_argument("--odometry", type=int, default=0, help="0 ICP (configs[1]), 2 ICP+RGB-D (configs[2])")
     args = ap.parse_args()
@@ -251,12 +252,16 @@ def main():
         i = start
         for _ in range(steps):
             j = pingpong(i, n)
+            jn = pingpong(i + 1, n)
+            # kt_prefetch_frame (public API hint): the next frame's copy and pose-independent front end overlap this frame's fusion
             if use_host:
                 tracker.process_frame(pin_depth[j].data_ptr(), pin_rgb[j].data_ptr(), i)
-                jn = pingpong(i + 1, n)                      # public-API hint: overlap the next frame's H2D with this frame's fusion
-                tracker.prefetch_frame(pin_depth[jn].data_ptr(), pin_rgb[jn].data_ptr())
+                if not args.no_prefetch:
+                    tracker.prefetch_frame(pin_depth[jn].data_ptr(), pin_rgb[jn].data_ptr())
             else:
                 tracker.process_frame_device(dev_depth[j], dev_rgb[j], i)
+                if not args.no_prefetch:
+                    tracker.prefetch_frame(dev_depth[jn], dev_rgb[jn])
             i += 1
         return i
 

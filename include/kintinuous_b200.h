@@ -92,11 +92,12 @@ KT_API int kt_reset(kt_ctx* ctx);                                         /* Kin
  * (backend/TrackerInterface.cpp:90-91).  depth: rows*cols u16 mm; rgb: rows*cols*3 u8 (PixelRGB r,g,b).
  * Host buffers (pinned memory from kt_alloc_pinned makes the copy asynchronous). */
 KT_API int kt_process_frame(kt_ctx* ctx, const uint16_t* depth_host, const uint8_t* rgb_host, uint64_t utime, kt_pose* out);
-/* Optional hint: start the host->device copy of the NEXT frame now (own copy stream, spare input buffers), so that it overlaps
- * the fusion / ray-cast of the current one.  A following kt_process_frame with the same two pointers consumes the prefetched data;
- * with other pointers the prefetch is simply ignored.  The host buffers must stay valid and unchanged until that call (pinned
- * memory makes the copy asynchronous).  Results are identical with or without the hint. */
-KT_API int kt_prefetch_frame(kt_ctx* ctx, const uint16_t* depth_host, const uint8_t* rgb_host);
+/* Optional hint: start on the NEXT frame now.  Its copy into spare input buffers and its pose-independent front end (scaleDepth,
+ * bilateral filter, depth pyramid, vertex / normal maps) run on a side stream and overlap the fusion / ray-cast of the current frame.
+ * A following kt_process_frame / kt_process_frame_device with the same two pointers consumes the prefetched set; with other pointers
+ * the hint is dropped.  Host (pinned, for an asynchronous copy) or device pointers; the buffers must stay valid and unchanged until
+ * that call.  Results are bit-identical with or without the hint. */
+KT_API int kt_prefetch_frame(kt_ctx* ctx, const uint16_t* depth, const uint8_t* rgb);
 /* Same, inputs already resident in device memory (DeviceArray2D arguments of processFrame). */
 KT_API int kt_process_frame_device(kt_ctx* ctx, const uint16_t* depth_dev, const uint8_t* rgb_dev, uint64_t utime, kt_pose* out);
 KT_API int kt_finalise(kt_ctx* ctx);                                      /* KintinuousTracker::finalise (.cpp:1003-1048) */

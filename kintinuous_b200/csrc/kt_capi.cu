@@ -66,7 +66,7 @@ int kt_op_create_nmap(const float* vmap, float* nmap, int rows, int cols, void* 
 
 int kt_op_create_maps(const float* k, const uint16_t* depth, float* vmap, float* nmap, int rows, int cols, void* s)
 {
-    MapsLevel L; L.depth = depth; L.vmap = vmap; L.nmap = nmap; L.rows = rows; L.cols = cols; L.k = intr4(k);
+    MapsLevel L; L.depth = depth; L.vmap = vmap; L.nmap = nmap; L.rows = rows; L.cols = cols; L.k = intr4(k); L.vstale = 0; L.nstale = 0;
     int r = create_maps_pyramid(&L, 1, st(s)); if (r) return r;
     KT_CUDA(cudaStreamSynchronize(st(s))); return KT_OK;
 }

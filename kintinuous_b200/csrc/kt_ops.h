@@ -27,7 +27,8 @@ int bilateral(const uint16_t* src, uint16_t* dst, int rows, int cols, cudaStream
 int pyrdown(const uint16_t* src, uint16_t* dst, int src_rows, int src_cols, cudaStream_t s);
 int create_vmap(const Intr& k, const uint16_t* depth, float* vmap, int rows, int cols, cudaStream_t s);
 int create_nmap(const float* vmap, float* nmap, int rows, int cols, cudaStream_t s);
-struct MapsLevel { const uint16_t* depth; float* vmap; float* nmap; int rows, cols; Intr k; float fx_inv, fy_inv; };
+struct MapsLevel { const uint16_t* depth; float* vmap; float* nmap; int rows, cols; Intr k; float fx_inv, fy_inv;
+                   const float* vstale; const float* nstale; };   // maps of the previous frame when the output is a spare set (Q7), else null
 int create_maps_pyramid(const MapsLevel* levels, int n_levels, cudaStream_t s);      // fused vmap+nmap, all levels, one launch
 int transform_maps(const float* vs, const float* ns, const Mat33& R, const float3& t, float* vd, float* nd, int rows, int cols, cudaStream_t s);
 struct TransformLevel { const float* vs; const float* ns; float* vd; float* nd; int rows, cols; };

@@ -22,7 +22,9 @@ namespace {
 const float SIGMA_COLOR = 30.f;      // mm   (bilateral_pyrdown.cu:56)
 const float SIGMA_SPACE = 4.5f;      // px   (bilateral_pyrdown.cu:57)
 
-enum { BIL_TX = 32, BIL_TY = 16, BIL_R = 6, BIL_W = BIL_TX + 2 * BIL_R, BIL_H = BIL_TY + 2 * BIL_R };
+// 32x4-pixel CTAs: at 640x480 the image is 1.35 % more than one full wave of 2048 threads x 148 SMs, so with 512-thread CTAs the
+// last 8 of 600 ran alone after everyone else (ncu: SMs active 66 % of the kernel); 128-thread CTAs make that tail one small CTA long.
+enum { BIL_TX = 32, BIL_TY = 4, BIL_R = 6, BIL_W = BIL_TX + 2 * BIL_R, BIL_H = BIL_TY + 2 * BIL_R };
 
 // One pixel's 13x13 window from the float tile, taps in the reference's order (rows, then columns).  PRED: window clipped to
 // [dx_lo, dx_hi) x [dy_lo, dy_hi) (image borders, Q1); otherwise the full window, everything known at compile time.
@@ -223,8 +225,9 @@ maps_pyramid_kernel(const MapsParams p)
     // Q7: like the reference, an invalid pixel only gets NaN in its x plane; the y/z planes keep what
     // they held (the integrate kernel can read a stale n_z for colour weighting, tsdf_volume.cu:601-622,
     // so reproducing the staleness keeps colour parity with the reference over a sequence).
+    // When the maps are built ahead of time into a spare buffer set, 'what they held' is the previous frame's map (vstale / nstale).
     if (ok00) { vm[i] = v00.x; vm[i + P] = v00.y; vm[i + 2 * P] = v00.z; }
-    else vm[i] = nan;
+    else { vm[i] = nan; if (L.vstale) { vm[i + P] = L.vstale[i + P]; vm[i + 2 * P] = L.vstale[i + 2 * P]; } }
     bool okn = false;
     if (ok00 && u != cols - 1 && v != rows - 1) {
         float3 v01, v10;
@@ -236,7 +239,7 @@ maps_pyramid_kernel(const MapsParams p)
             okn = true;
         }
     }
-    if (!okn) nm[i] = nan;
+    if (!okn) { nm[i] = nan; if (L.nstale) { nm[i + P] = L.nstale[i + P]; nm[i + 2 * P] = L.nstale[i + 2 * P]; } }
 }
 
 struct TransformParams { TransformLevel lv[LEVELS]; Mat33 R; float3 t; };

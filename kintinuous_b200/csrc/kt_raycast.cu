@@ -156,7 +156,9 @@ __device__ __forceinline__ float getMaxTime(const float3& volume_max, const floa
     return fmin(fmin(txmax, tymax), tzmax);
 }
 
-enum { RC_X = 32, RC_Y = 8 };
+// 16x8-pixel CTAs (a warp = 16x2 pixels): 2400 CTAs at 640x480 instead of 1200 halve the scheduling quantum of a launch that is only
+// ~2 CTA rounds long (ncu: SMs active 77 % of the duration with 32x8), and a 16x2 warp footprint keeps the rays of a warp closer.
+enum { RC_X = 16, RC_Y = 8 };
 
 // One ray.  Returns validity of vertex / normal; outputs by reference.
 template <bool POW2, typename IdxT, int RS, bool MG>
@@ -315,7 +317,7 @@ raycast_kernel(const RayParams p)
     s0[1][0][threadIdx.y][threadIdx.x] = n_ok ? nrm.x : nan; s0[1][1][threadIdx.y][threadIdx.x] = nrm.y; s0[1][2][threadIdx.y][threadIdx.x] = nrm.z;
     __syncthreads();
 
-    // level 1: 16 x 4 outputs per tile
+    // level 1: RC_X/2 x RC_Y/2 outputs per tile
     {
         const int W = RC_X / 2, H = RC_Y / 2;
         const int rows1 = p.rows >> 1, cols1 = p.cols >> 1;
@@ -383,7 +385,7 @@ int raycast(const RaycastArgs& a, cudaStream_t s)
     p.vmap_color = (uchar4*)a.vmap_color; p.rows = a.rows; p.cols = a.cols;
     p.n_levels = a.n_levels; p.z_begin = 0; p.tile_row_begin = 0; p.n_out = 1;
     // the in-tile pyramid needs every level's tile to be whole
-    if (p.n_levels > 1 && ((a.cols % RC_X) != 0 || (a.rows % RC_Y) != 0)) { set_error("raycast: fused pyramid needs cols %% 32 == 0 and rows %% 8 == 0"); return -1; }
+    if (p.n_levels > 1 && ((a.cols % RC_X) != 0 || (a.rows % RC_Y) != 0)) { set_error("raycast: fused pyramid needs cols %% 16 == 0 and rows %% 8 == 0"); return -1; }
     dim3 block(RC_X, RC_Y), grid(div_up(a.cols, RC_X), div_up(a.rows, RC_Y));
     const bool pow2 = (a.vol & (a.vol - 1)) == 0;
     static const bool force64 = getenv("KT_FORCE_IDX64") != nullptr;     // test hook, see kt_tsdf.cu
@@ -395,16 +397,16 @@ int raycast(const RaycastArgs& a, cudaStream_t s)
         p.vv = a.vv; p.tile_row_begin = a.tile_row_begin; p.n_out = a.vv.world;
         for (int g = 0; g < MAX_GPUS; ++g) { for (int l = 0; l < LEVELS; ++l) { p.peer_vmap[g][l] = a.peer_vmap[g][l]; p.peer_nmap[g][l] = a.peer_nmap[g][l]; } p.peer_vcol[g] = (uchar4*)a.peer_vcol[g]; }
         grid.y = a.tile_row_end - a.tile_row_begin;
-        if (grid.y > 0) raycast_kernel<true, size_t, 8, 4, true><<<grid, block, 0, s>>>(p);
+        if (grid.y > 0) raycast_kernel<true, size_t, 8, 8, true><<<grid, block, 0, s>>>(p);
     }
     else if (pow2 && idx32) {
-        if (variant == 0) raycast_kernel<true, unsigned int, 4, 4, false><<<grid, block, 0, s>>>(p);
-        else if (variant == 2) raycast_kernel<true, unsigned int, 8, 5, false><<<grid, block, 0, s>>>(p);
-        else raycast_kernel<true, unsigned int, 8, 4, false><<<grid, block, 0, s>>>(p);
+        if (variant == 0) raycast_kernel<true, unsigned int, 4, 8, false><<<grid, block, 0, s>>>(p);
+        else if (variant == 2) raycast_kernel<true, unsigned int, 8, 10, false><<<grid, block, 0, s>>>(p);
+        else raycast_kernel<true, unsigned int, 8, 8, false><<<grid, block, 0, s>>>(p);
     }
-    else if (pow2) raycast_kernel<true, size_t, 8, 4, false><<<grid, block, 0, s>>>(p);
-    else if (idx32) raycast_kernel<false, unsigned int, 8, 4, false><<<grid, block, 0, s>>>(p);
-    else raycast_kernel<false, size_t, 8, 4, false><<<grid, block, 0, s>>>(p);
+    else if (pow2) raycast_kernel<true, size_t, 8, 8, false><<<grid, block, 0, s>>>(p);
+    else if (idx32) raycast_kernel<false, unsigned int, 8, 8, false><<<grid, block, 0, s>>>(p);
+    else raycast_kernel<false, size_t, 8, 8, false><<<grid, block, 0, s>>>(p);
     KT_LAUNCH_CHECK();
     return 0;
 }

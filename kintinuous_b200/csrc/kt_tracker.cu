@@ -11,6 +11,7 @@
 // copies; here: 5 pyramid launches, 1 + 19 odometry launches (solve on device), 3 fusion launches, 1 raycast
 // launch that also builds the model pyramid, one 200-byte D2H.
 #include "kt_ops.h"
+#include <cstdlib>
 #include "../../include/kintinuous_b200.h"
 #include <vector>
 #include <cstring>
@@ -83,6 +84,11 @@ struct kt_ctx {
     uint16_t* depth_raw; uint8_t* rgb;
     // double-buffered inputs: kt_prefetch_frame fills the spare set on a copy stream while the previous frame is still being fused
     uint16_t* depth_alt; uint8_t* rgb_alt; const void* pf_depth; const void* pf_rgb; bool pf_valid;
+    // ... and the pose-independent front end of the NEXT frame (scaleDepth, bilateral, pyrDown, vertex / normal maps) is built into a
+    // spare set on the same side stream, so that it overlaps the integrate / ray-cast of the frame before (they leave issue slots idle)
+    uint16_t* depths_alt[LEVELS]; float* vmaps_alt[LEVELS]; float* nmaps_alt[LEVELS]; float* depth_scaled_alt;
+    bool pf_built;             // the prefetched set holds the finished front end
+    bool frontend_ready;       // set for the duration of one process_frame_device call
     cudaStream_t stream_copy; cudaEvent_t ev_prefetch, ev_done[2]; int last_parity;
     uint16_t* depths_curr[LEVELS];
     float* vmaps_g_prev[LEVELS]; float* nmaps_g_prev[LEVELS]; float* vmaps_curr[LEVELS]; float* nmaps_curr[LEVELS];
@@ -289,6 +295,29 @@ int mg_barrier(kt_ctx* c)
     return xgpu_barrier(c->peer_flags_dev, (unsigned int*)(c->arena + c->off_flags), c->rank, c->world, c->epoch, c->mg_error_dev, c->stream);
 }
 
+// Pose-independent front end of one frame: scaleDepth (for integrate) on s_scale, bilateral + pyrDown + vertex / normal maps of all
+// levels on s_pyr.  vstale / nstale: the previous frame's maps when the outputs are a spare set (Q7 staleness), else null.
+int build_frontend(kt_ctx* c, const uint16_t* depth_raw, float* depth_scaled, uint16_t* const* depths, float* const* vmaps, float* const* nmaps,
+                   float* const* vstale, float* const* nstale, cudaStream_t s_scale, cudaStream_t s_pyr)
+{
+    const int rows = c->cfg.rows, cols = c->cfg.cols, mode = c->cfg.odometry;
+    int r;
+    Intr K = {c->cfg.fx, c->cfg.fy, c->cfg.cx, c->cfg.cy};
+    if ((r = scale_depth(depth_raw, depth_scaled, rows, cols, K, c->cfg.angle_color != 0, s_scale))) return r;
+    const bool use_icp_maps = (mode == 0) || (mode == 2) || c->cfg.angle_color;        // KintinuousTracker.cpp:465 (Q10)
+    if (use_icp_maps) {
+        if ((r = bilateral(depth_raw, depths[0], rows, cols, s_pyr))) return r;
+        for (int i = 1; i < LEVELS; ++i) if ((r = pyrdown(depths[i - 1], depths[i], rows >> (i - 1), cols >> (i - 1), s_pyr))) return r;
+        MapsLevel ml[LEVELS];
+        for (int i = 0; i < LEVELS; ++i) {
+            ml[i].depth = depths[i]; ml[i].vmap = vmaps[i]; ml[i].nmap = nmaps[i]; ml[i].rows = rows >> i; ml[i].cols = cols >> i; ml[i].k = intr_level(K, i);
+            ml[i].vstale = vstale ? vstale[i] : 0; ml[i].nstale = nstale ? nstale[i] : 0;
+        }
+        if ((r = create_maps_pyramid(ml, LEVELS, s_pyr))) return r;
+    }
+    return 0;
+}
+
 void mark(kt_ctx* c, int i) { if (c->timing) cudaEventRecord(c->ev[i], c->stream); }
 
 int process_frame_device(kt_ctx* c, uint64_t utime, kt_pose* out)
@@ -297,22 +326,13 @@ int process_frame_device(kt_ctx* c, uint64_t utime, kt_pose* out)
     const int mode = c->cfg.odometry;
     int r;
     c->shifted_last = 0;
-    {   // fork: scaleDepth (tsdf_volume.cu:491-538) only needs the raw depth; it overlaps the pyramid on a second stream
-        Intr k0 = {c->cfg.fx, c->cfg.fy, c->cfg.cx, c->cfg.cy};
+    mark(c, 0);
+    if (!c->frontend_ready) {
+        // fork: scaleDepth (tsdf_volume.cu:491-538) only needs the raw depth; it overlaps the pyramid on a second stream
         KT_CUDA(cudaEventRecord(c->ev_input, c->stream));
         KT_CUDA(cudaStreamWaitEvent(c->stream2, c->ev_input, 0));
-        if ((r = scale_depth(c->depth_raw, c->depth_scaled, rows, cols, k0, c->cfg.angle_color != 0, c->stream2))) return r;
+        if ((r = build_frontend(c, c->depth_raw, c->depth_scaled, c->depths_curr, c->vmaps_curr, c->nmaps_curr, 0, 0, c->stream2, c->stream))) return r;
         KT_CUDA(cudaEventRecord(c->ev_scaled, c->stream2));
-    }
-    mark(c, 0);
-    const bool use_icp_maps = (mode == 0) || (mode == 2) || c->cfg.angle_color;        // KintinuousTracker.cpp:465 (Q10)
-    if (use_icp_maps) {
-        if ((r = bilateral(c->depth_raw, c->depths_curr[0], rows, cols, c->stream))) return r;
-        for (int i = 1; i < LEVELS; ++i) if ((r = pyrdown(c->depths_curr[i - 1], c->depths_curr[i], rows >> (i - 1), cols >> (i - 1), c->stream))) return r;
-        MapsLevel ml[LEVELS];
-        Intr K = {c->cfg.fx, c->cfg.fy, c->cfg.cx, c->cfg.cy};
-        for (int i = 0; i < LEVELS; ++i) { ml[i].depth = c->depths_curr[i]; ml[i].vmap = c->vmaps_curr[i]; ml[i].nmap = c->nmaps_curr[i]; ml[i].rows = rows >> i; ml[i].cols = cols >> i; ml[i].k = intr_level(K, i); }
-        if ((r = create_maps_pyramid(ml, LEVELS, c->stream))) return r;
     }
     mark(c, 1);
 
@@ -448,6 +468,8 @@ int kt_reset(kt_ctx* c)
     for (int i = 0; i < 3; ++i) { c->voxelWrap[i] = 0; c->currentGlobalCamera[i] = c->volumeBasis[i] - c->size * 0.5f; }
     c->slices.clear();
     c->trace_iters = 0; c->shifted_last = 0; c->cloud_count = 0;
+    c->pf_valid = false; c->pf_built = false; c->frontend_ready = false;
+    if (c->stream_copy) cudaStreamSynchronize(c->stream_copy);
     int r = init_slab(c->tsdf, c->color, c->cfg.vol, c->slab_z, c->stream);
     if (r) return r;
     // Q7: stale y/z planes of invalid pixels start from a defined state (zeros)
@@ -456,6 +478,7 @@ int kt_reset(kt_ctx* c)
         size_t Pl = P >> (2 * l);
         KT_CUDA(cudaMemsetAsync(c->vmaps_g_prev[l], 0, Pl * 12, c->stream)); KT_CUDA(cudaMemsetAsync(c->nmaps_g_prev[l], 0, Pl * 12, c->stream));
         KT_CUDA(cudaMemsetAsync(c->vmaps_curr[l], 0, Pl * 12, c->stream)); KT_CUDA(cudaMemsetAsync(c->nmaps_curr[l], 0, Pl * 12, c->stream));
+        KT_CUDA(cudaMemsetAsync(c->vmaps_alt[l], 0, Pl * 12, c->stream)); KT_CUDA(cudaMemsetAsync(c->nmaps_alt[l], 0, Pl * 12, c->stream));
     }
     KT_CUDA(cudaMemsetAsync(c->vmap_curr_color, 0, P * 4, c->stream));
     KT_CUDA(cudaMemsetAsync(c->state, 0, sizeof(OdomState), c->stream));
@@ -535,6 +558,7 @@ int kt_create(const kt_config* cfg, kt_ctx** out)
         KT_TRY(dev_alloc(c, &c->depths_curr[l], Pl));
         c->vmaps_g_prev[l] = (float*)(c->arena + c->off_vmap[l]); c->nmaps_g_prev[l] = (float*)(c->arena + c->off_nmap[l]);
         KT_TRY(dev_alloc(c, &c->vmaps_curr[l], Pl * 3)); KT_TRY(dev_alloc(c, &c->nmaps_curr[l], Pl * 3));
+        KT_TRY(dev_alloc(c, &c->depths_alt[l], Pl)); KT_TRY(dev_alloc(c, &c->vmaps_alt[l], Pl * 3)); KT_TRY(dev_alloc(c, &c->nmaps_alt[l], Pl * 3));
         c->lastDepth[l] = c->nextDepth[l] = 0; c->lastImage[l] = c->nextImage[l] = 0; c->nextdIdx[l] = c->nextdIdy[l] = 0; c->pointClouds[l] = 0; c->corresImg[l] = 0;
         if (cfg->odometry != 0) {
             KT_TRY(dev_alloc(c, &c->lastDepth[l], Pl)); KT_TRY(dev_alloc(c, &c->nextDepth[l], Pl));
@@ -544,7 +568,7 @@ int kt_create(const kt_config* cfg, kt_ctx** out)
             uint8_t* ci = 0; KT_TRY(dev_alloc(c, &ci, Pl * 16)); c->corresImg[l] = ci;
         }
     }
-    c->vmap_curr_color = c->arena + c->off_vcol; KT_TRY(dev_alloc(c, &c->depth_scaled, P));
+    c->vmap_curr_color = c->arena + c->off_vcol; KT_TRY(dev_alloc(c, &c->depth_scaled, P)); KT_TRY(dev_alloc(c, &c->depth_scaled_alt, P)); c->pf_built = false; c->frontend_ready = false;
     KT_TRY(dev_alloc(c, &c->ztable, (size_t)2 * cfg->vol));
     KT_TRY(dev_alloc(c, &c->state, 1)); KT_TRY(dev_alloc(c, &c->partials, (size_t)MAX_PARTIALS * 32));
     KT_TRY(kt::cuda_check(cudaMemset(c->partials, 0, (size_t)MAX_PARTIALS * 32 * sizeof(float)), "memset", __FILE__, __LINE__));   // tags start at 0
@@ -593,14 +617,39 @@ int kt_destroy(kt_ctx* c)
     return KT_OK;
 }
 
+// If (depth, rgb) is the frame kt_prefetch_frame was given, make the prefetched buffer set the current one.
+static bool adopt_prefetched(kt_ctx* c, const void* depth, const void* rgb)
+{
+    if (!(c->pf_valid && c->pf_depth == depth && c->pf_rgb == rgb)) { c->pf_valid = false; c->pf_built = false; return false; }   // a stale hint is dropped
+    std::swap(c->depth_raw, c->depth_alt); std::swap(c->rgb, c->rgb_alt);
+    if (c->pf_built) {
+        std::swap(c->depth_scaled, c->depth_scaled_alt);
+        for (int l = 0; l < LEVELS; ++l) { std::swap(c->depths_curr[l], c->depths_alt[l]); std::swap(c->vmaps_curr[l], c->vmaps_alt[l]); std::swap(c->nmaps_curr[l], c->nmaps_alt[l]); }
+        c->frontend_ready = true;
+    }
+    cudaStreamWaitEvent(c->stream, c->ev_prefetch, 0);          // the compute stream waits for the copy (and the front end)
+    c->pf_valid = false; c->pf_built = false;
+    return true;
+}
+
+static int finish_frame(kt_ctx* c, int r)
+{
+    c->frontend_ready = false;
+    c->last_parity ^= 1;
+    cudaEventRecord(c->ev_done[c->last_parity], c->stream);      // completion of this frame's last kernel
+    return r;
+}
+
 int kt_process_frame_device(kt_ctx* c, const uint16_t* depth_dev, const uint8_t* rgb_dev, uint64_t utime, kt_pose* out)
 {
     if (!c || !depth_dev || !rgb_dev) { set_error("kt_process_frame_device: null argument"); return KT_ERR_INVALID; }
     KT_CUDA(cudaSetDevice(c->cfg.device));
     const size_t P = (size_t)c->cfg.rows * c->cfg.cols;
-    KT_CUDA(cudaMemcpyAsync(c->depth_raw, depth_dev, P * 2, cudaMemcpyDeviceToDevice, c->stream));
-    KT_CUDA(cudaMemcpyAsync(c->rgb, rgb_dev, P * 3, cudaMemcpyDeviceToDevice, c->stream));
-    return process_frame_device(c, utime, out);
+    if (!adopt_prefetched(c, depth_dev, rgb_dev)) {
+        KT_CUDA(cudaMemcpyAsync(c->depth_raw, depth_dev, P * 2, cudaMemcpyDeviceToDevice, c->stream));
+        KT_CUDA(cudaMemcpyAsync(c->rgb, rgb_dev, P * 3, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    return finish_frame(c, process_frame_device(c, utime, out));
 }
 
 int kt_process_frame(kt_ctx* c, const uint16_t* depth_host, const uint8_t* rgb_host, uint64_t utime, kt_pose* out)
@@ -608,33 +657,34 @@ int kt_process_frame(kt_ctx* c, const uint16_t* depth_host, const uint8_t* rgb_h
     if (!c || !depth_host || !rgb_host) { set_error("kt_process_frame: null argument"); return KT_ERR_INVALID; }
     KT_CUDA(cudaSetDevice(c->cfg.device));
     const size_t P = (size_t)c->cfg.rows * c->cfg.cols;
-    if (c->pf_valid && c->pf_depth == depth_host && c->pf_rgb == rgb_host) {
-        // the frame was prefetched into the spare input set: swap the sets and make the compute stream wait for the copy
-        std::swap(c->depth_raw, c->depth_alt); std::swap(c->rgb, c->rgb_alt);
-        KT_CUDA(cudaStreamWaitEvent(c->stream, c->ev_prefetch, 0));
-        c->pf_valid = false;
-    } else {
+    if (!adopt_prefetched(c, depth_host, rgb_host)) {
         KT_CUDA(cudaMemcpyAsync(c->depth_raw, depth_host, P * 2, cudaMemcpyHostToDevice, c->stream));   // TrackerInterface.cpp:90
         KT_CUDA(cudaMemcpyAsync(c->rgb, rgb_host, P * 3, cudaMemcpyHostToDevice, c->stream));           // TrackerInterface.cpp:91
     }
-    int r = process_frame_device(c, utime, out);
-    c->last_parity ^= 1;
-    cudaEventRecord(c->ev_done[c->last_parity], c->stream);      // completion of this frame's last kernel
-    return r;
+    return finish_frame(c, process_frame_device(c, utime, out));
 }
 
-int kt_prefetch_frame(kt_ctx* c, const uint16_t* depth_host, const uint8_t* rgb_host)
+int kt_prefetch_frame(kt_ctx* c, const uint16_t* depth, const uint8_t* rgb)
 {
-    if (!c || !depth_host || !rgb_host) { set_error("kt_prefetch_frame: null argument"); return KT_ERR_INVALID; }
+    if (!c || !depth || !rgb) { set_error("kt_prefetch_frame: null argument"); return KT_ERR_INVALID; }
     KT_CUDA(cudaSetDevice(c->cfg.device));
     const size_t P = (size_t)c->cfg.rows * c->cfg.cols;
-    // the spare input set was read by the frame BEFORE the last one; wait for that frame's completion event only, so the copy
-    // overlaps the last frame's integrate / ray-cast
+    // the spare set was last read by the frame BEFORE the last one; wait for that frame's completion event only, so the copy and the
+    // front end overlap the last frame's integrate / ray-cast.  Host (pinned) or device pointers.
     KT_CUDA(cudaStreamWaitEvent(c->stream_copy, c->ev_done[c->last_parity ^ 1], 0));
-    KT_CUDA(cudaMemcpyAsync(c->depth_alt, depth_host, P * 2, cudaMemcpyHostToDevice, c->stream_copy));
-    KT_CUDA(cudaMemcpyAsync(c->rgb_alt, rgb_host, P * 3, cudaMemcpyHostToDevice, c->stream_copy));
+    KT_CUDA(cudaMemcpyAsync(c->depth_alt, depth, P * 2, cudaMemcpyDefault, c->stream_copy));
+    KT_CUDA(cudaMemcpyAsync(c->rgb_alt, rgb, P * 3, cudaMemcpyDefault, c->stream_copy));
+    c->pf_built = false;
+    static const bool lookahead = getenv("KT_NO_LOOKAHEAD") == nullptr;       // A/B knob: copy only
+    if (lookahead && c->global_time > 0) {
+        // invalid pixels keep the y/z planes of the previous frame's maps = the set that is current now (Q7)
+        int r = build_frontend(c, c->depth_alt, c->depth_scaled_alt, c->depths_alt, c->vmaps_alt, c->nmaps_alt, c->vmaps_curr, c->nmaps_curr,
+                               c->stream_copy, c->stream_copy);
+        if (r) return r;
+        c->pf_built = true;
+    }
     KT_CUDA(cudaEventRecord(c->ev_prefetch, c->stream_copy));
-    c->pf_depth = depth_host; c->pf_rgb = rgb_host; c->pf_valid = true;
+    c->pf_depth = depth; c->pf_rgb = rgb; c->pf_valid = true;
     return KT_OK;
 }
 

@@ -119,13 +119,14 @@ struct IntegrateParams {
     int16_t* tsdf; uchar4* color; int V; int3 wrap; const uint8_t* rgb; const float* nmap; bool angle_color;
     const float* ztable; int zchunk;
     int lz_lo, lz_hi;          // LOGICAL z range walked by this launch (a slab is one or two such ranges)
+    int z_far_first;           // schedule the z chunks from high z to low z (see integrate())
     int z_begin, z_end;        // storage-z range owned here; volume pointers are indexed with (sz - z_begin)
 };
 
 #define KT_MAX_WEIGHT 128          // Tsdf::MAX_WEIGHT (tsdf_volume.cu:486)
 #define KT_RGB_VIEW_ANGLE_WEIGHT 0.75f
 
-template <typename IdxT>
+template <typename IdxT, int ZU>
 __global__ void __launch_bounds__(256, 4)
 integrate_kernel(const IntegrateParams p)
 {
@@ -135,7 +136,7 @@ integrate_kernel(const IntegrateParams p)
     if (sx >= V || sy >= V) return;
     int x = sx - p.wrap.x; if (x < 0) x += V;             // logical voxel
     int y = sy - p.wrap.y; if (y < 0) y += V;
-    const int z0 = p.lz_lo + blockIdx.z * p.zchunk;
+    const int z0 = p.lz_lo + (p.z_far_first ? (int)(gridDim.z - 1 - blockIdx.z) : (int)blockIdx.z) * p.zchunk;
     const int z1 = min(z0 + p.zchunk, p.lz_hi);
 
     const float3 cell_size = p.cell;
@@ -222,7 +223,6 @@ integrate_kernel(const IntegrateParams p)
     // The z loop is processed in batches of ZU voxels in three phases (project + depth gather / sdf test + volume loads /
     // blend + stores) so that ZU independent memory round trips are in flight per thread; the per-voxel arithmetic and the
     // running sums are exactly the reference's (storage addresses of different z never alias, which the compiler cannot know).
-    enum { ZU = 2 };
     for (int zb = zlo; zb < zhi; zb += ZU) {
         float vgz[ZU], Dp[ZU];
         IdxT pix[ZU], addr[ZU];
@@ -387,8 +387,17 @@ int integrate(const IntegrateArgs& a, float* ztable_dev, cudaStream_t s)
     IntegrateParams p;
     p.depth_scaled = a.depth_scaled; p.rows = a.rows; p.cols = a.cols; p.k = a.k; p.cell = cell; p.Rinv = a.Rinv; p.t = a.t; p.trunc = a.trunc;
     p.tsdf = a.tsdf; p.color = (uchar4*)a.color; p.V = V; p.wrap = a.wrap; p.rgb = a.rgb; p.nmap = a.nmap_curr; p.angle_color = a.angle_color;
-    p.ztable = ztable_dev; p.zchunk = V >= 64 ? V / 8 : V;
+    static int n_chunks = -1, order = -1;          // tuning knobs: KT_INT_ZCHUNKS (default 16), KT_INT_ORDER (0 near-first = default, 1 far-first)
+    if (n_chunks < 0) { const char* e = getenv("KT_INT_ZCHUNKS"); n_chunks = e ? atoi(e) : 16; if (n_chunks < 1) n_chunks = 1; }
+    if (order < 0) { const char* e = getenv("KT_INT_ORDER"); order = e ? atoi(e) : 0; }
+    static int zu = -1;
+    if (zu < 0) { const char* e = getenv("KT_INT_ZU"); zu = e ? atoi(e) : 2; }
+    p.ztable = ztable_dev; p.zchunk = V >= 64 ? (V + n_chunks - 1) / n_chunks : V;
     p.z_begin = a.z_begin; p.z_end = a.z_end;
+    // z chunks: a warp walks its columns' voxels serially, so a chunk's length is the scheduling quantum of the launch.  Measured on
+    // B200 (640x480 into 512^3, tools/stage_ab.py): 8 chunks 100 us, 16 chunks 78 us, 32 chunks 96 us (per-chunk column setup and the
+    // replay of the running sums grow); dispatching the far chunks first was slower at every chunk count (89-109 us).
+    p.z_far_first = (a.Rinv.r2.z > 0.f) == (order != 0) ? 1 : 0;          // z component of the camera's viewing axis in the volume frame
     // logical z ranges of the owned storage planes [z_begin, z_end): storage = (logical + wrap.z) mod V
     const int slab = a.z_end - a.z_begin;
     int lo[2], hi[2], n = 0;
@@ -404,8 +413,8 @@ int integrate(const IntegrateArgs& a, float* ztable_dev, cudaStream_t s)
     for (int i = 0; i < n; ++i) {
         p.lz_lo = lo[i]; p.lz_hi = hi[i];
         dim3 block(32, 8), grid(div_up(V, 32), div_up(V, 8), div_up(hi[i] - lo[i], p.zchunk));
-        if (idx32) integrate_kernel<unsigned int><<<grid, block, 0, s>>>(p);
-        else integrate_kernel<size_t><<<grid, block, 0, s>>>(p);
+        if (idx32) { if (zu == 4) integrate_kernel<unsigned int, 4><<<grid, block, 0, s>>>(p); else integrate_kernel<unsigned int, 2><<<grid, block, 0, s>>>(p); }
+        else integrate_kernel<size_t, 2><<<grid, block, 0, s>>>(p);
         KT_LAUNCH_CHECK();
     }
     return 0;

@@ -156,22 +156,46 @@ def test_full_size_properties_512(built, frames):
     assert results[0] == results[1]                                                              # cyclic offset changes storage, not content
 
 
-def test_prefetch_hint_does_not_change_results(built, frames):
-    """kt_prefetch_frame only moves the H2D copy earlier (double-buffered inputs on a copy stream)."""
+@pytest.mark.parametrize("odometry", [0, 2])
+def test_prefetch_hint_does_not_change_results(built, frames, odometry):
+    """kt_prefetch_frame moves the copy AND the pose-independent front end of the next frame (scaleDepth, bilateral, pyramid, maps) onto a
+    side stream, into a spare buffer set.  Results must be bit-identical with the hint, without it, and with hints given only for some
+    frames -- including the stale y/z planes of invalid map pixels (Q7) that the colour integration can read, hence the depth holes."""
     import torch
     import kintinuous_b200 as kb
-    pd = [torch.from_numpy(f[0].view(np.int16)).pin_memory() for f in frames[:6]]
-    pc = [torch.from_numpy(f[1]).pin_memory() for f in frames[:6]]
-    a = kb.Tracker(kb.Config.default(vol=256)); b = kb.Tracker(kb.Config.default(vol=256))
-    for k in range(6):
-        pa = a.process_frame(frames[k][0], frames[k][1], k)
-        pb = b.process_frame(pd[k].data_ptr(), pc[k].data_ptr(), k)
-        if k + 1 < 6:
-            b.prefetch_frame(pd[k + 1].data_ptr(), pc[k + 1].data_ptr())
-        assert list(pa.t) == list(pb.t) and list(pa.R) == list(pb.R)
-    ta, ca = a.export_volume(); tb, cb = b.export_volume()
-    assert (ta == tb).all() and (ca == cb).all()
-    a.close(); b.close()
+    rng = np.random.default_rng(7)
+    n = 9
+    fr = []
+    for k in range(n):
+        d = frames[k][0].copy()
+        d[rng.random(d.shape) < 0.04] = 0                       # holes that move from frame to frame
+        fr.append((d, frames[k][1]))
+    pd = [torch.from_numpy(f[0].view(np.int16)).pin_memory() for f in fr]
+    pc = [torch.from_numpy(f[1]).pin_memory() for f in fr]
+    dd = [t.cuda() for t in pd]; dc = [t.cuda() for t in pc]
+    cfg = dict(vol=256, odometry=odometry, voxel_shift=4)
+    ref = kb.Tracker(kb.Config.default(**cfg))
+    hinted = kb.Tracker(kb.Config.default(**cfg))             # hint before every frame, host pointers
+    mixed = kb.Tracker(kb.Config.default(**cfg))              # hint before some frames only, device pointers
+    skip = {3, 6}
+    for k in range(n):
+        pa = ref.process_frame(fr[k][0], fr[k][1], k)
+        pb = hinted.process_frame(pd[k].data_ptr(), pc[k].data_ptr(), k)
+        pm = mixed.process_frame_device(dd[k], dc[k], k)
+        if k + 1 < n:
+            hinted.prefetch_frame(pd[k + 1].data_ptr(), pc[k + 1].data_ptr())
+            if (k + 1) not in skip:
+                mixed.prefetch_frame(dd[k + 1], dc[k + 1])
+        for p in (pb, pm):
+            assert list(pa.t) == list(p.t) and list(pa.R) == list(p.R) and list(pa.voxel_wrap) == list(p.voxel_wrap), k
+    ta, ca = ref.export_volume()
+    for trk in (hinted, mixed):
+        tb, cb = trk.export_volume()
+        assert (ta == tb).all() and (ca == cb).all()
+        for which in (0, 1, 2, 3):
+            assert np.array_equal(ref.download_map(which, 0), trk.download_map(which, 0), equal_nan=True)
+        trk.close()
+    ref.close()
 
 
 _IDX64_SCRIPT = r"""
