@@ -126,8 +126,8 @@ struct IntegrateParams {
 #define KT_MAX_WEIGHT 128          // Tsdf::MAX_WEIGHT (tsdf_volume.cu:486)
 #define KT_RGB_VIEW_ANGLE_WEIGHT 0.75f
 
-template <typename IdxT, int ZU>
-__global__ void __launch_bounds__(256, 4)
+template <typename IdxT, int ZU, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 integrate_kernel(const IntegrateParams p)
 {
     const int V = p.V;
@@ -413,8 +413,17 @@ int integrate(const IntegrateArgs& a, float* ztable_dev, cudaStream_t s)
     for (int i = 0; i < n; ++i) {
         p.lz_lo = lo[i]; p.lz_hi = hi[i];
         dim3 block(32, 8), grid(div_up(V, 32), div_up(V, 8), div_up(hi[i] - lo[i], p.zchunk));
-        if (idx32) { if (zu == 4) integrate_kernel<unsigned int, 4><<<grid, block, 0, s>>>(p); else integrate_kernel<unsigned int, 2><<<grid, block, 0, s>>>(p); }
-        else integrate_kernel<size_t, 2><<<grid, block, 0, s>>>(p);
+        if (idx32) {
+            switch (zu) {                                    // tuning knob KT_INT_ZU: batch depth / CTAs per SM
+            case 4: integrate_kernel<unsigned int, 4, 3><<<grid, block, 0, s>>>(p); break;
+            case 5: integrate_kernel<unsigned int, 2, 5><<<grid, block, 0, s>>>(p); break;
+            case 6: integrate_kernel<unsigned int, 2, 6><<<grid, block, 0, s>>>(p); break;
+            case 3: integrate_kernel<unsigned int, 3, 4><<<grid, block, 0, s>>>(p); break;
+            case 1: integrate_kernel<unsigned int, 1, 6><<<grid, block, 0, s>>>(p); break;
+            default: integrate_kernel<unsigned int, 2, 4><<<grid, block, 0, s>>>(p); break;
+            }
+        }
+        else integrate_kernel<size_t, 2, 4><<<grid, block, 0, s>>>(p);
         KT_LAUNCH_CHECK();
     }
     return 0;
