@@ -186,7 +186,7 @@ def run_reference(args, world, rank, local):
         t = ref.tracker(refbind.TrackerConfig.from_kt(cfg))
         sync = torch.cuda.synchronize
         kind, cores = "reference", 1
-        sample = "every step: the reference's own CUDA kernels (oracle/_ref/libkt_ref_512.so = /root/reference src/frontend/cuda/*.cu recompiled for sm_100) on cuda:0, original launch shapes and 26 syncs/frame, restated host loop on 1 host thread, blocking H2D from pageable memory"
+        sample = "every step: the reference's own CUDA kernels (oracle/_ref/libkt_ref_<vol>.so = /root/reference src/frontend/cuda/*.cu recompiled for sm_100) on cuda:0, original launch shapes and 26 syncs/frame, restated host loop on 1 host thread, blocking H2D from pageable memory"
     else:
         o = refbind.CpuOracle()
         cores = o.lib.ktoracle_hardware_threads() or 1
@@ -336,7 +336,7 @@ def main():
     traffic = None
     try:                                                      # dram__bytes_read.sum + dram__bytes_write.sum of the committed ncu capture
         import csv
-        rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "r1_ncu_full_v4_icp_frame_kernel.csv" if args.odometry == 0 else "r1_ncu_full_v9_rgbd_frame_kernel.csv"))))
+        rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "r1_ncu_full_v10_icp_frame_kernel.csv" if args.odometry == 0 else "r1_ncu_full_v10_rgbd_frame_kernel.csv"))))
         H, U, Vv = rows[0], rows[1], rows[2]
         def val(name):
             i = H.index(name); x = float(Vv[i]); u = U[i].lower()

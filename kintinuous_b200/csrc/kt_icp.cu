@@ -151,6 +151,7 @@ struct IcpFrameParams {
     unsigned int bar_base;     // value of the counter when this launch starts
     long long* prof;           // optional: 5 clock64() stamps per iteration from CTA 0 (debug)
     int stage_k;               // passes of FRAME_THREADS pixels per CTA that fit the shared-memory stage (0 = no staging)
+    SpecArgs spec;
 };
 
 __global__ void __launch_bounds__(FRAME_THREADS, 1)
@@ -161,6 +162,7 @@ icp_frame_kernel(const IcpFrameParams p)
     __shared__ double s_Rt[16];
     __shared__ float s_red[FRAME_THREADS / 32][32];
     __shared__ float s_sum[32];
+    __shared__ double s_sumd[32];          // the same totals widened by the lanes that produced them (thread 0's solve reads doubles)
     __shared__ __align__(8) unsigned long long s_mbar;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int G = gridDim.x;
@@ -220,7 +222,7 @@ icp_frame_kernel(const IcpFrameParams p)
             Rcurr.r0 = make_float3(s_R[0], s_R[1], s_R[2]); Rcurr.r1 = make_float3(s_R[3], s_R[4], s_R[5]); Rcurr.r2 = make_float3(s_R[6], s_R[7], s_R[8]);
             tcurr = make_float3(s_t[0], s_t[1], s_t[2]);
             const bool prof = (p.prof != 0) && blockIdx.x == 0 && tid == 0 && it < 64;
-            if (prof) p.prof[it * 5 + 0] = clock64();
+            if (prof) p.prof[it * 8 + 0] = clock64();
             float sum[32];
 #pragma unroll
             for (int k = 0; k < 32; ++k) sum[k] = 0.f;
@@ -273,9 +275,9 @@ icp_frame_kernel(const IcpFrameParams p)
                 part[(size_t)tid * G + blockIdx.x] = v;
             }
             target += (unsigned int)G;
-            if (prof) p.prof[it * 5 + 1] = clock64();
+            if (prof) p.prof[it * 8 + 1] = clock64();
             grid_barrier(p.bar, target);
-            if (prof) p.prof[it * 5 + 2] = clock64();
+            if (prof) p.prof[it * 8 + 2] = clock64();
             // every CTA: fixed-order total of the G partials of each component (16 lanes per component, loads issued together)
             {
                 const int comp = tid >> 4, sub = tid & 15;
@@ -293,10 +295,10 @@ icp_frame_kernel(const IcpFrameParams p)
                 v += __shfl_xor_sync(0xffffffffu, v, 4);
                 v += __shfl_xor_sync(0xffffffffu, v, 2);
                 v += __shfl_xor_sync(0xffffffffu, v, 1);
-                if (sub == 0 && comp < NSUM) s_sum[comp] = v;
+                if (sub == 0 && comp < NSUM) { s_sum[comp] = v; s_sumd[comp] = (double)v; }
             }
             __syncthreads();
-            if (prof) p.prof[it * 5 + 3] = clock64();
+            if (prof) p.prof[it * 8 + 3] = clock64();
             if (tid == 0) {
                 // unpack 27 sums -> symmetric A (row-major) and b, constant indices only (registers, no local memory)
                 double dA[36], db[6];
@@ -306,7 +308,7 @@ icp_frame_kernel(const IcpFrameParams p)
                     for (int i = 0; i < 6; ++i)
 #pragma unroll
                         for (int j = i; j < 7; ++j) {
-                            const double value = (double)s_sum[shift++];
+                            const double value = s_sumd[shift++];
                             if (j == 6) db[i] = value; else { dA[j * 6 + i] = value; dA[i * 6 + j] = value; }
                         }
                 }
@@ -318,8 +320,9 @@ icp_frame_kernel(const IcpFrameParams p)
                     for (int k = 0; k < 6; ++k) t[36 + k] = (float)db[k];
                     t[42] = s_sum[27]; t[43] = s_sum[28];
                 }
-                gauss_newton_update_p(dA, db, s_Rt, s_Rp, s_tp, s_R, s_t);
-                if (prof) p.prof[it * 5 + 4] = clock64();
+                if (prof) p.prof[it * 8 + 5] = clock64();
+                gauss_newton_update_p(dA, db, s_Rt, s_Rp, s_tp, s_R, s_t, prof ? p.prof + it * 8 + 6 : (long long*)0);
+                if (prof) p.prof[it * 8 + 4] = clock64();
             }
             __syncthreads();
         }
@@ -328,6 +331,7 @@ icp_frame_kernel(const IcpFrameParams p)
         if (tid < 9) p.st->Rcurr[tid] = s_R[tid]; else p.st->tcurr[tid - 9] = s_t[tid - 9];
         if (tid == 0) p.st->iter = it;
     }
+    if (blockIdx.x == 0 && tid == 0 && p.spec.fp) publish_frame_pose(p.spec, s_R, s_t, s_tp);
 }
 
 __global__ void odom_begin_kernel(OdomState* st, const float* pose12)
@@ -385,9 +389,10 @@ int odom_begin_frame(OdomState* state, const float* pose12_dev, cudaStream_t s)
 // Whole-frame ICP (ICP-only odometry).  pose12 = Rprev (9) + tprev (3) on the host; the result lands in state->Rcurr/tcurr.
 // bar_dev: one unsigned int, zeroed once at allocation; *bar_count (host) tracks its value across launches.
 int icp_frame(const IcpLevelArgs* levels, const int* iters, const float* pose12_host, OdomState* state, float* partials,
-              float* trace, unsigned int* bar_dev, unsigned int* bar_count, long long* prof_dev, cudaStream_t s)
+              float* trace, unsigned int* bar_dev, unsigned int* bar_count, long long* prof_dev, const SpecArgs* spec, cudaStream_t s)
 {
     IcpFrameParams p;
+    if (spec) p.spec = *spec; else p.spec.fp = 0;
     p.prof = prof_dev;
     int total = 0;
     for (int l = 0; l < LEVELS; ++l) { p.lv[l] = levels[l]; p.iters[l] = iters[l]; total += iters[l]; }

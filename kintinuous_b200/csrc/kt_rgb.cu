@@ -337,6 +337,7 @@ struct RgbdFrameParams {
     unsigned int* bar; unsigned int bar_base;
     int stage_k;               // chunks of FRAME_THREADS pixels per CTA (<= RGBD_MAX_K)
     int with_icp;
+    SpecArgs spec;
 };
 
 enum { RGBD_MAX_K = 5 };
@@ -351,6 +352,7 @@ rgbd_frame_kernel(const RgbdFrameParams p)
     __shared__ double s_Rt[16];
     __shared__ float s_red[FRAME_THREADS / 32][32];
     __shared__ float s_sum[32], s_sum_icp[32];
+    __shared__ double s_sumd[32];          // merged normal equations in double, written by the lanes that own the components
     __shared__ int s_cnt[FRAME_THREADS / 32][2];
     __shared__ int s_tot[2];
     __shared__ __align__(8) unsigned long long s_mbar;
@@ -571,28 +573,43 @@ rgbd_frame_kernel(const RgbdFrameParams p)
                 if (comp < NSUM) for (int b = sub; b < G; b += 16) v += __ldcg(&partB[(size_t)comp * G + b]);
                 v += __shfl_xor_sync(0xffffffffu, v, 8); v += __shfl_xor_sync(0xffffffffu, v, 4);
                 v += __shfl_xor_sync(0xffffffffu, v, 2); v += __shfl_xor_sync(0xffffffffu, v, 1);
-                if (sub == 0 && comp < NSUM) s_sum[comp] = v;
+                if (sub == 0 && comp < NSUM) {
+                    s_sum[comp] = v;
+                    // A = A_rgb + 100 A_icp, b = b_rgb + 10 b_icp in double (RGBDOdometry.cpp:316-321); the b sums are components
+                    // 6, 12, 17, 21, 24, 26 of the 27 (internal.h:101-106 order)
+                    double m = (double)v;
+                    if (WITH_ICP) {
+                        const bool is_b = (comp == 6) || (comp == 12) || (comp == 17) || (comp == 21) || (comp == 24) || (comp == 26);
+                        m = fma(is_b ? 10.0 : 100.0, (double)s_sum_icp[comp], m);
+                    }
+                    s_sumd[comp] = m;
+                }
             }
             __syncthreads();
             if (tid == 0) {
-                float A[36], b[6];
-                unpack_normal_equations(s_sum, A, b);
-                if (p.trace && blockIdx.x == 0 && it < 64) {
-                    float* t = p.trace + (size_t)it * TRACE_STRIDE;
-                    for (int k = 0; k < 36; ++k) t[k] = A[k];
-                    for (int k = 0; k < 6; ++k) t[36 + k] = b[k];
-                    t[42] = (float)rgb_sigma; t[43] = (float)rgb_count;
-                }
+                // unpack 27 sums -> symmetric A (row-major) and b, constant indices only (registers, no local memory)
                 double dA[36], db[6];
-                if (WITH_ICP) {                                         // RGBDOdometry.cpp:316-321
-                    float Ai[36], bi[6];
-                    unpack_normal_equations(s_sum_icp, Ai, bi);
-                    const double w = 10;
-                    for (int k = 0; k < 36; ++k) dA[k] = (double)A[k] + w * w * (double)Ai[k];
-                    for (int k = 0; k < 6; ++k) db[k] = (double)b[k] + w * (double)bi[k];
-                } else {
-                    for (int k = 0; k < 36; ++k) dA[k] = A[k];
-                    for (int k = 0; k < 6; ++k) db[k] = b[k];
+                {
+                    int shift = 0;
+#pragma unroll
+                    for (int i = 0; i < 6; ++i)
+#pragma unroll
+                        for (int j = i; j < 7; ++j) {
+                            const double value = s_sumd[shift++];
+                            if (j == 6) db[i] = value; else { dA[j * 6 + i] = value; dA[i * 6 + j] = value; }
+                        }
+                }
+                if (p.trace && blockIdx.x == 0 && it < 64) {            // the photometric part alone, like the reference's A_rgb / b_rgb
+                    float* t = p.trace + (size_t)it * TRACE_STRIDE;
+                    int shift = 0;
+#pragma unroll
+                    for (int i = 0; i < 6; ++i)
+#pragma unroll
+                        for (int j = i; j < 7; ++j) {
+                            const float value = s_sum[shift++];
+                            if (j == 6) t[36 + i] = value; else { t[j * 6 + i] = value; t[i * 6 + j] = value; }
+                        }
+                    t[42] = (float)rgb_sigma; t[43] = (float)rgb_count;
                 }
                 gauss_newton_update_p(dA, db, s_Rt, s_Rp, s_tp, s_R, s_t);
             }
@@ -603,6 +620,7 @@ rgbd_frame_kernel(const RgbdFrameParams p)
         if (tid < 9) p.st->Rcurr[tid] = s_R[tid]; else p.st->tcurr[tid - 9] = s_t[tid - 9];
         if (tid == 0) p.st->iter = it;
     }
+    if (blockIdx.x == 0 && tid == 0 && p.spec.fp) publish_frame_pose(p.spec, s_R, s_t, s_tp);
 }
 
 } // namespace
@@ -655,17 +673,21 @@ int rgb_iteration(const RgbLevelArgs& a, OdomState* state, float* partials, floa
 // Whole-frame RGB-D / ICP+RGB-D odometry.  Returns 1 (and launches nothing) when the image does not fit the shared-memory stage,
 // in which case the caller falls back to the per-iteration kernels above.
 int rgbd_frame(const IcpLevelArgs* icp_levels, const RgbLevelArgs* rgb_levels, const int* iters, int with_icp, const float* pose12_host, OdomState* state,
-               float* partials, float* trace, unsigned int* bar_dev, unsigned int* bar_count, cudaStream_t s)
+               float* partials, float* trace, unsigned int* bar_dev, unsigned int* bar_count, const SpecArgs* spec, cudaStream_t s)
 {
     RgbdFrameParams p;
+    if (spec) p.spec = *spec; else p.spec.fp = 0;
     int total = 0;
     for (int l = 0; l < LEVELS; ++l) { p.icp[l] = icp_levels[l]; p.rgb[l] = rgb_levels[l]; p.iters[l] = iters[l]; total += iters[l]; }
     for (int k = 0; k < 12; ++k) p.pose12[k] = pose12_host[k];
     p.st = state; p.partials = partials; p.trace = trace; p.bar = bar_dev; p.bar_base = *bar_count; p.with_icp = with_icp;
-    int dev = 0, sms = 0, smem_optin = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    static int sms = 0, smem_optin = 0;                      // one device per process (one process per GPU)
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    }
     int grid = sms > 0 ? sms : 148;
     if (grid * 64 * 2 > MAX_PARTIALS * 32) grid = MAX_PARTIALS * 32 / 128;
     int need_k = 0;

@@ -131,12 +131,14 @@ __device__ __forceinline__ float dot3_rn(float a0, float a1, float a2, float b0,
 
 // Solve for the increment and update resultRt (4x4 double) and the float pose (Rcurr, tcurr) given (Rprev, tprev).
 __device__ __forceinline__ void gauss_newton_update_p(const double* dA, const double* db, double* resultRt,
-                                                      const float* Rp, const float* tprev, float* Rcurr, float* tcurr)
+                                                      const float* Rp, const float* tprev, float* Rcurr, float* tcurr, long long* stamps = 0)
 {
     double x[6];
     ldlt6_solve(dA, db, x);
+    if (stamps) stamps[0] = clock64();            // debug (tools/icp_prof.py)
     double R[9];
     rodrigues(x + 3, R);
+    if (stamps) stamps[1] = clock64();
     const double cur[16] = {R[0], R[1], R[2], x[0], R[3], R[4], R[5], x[1], R[6], R[7], R[8], x[2], 0, 0, 0, 1};
     double res[16];
 #pragma unroll
@@ -168,6 +170,30 @@ __device__ __forceinline__ void gauss_newton_update_p(const double* dA, const do
             Rcurr[i * 3 + j] = dot3_rn(Rp[i * 3 + 0], Rp[i * 3 + 1], Rp[i * 3 + 2], rot[j * 3 + 0], rot[j * 3 + 1], rot[j * 3 + 2]);
         tcurr[i] = __fadd_rn(dot3_rn(Rp[i * 3 + 0], Rp[i * 3 + 1], Rp[i * 3 + 2], tinv[0], tinv[1], tinv[2]), tprev[i]);
     }
+}
+
+// Tail of the whole-frame odometry kernels (one thread): publish the final pose for speculatively launched volume kernels.
+// spec_ok is conservative: 1 only if the host's exact tests (KintinuousTracker.cpp:636-667 shift thresholds, RGBDOdometry.cpp:383-387
+// 0.3 m jump guard) certainly come out as "no shift, pose accepted"; margins are orders of magnitude above float rounding.
+__device__ inline void publish_frame_pose(const SpecArgs& sp, const float* R, const float* t, const float* tprev)
+{
+    FramePose* fp = sp.fp;
+    float Rinv[9];
+    mat3f_inverse(R, Rinv);                                    // Rcurr.inverse(), KintinuousTracker.cpp:627 (same IEEE ops as the host path)
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { fp->R[k] = R[k]; fp->Rinv[k] = Rinv[k]; ok = ok && (fabsf(R[k]) <= 2.f); }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        fp->t[k] = t[k];
+        const float q = (t[k] - sp.basis[k]) / sp.voxel;       // host: floor(q) >= thresh or <= -thresh shifts the volume
+        ok = ok && (q > -sp.thresh + 1.01f) && (q < sp.thresh - 0.01f);
+    }
+    if (sp.guard_jump) {
+        const float dx = t[0] - tprev[0], dy = t[1] - tprev[1], dz = t[2] - tprev[2];
+        ok = ok && (dx * dx + dy * dy + dz * dz < 0.29f * 0.29f);
+    }
+    fp->spec_ok = ok ? 1 : 0;
 }
 
 __device__ __forceinline__ void gauss_newton_update(const double* dA, const double* db, OdomState* st)
