@@ -170,9 +170,9 @@ def run_reference(args, world, rank, local):
     cfg = kb.Config.default(rows=ROWS, cols=COLS, vol=args.vol, odometry=args.odometry)
     n_frames = min(N_INPUT_FRAMES, max(8, args.steps + args.warmup + 1))
     frames = make_stream(n_frames)
-    line = {"metric": f"frames/s 640x480 into {args.vol}^3 TSDF ({METRIC_TAGS[args.odometry]} tracker)", "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+    line = {"metric": f"frames/s {COLS}x{ROWS} into {args.vol}^3 TSDF ({METRIC_TAGS[args.odometry]} tracker)", "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": {"workload": f"synthetic 640x480 RGB-D stream, {args.vol}^3 volume (6 m), {TRACKER_NAMES[args.odometry]} {{10,5,4}}, shifting on (-t 14)", "frames_cycled": n_frames}}
+            "config": {"workload": f"synthetic {COLS}x{ROWS} RGB-D stream, {args.vol}^3 volume (6 m), {TRACKER_NAMES[args.odometry]} {{10,5,4}}, shifting on (-t 14)", "frames_cycled": n_frames}}
     use_cuda = False
     try:
         import torch
@@ -222,8 +222,14 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=48)
     ap.add_argument("--no-prefetch", action="store_true", help="do not give the kt_prefetch_frame hint (A/B)")
     ap.add_argument("--vol", type=int, default=VOL)
+    ap.add_argument("--scale", type=int, default=1, help="image scale: 1 = 640x480 (configs 1-3), 2 = 1280x960 (configs[4])")
     ap.add_argument("--odometry", type=int, default=0, help="0 ICP (configs[1]), 2 ICP+RGB-D (configs[2])")
     args = ap.parse_args()
+    global ROWS, COLS, P_LEVELS, N_INPUT_FRAMES
+    if args.scale != 1:
+        ROWS, COLS = 480 * args.scale, 640 * args.scale
+        P_LEVELS = [ROWS * COLS >> (2 * l) for l in range(4)]
+        N_INPUT_FRAMES = max(8, N_INPUT_FRAMES // (args.scale * args.scale))      # same bytes of distinct input
     world, rank, local = dist_setup(args.gpus)
     if args.impl == "reference":
         run_reference(args, world, rank, local)
@@ -353,10 +359,10 @@ def main():
     streams = 1 if zslab else world          # z-slab: all ranks work on ONE stream (strong scaling)
     value = streams * args.steps / dt
     e2e_v = streams * args.steps / results["host"]["dt"]
-    line = {"metric": f"frames/s 640x480 into {args.vol}^3 TSDF ({METRIC_TAGS[args.odometry]} tracker)", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
+    line = {"metric": f"frames/s {COLS}x{ROWS} into {args.vol}^3 TSDF ({METRIC_TAGS[args.odometry]} tracker)", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
             "ms_per_step": 1e3 * dt / args.steps, "wall_ms_per_step": 1e3 * results["device"]["wall"] / args.steps, "timing": "CUDA events on the tracker stream, max over ranks", "higher_is_better": True, "scaling": "strong" if zslab else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"synthetic 640x480 RGB-D stream, {args.vol}^3 volume (6 m), {tracker_name} {{10,5,4}}, shifting on (-t 14)", "parallelism": (f"one stream, volume z-slab sharded over {world} GPUs (P2P raycast, replicated ICP)" if zslab else f"{world} independent streams"), "vol": args.vol, "odometry": args.odometry,
-                       "l2": f"inputs larger than L2: {n} frames x 1.54 MB = {n * 1.536:.0f} MB cycled (ping-pong)"},
+            "config": {"workload": f"synthetic {COLS}x{ROWS} RGB-D stream, {args.vol}^3 volume (6 m), {tracker_name} {{10,5,4}}, shifting on (-t 14)", "parallelism": (f"one stream, volume z-slab sharded over {world} GPUs (P2P raycast, replicated ICP)" if zslab else f"{world} independent streams"), "vol": args.vol, "odometry": args.odometry,
+                       "l2": f"inputs larger than L2: {n} frames x {ROWS * COLS * 5 / 1e6:.2f} MB = {n * ROWS * COLS * 5 / 1e6:.0f} MB cycled (ping-pong)"},
             "e2e": {"value": e2e_v, "unit": "frames/s", "h2d_bytes_per_step": ROWS * COLS * 5, "d2h_bytes_per_step": 48},
             "gpu_launches": int(results["device"]["launches"]), "clocks": clocks, "roofline": roofline, "stages": stages}
     if not args.no_cpu_baseline:

@@ -125,10 +125,6 @@ KT_API int kt_get_stage_ms(kt_ctx* ctx, float* ms6);
 KT_API int kt_set_stage_timing(kt_ctx* ctx, int enabled);
 /* CUDA-event duration of the last whole-frame ICP launch (icp_frame_kernel), ms; 0 unless stage timing is on and odometry == 0 */
 KT_API float kt_get_icp_kernel_ms(kt_ctx* ctx);
-/* Frames whose volume stage (integrate + ray cast) was launched speculatively behind the odometry kernel and accepted (hits) or
- * skipped on the device and redone after the host's decision (misses: volume shifts, rejected poses).  KT_NO_SPEC=1 in the
- * environment at kt_create turns the speculation off; results are bit-identical either way. */
-KT_API int kt_spec_stats(kt_ctx* ctx, long long* hits, long long* misses);
 /* Device-side stopwatch on the tracker's own stream: mark(0) ... frames ... mark(1), then the CUDA-event time between the two
  * marks (ms, synchronises on mark 1; < 0 on error).  bench.py times its region with this, not with the host clock. */
 KT_API int kt_span_mark(kt_ctx* ctx, int which);

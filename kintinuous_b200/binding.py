@@ -195,11 +195,6 @@ class Tracker:
     def launch_count(self):
         return int(self.lib.kt_launch_count(self.h))
 
-    def spec_stats(self):
-        h, m = C.c_longlong(0), C.c_longlong(0)
-        _check(self.lib.kt_spec_stats(self.h, C.byref(h), C.byref(m)))
-        return int(h.value), int(m.value)
-
     def span_mark(self, which):
         _check(self.lib.kt_span_mark(self.h, int(which)))
 

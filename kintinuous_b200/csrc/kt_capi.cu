@@ -105,7 +105,7 @@ int kt_op_integrate(const uint16_t* depth_raw, int rows, int cols, const float* 
 {
     int r = ensure_ztable(vol); if (r) return r;
     r = scale_depth(depth_raw, depth_scaled, rows, cols, intr4(k), angle_color != 0, st(s)); if (r) return r;
-    IntegrateArgs a; a.fp = 0;
+    IntegrateArgs a;
     a.depth_scaled = depth_scaled; a.rows = rows; a.cols = cols; a.k = intr4(k); a.volume_size = make_float3(vs[0], vs[1], vs[2]);
     a.Rinv = mat33(Rinv); a.t = make_float3(t[0], t[1], t[2]); a.trunc = trunc; a.tsdf = tsdf; a.color = color; a.vol = vol;
     a.wrap = make_int3(wrap[0], wrap[1], wrap[2]); a.rgb = rgb; a.nmap_curr = nmap_curr; a.angle_color = angle_color != 0;
@@ -119,7 +119,7 @@ int kt_op_raycast(const float* k, const float* R, const float* t, float trunc, c
                   const int16_t* tsdf, int vol, float* vmap, float* nmap, int rows, int cols,
                   const int* wrap, uint8_t* vmap_color, const uint8_t* color, void* s)
 {
-    RaycastArgs a; a.fp = 0;
+    RaycastArgs a;
     a.k = intr4(k); a.R = mat33(R); a.t = make_float3(t[0], t[1], t[2]); a.trunc = trunc; a.volume_size = make_float3(vs[0], vs[1], vs[2]);
     a.tsdf = tsdf; a.color = color; a.vol = vol; a.wrap = make_int3(wrap[0], wrap[1], wrap[2]);
     for (int l = 0; l < LEVELS; ++l) { a.vmap[l] = vmap; a.nmap[l] = nmap; }

@@ -6,7 +6,7 @@
 
 namespace kt {
 
-enum { FRAME_THREADS = 512, STAGE_MAX_K = 8 };
+enum { FRAME_THREADS = 512, STAGE_MAX_K = 17 };   // 17 passes x 6 planes x 2 KB = 204 KB of shared memory: 1280x960 level 0 still fits
 
 __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int target)
 {

@@ -151,7 +151,6 @@ struct IcpFrameParams {
     unsigned int bar_base;     // value of the counter when this launch starts
     long long* prof;           // optional: 5 clock64() stamps per iteration from CTA 0 (debug)
     int stage_k;               // passes of FRAME_THREADS pixels per CTA that fit the shared-memory stage (0 = no staging)
-    SpecArgs spec;
 };
 
 __global__ void __launch_bounds__(FRAME_THREADS, 1)
@@ -331,7 +330,6 @@ icp_frame_kernel(const IcpFrameParams p)
         if (tid < 9) p.st->Rcurr[tid] = s_R[tid]; else p.st->tcurr[tid - 9] = s_t[tid - 9];
         if (tid == 0) p.st->iter = it;
     }
-    if (blockIdx.x == 0 && tid == 0 && p.spec.fp) publish_frame_pose(p.spec, s_R, s_t, s_tp);
 }
 
 __global__ void odom_begin_kernel(OdomState* st, const float* pose12)
@@ -389,10 +387,9 @@ int odom_begin_frame(OdomState* state, const float* pose12_dev, cudaStream_t s)
 // Whole-frame ICP (ICP-only odometry).  pose12 = Rprev (9) + tprev (3) on the host; the result lands in state->Rcurr/tcurr.
 // bar_dev: one unsigned int, zeroed once at allocation; *bar_count (host) tracks its value across launches.
 int icp_frame(const IcpLevelArgs* levels, const int* iters, const float* pose12_host, OdomState* state, float* partials,
-              float* trace, unsigned int* bar_dev, unsigned int* bar_count, long long* prof_dev, const SpecArgs* spec, cudaStream_t s)
+              float* trace, unsigned int* bar_dev, unsigned int* bar_count, long long* prof_dev, cudaStream_t s)
 {
     IcpFrameParams p;
-    if (spec) p.spec = *spec; else p.spec.fp = 0;
     p.prof = prof_dev;
     int total = 0;
     for (int l = 0; l < LEVELS; ++l) { p.lv[l] = levels[l]; p.iters[l] = iters[l]; total += iters[l]; }

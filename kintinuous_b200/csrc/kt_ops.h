@@ -71,13 +71,8 @@ struct IcpLevelArgs {
 //   mode 1: reduce + LDLT solve + pose update on device (ICP-only odometry)
 int icp_iteration(const IcpLevelArgs& a, OdomState* state, float* partials, float* trace, int mode, cudaStream_t s);
 
-// Speculative hand-over of the frame's pose to the volume kernels without a host round trip: the odometry kernel's tail publishes
-// the pose (+ its inverse) in device memory and decides, conservatively, whether the host will certainly NOT shift the volume and
-// NOT reject the pose; integrate / raycast launched right behind it read the pose from there and do nothing when spec_ok == 0.
-struct FramePose { float R[9]; float t[3]; float Rinv[9]; int spec_ok; };
-struct SpecArgs { FramePose* fp; float basis[3]; float voxel; float thresh; int guard_jump; };      // fp == null: off
 int icp_frame(const IcpLevelArgs* levels, const int* iters, const float* pose12_host, OdomState* state, float* partials,
-              float* trace, unsigned int* bar_dev, unsigned int* bar_count, long long* prof_dev, const SpecArgs* spec, cudaStream_t s);
+              float* trace, unsigned int* bar_dev, unsigned int* bar_count, long long* prof_dev, cudaStream_t s);
 
 struct RgbLevelArgs {
     const int16_t* dIdx; const int16_t* dIdy; const float* last_depth; const float* next_depth;
@@ -88,7 +83,7 @@ struct RgbLevelArgs {
 int rgb_residual(const RgbLevelArgs& a, OdomState* state, int* partials, int use_state_warp, cudaStream_t s);
 // mode 0: reduce only; 1: solve RGB-only; 2: solve A_rgb + 100 A_icp (RGBDOdometry.cpp:316-321)
 int rgbd_frame(const IcpLevelArgs* icp_levels, const RgbLevelArgs* rgb_levels, const int* iters, int with_icp, const float* pose12_host, OdomState* state,
-               float* partials, float* trace, unsigned int* bar_dev, unsigned int* bar_count, const SpecArgs* spec, cudaStream_t s);
+               float* partials, float* trace, unsigned int* bar_dev, unsigned int* bar_count, cudaStream_t s);
 int rgb_iteration(const RgbLevelArgs& a, OdomState* state, float* partials, float* trace, int mode, float sigma_override, cudaStream_t s);
 // pose12_dev: Rprev (9) + tprev (3) in device memory
 int odom_begin_frame(OdomState* state, const float* pose12_dev, cudaStream_t s);
@@ -105,7 +100,6 @@ struct IntegrateArgs {
     const float* depth_scaled; int rows, cols; Intr k; float3 volume_size; Mat33 Rinv; float3 t; float trunc;
     int16_t* tsdf; uint8_t* color; int vol; int3 wrap; const uint8_t* rgb; const float* nmap_curr; bool angle_color;
     int z_begin, z_end;          // storage-z slab owned by this GPU ([0, vol) on a single GPU)
-    const FramePose* fp;         // non-null: Rinv / t come from device memory (speculative launch), the kernel is a no-op unless fp->spec_ok
 };
 int integrate(const IntegrateArgs& a, float* ztable_dev /* 2*vol floats */, cudaStream_t s);
 struct RaycastArgs {
@@ -115,7 +109,6 @@ struct RaycastArgs {
     // its results into EVERY rank's model maps (P2P stores = the all-gather, fused into the kernel epilogue)
     int multi; VolumeView vv; int tile_row_begin, tile_row_end;
     float* peer_vmap[MAX_GPUS][LEVELS]; float* peer_nmap[MAX_GPUS][LEVELS]; uint8_t* peer_vcol[MAX_GPUS];
-    const FramePose* fp;         // non-null: R / t come from device memory (speculative launch), no-op unless fp->spec_ok
 };
 int raycast(const RaycastArgs& a, cudaStream_t s);
 int extract_slice(const int16_t* tsdf, const float3& volume_size, int vol, void* out, size_t capacity, const int3& wrap,

@@ -25,7 +25,6 @@ struct RayParams {
     // multi-GPU
     VolumeView vv; int tile_row_begin; int n_out;
     float* peer_vmap[MAX_GPUS][LEVELS]; float* peer_nmap[MAX_GPUS][LEVELS]; uchar4* peer_vcol[MAX_GPUS];
-    const FramePose* fp;    // speculative launch: pose from device memory, no-op unless spec_ok
 };
 
 // POW2: V is a power of two (cyclic wrap by mask, plane / row offsets by shift); IdxT: 32-bit voxel index when V^3 <= 2^31.
@@ -163,17 +162,17 @@ enum { RC_X = 16, RC_Y = 8 };
 
 // One ray.  Returns validity of vertex / normal; outputs by reference.
 template <bool POW2, typename IdxT, int RS, bool MG>
-__device__ __forceinline__ void cast_ray(const RayParams& p, const Mat33& Rcurr, const float3& tcurr, int x, int y, bool& v_ok, float3& vtx, bool& n_ok, float3& nrm,
+__device__ __forceinline__ void cast_ray(const RayParams& p, int x, int y, bool& v_ok, float3& vtx, bool& n_ok, float3& nrm,
                                          bool& c_ok, uchar4& col)
 {
     v_ok = false; n_ok = false; c_ok = false;
     Caster<POW2, IdxT, MG> rc(p);
-    float3 ray_start = tcurr;
+    float3 ray_start = p.tcurr;
     float3 ray_next_c;
     ray_next_c.x = (x - p.intr.cx) / p.intr.fx;
     ray_next_c.y = (y - p.intr.cy) / p.intr.fy;
     ray_next_c.z = 1;
-    float3 ray_next = add3(mul33(Rcurr, ray_next_c), tcurr);
+    float3 ray_next = add3(mul33(p.Rcurr, ray_next_c), p.tcurr);
     float3 ray_dir = normalized3(sub3(ray_next, ray_start));
     ray_dir.x = (ray_dir.x == 0.f) ? 1e-15 : ray_dir.x;
     ray_dir.y = (ray_dir.y == 0.f) ? 1e-15 : ray_dir.y;
@@ -296,13 +295,6 @@ raycast_kernel(const RayParams p)
     __shared__ float s1[2][3][RC_Y / 2][RC_X / 2];
     __shared__ float s2[2][3][RC_Y / 4][RC_X / 4];
 
-    Mat33 Rcurr = p.Rcurr; float3 tcurr = p.tcurr;
-    if (p.fp) {
-        const FramePose* fp = p.fp;
-        if (!fp->spec_ok) return;
-        Rcurr.r0 = make_float3(fp->R[0], fp->R[1], fp->R[2]); Rcurr.r1 = make_float3(fp->R[3], fp->R[4], fp->R[5]);
-        Rcurr.r2 = make_float3(fp->R[6], fp->R[7], fp->R[8]); tcurr = make_float3(fp->t[0], fp->t[1], fp->t[2]);
-    }
     const int tile_y = blockIdx.y + (MG ? p.tile_row_begin : 0);
     const int x = threadIdx.x + blockIdx.x * RC_X;
     const int y = threadIdx.y + tile_y * RC_Y;
@@ -313,7 +305,7 @@ raycast_kernel(const RayParams p)
     float3 vtx = make_float3(nan, nan, nan), nrm = make_float3(nan, nan, nan);
     uchar4 col;
     if (inside) {
-        cast_ray<POW2, IdxT, RS, MG>(p, Rcurr, tcurr, x, y, v_ok, vtx, n_ok, nrm, c_ok, col);
+        cast_ray<POW2, IdxT, RS, MG>(p, x, y, v_ok, vtx, n_ok, nrm, c_ok, col);
         const size_t P = (size_t)p.rows * p.cols, i = (size_t)y * p.cols + x;
         // like the reference: x planes are always written (NaN = no surface), y/z only on success
         store_maps<MG>(p, 0, i, P, v_ok, vtx, n_ok, nrm);
@@ -391,7 +383,7 @@ int raycast(const RaycastArgs& a, cudaStream_t s)
     p.volume = a.tsdf; p.color_volume = (const uchar4*)a.color; p.V = a.vol; p.wrap = a.wrap;
     for (int l = 0; l < LEVELS; ++l) { p.vmap[l] = a.vmap[l]; p.nmap[l] = a.nmap[l]; }
     p.vmap_color = (uchar4*)a.vmap_color; p.rows = a.rows; p.cols = a.cols;
-    p.n_levels = a.n_levels; p.z_begin = 0; p.tile_row_begin = 0; p.n_out = 1; p.fp = a.fp;
+    p.n_levels = a.n_levels; p.z_begin = 0; p.tile_row_begin = 0; p.n_out = 1;
     // the in-tile pyramid needs every level's tile to be whole
     if (p.n_levels > 1 && ((a.cols % RC_X) != 0 || (a.rows % RC_Y) != 0)) { set_error("raycast: fused pyramid needs cols %% 16 == 0 and rows %% 8 == 0"); return -1; }
     dim3 block(RC_X, RC_Y), grid(div_up(a.cols, RC_X), div_up(a.rows, RC_Y));

@@ -337,7 +337,6 @@ struct RgbdFrameParams {
     unsigned int* bar; unsigned int bar_base;
     int stage_k;               // chunks of FRAME_THREADS pixels per CTA (<= RGBD_MAX_K)
     int with_icp;
-    SpecArgs spec;
 };
 
 enum { RGBD_MAX_K = 5 };
@@ -620,7 +619,6 @@ rgbd_frame_kernel(const RgbdFrameParams p)
         if (tid < 9) p.st->Rcurr[tid] = s_R[tid]; else p.st->tcurr[tid - 9] = s_t[tid - 9];
         if (tid == 0) p.st->iter = it;
     }
-    if (blockIdx.x == 0 && tid == 0 && p.spec.fp) publish_frame_pose(p.spec, s_R, s_t, s_tp);
 }
 
 } // namespace
@@ -673,10 +671,9 @@ int rgb_iteration(const RgbLevelArgs& a, OdomState* state, float* partials, floa
 // Whole-frame RGB-D / ICP+RGB-D odometry.  Returns 1 (and launches nothing) when the image does not fit the shared-memory stage,
 // in which case the caller falls back to the per-iteration kernels above.
 int rgbd_frame(const IcpLevelArgs* icp_levels, const RgbLevelArgs* rgb_levels, const int* iters, int with_icp, const float* pose12_host, OdomState* state,
-               float* partials, float* trace, unsigned int* bar_dev, unsigned int* bar_count, const SpecArgs* spec, cudaStream_t s)
+               float* partials, float* trace, unsigned int* bar_dev, unsigned int* bar_count, cudaStream_t s)
 {
     RgbdFrameParams p;
-    if (spec) p.spec = *spec; else p.spec.fp = 0;
     int total = 0;
     for (int l = 0; l < LEVELS; ++l) { p.icp[l] = icp_levels[l]; p.rgb[l] = rgb_levels[l]; p.iters[l] = iters[l]; total += iters[l]; }
     for (int k = 0; k < 12; ++k) p.pose12[k] = pose12_host[k];

@@ -172,30 +172,6 @@ __device__ __forceinline__ void gauss_newton_update_p(const double* dA, const do
     }
 }
 
-// Tail of the whole-frame odometry kernels (one thread): publish the final pose for speculatively launched volume kernels.
-// spec_ok is conservative: 1 only if the host's exact tests (KintinuousTracker.cpp:636-667 shift thresholds, RGBDOdometry.cpp:383-387
-// 0.3 m jump guard) certainly come out as "no shift, pose accepted"; margins are orders of magnitude above float rounding.
-__device__ inline void publish_frame_pose(const SpecArgs& sp, const float* R, const float* t, const float* tprev)
-{
-    FramePose* fp = sp.fp;
-    float Rinv[9];
-    mat3f_inverse(R, Rinv);                                    // Rcurr.inverse(), KintinuousTracker.cpp:627 (same IEEE ops as the host path)
-    bool ok = true;
-#pragma unroll
-    for (int k = 0; k < 9; ++k) { fp->R[k] = R[k]; fp->Rinv[k] = Rinv[k]; ok = ok && (fabsf(R[k]) <= 2.f); }
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        fp->t[k] = t[k];
-        const float q = (t[k] - sp.basis[k]) / sp.voxel;       // host: floor(q) >= thresh or <= -thresh shifts the volume
-        ok = ok && (q > -sp.thresh + 1.01f) && (q < sp.thresh - 0.01f);
-    }
-    if (sp.guard_jump) {
-        const float dx = t[0] - tprev[0], dy = t[1] - tprev[1], dz = t[2] - tprev[2];
-        ok = ok && (dx * dx + dy * dy + dz * dz < 0.29f * 0.29f);
-    }
-    fp->spec_ok = ok ? 1 : 0;
-}
-
 __device__ __forceinline__ void gauss_newton_update(const double* dA, const double* db, OdomState* st)
 {
     gauss_newton_update_p(dA, db, st->resultRt, st->Rprev, st->tprev, st->Rcurr, st->tcurr);

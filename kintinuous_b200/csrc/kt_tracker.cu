@@ -87,9 +87,6 @@ struct kt_ctx {
     // ... and the pose-independent front end of the NEXT frame (scaleDepth, bilateral, pyrDown, vertex / normal maps) is built into a
     // spare set on the same side stream, so that it overlaps the integrate / ray-cast of the frame before (they leave issue slots idle)
     uint16_t* depths_alt[LEVELS]; float* vmaps_alt[LEVELS]; float* nmaps_alt[LEVELS]; float* depth_scaled_alt;
-    // speculative volume stage: integrate + raycast are enqueued right behind the odometry kernel and take the pose from device memory
-    // (FramePose, published by the odometry kernel's tail), so the GPU does not idle while the host reads the pose back and decides
-    FramePose* fpose_dev; FramePose* fpose_host; cudaEvent_t ev_pose; bool spec_enabled; long long spec_hits, spec_misses;
     bool pf_built;             // the prefetched set holds the finished front end
     bool frontend_ready;       // set for the duration of one process_frame_device call
     cudaStream_t stream_copy; cudaEvent_t ev_prefetch, ev_done[2]; int last_parity;
@@ -164,18 +161,30 @@ int push_slice(kt_ctx* c, int dimension)
     return 0;
 }
 
-int populate_rgbd(kt_ctx* c, float** destDepths, uint8_t** destImages)             // RGBDOdometry::populateRGBDData (.cpp:140-158)
+int populate_rgbd(kt_ctx* c, const uint16_t* depth_raw, const uint8_t* rgb, float** destDepths, uint8_t** destImages, cudaStream_t s)   // RGBDOdometry::populateRGBDData (.cpp:140-158)
 {
     const int rows = c->cfg.rows, cols = c->cfg.cols;
     int r;
-    if ((r = short_depth_to_metres(c->depth_raw, destDepths[0], rows, cols, (int)(6.0 * 1000), c->stream))) return r;
-    for (int i = 0; i + 1 < LEVELS; ++i) if ((r = pyrdown_gauss_f(destDepths[i], destDepths[i + 1], rows >> i, cols >> i, c->stream))) return r;
-    if ((r = bgr_to_intensity(c->rgb, destImages[0], rows, cols, c->stream))) return r;
-    for (int i = 0; i + 1 < LEVELS; ++i) if ((r = pyrdown_uchar_gauss(destImages[i], destImages[i + 1], rows >> i, cols >> i, c->stream))) return r;
+    if ((r = short_depth_to_metres(depth_raw, destDepths[0], rows, cols, (int)(6.0 * 1000), s))) return r;
+    for (int i = 0; i + 1 < LEVELS; ++i) if ((r = pyrdown_gauss_f(destDepths[i], destDepths[i + 1], rows >> i, cols >> i, s))) return r;
+    if ((r = bgr_to_intensity(rgb, destImages[0], rows, cols, s))) return r;
+    for (int i = 0; i + 1 < LEVELS; ++i) if ((r = pyrdown_uchar_gauss(destImages[i], destImages[i + 1], rows >> i, cols >> i, s))) return r;
     return 0;
 }
 
-int do_integrate(kt_ctx* c, const M3& Rinv, const V3& t, const int* wrap, const FramePose* fp = 0)
+// Photometric front end of a frame (pose-independent): float depth + intensity pyramids and the image gradients of all levels
+// (RGBDOdometry.cpp:140-158 + computeDerivativeImages, :172-175), into the "next" buffers.
+int rgbd_frontend(kt_ctx* c, const uint16_t* depth_raw, const uint8_t* rgb, cudaStream_t s)
+{
+    const int rows = c->cfg.rows, cols = c->cfg.cols;
+    int r;
+    if ((r = populate_rgbd(c, depth_raw, rgb, c->nextDepth, c->nextImage, s))) return r;
+    for (int i = 0; i < LEVELS; ++i)
+        if ((r = derivative_images(c->nextImage[i], c->nextdIdx[i], c->nextdIdy[i], rows >> i, cols >> i, s))) return r;
+    return 0;
+}
+
+int do_integrate(kt_ctx* c, const M3& Rinv, const V3& t, const int* wrap)
 {
     const int rows = c->cfg.rows, cols = c->cfg.cols;
     Intr k = {c->cfg.fx, c->cfg.fy, c->cfg.cx, c->cfg.cy};
@@ -185,51 +194,12 @@ int do_integrate(kt_ctx* c, const M3& Rinv, const V3& t, const int* wrap, const 
     a.Rinv = to_mat33(Rinv.m); a.t = make_float3(t.v[0], t.v[1], t.v[2]); a.trunc = c->trunc;
     a.tsdf = c->tsdf; a.color = c->color; a.vol = c->cfg.vol; a.wrap = make_int3(wrap[0], wrap[1], wrap[2]);
     a.rgb = c->rgb; a.nmap_curr = c->nmaps_curr[0]; a.angle_color = c->cfg.angle_color != 0;
-    a.z_begin = c->z_begin; a.z_end = c->z_end; a.fp = fp;
+    a.z_begin = c->z_begin; a.z_end = c->z_end;
     return integrate(a, c->ztable, c->stream);
 }
 
-int mg_barrier(kt_ctx* c);
-void mark(kt_ctx* c, int i);
-
-// Volume stage of a frame: integrate (.cpp:864-876), then predict the surface for the next frame (.cpp:878-899).  With fp the pose
-// arguments are placeholders: the kernels read the pose from device memory and do nothing unless fp->spec_ok.
-int volume_stage(kt_ctx* c, const M3& Rcurr, const M3& Rcurr_inv, const V3& tcurr, const FramePose* fp)
+int run_odometry(kt_ctx* c, const M3& Rprev, const V3& tprev, M3* Rcurr, V3* tcurr)
 {
-    const int rows = c->cfg.rows, cols = c->cfg.cols, V = c->cfg.vol, mode = c->cfg.odometry;
-    int r, vWrapCopy[3];
-    vwrap_copy(c, vWrapCopy);
-    if ((r = do_integrate(c, Rcurr_inv, tcurr, vWrapCopy, fp))) return r;
-    if ((r = mg_barrier(c))) return r;                                                   // every slab holds this frame before any ray reads it
-    mark(c, 4);
-    RaycastArgs ra;
-    ra.k.fx = c->cfg.fx; ra.k.fy = c->cfg.fy; ra.k.cx = c->cfg.cx; ra.k.cy = c->cfg.cy;
-    ra.R = to_mat33(Rcurr.m); ra.t = make_float3(tcurr.v[0], tcurr.v[1], tcurr.v[2]); ra.trunc = c->trunc;
-    ra.volume_size = make_float3(c->size, c->size, c->size); ra.tsdf = c->tsdf; ra.color = c->color; ra.vol = V;
-    ra.wrap = make_int3(vWrapCopy[0], vWrapCopy[1], vWrapCopy[2]);
-    for (int l = 0; l < LEVELS; ++l) { ra.vmap[l] = c->vmaps_g_prev[l]; ra.nmap[l] = c->nmaps_g_prev[l]; }
-    ra.rows = rows; ra.cols = cols; ra.vmap_color = c->vmap_curr_color;
-    ra.n_levels = (mode == 0 || mode == 2) ? LEVELS : 1;                                 // .cpp:892-899
-    ra.multi = c->world > 1 ? 1 : 0; ra.fp = fp;
-    if (ra.multi) {
-        ra.n_levels = LEVELS;
-        ra.vv = c->vv;
-        const int tiles_y = rows / 8;
-        ra.tile_row_begin = c->rank * tiles_y / c->world; ra.tile_row_end = (c->rank + 1) * tiles_y / c->world;
-        for (int g = 0; g < c->world; ++g) {
-            for (int l = 0; l < LEVELS; ++l) { ra.peer_vmap[g][l] = (float*)(c->peer_arena[g] + c->off_vmap[l]); ra.peer_nmap[g][l] = (float*)(c->peer_arena[g] + c->off_nmap[l]); }
-            ra.peer_vcol[g] = c->peer_arena[g] + c->off_vcol;
-        }
-    }
-    if ((r = raycast(ra, c->stream))) return r;
-    if ((r = mg_barrier(c))) return r;                                                   // all tiles of the predicted surface have landed everywhere
-    mark(c, 5);
-    return 0;
-}
-
-int run_odometry(kt_ctx* c, const M3& Rprev, const V3& tprev, M3* Rcurr, V3* tcurr, bool* spec_done)
-{
-    *spec_done = false;
     const int rows = c->cfg.rows, cols = c->cfg.cols;
     const int mode = c->cfg.odometry;
     int r;
@@ -238,17 +208,9 @@ int run_odometry(kt_ctx* c, const M3& Rprev, const V3& tprev, M3* Rcurr, V3* tcu
     const float distThres = 0.10f, angleThres = sinf(20.f * 3.14159254f / 180.f);      // ICPOdometry.h:35-36
     Intr K = {c->cfg.fx, c->cfg.fy, c->cfg.cx, c->cfg.cy};
     if (mode != 0) {
-        if ((r = populate_rgbd(c, c->nextDepth, c->nextImage))) return r;
-        for (int i = 0; i < LEVELS; ++i)
-            if ((r = derivative_images(c->nextImage[i], c->nextdIdx[i], c->nextdIdy[i], rows >> i, cols >> i, c->stream))) return r;
+        // built ahead of time by kt_prefetch_frame when the frame was prefetched (the "next" buffers are free between two frames)
+        if (!c->frontend_ready && (r = rgbd_frontend(c, c->depth_raw, c->rgb, c->stream))) return r;
     }
-    // the odometry kernel's tail publishes the pose in device memory; with speculation on it also clears the volume stage for take-off
-    const bool want_spec = c->spec_enabled && c->world == 1 && !c->timing;
-    SpecArgs spec;
-    spec.fp = c->fpose_dev; spec.voxel = c->voxel; spec.guard_jump = mode != 0 ? 1 : 0;
-    for (int i = 0; i < 3; ++i) spec.basis[i] = c->volumeBasis[i];
-    spec.thresh = !want_spec ? -1.f : (c->parked ? 1e30f : (float)c->cfg.voxel_shift);      // thresh < 0: spec_ok can never be set
-    bool whole_frame = false;
     int total_iters = 0;
     if (mode == 0) {
         // ICP-only: the whole coarse-to-fine loop is ONE cooperative launch (kt_icp.cu, icp_frame_kernel)
@@ -260,8 +222,7 @@ int run_odometry(kt_ctx* c, const M3& Rprev, const V3& tprev, M3* Rcurr, V3* tcu
             total_iters += c->iterations[level];
         }
         if (c->timing) cudaEventRecord(c->ev_icp[0], c->stream);
-        if ((r = icp_frame(la, c->iterations, c->pose12_host, c->state, c->partials, c->trace_dev, c->bar_dev, &c->bar_count, c->timing ? c->prof_dev : 0, &spec, c->stream))) return r;
-        whole_frame = true;
+        if ((r = icp_frame(la, c->iterations, c->pose12_host, c->state, c->partials, c->trace_dev, c->bar_dev, &c->bar_count, c->timing ? c->prof_dev : 0, c->stream))) return r;
         if (c->timing) cudaEventRecord(c->ev_icp[1], c->stream);
     }
     const double SOBEL_SCALE = 1.0 / std::pow(2.0, 3);
@@ -284,9 +245,9 @@ int run_odometry(kt_ctx* c, const M3& Rprev, const V3& tprev, M3* Rcurr, V3* tcu
             ra.max_depth_delta = 0.07f; ra.fx = kl.fx; ra.fy = kl.fy; ra.sobel_scale = (float)SOBEL_SCALE;
             ra.Kfx = (double)K.fx / div; ra.Kfy = (double)K.fy / div; ra.Kcx = (double)K.cx / div; ra.Kcy = (double)K.cy / div;
         }
-        r = rgbd_frame(la, ra4, c->iterations, mode == 2 ? 1 : 0, c->pose12_host, c->state, c->partials, c->trace_dev, c->bar_dev, &c->bar_count, &spec, c->stream);
+        r = rgbd_frame(la, ra4, c->iterations, mode == 2 ? 1 : 0, c->pose12_host, c->state, c->partials, c->trace_dev, c->bar_dev, &c->bar_count, c->stream);
         if (r < 0) return r;
-        if (r == 0) { per_iteration_path = false; whole_frame = true; for (int level = 0; level < LEVELS; ++level) total_iters += c->iterations[level]; }
+        if (r == 0) { per_iteration_path = false; for (int level = 0; level < LEVELS; ++level) total_iters += c->iterations[level]; }
         else {       // image too large for the shared-memory stage: per-iteration kernels
             KT_CUDA(cudaMemcpyAsync(c->pose12_dev, c->pose12_host, 12 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
             if ((r = odom_begin_frame(c->state, c->pose12_dev, c->stream))) return r;
@@ -322,32 +283,13 @@ int run_odometry(kt_ctx* c, const M3& Rprev, const V3& tprev, M3* Rcurr, V3* tcu
         }
     }
     c->trace_iters = std::min(total_iters, MAX_TRACE_ITERS);
-    // one small read-back of the estimate (+ the trace when someone asked for it later: it stays on the device)
-    if (whole_frame) {
-        KT_CUDA(cudaMemcpyAsync(c->fpose_host, c->fpose_dev, sizeof(FramePose), cudaMemcpyDeviceToHost, c->stream));
-        KT_CUDA(cudaEventRecord(c->ev_pose, c->stream));
-        if (want_spec) {
-            // enqueue the volume stage NOW, behind the odometry kernel: it reads the pose from fpose_dev and is a no-op if the
-            // kernel's tail saw a possible shift / rejected pose (then the normal path below runs it after the host's decision)
-            M3 Rprev_inv = m3_inverse(Rprev);
-            if ((r = volume_stage(c, Rprev, Rprev_inv, tprev, c->fpose_dev))) return r;
-        }
-        KT_CUDA(cudaEventSynchronize(c->ev_pose));
-        for (int k = 0; k < 9; ++k) Rcurr->m[k] = c->fpose_host->R[k];
-        for (int k = 0; k < 3; ++k) tcurr->v[k] = c->fpose_host->t[k];
-        *spec_done = want_spec && c->fpose_host->spec_ok != 0;
-        if (want_spec) { if (*spec_done) ++c->spec_hits; else ++c->spec_misses; }
-    } else {
-        KT_CUDA(cudaMemcpyAsync(c->result_host->Rcurr, (char*)c->state + offsetof(OdomState, Rcurr), 12 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-        if (c->world > 1) KT_CUDA(cudaMemcpyAsync(c->mg_error_host, c->mg_error_dev, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-        KT_CUDA(cudaStreamSynchronize(c->stream));
-        for (int k = 0; k < 9; ++k) Rcurr->m[k] = c->result_host->Rcurr[k];
-        for (int k = 0; k < 3; ++k) tcurr->v[k] = c->result_host->tcurr[k];
-    }
-    if (c->world > 1) {
-        if (whole_frame) { KT_CUDA(cudaMemcpyAsync(c->mg_error_host, c->mg_error_dev, sizeof(int), cudaMemcpyDeviceToHost, c->stream)); KT_CUDA(cudaStreamSynchronize(c->stream)); }
-        if (*c->mg_error_host) { set_error("cross-GPU barrier timed out waiting for rank %d", *c->mg_error_host - 1); return KT_ERR_STATE; }
-    }
+    // one 64-byte read-back of the estimate (+ the trace when someone asked for it later: it stays on the device)
+    KT_CUDA(cudaMemcpyAsync(c->result_host->Rcurr, (char*)c->state + offsetof(OdomState, Rcurr), 12 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    if (c->world > 1) KT_CUDA(cudaMemcpyAsync(c->mg_error_host, c->mg_error_dev, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    KT_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->world > 1 && *c->mg_error_host) { set_error("cross-GPU barrier timed out waiting for rank %d", *c->mg_error_host - 1); return KT_ERR_STATE; }
+    for (int k = 0; k < 9; ++k) Rcurr->m[k] = c->result_host->Rcurr[k];
+    for (int k = 0; k < 3; ++k) tcurr->v[k] = c->result_host->tcurr[k];
     if (mode != 0) {
         for (int i = 0; i < LEVELS; ++i) { std::swap(c->lastDepth[i], c->nextDepth[i]); std::swap(c->lastImage[i], c->nextImage[i]); }   // RGBDOdometry.cpp:377-381
         float dx = tcurr->v[0] - tprev.v[0], dy = tcurr->v[1] - tprev.v[1], dz = tcurr->v[2] - tprev.v[2];
@@ -409,7 +351,7 @@ int process_frame_device(kt_ctx* c, uint64_t utime, kt_pose* out)
         M3 Rcam = c->rmats.back(); V3 tcam = c->tvecs.back();
         M3 Rcam_inv = m3_inverse(Rcam);
         int emptyVoxel[3] = {0, 0, 0};
-        if (mode != 0 && (r = populate_rgbd(c, c->lastDepth, c->lastImage))) return r;    // rgbd->firstRun
+        if (mode != 0 && (r = populate_rgbd(c, c->depth_raw, c->rgb, c->lastDepth, c->lastImage, c->stream))) return r;    // rgbd->firstRun
         mark(c, 2); mark(c, 3);
         if ((r = do_integrate(c, Rcam_inv, tcam, emptyVoxel))) return r;
         mark(c, 4);
@@ -425,8 +367,7 @@ int process_frame_device(kt_ctx* c, uint64_t utime, kt_pose* out)
 
     M3 Rprev = c->rmats.back(); V3 tprev = c->tvecs.back();
     M3 Rcurr = Rprev; V3 tcurr = tprev;
-    bool spec_done = false;
-    if ((r = run_odometry(c, Rprev, tprev, &Rcurr, &tcurr, &spec_done))) return r;
+    if ((r = run_odometry(c, Rprev, tprev, &Rcurr, &tcurr))) return r;
     mark(c, 2);
     c->current_utime = utime;
     c->rmats.push_back(Rcurr); c->tvecs.push_back(tcurr);                                // .cpp:578-579
@@ -479,16 +420,35 @@ int process_frame_device(kt_ctx* c, uint64_t utime, kt_pose* out)
             ++c->shifted_last;
         }
     }
+    vwrap_copy(c, vWrapCopy);
     mark(c, 3);
-    if (spec_done) {
-        // the volume stage already runs behind the odometry kernel with exactly this pose; the device only clears it when the host's
-        // tests above cannot fire (margins in publish_frame_pose), so a shift here means the two disagree: refuse to continue
-        if (c->shifted_last) { set_error("speculative volume stage ran on a frame that shifted the volume"); return KT_ERR_STATE; }
-        if (std::memcmp(Rcurr.m, c->fpose_host->R, sizeof(Rcurr.m)) != 0 || std::memcmp(tcurr.v, c->fpose_host->t, sizeof(tcurr.v)) != 0) {
-            set_error("speculative volume stage ran on a rejected pose"); return KT_ERR_STATE; }
-    } else {
-        if ((r = volume_stage(c, Rcurr, Rcurr_inv, tcurr, 0))) return r;
+
+    if ((r = do_integrate(c, Rcurr_inv, tcurr, vWrapCopy))) return r;                    // .cpp:864-876
+    if ((r = mg_barrier(c))) return r;                                                   // every slab holds this frame before any ray reads it
+    mark(c, 4);
+    vwrap_copy(c, vWrapCopy);
+    RaycastArgs ra;
+    ra.k.fx = c->cfg.fx; ra.k.fy = c->cfg.fy; ra.k.cx = c->cfg.cx; ra.k.cy = c->cfg.cy;
+    ra.R = to_mat33(Rcurr.m); ra.t = make_float3(tcurr.v[0], tcurr.v[1], tcurr.v[2]); ra.trunc = c->trunc;
+    ra.volume_size = make_float3(c->size, c->size, c->size); ra.tsdf = c->tsdf; ra.color = c->color; ra.vol = V;
+    ra.wrap = make_int3(vWrapCopy[0], vWrapCopy[1], vWrapCopy[2]);
+    for (int l = 0; l < LEVELS; ++l) { ra.vmap[l] = c->vmaps_g_prev[l]; ra.nmap[l] = c->nmaps_g_prev[l]; }
+    ra.rows = rows; ra.cols = cols; ra.vmap_color = c->vmap_curr_color;
+    ra.n_levels = (mode == 0 || mode == 2) ? LEVELS : 1;                                 // .cpp:892-899
+    ra.multi = c->world > 1 ? 1 : 0;
+    if (ra.multi) {
+        ra.n_levels = LEVELS;
+        ra.vv = c->vv;
+        const int tiles_y = rows / 8;
+        ra.tile_row_begin = c->rank * tiles_y / c->world; ra.tile_row_end = (c->rank + 1) * tiles_y / c->world;
+        for (int g = 0; g < c->world; ++g) {
+            for (int l = 0; l < LEVELS; ++l) { ra.peer_vmap[g][l] = (float*)(c->peer_arena[g] + c->off_vmap[l]); ra.peer_nmap[g][l] = (float*)(c->peer_arena[g] + c->off_nmap[l]); }
+            ra.peer_vcol[g] = c->peer_arena[g] + c->off_vcol;
+        }
     }
+    if ((r = raycast(ra, c->stream))) return r;
+    if ((r = mg_barrier(c))) return r;                                                   // all tiles of the predicted surface have landed everywhere
+    mark(c, 5);
     ++c->global_time;
     if (out) kt_get_pose(c, out);
     return 0;
@@ -629,10 +589,6 @@ int kt_create(const kt_config* cfg, kt_ctx** out)
     c->cloud_capacity = (size_t)c->cfg.cloud_capacity;
     KT_TRY(dev_alloc(c, &c->cloud_dev, c->cloud_capacity)); KT_TRY(dev_alloc(c, &c->counter_dev, 1));
     KT_TRY(kt::cuda_check(cudaMallocHost((void**)&c->pose12_host, 12 * sizeof(float)), "pinned", __FILE__, __LINE__));
-    KT_TRY(kt::cuda_check(cudaMallocHost((void**)&c->fpose_host, sizeof(FramePose)), "pinned", __FILE__, __LINE__));
-    KT_TRY(dev_alloc(c, &c->fpose_dev, 1)); KT_TRY(kt::cuda_check(cudaMemset(c->fpose_dev, 0, sizeof(FramePose)), "memset", __FILE__, __LINE__));
-    KT_TRY(kt::cuda_check(cudaEventCreateWithFlags(&c->ev_pose, cudaEventDisableTiming), "event", __FILE__, __LINE__));
-    c->spec_enabled = getenv("KT_NO_SPEC") == nullptr; c->spec_hits = c->spec_misses = 0;
     KT_TRY(kt::cuda_check(cudaMallocHost((void**)&c->result_host, sizeof(OdomResult)), "pinned", __FILE__, __LINE__));
     KT_TRY(kt::cuda_check(cudaMallocHost((void**)&c->trace_host, (size_t)MAX_TRACE_ITERS * TRACE_STRIDE * sizeof(float)), "pinned", __FILE__, __LINE__));
     KT_TRY(kt::cuda_check(cudaMallocHost((void**)&c->counter_host, sizeof(unsigned int)), "pinned", __FILE__, __LINE__));
@@ -655,8 +611,6 @@ int kt_destroy(kt_ctx* c)
     if (c->mg_error_host) cudaFreeHost(c->mg_error_host);
     for (void* p : c->allocs) cudaFree(p);
     if (c->pose12_host) cudaFreeHost(c->pose12_host);
-    if (c->fpose_host) cudaFreeHost(c->fpose_host);
-    if (c->ev_pose) cudaEventDestroy(c->ev_pose);
     if (c->result_host) cudaFreeHost(c->result_host);
     if (c->trace_host) cudaFreeHost(c->trace_host);
     if (c->counter_host) cudaFreeHost(c->counter_host);
@@ -677,7 +631,12 @@ int kt_destroy(kt_ctx* c)
 // If (depth, rgb) is the frame kt_prefetch_frame was given, make the prefetched buffer set the current one.
 static bool adopt_prefetched(kt_ctx* c, const void* depth, const void* rgb)
 {
-    if (!(c->pf_valid && c->pf_depth == depth && c->pf_rgb == rgb)) { c->pf_valid = false; c->pf_built = false; return false; }   // a stale hint is dropped
+    if (!(c->pf_valid && c->pf_depth == depth && c->pf_rgb == rgb)) {
+        // a stale hint is dropped; its front end may still be writing the photometric "next" buffers this frame is about to rebuild
+        if (c->pf_valid) cudaStreamWaitEvent(c->stream, c->ev_prefetch, 0);
+        c->pf_valid = false; c->pf_built = false;
+        return false;
+    }
     std::swap(c->depth_raw, c->depth_alt); std::swap(c->rgb, c->rgb_alt);
     if (c->pf_built) {
         std::swap(c->depth_scaled, c->depth_scaled_alt);
@@ -738,6 +697,9 @@ int kt_prefetch_frame(kt_ctx* c, const uint16_t* depth, const uint8_t* rgb)
         int r = build_frontend(c, c->depth_alt, c->depth_scaled_alt, c->depths_alt, c->vmaps_alt, c->nmaps_alt, c->vmaps_curr, c->nmaps_curr,
                                c->stream_copy, c->stream_copy);
         if (r) return r;
+        // photometric odometry: its "next" pyramids were swapped to "last" when the previous frame's odometry finished, so the
+        // buffers now called next are free until the coming frame
+        if (c->cfg.odometry != 0 && (r = rgbd_frontend(c, c->depth_alt, c->rgb_alt, c->stream_copy))) return r;
         c->pf_built = true;
     }
     KT_CUDA(cudaEventRecord(c->ev_prefetch, c->stream_copy));
@@ -909,14 +871,6 @@ float kt_span_elapsed_ms(kt_ctx* c)
     float t = 0.f;
     if (cudaEventSynchronize(c->ev_span[1]) != cudaSuccess || cudaEventElapsedTime(&t, c->ev_span[0], c->ev_span[1]) != cudaSuccess) { cudaGetLastError(); return -1.f; }
     return t;
-}
-
-int kt_spec_stats(kt_ctx* c, long long* hits, long long* misses)
-{
-    if (!c) return KT_ERR_INVALID;
-    if (hits) *hits = c->spec_hits;
-    if (misses) *misses = c->spec_misses;
-    return KT_OK;
 }
 
 long long kt_launch_count(kt_ctx* c) { return c ? g_launches - c->launches_at_create : g_launches; }

@@ -101,10 +101,9 @@ scale_depth_kernel(const uint16_t* __restrict__ depth, float* __restrict__ scale
 
 // ------------------------------------------------------------------------------------------------
 // z tables: v_g_z(z) and z_scaled(z) as the reference's running sums produce them (tsdf_volume.cu:555,563,570-571)
-__global__ void ztable_kernel(float* __restrict__ table, int V, float cell_z, float t_z, const FramePose* fp)
+__global__ void ztable_kernel(float* __restrict__ table, int V, float cell_z, float t_z)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    if (fp) { if (!fp->spec_ok) return; t_z = fp->t[2]; }
     float v_g_z = (0 + 0.5f) * cell_z - t_z;
     float z_scaled = 0;
     for (int z = 0; z < V; ++z) {
@@ -122,7 +121,6 @@ struct IntegrateParams {
     int lz_lo, lz_hi;          // LOGICAL z range walked by this launch (a slab is one or two such ranges)
     int z_far_first;           // schedule the z chunks from high z to low z (see integrate())
     int z_begin, z_end;        // storage-z range owned here; volume pointers are indexed with (sz - z_begin)
-    const FramePose* fp;       // speculative launch: pose from device memory, no-op unless spec_ok
 };
 
 #define KT_MAX_WEIGHT 128          // Tsdf::MAX_WEIGHT (tsdf_volume.cu:486)
@@ -143,14 +141,8 @@ integrate_kernel(const IntegrateParams p)
 
     const float3 cell_size = p.cell;
     const Intr intr = p.k;
-    Mat33 Rcurr_inv = p.Rinv;
-    float3 tcurr = p.t;
-    if (p.fp) {
-        const FramePose* fp = p.fp;
-        if (!fp->spec_ok) return;
-        Rcurr_inv.r0 = make_float3(fp->Rinv[0], fp->Rinv[1], fp->Rinv[2]); Rcurr_inv.r1 = make_float3(fp->Rinv[3], fp->Rinv[4], fp->Rinv[5]);
-        Rcurr_inv.r2 = make_float3(fp->Rinv[6], fp->Rinv[7], fp->Rinv[8]); tcurr = make_float3(fp->t[0], fp->t[1], fp->t[2]);
-    }
+    const Mat33 Rcurr_inv = p.Rinv;
+    const float3 tcurr = p.t;
     const float tranc_dist = p.trunc;
     const int cols = p.cols, rows = p.rows;
 
@@ -390,7 +382,7 @@ int integrate(const IntegrateArgs& a, float* ztable_dev, cudaStream_t s)
 {
     const int V = a.vol;
     float3 cell = make_float3(a.volume_size.x / V, a.volume_size.y / V, a.volume_size.z / V);   // host division, tsdf_volume.cu:659-661
-    ztable_kernel<<<1, 32, 0, s>>>(ztable_dev, V, cell.z, a.t.z, a.fp);
+    ztable_kernel<<<1, 32, 0, s>>>(ztable_dev, V, cell.z, a.t.z);
     KT_LAUNCH_CHECK();
     IntegrateParams p;
     p.depth_scaled = a.depth_scaled; p.rows = a.rows; p.cols = a.cols; p.k = a.k; p.cell = cell; p.Rinv = a.Rinv; p.t = a.t; p.trunc = a.trunc;
@@ -401,7 +393,7 @@ int integrate(const IntegrateArgs& a, float* ztable_dev, cudaStream_t s)
     static int zu = -1;
     if (zu < 0) { const char* e = getenv("KT_INT_ZU"); zu = e ? atoi(e) : 2; }
     p.ztable = ztable_dev; p.zchunk = V >= 64 ? (V + n_chunks - 1) / n_chunks : V;
-    p.z_begin = a.z_begin; p.z_end = a.z_end; p.fp = a.fp;
+    p.z_begin = a.z_begin; p.z_end = a.z_end;
     // z chunks: a warp walks its columns' voxels serially, so a chunk's length is the scheduling quantum of the launch.  Measured on
     // B200 (640x480 into 512^3, tools/stage_ab.py): 8 chunks 100 us, 16 chunks 78 us, 32 chunks 96 us (per-chunk column setup and the
     // replay of the running sums grow); dispatching the far chunks first was slower at every chunk count (89-109 us).

@@ -240,44 +240,6 @@ def test_prefetch_hint_does_not_change_results(built, frames, odometry):
     ref.close()
 
 
-@pytest.mark.parametrize("odometry,voxel_shift", [(0, 14), (0, 2), (2, 4)])
-def test_speculative_volume_stage_is_bit_identical(built, frames, odometry, voxel_shift, monkeypatch):
-    """integrate + ray cast are enqueued behind the odometry kernel and read the pose from device memory; frames that shift the volume
-    must fall back to the host-ordered path.  Poses, volume, model maps and slices are bit-identical to the non-speculative run."""
-    import kintinuous_b200 as kb
-    outs = []
-    for spec in (True, False):
-        if spec:
-            monkeypatch.delenv("KT_NO_SPEC", raising=False)
-        else:
-            monkeypatch.setenv("KT_NO_SPEC", "1")
-        trk = kb.Tracker(kb.Config.default(vol=256, odometry=odometry, voxel_shift=voxel_shift))
-        poses = []
-        for k in range(10):
-            p = trk.process_frame(frames[k][0], frames[k][1], k)
-            poses.append(np.concatenate([np.array(p.R), np.array(p.t), np.array(p.voxel_wrap, dtype=np.float32)]))
-        hits, misses = trk.spec_stats()
-        ts, cs = trk.export_volume()
-        maps = [trk.download_map(w, 0).copy() for w in (2, 3, 5)]
-        trk.finalise()
-        sl = [trk.get_slice(i) for i in range(trk.num_slices())]
-        outs.append((np.array(poses), ts.copy(), cs.copy(), maps, sl, hits, misses))
-        trk.close()
-    a, b = outs
-    assert a[5] > 0 and b[5] == 0 and b[6] == 0                      # speculation really ran in the first run
-    if voxel_shift == 2:
-        assert a[6] > 0                                              # ... and fell back on the frames that shifted
-    assert (a[0].view(np.uint32) == b[0].view(np.uint32)).all()
-    assert (a[1] == b[1]).all() and (a[2] == b[2]).all()
-    for ma, mb in zip(a[3], b[3]):
-        assert np.array_equal(ma, mb, equal_nan=True)
-    assert len(a[4]) == len(b[4])
-    for (pa, da, _), (pb, db, _) in zip(a[4], b[4]):
-        assert da == db and len(pa) == len(pb)
-        ra, rb = pa.view(np.uint8).reshape(len(pa), -1), pb.view(np.uint8).reshape(len(pb), -1)    # extraction order is undefined: compare as multisets
-        assert np.array_equal(ra[np.lexsort(ra.T[::-1])], rb[np.lexsort(rb.T[::-1])])
-
-
 _IDX64_SCRIPT = r"""
 import hashlib, sys
 import numpy as np
