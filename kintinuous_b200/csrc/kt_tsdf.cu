@@ -126,7 +126,7 @@ struct IntegrateParams {
 #define KT_MAX_WEIGHT 128          // Tsdf::MAX_WEIGHT (tsdf_volume.cu:486)
 #define KT_RGB_VIEW_ANGLE_WEIGHT 0.75f
 
-template <typename IdxT, int ZU, int MINB>
+template <typename IdxT, int ZU, int MINB, bool EARLY = false>
 __global__ void __launch_bounds__(256, MINB)
 integrate_kernel(const IntegrateParams p)
 {
@@ -227,6 +227,8 @@ integrate_kernel(const IntegrateParams p)
         float vgz[ZU], Dp[ZU];
         IdxT pix[ZU], addr[ZU];
         bool ok[ZU];
+        float nx[ZU], nz[ZU];
+        int16_t tprev[ZU]; uchar4 cprev[ZU]; uchar3 rgbv[ZU];
 #pragma unroll
         for (int u = 0; u < ZU; ++u) {
             const int z = zb + u;
@@ -244,6 +246,13 @@ integrate_kernel(const IntegrateParams p)
                             pix[u] = (IdxT)coo.y * cols + coo.x;
                             addr[u] = (IdxT)(sz - p.z_begin) * plane + col_off;
                             Dp[u] = depthScaled[pix[u]];
+                            if (EARLY) {      // every load of the voxel in ONE round trip (the volume / image addresses do not depend on the depth)
+                                tprev[u] = p.tsdf[addr[u]];
+                                cprev[u] = p.color[addr[u]];
+                                nx[u] = nmap_curr[pix[u]];
+                                nz[u] = nmap_curr[pix[u] + 2 * P];
+                                rgbv[u] = colors[pix[u]];
+                            }
                         }
                     }
                 }
@@ -252,8 +261,7 @@ integrate_kernel(const IntegrateParams p)
             }
         }
         bool upd[ZU], nocol[ZU];
-        float tsdf_new[ZU], nx[ZU], nz[ZU];
-        int16_t tprev[ZU]; uchar4 cprev[ZU]; uchar3 rgbv[ZU];
+        float tsdf_new[ZU];
 #pragma unroll
         for (int u = 0; u < ZU; ++u) {
             upd[u] = false;
@@ -265,11 +273,13 @@ integrate_kernel(const IntegrateParams p)
                 if (Dp_scaled != 0 && sdf >= -tranc_dist) {
                     upd[u] = true; nocol[u] = no_color;
                     tsdf_new[u] = fmin(1.0f, sdf * tranc_dist_inv);
-                    tprev[u] = p.tsdf[addr[u]];
-                    cprev[u] = p.color[addr[u]];
-                    nx[u] = nmap_curr[pix[u]];
-                    nz[u] = nmap_curr[pix[u] + 2 * P];
-                    rgbv[u] = colors[pix[u]];
+                    if (!EARLY) {
+                        tprev[u] = p.tsdf[addr[u]];
+                        cprev[u] = p.color[addr[u]];
+                        nx[u] = nmap_curr[pix[u]];
+                        nz[u] = nmap_curr[pix[u] + 2 * P];
+                        rgbv[u] = colors[pix[u]];
+                    }
                 }
             }
         }
@@ -420,6 +430,9 @@ int integrate(const IntegrateArgs& a, float* ztable_dev, cudaStream_t s)
             case 6: integrate_kernel<unsigned int, 2, 6><<<grid, block, 0, s>>>(p); break;
             case 3: integrate_kernel<unsigned int, 3, 4><<<grid, block, 0, s>>>(p); break;
             case 1: integrate_kernel<unsigned int, 1, 6><<<grid, block, 0, s>>>(p); break;
+            case 7: integrate_kernel<unsigned int, 2, 4, true><<<grid, block, 0, s>>>(p); break;
+            case 8: integrate_kernel<unsigned int, 1, 6, true><<<grid, block, 0, s>>>(p); break;
+            case 9: integrate_kernel<unsigned int, 2, 3, true><<<grid, block, 0, s>>>(p); break;
             default: integrate_kernel<unsigned int, 2, 4><<<grid, block, 0, s>>>(p); break;
             }
         }
