@@ -126,7 +126,7 @@ struct IntegrateParams {
 #define KT_MAX_WEIGHT 128          // Tsdf::MAX_WEIGHT (tsdf_volume.cu:486)
 #define KT_RGB_VIEW_ANGLE_WEIGHT 0.75f
 
-template <typename IdxT, int ZU, int MINB, bool EARLY = false>
+template <typename IdxT, int ZU, int MINB>
 __global__ void __launch_bounds__(256, MINB)
 integrate_kernel(const IntegrateParams p)
 {
@@ -246,13 +246,6 @@ integrate_kernel(const IntegrateParams p)
                             pix[u] = (IdxT)coo.y * cols + coo.x;
                             addr[u] = (IdxT)(sz - p.z_begin) * plane + col_off;
                             Dp[u] = depthScaled[pix[u]];
-                            if (EARLY) {      // every load of the voxel in ONE round trip (the volume / image addresses do not depend on the depth)
-                                tprev[u] = p.tsdf[addr[u]];
-                                cprev[u] = p.color[addr[u]];
-                                nx[u] = nmap_curr[pix[u]];
-                                nz[u] = nmap_curr[pix[u] + 2 * P];
-                                rgbv[u] = colors[pix[u]];
-                            }
                         }
                     }
                 }
@@ -273,13 +266,12 @@ integrate_kernel(const IntegrateParams p)
                 if (Dp_scaled != 0 && sdf >= -tranc_dist) {
                     upd[u] = true; nocol[u] = no_color;
                     tsdf_new[u] = fmin(1.0f, sdf * tranc_dist_inv);
-                    if (!EARLY) {
-                        tprev[u] = p.tsdf[addr[u]];
-                        cprev[u] = p.color[addr[u]];
-                        nx[u] = nmap_curr[pix[u]];
-                        nz[u] = nmap_curr[pix[u] + 2 * P];
-                        rgbv[u] = colors[pix[u]];
-                    }
+                    // (issuing these loads together with the depth gather, before the test, was slower: 78 -> 88 us at 512^3)
+                    tprev[u] = p.tsdf[addr[u]];
+                    cprev[u] = p.color[addr[u]];
+                    nx[u] = nmap_curr[pix[u]];
+                    nz[u] = nmap_curr[pix[u] + 2 * P];
+                    rgbv[u] = colors[pix[u]];
                 }
             }
         }
@@ -401,7 +393,7 @@ int integrate(const IntegrateArgs& a, float* ztable_dev, cudaStream_t s)
     if (n_chunks < 0) { const char* e = getenv("KT_INT_ZCHUNKS"); n_chunks = e ? atoi(e) : 16; if (n_chunks < 1) n_chunks = 1; }
     if (order < 0) { const char* e = getenv("KT_INT_ORDER"); order = e ? atoi(e) : 0; }
     static int zu = -1;
-    if (zu < 0) { const char* e = getenv("KT_INT_ZU"); zu = e ? atoi(e) : 2; }
+    if (zu < 0) { const char* e = getenv("KT_INT_ZU"); zu = e ? atoi(e) : 0; }
     p.ztable = ztable_dev; p.zchunk = V >= 64 ? (V + n_chunks - 1) / n_chunks : V;
     p.z_begin = a.z_begin; p.z_end = a.z_end;
     // z chunks: a warp walks its columns' voxels serially, so a chunk's length is the scheduling quantum of the launch.  Measured on
@@ -430,13 +422,11 @@ int integrate(const IntegrateArgs& a, float* ztable_dev, cudaStream_t s)
             case 6: integrate_kernel<unsigned int, 2, 6><<<grid, block, 0, s>>>(p); break;
             case 3: integrate_kernel<unsigned int, 3, 4><<<grid, block, 0, s>>>(p); break;
             case 1: integrate_kernel<unsigned int, 1, 6><<<grid, block, 0, s>>>(p); break;
-            case 7: integrate_kernel<unsigned int, 2, 4, true><<<grid, block, 0, s>>>(p); break;
-            case 8: integrate_kernel<unsigned int, 1, 6, true><<<grid, block, 0, s>>>(p); break;
-            case 9: integrate_kernel<unsigned int, 2, 3, true><<<grid, block, 0, s>>>(p); break;
             default: integrate_kernel<unsigned int, 2, 4><<<grid, block, 0, s>>>(p); break;
             }
         }
-        else integrate_kernel<size_t, 2, 4><<<grid, block, 0, s>>>(p);
+        else if (zu == 2) integrate_kernel<size_t, 2, 4><<<grid, block, 0, s>>>(p);
+        else integrate_kernel<size_t, 1, 6><<<grid, block, 0, s>>>(p);
         KT_LAUNCH_CHECK();
     }
     return 0;
