@@ -187,6 +187,8 @@ public:
     kt_pose processFrame(const unsigned short* depthHost, const unsigned char* rgbHost, uint64_t utime) { kt_pose p; kt::check(kt_process_frame(ctx_, depthHost, rgbHost, utime, &p)); return p; }
     kt_pose processFrame(const DeviceArray2D<unsigned short>& depth, const DeviceArray2D<PixelRGB>& colors, uint64_t utime)
     { kt_pose p; kt::check(kt_process_frame_device(ctx_, depth.ptr(), (const uint8_t*)colors.ptr(), utime, &p)); return p; }
+    // optional hint (no counterpart in the reference): start the next frame's upload and pose-independent front end now
+    void prefetchFrame(const unsigned short* depth, const unsigned char* rgb) { kt::check(kt_prefetch_frame(ctx_, depth, rgb)); }
     void finalise() { kt::check(kt_finalise(ctx_)); }
     void reset() { kt::check(kt_reset(ctx_)); }
     float getVoxelSize() const { return kt_get_voxel_size(ctx_); }
