@@ -100,6 +100,7 @@ struct IntegrateArgs {
     const float* depth_scaled; int rows, cols; Intr k; float3 volume_size; Mat33 Rinv; float3 t; float trunc;
     int16_t* tsdf; uint8_t* color; int vol; int3 wrap; const uint8_t* rgb; const float* nmap_curr; bool angle_color;
     int z_begin, z_end;          // storage-z slab owned by this GPU ([0, vol) on a single GPU)
+    float* cw; float4* rgbf;     // optional per-pixel scratch (rows*cols each): colour weight + float RGB prepared once per frame
 };
 int integrate(const IntegrateArgs& a, float* ztable_dev /* 2*vol floats */, cudaStream_t s);
 struct RaycastArgs {

@@ -118,6 +118,7 @@ struct IntegrateParams {
     const float* depth_scaled; int rows, cols; Intr k; float3 cell; Mat33 Rinv; float3 t; float trunc;
     int16_t* tsdf; uchar4* color; int V; int3 wrap; const uint8_t* rgb; const float* nmap; bool angle_color;
     const float* ztable; int zchunk;
+    const float* cw; const float4* rgbf;   // PREP: per-pixel colour weight (sign bit = normal invalid) and RGB as floats
     int lz_lo, lz_hi;          // LOGICAL z range walked by this launch (a slab is one or two such ranges)
     int z_far_first;           // schedule the z chunks from high z to low z (see integrate())
     int z_begin, z_end;        // storage-z range owned here; volume pointers are indexed with (sz - z_begin)
@@ -126,7 +127,31 @@ struct IntegrateParams {
 #define KT_MAX_WEIGHT 128          // Tsdf::MAX_WEIGHT (tsdf_volume.cu:486)
 #define KT_RGB_VIEW_ANGLE_WEIGHT 0.75f
 
-template <typename IdxT, int ZU, int MINB>
+// Per-pixel part of the colour update, once per frame instead of once per voxel (tsdf_volume.cu:601-622): the view-angle weight
+// Wrkc = min(1, |n_z| / 0.75) * 2 (or 2 without angle weighting) depends only on the pixel; its sign bit carries isnan(n_x).  RGB is
+// widened to float (exact).  The voxel loop then needs 2 loads (4 B + 16 B) instead of 5 and no per-voxel conversion of the image.
+__global__ void __launch_bounds__(256)
+color_prep_kernel(const float* __restrict__ nmap, const uchar3* __restrict__ rgb, int n, bool angle_color, float* __restrict__ cw, float4* __restrict__ rgbf)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float nx = nmap[i];
+    float nz = nmap[i + 2 * (size_t)n];
+    if (nz < 0) nz = -nz;
+    const float Wrkc = (angle_color ? min(1.0f, nz / KT_RGB_VIEW_ANGLE_WEIGHT) : 1.0f) * 2.0f;
+    cw[i] = isnan(nx) ? -Wrkc : Wrkc;
+    const uchar3 c = rgb[i];
+    rgbf[i] = make_float4((float)c.x, (float)c.y, (float)c.z, 0.f);
+}
+
+__device__ __forceinline__ unsigned int sat_u8_rn(float x)       // == min(255, max(0, __float2int_rn(x))), one instruction
+{
+    unsigned int r;
+    asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+
+template <typename IdxT, int ZU, int MINB, bool PREP = false>
 __global__ void __launch_bounds__(256, MINB)
 integrate_kernel(const IntegrateParams p)
 {
@@ -228,7 +253,7 @@ integrate_kernel(const IntegrateParams p)
         IdxT pix[ZU], addr[ZU];
         bool ok[ZU];
         float nx[ZU], nz[ZU];
-        int16_t tprev[ZU]; uchar4 cprev[ZU]; uchar3 rgbv[ZU];
+        int16_t tprev[ZU]; uchar4 cprev[ZU]; uchar3 rgbv[ZU]; float4 rgbq[ZU];
 #pragma unroll
         for (int u = 0; u < ZU; ++u) {
             const int z = zb + u;
@@ -269,17 +294,18 @@ integrate_kernel(const IntegrateParams p)
                     // (issuing these loads together with the depth gather, before the test, was slower: 78 -> 88 us at 512^3)
                     tprev[u] = p.tsdf[addr[u]];
                     cprev[u] = p.color[addr[u]];
-                    nx[u] = nmap_curr[pix[u]];
-                    nz[u] = nmap_curr[pix[u] + 2 * P];
-                    rgbv[u] = colors[pix[u]];
+                    if (PREP) { nx[u] = p.cw[pix[u]]; rgbq[u] = p.rgbf[pix[u]]; }
+                    else {
+                        nx[u] = nmap_curr[pix[u]];
+                        nz[u] = nmap_curr[pix[u] + 2 * P];
+                        rgbv[u] = colors[pix[u]];
+                    }
                 }
             }
         }
 #pragma unroll
         for (int u = 0; u < ZU; ++u) {
             if (!upd[u]) continue;
-            float3 ncurr; ncurr.x = nx[u]; ncurr.z = nz[u];
-            if (ncurr.z < 0) ncurr.z = -ncurr.z;
             float tsdf = tsdf_new[u];
             float tsdf_prev = unpack_tsdf(tprev[u]);
             uchar4 c = cprev[u];
@@ -287,15 +313,31 @@ integrate_kernel(const IntegrateParams p)
             const float Wrk = 1;
             p.tsdf[addr[u]] = pack_tsdf((tsdf_prev * weight_prev + Wrk * tsdf) / (weight_prev + Wrk));
             c.w = min(weight_prev + Wrk, (float)KT_MAX_WEIGHT);
-            if ((!isnan(ncurr.x) && !nocol[u]) || (c.x == 0 && c.y == 0 && c.z == 0)) {
-                const float Wrkc = (p.angle_color ? min(1.0f, ncurr.z / KT_RGB_VIEW_ANGLE_WEIGHT) : 1.0f) * 2.0f;
-                uchar3 rgb = rgbv[u];
-                float new_x = (c.x * weight_prev + Wrkc * rgb.x) / (weight_prev + Wrkc);
-                float new_y = (c.y * weight_prev + Wrkc * rgb.y) / (weight_prev + Wrkc);
-                float new_z = (c.z * weight_prev + Wrkc * rgb.z) / (weight_prev + Wrkc);
-                c.x = min(255, max(0, __float2int_rn(new_x)));
-                c.y = min(255, max(0, __float2int_rn(new_y)));
-                c.z = min(255, max(0, __float2int_rn(new_z)));
+            if (PREP) {
+                const float cwv = nx[u];
+                if ((__float_as_int(cwv) >= 0 && !nocol[u]) || (c.x == 0 && c.y == 0 && c.z == 0)) {
+                    const float Wrkc = fabsf(cwv);
+                    const float4 rgb = rgbq[u];
+                    float new_x = (c.x * weight_prev + Wrkc * rgb.x) / (weight_prev + Wrkc);
+                    float new_y = (c.y * weight_prev + Wrkc * rgb.y) / (weight_prev + Wrkc);
+                    float new_z = (c.z * weight_prev + Wrkc * rgb.z) / (weight_prev + Wrkc);
+                    c.x = sat_u8_rn(new_x);
+                    c.y = sat_u8_rn(new_y);
+                    c.z = sat_u8_rn(new_z);
+                }
+            } else {
+                float3 ncurr; ncurr.x = nx[u]; ncurr.z = nz[u];
+                if (ncurr.z < 0) ncurr.z = -ncurr.z;
+                if ((!isnan(ncurr.x) && !nocol[u]) || (c.x == 0 && c.y == 0 && c.z == 0)) {
+                    const float Wrkc = (p.angle_color ? min(1.0f, ncurr.z / KT_RGB_VIEW_ANGLE_WEIGHT) : 1.0f) * 2.0f;
+                    uchar3 rgb = rgbv[u];
+                    float new_x = (c.x * weight_prev + Wrkc * rgb.x) / (weight_prev + Wrkc);
+                    float new_y = (c.y * weight_prev + Wrkc * rgb.y) / (weight_prev + Wrkc);
+                    float new_z = (c.z * weight_prev + Wrkc * rgb.z) / (weight_prev + Wrkc);
+                    c.x = min(255, max(0, __float2int_rn(new_x)));
+                    c.y = min(255, max(0, __float2int_rn(new_y)));
+                    c.z = min(255, max(0, __float2int_rn(new_z)));
+                }
             }
             p.color[addr[u]] = c;
         }
@@ -394,6 +436,15 @@ int integrate(const IntegrateArgs& a, float* ztable_dev, cudaStream_t s)
     if (order < 0) { const char* e = getenv("KT_INT_ORDER"); order = e ? atoi(e) : 0; }
     static int zu = -1;
     if (zu < 0) { const char* e = getenv("KT_INT_ZU"); zu = e ? atoi(e) : 0; }
+    static int prep_knob = -1;                      // KT_INT_PREP=0 keeps the per-voxel colour arithmetic (A/B)
+    if (prep_knob < 0) { const char* e = getenv("KT_INT_PREP"); prep_knob = e ? atoi(e) : 1; }
+    const bool prep = prep_knob != 0 && a.cw && a.rgbf;
+    p.cw = a.cw; p.rgbf = a.rgbf;
+    if (prep) {
+        const int n = a.rows * a.cols;
+        color_prep_kernel<<<div_up(n, 256), 256, 0, s>>>(a.nmap_curr, reinterpret_cast<const uchar3*>(a.rgb), n, a.angle_color, a.cw, a.rgbf);
+        KT_LAUNCH_CHECK();
+    }
     p.ztable = ztable_dev; p.zchunk = V >= 64 ? (V + n_chunks - 1) / n_chunks : V;
     p.z_begin = a.z_begin; p.z_end = a.z_end;
     // z chunks: a warp walks its columns' voxels serially, so a chunk's length is the scheduling quantum of the launch.  Measured on
@@ -425,6 +476,7 @@ int integrate(const IntegrateArgs& a, float* ztable_dev, cudaStream_t s)
             default: integrate_kernel<unsigned int, 2, 4><<<grid, block, 0, s>>>(p); break;
             }
         }
+        else if (prep) integrate_kernel<size_t, 1, 6, true><<<grid, block, 0, s>>>(p);
         else if (zu == 2) integrate_kernel<size_t, 2, 4><<<grid, block, 0, s>>>(p);
         else integrate_kernel<size_t, 1, 6><<<grid, block, 0, s>>>(p);
         KT_LAUNCH_CHECK();

@@ -260,20 +260,24 @@ print("HASH", h.hexdigest())
 """
 
 
-def test_64bit_index_paths_are_bit_identical(built):
-    """The 2048^3 volume (BASELINE config 5) needs 64-bit voxel indices in integrate and raycast; the reference cannot run there
-    (its int index overflows).  KT_FORCE_IDX64 selects those template instances on a 256^3 volume, where the result
-    must be bit-identical to the 32-bit instances that the golden tests pin against the reference."""
+def test_kernel_variants_are_bit_identical(built):
+    """Template instances that the default configuration does not take must give bit-identical trackers:
+    * KT_FORCE_IDX64: 64-bit voxel indices in integrate and raycast (what the 2048^3 volume of BASELINE config 5 needs; the reference
+      cannot run there, its int index overflows -- SURVEY.md D5), here on a 256^3 volume;
+    * KT_INT_PREP=0: the colour update with the reference's per-voxel arithmetic (the operator-level golden tests pin that form against
+      the reference) versus the default, which prepares the per-pixel colour weight and float RGB once per frame;
+    * KT_INT_ZU=1: one voxel per step at 6 CTAs/SM (the default for volumes >= 1024^3)."""
     import subprocess
     import sys
     from conftest import ROOT
     out = {}
-    for tag, extra in (("idx32", {}), ("idx64", {"KT_FORCE_IDX64": "1"})):
+    for tag, extra in (("default", {}), ("idx64", {"KT_FORCE_IDX64": "1"}), ("noprep", {"KT_INT_PREP": "0"}), ("zu1", {"KT_INT_ZU": "1"}),
+                       ("idx64_noprep", {"KT_FORCE_IDX64": "1", "KT_INT_PREP": "0"})):
         env = dict(os.environ, PYTHONPATH=ROOT, **extra)
         r = subprocess.run([sys.executable, "-c", _IDX64_SCRIPT], env=env, capture_output=True, text=True, timeout=600, cwd=ROOT)
         assert r.returncode == 0, r.stderr[-2000:]
         out[tag] = [l for l in r.stdout.splitlines() if l.startswith("HASH")][0]
-    assert out["idx32"] == out["idx64"]
+    assert len(set(out.values())) == 1, out
 
 
 def test_config5_1280x960_into_2048(built):
