@@ -88,11 +88,12 @@ struct kt_ctx {
     // spare set on the same side stream, so that it overlaps the integrate / ray-cast of the frame before (they leave issue slots idle)
     uint16_t* depths_alt[LEVELS]; float* vmaps_alt[LEVELS]; float* nmaps_alt[LEVELS]; float* depth_scaled_alt;
     bool pf_built;             // the prefetched set holds the finished front end
+    bool color_prepared;       // cw_scratch / rgbf_scratch hold this frame's per-pixel colour inputs
     bool frontend_ready;       // set for the duration of one process_frame_device call
     cudaStream_t stream_copy; cudaEvent_t ev_prefetch, ev_done[2]; int last_parity;
     uint16_t* depths_curr[LEVELS];
     float* vmaps_g_prev[LEVELS]; float* nmaps_g_prev[LEVELS]; float* vmaps_curr[LEVELS]; float* nmaps_curr[LEVELS];
-    uint8_t* vmap_curr_color; float* depth_scaled; float* ztable; float* cw_scratch; float* rgbf_scratch;
+    uint8_t* vmap_curr_color; float* depth_scaled; float* ztable; float* cw_scratch; float* rgbf_scratch; float* cw_alt; float* rgbf_alt;
     OdomState* state; float* partials; int* ipartials; float* trace_dev; float* pose12_dev; unsigned int* bar_dev; unsigned int bar_count; long long* prof_dev;
     kt_point_xyzrgb* cloud_dev; unsigned int* counter_dev; size_t cloud_capacity; size_t cloud_count;
     // RGB-D
@@ -194,7 +195,7 @@ int do_integrate(kt_ctx* c, const M3& Rinv, const V3& t, const int* wrap)
     a.Rinv = to_mat33(Rinv.m); a.t = make_float3(t.v[0], t.v[1], t.v[2]); a.trunc = c->trunc;
     a.tsdf = c->tsdf; a.color = c->color; a.vol = c->cfg.vol; a.wrap = make_int3(wrap[0], wrap[1], wrap[2]);
     a.rgb = c->rgb; a.nmap_curr = c->nmaps_curr[0]; a.angle_color = c->cfg.angle_color != 0;
-    a.z_begin = c->z_begin; a.z_end = c->z_end; a.cw = c->cw_scratch; a.rgbf = (float4*)c->rgbf_scratch;
+    a.z_begin = c->z_begin; a.z_end = c->z_end; a.cw = c->color_prepared ? c->cw_scratch : 0; a.rgbf = c->color_prepared ? (float4*)c->rgbf_scratch : 0;
     return integrate(a, c->ztable, c->stream);
 }
 
@@ -308,8 +309,8 @@ int mg_barrier(kt_ctx* c)
 
 // Pose-independent front end of one frame: scaleDepth (for integrate) on s_scale, bilateral + pyrDown + vertex / normal maps of all
 // levels on s_pyr.  vstale / nstale: the previous frame's maps when the outputs are a spare set (Q7 staleness), else null.
-int build_frontend(kt_ctx* c, const uint16_t* depth_raw, float* depth_scaled, uint16_t* const* depths, float* const* vmaps, float* const* nmaps,
-                   float* const* vstale, float* const* nstale, cudaStream_t s_scale, cudaStream_t s_pyr)
+int build_frontend(kt_ctx* c, const uint16_t* depth_raw, const uint8_t* rgb, float* depth_scaled, uint16_t* const* depths, float* const* vmaps, float* const* nmaps,
+                   float* const* vstale, float* const* nstale, float* cw, float* rgbf, cudaStream_t s_scale, cudaStream_t s_pyr)
 {
     const int rows = c->cfg.rows, cols = c->cfg.cols, mode = c->cfg.odometry;
     int r;
@@ -325,7 +326,10 @@ int build_frontend(kt_ctx* c, const uint16_t* depth_raw, float* depth_scaled, ui
             ml[i].vstale = vstale ? vstale[i] : 0; ml[i].nstale = nstale ? nstale[i] : 0;
         }
         if ((r = create_maps_pyramid(ml, LEVELS, s_pyr))) return r;
-    }
+        // colour integration inputs that depend only on the pixel (normal validity, view-angle weight, RGB as float)
+        if ((r = color_prep(nmaps[0], rgb, rows, cols, c->cfg.angle_color != 0, cw, (float4*)rgbf, s_pyr))) return r;
+        c->color_prepared = true;
+    } else c->color_prepared = false;
     return 0;
 }
 
@@ -342,7 +346,7 @@ int process_frame_device(kt_ctx* c, uint64_t utime, kt_pose* out)
         // fork: scaleDepth (tsdf_volume.cu:491-538) only needs the raw depth; it overlaps the pyramid on a second stream
         KT_CUDA(cudaEventRecord(c->ev_input, c->stream));
         KT_CUDA(cudaStreamWaitEvent(c->stream2, c->ev_input, 0));
-        if ((r = build_frontend(c, c->depth_raw, c->depth_scaled, c->depths_curr, c->vmaps_curr, c->nmaps_curr, 0, 0, c->stream2, c->stream))) return r;
+        if ((r = build_frontend(c, c->depth_raw, c->rgb, c->depth_scaled, c->depths_curr, c->vmaps_curr, c->nmaps_curr, 0, 0, c->cw_scratch, c->rgbf_scratch, c->stream2, c->stream))) return r;
         KT_CUDA(cudaEventRecord(c->ev_scaled, c->stream2));
     }
     mark(c, 1);
@@ -580,7 +584,7 @@ int kt_create(const kt_config* cfg, kt_ctx** out)
         }
     }
     c->vmap_curr_color = c->arena + c->off_vcol; KT_TRY(dev_alloc(c, &c->depth_scaled, P)); KT_TRY(dev_alloc(c, &c->depth_scaled_alt, P)); c->pf_built = false; c->frontend_ready = false;
-    KT_TRY(dev_alloc(c, &c->ztable, (size_t)2 * cfg->vol)); KT_TRY(dev_alloc(c, &c->cw_scratch, P)); KT_TRY(dev_alloc(c, &c->rgbf_scratch, P * 4));
+    KT_TRY(dev_alloc(c, &c->ztable, (size_t)2 * cfg->vol)); KT_TRY(dev_alloc(c, &c->cw_scratch, P)); KT_TRY(dev_alloc(c, &c->rgbf_scratch, P * 4)); KT_TRY(dev_alloc(c, &c->cw_alt, P)); KT_TRY(dev_alloc(c, &c->rgbf_alt, P * 4));
     KT_TRY(dev_alloc(c, &c->state, 1)); KT_TRY(dev_alloc(c, &c->partials, (size_t)MAX_PARTIALS * 32));
     KT_TRY(kt::cuda_check(cudaMemset(c->partials, 0, (size_t)MAX_PARTIALS * 32 * sizeof(float)), "memset", __FILE__, __LINE__));   // tags start at 0
     KT_TRY(dev_alloc(c, &c->bar_dev, 1)); KT_TRY(kt::cuda_check(cudaMemset(c->bar_dev, 0, sizeof(unsigned int)), "memset", __FILE__, __LINE__)); c->bar_count = 0;
@@ -639,7 +643,7 @@ static bool adopt_prefetched(kt_ctx* c, const void* depth, const void* rgb)
     }
     std::swap(c->depth_raw, c->depth_alt); std::swap(c->rgb, c->rgb_alt);
     if (c->pf_built) {
-        std::swap(c->depth_scaled, c->depth_scaled_alt);
+        std::swap(c->depth_scaled, c->depth_scaled_alt); std::swap(c->cw_scratch, c->cw_alt); std::swap(c->rgbf_scratch, c->rgbf_alt);
         for (int l = 0; l < LEVELS; ++l) { std::swap(c->depths_curr[l], c->depths_alt[l]); std::swap(c->vmaps_curr[l], c->vmaps_alt[l]); std::swap(c->nmaps_curr[l], c->nmaps_alt[l]); }
         c->frontend_ready = true;
     }
@@ -694,8 +698,8 @@ int kt_prefetch_frame(kt_ctx* c, const uint16_t* depth, const uint8_t* rgb)
     static const bool lookahead = getenv("KT_NO_LOOKAHEAD") == nullptr;       // A/B knob: copy only
     if (lookahead && c->global_time > 0) {
         // invalid pixels keep the y/z planes of the previous frame's maps = the set that is current now (Q7)
-        int r = build_frontend(c, c->depth_alt, c->depth_scaled_alt, c->depths_alt, c->vmaps_alt, c->nmaps_alt, c->vmaps_curr, c->nmaps_curr,
-                               c->stream_copy, c->stream_copy);
+        int r = build_frontend(c, c->depth_alt, c->rgb_alt, c->depth_scaled_alt, c->depths_alt, c->vmaps_alt, c->nmaps_alt, c->vmaps_curr, c->nmaps_curr,
+                               c->cw_alt, c->rgbf_alt, c->stream_copy, c->stream_copy);
         if (r) return r;
         // photometric odometry: its "next" pyramids were swapped to "last" when the previous frame's odometry finished, so the
         // buffers now called next are free until the coming frame

@@ -414,6 +414,14 @@ int clear_volume_slab(int axis, int back, int16_t* tsdf, uint8_t* color, int vol
     return 0;
 }
 
+int color_prep(const float* nmap, const uint8_t* rgb, int rows, int cols, bool angle_color, float* cw, float4* rgbf, cudaStream_t s)
+{
+    const int n = rows * cols;
+    color_prep_kernel<<<div_up(n, 256), 256, 0, s>>>(nmap, reinterpret_cast<const uchar3*>(rgb), n, angle_color, cw, rgbf);
+    KT_LAUNCH_CHECK();
+    return 0;
+}
+
 int scale_depth(const uint16_t* depth, float* scaled, int rows, int cols, const Intr& k, bool angle_color, cudaStream_t s)
 {
     dim3 block(32, 8), grid(div_up(cols, 32), div_up(rows, 8));
@@ -438,13 +446,8 @@ int integrate(const IntegrateArgs& a, float* ztable_dev, cudaStream_t s)
     if (zu < 0) { const char* e = getenv("KT_INT_ZU"); zu = e ? atoi(e) : 0; }
     static int prep_knob = -1;                      // KT_INT_PREP=0 keeps the per-voxel colour arithmetic (A/B)
     if (prep_knob < 0) { const char* e = getenv("KT_INT_PREP"); prep_knob = e ? atoi(e) : 1; }
-    const bool prep = prep_knob != 0 && a.cw && a.rgbf;
+    const bool prep = prep_knob != 0 && a.cw && a.rgbf;      // the caller ran color_prep() on this frame's normal map and image
     p.cw = a.cw; p.rgbf = a.rgbf;
-    if (prep) {
-        const int n = a.rows * a.cols;
-        color_prep_kernel<<<div_up(n, 256), 256, 0, s>>>(a.nmap_curr, reinterpret_cast<const uchar3*>(a.rgb), n, a.angle_color, a.cw, a.rgbf);
-        KT_LAUNCH_CHECK();
-    }
     p.ztable = ztable_dev; p.zchunk = V >= 64 ? (V + n_chunks - 1) / n_chunks : V;
     p.z_begin = a.z_begin; p.z_end = a.z_end;
     // z chunks: a warp walks its columns' voxels serially, so a chunk's length is the scheduling quantum of the launch.  Measured on
@@ -467,7 +470,14 @@ int integrate(const IntegrateArgs& a, float* ztable_dev, cudaStream_t s)
         p.lz_lo = lo[i]; p.lz_hi = hi[i];
         dim3 block(32, 8), grid(div_up(V, 32), div_up(V, 8), div_up(hi[i] - lo[i], p.zchunk));
         if (idx32) {
-            switch (zu) {                                    // tuning knob KT_INT_ZU: batch depth / CTAs per SM
+            // batch depth / CTAs per SM (KT_INT_ZU overrides).  Measured (tools/stage_ab.py, 640x480): 512^3 2-voxel batches at 4 CTAs/SM
+            // 78 us vs 81 us for 1-voxel steps at 6 CTAs/SM; 1024^3 395 vs 351 us: once the updated region outgrows L2, occupancy wins
+            const int variant = zu ? zu : (V >= 1024 ? 1 : 2);
+            if (prep && (variant == 1 || variant == 2)) {
+                if (variant == 1) integrate_kernel<unsigned int, 1, 6, true><<<grid, block, 0, s>>>(p);
+                else integrate_kernel<unsigned int, 2, 4, true><<<grid, block, 0, s>>>(p);
+            } else
+            switch (variant) {
             case 4: integrate_kernel<unsigned int, 4, 3><<<grid, block, 0, s>>>(p); break;
             case 5: integrate_kernel<unsigned int, 2, 5><<<grid, block, 0, s>>>(p); break;
             case 6: integrate_kernel<unsigned int, 2, 6><<<grid, block, 0, s>>>(p); break;
