@@ -7,6 +7,7 @@
 // different (fixed, deterministic) summation tree and agree to float rounding.
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <stdint.h>
 #include <math.h>
 
@@ -55,7 +56,7 @@ __device__ __forceinline__ float qnan() { return __int_as_float(0x7fffffff); }
 namespace kt {
 void set_error(const char* fmt, ...);
 int cuda_check(cudaError_t e, const char* what, const char* file, int line);
-extern long long g_launches;      // kernels launched by this library (bench.py: gpu_launches)
+extern std::atomic<long long> g_launches;      // kernels launched by this library (bench.py: gpu_launches); contexts may live on several host threads
 }
 #define KT_CUDA(expr) do { int _s = kt::cuda_check((expr), #expr, __FILE__, __LINE__); if (_s) return _s; } while (0)
 #define KT_LAUNCH_CHECK() do { ++kt::g_launches; int _s = kt::cuda_check(cudaGetLastError(), "kernel launch", __FILE__, __LINE__); if (_s) return _s; } while (0)

@@ -332,7 +332,7 @@ int create_nmap(const float* vmap, float* nmap, int rows, int cols, cudaStream_t
 
 int create_maps_pyramid(const MapsLevel* levels, int n, cudaStream_t s)
 {
-    MapsParams p;
+    MapsParams p = {};
     for (int i = 0; i < n; ++i) { p.lv[i] = levels[i]; p.lv[i].fx_inv = 1.f / levels[i].k.fx; p.lv[i].fy_inv = 1.f / levels[i].k.fy; }
     for (int i = n; i < LEVELS; ++i) p.lv[i] = p.lv[n - 1];
     dim3 block(32, 8), grid(div_up(levels[0].cols, 32), div_up(levels[0].rows, 8), n);

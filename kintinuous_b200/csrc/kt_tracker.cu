@@ -25,7 +25,7 @@ namespace kt {
 
 // ---- error plumbing ------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
-long long g_launches = 0;
+std::atomic<long long> g_launches(0);
 void set_error(const char* fmt, ...)
 {
     va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
@@ -122,7 +122,8 @@ const int MAX_TRACE_ITERS = 64;
 template <class T> int dev_alloc(kt_ctx* c, T** p, size_t count)
 {
     void* q = 0;
-    KT_CUDA(cudaMalloc(&q, count * sizeof(T) ? count * sizeof(T) : 1));
+    const size_t bytes = count * sizeof(T);
+    KT_CUDA(cudaMalloc(&q, bytes ? bytes : 1));
     c->allocs.push_back(q);
     *p = (T*)q;
     return 0;
@@ -516,7 +517,7 @@ int kt_create(const kt_config* cfg, kt_ctx** out)
     KT_CUDA(cudaSetDevice(cfg->device));
     kt_ctx* c = new kt_ctx();
     c->cfg = *cfg;
-    c->launches_at_create = g_launches;
+    c->launches_at_create = g_launches.load();
     if (c->cfg.cloud_capacity <= 0) c->cfg.cloud_capacity = 3 * cfg->rows * cfg->cols;          // KintinuousTracker.cpp:77
     c->overlap = cfg->overlap; c->parked = cfg->parked;
     c->size = cfg->volume_size;
@@ -877,7 +878,7 @@ float kt_span_elapsed_ms(kt_ctx* c)
     return t;
 }
 
-long long kt_launch_count(kt_ctx* c) { return c ? g_launches - c->launches_at_create : g_launches; }
+long long kt_launch_count(kt_ctx* c) { return c ? g_launches.load() - c->launches_at_create : g_launches.load(); }
 
 int kt_alloc_pinned(void** ptr, size_t bytes) { KT_CUDA(cudaMallocHost(ptr, bytes)); return KT_OK; }
 int kt_free_pinned(void* ptr) { if (ptr) KT_CUDA(cudaFreeHost(ptr)); return KT_OK; }
