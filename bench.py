@@ -154,11 +154,11 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def dist_setup(n_gpus):
+def dist_setup(n_gpus, init=True):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
+    if world > 1 and init:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl" if not os.environ.get("KT_BENCH_GLOO") else "gloo")
@@ -269,10 +269,11 @@ def main():
         ROWS, COLS = 480 * args.scale, 640 * args.scale
         P_LEVELS = [ROWS * COLS >> (2 * l) for l in range(4)]
         N_INPUT_FRAMES = max(8, N_INPUT_FRAMES // (args.scale * args.scale))      # same bytes of distinct input
-    world, rank, local = dist_setup(args.gpus)
-    if args.impl == "reference":
+    if args.impl == "reference":                      # rank 0 alone runs it; no process group, no collective
+        world, rank, local = dist_setup(args.gpus, init=False)
         run_reference(args, world, rank, local)
         return
+    world, rank, local = dist_setup(args.gpus)
 
     import torch
     import kintinuous_b200 as kb
@@ -357,6 +358,10 @@ def main():
             results["icp_kernel_ms"] = icp_ms / max(1, m)
         trk.close()
 
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     peak, peak_src = measured_peak()
