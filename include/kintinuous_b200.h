@@ -111,6 +111,11 @@ KT_API int kt_num_slices(kt_ctx* ctx);
 /* Copies up to max_points points of slice idx; *count = the slice's size; dimension = CloudSlice::Dimension
  * (CloudSlice.h:33-44: XPlus..ZMinus, FIRST, FINAL, TSDF); camera_t = 3 floats, may be NULL. */
 KT_API int kt_get_slice(kt_ctx* ctx, int idx, kt_point_xyzrgb* points, size_t max_points, size_t* count, int* dimension, float* camera_t);
+/* The rest of the CloudSlice record (CloudSlice.h:47-60): which odometry produced the pose (CloudSlice::Odometry: 0 ICP, 2 RGBD --
+ * KintinuousTracker.cpp:137-176,565: the kind of the active OdometryProvider), the camera pose at hand-over (volume-global
+ * translation, row-major rotation) and the frame's timestamp. */
+typedef struct kt_slice_info { int dimension; int odometry; float camera_t[3]; float camera_R[9]; uint64_t utime; size_t count; } kt_slice_info;
+KT_API int kt_get_slice_info(kt_ctx* ctx, int idx, kt_slice_info* info);
 /* Per-iteration normal equations of the last frame, n x 44 floats (A 6x6 row-major, b 6, residual, inliers):
  * what icpStep / rgbStep hand back to the host each iteration (cuda/reduce.cu:404-418). */
 KT_API int kt_get_trace(kt_ctx* ctx, float* dst, int max_iters, int* n_iters);

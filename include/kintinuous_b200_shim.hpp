@@ -15,8 +15,10 @@
 
 #include <cuda_runtime_api.h>
 #include <vector_types.h>
+#include <vector_functions.h>
 #include <cstddef>
 #include <cstdint>
+#include <cstdio>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -177,6 +179,113 @@ inline void rgbStep(const DeviceArray2D<DataTerm>& corresImg, const float& sigma
     kt::check(kt_op_rgb_step(corresImg.ptr(), sigma, (const float*)cloud.ptr(), fx, fy, dIdx.ptr(), dIdy.ptr(), sobelScale, corresImg.rows(), corresImg.cols(), matrixA_host, vectorB_host, 0));
 }
 
+// ---- TsdfVolume / ColorVolume (TSDFVolume.h:68-158, TSDFVolume.cpp:60-215, ColorVolume.h:65-94) without Eigen ----
+// The reference constructs TsdfVolume(Eigen::Vector3i) + ColorVolume(tsdf) and hands `data()` of both to integrateTsdfVolume / raycast /
+// extractCloudSlice / clearVolume*; these two classes own the same two device planes (short[V^3], uchar4[V^3] with the weight in .w) and
+// keep the reference's parameter logic (truncation distance clamp, voxel size).
+class ColorVolume;
+class TsdfVolume {
+public:
+    enum { DEFAULT_CLOUD_BUFFER_SIZE = 10 * 1000 * 1000 };
+    // resolution: voxels per side (the reference asserts a cube); volumeSize: Volume::get().getVolumeSize() in metres
+    explicit TsdfVolume(int resolution, float volumeSize = 6.f) : res_(resolution), tranc_dist_(0.03f)
+    {
+        kt::shim::set_volume_resolution(resolution);
+        volume_.create(resolution * resolution, resolution);
+        size_ = make_float3(volumeSize, volumeSize, volumeSize);
+        setTsdfTruncDist(0.03f);                                     // default_tranc_dist (TSDFVolume.cpp:73)
+        kt::cuda(cudaMemset(volume_.ptr(), 0, (size_t)resolution * resolution * resolution * sizeof(short)));
+    }
+    void setSize(const float3& size) { size_ = size; setTsdfTruncDist(tranc_dist_); }
+    void setTsdfTruncDist(float distance)                          // TSDFVolume.cpp:89-97: at least 2.1 voxels
+    {
+        const float cx = size_.x / res_, cy = size_.y / res_, cz = size_.z / res_;
+        const float m = cx > cy ? (cx > cz ? cx : cz) : (cy > cz ? cy : cz);
+        tranc_dist_ = distance > 2.1f * m ? distance : 2.1f * m;
+    }
+    DeviceArray2D<short> data() const { return volume_; }
+    const float3& getSize() const { return size_; }
+    int getResolution() const { return res_; }
+    float3 getVoxelSize() const { return make_float3(size_.x / res_, size_.y / res_, size_.z / res_); }
+    float getTsdfTruncDist() const { return tranc_dist_; }
+    // reset(): the reference clears the TSDF plane here and the colour plane in ColorVolume::reset(); one kernel clears both
+    inline void reset(ColorVolume& color);
+    // fetchCloud (TSDFVolume.cpp:137-172): returns a non-owning view of the filled part of cloud_buffer
+    DeviceArray<PointXYZRGB> fetchCloud(DeviceArray<PointXYZRGB>& cloud_buffer, int3& voxelWrap, PtrStep<uchar4> color_volume, int minX, int maxX,
+                                        int minY, int maxY, int minZ, int maxZ, int3 realVoxelWrap, int subsample = 1) const
+    {
+        if (cloud_buffer.empty()) cloud_buffer.create(DEFAULT_CLOUD_BUFFER_SIZE);
+        const size_t n = extractCloudSlice(PtrStep<short>(const_cast<short*>(volume_.ptr()), volume_.step()), size_,
+                                           PtrSz<PointXYZRGB>(cloud_buffer.ptr(), cloud_buffer.size()), voxelWrap, color_volume,
+                                           minX, maxX, minY, maxY, minZ, maxZ, subsample, realVoxelWrap);
+        return DeviceArray<PointXYZRGB>(cloud_buffer.ptr(), n);
+    }
+    // downloadTsdf (TSDFVolume.cpp:174-185): value / DIVISOR per voxel, index res*res*z + res*y + x in STORAGE order.  The reference still
+    // reads the volume as the short2 {tsdf, weight} pairs of its PCL ancestor (it copies cols*sizeof(int) bytes per row of a short
+    // volume); here the volume is read as what it is, one short per voxel.
+    void downloadTsdf(std::vector<float>& tsdf) const
+    {
+        std::vector<short> raw((size_t)res_ * res_ * res_);
+        kt::cuda(cudaMemcpy(&raw[0], volume_.ptr(), raw.size() * sizeof(short), cudaMemcpyDeviceToHost));
+        tsdf.resize(raw.size());
+        for (size_t i = 0; i < raw.size(); ++i) tsdf[i] = (float)raw[i] / 32767.f;      // DIVISOR (cuda/device.hpp)
+    }
+    // downloadTsdfAndWeighs (TSDFVolume.cpp:187-201): the weights live in the .w byte of the colour volume
+    inline void downloadTsdfAndWeighs(const ColorVolume& color, std::vector<float>& tsdf, std::vector<short>& weights) const;
+    // saveTsdfToDisk (TSDFVolume.cpp:203-215+): <name>_tsdf.bin (float) and <name>_weights.bin (short)
+    inline void saveTsdfToDisk(const ColorVolume& color, const std::string& filename) const;
+private:
+    TsdfVolume(const TsdfVolume&); TsdfVolume& operator=(const TsdfVolume&);
+    int res_; float3 size_; DeviceArray2D<short> volume_; float tranc_dist_;
+};
+
+class ColorVolume {
+public:
+    explicit ColorVolume(const TsdfVolume& tsdf) : res_(tsdf.getResolution())
+    {
+        color_volume_.create(res_ * res_, res_);
+        reset();
+    }
+    void reset() { kt::cuda(cudaMemset(color_volume_.ptr(), 0, (size_t)res_ * res_ * res_ * sizeof(int))); }
+    DeviceArray2D<int> data() const { return color_volume_; }         // declared int, used as uchar4 (ColorVolume.h:93, Q11)
+    PtrStep<uchar4> view() const { return PtrStep<uchar4>((uchar4*)const_cast<int*>(color_volume_.ptr()), color_volume_.step()); }
+private:
+    ColorVolume(const ColorVolume&); ColorVolume& operator=(const ColorVolume&);
+    int res_; DeviceArray2D<int> color_volume_;
+};
+
+inline void TsdfVolume::reset(ColorVolume& color)
+{ initVolumes(PtrStep<short>(volume_.ptr(), volume_.step()), color.view()); }
+inline void TsdfVolume::downloadTsdfAndWeighs(const ColorVolume& color, std::vector<float>& tsdf, std::vector<short>& weights) const
+{
+    downloadTsdf(tsdf);
+    std::vector<int> raw((size_t)res_ * res_ * res_);
+    kt::cuda(cudaMemcpy(&raw[0], color.data().ptr(), raw.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    weights.resize(raw.size());
+    for (size_t i = 0; i < raw.size(); ++i) weights[i] = (short)(((unsigned int)raw[i]) >> 24);      // uchar4 .w
+}
+inline void TsdfVolume::saveTsdfToDisk(const ColorVolume& color, const std::string& filename) const
+{
+    std::vector<float> tsdf; std::vector<short> weights;
+    downloadTsdfAndWeighs(color, tsdf, weights);
+    FILE* fp = std::fopen((filename + "_tsdf.bin").c_str(), "wb");
+    if (!fp) throw kt::Error("saveTsdfToDisk: cannot open " + filename + "_tsdf.bin");
+    std::fwrite(&tsdf[0], sizeof(float), tsdf.size(), fp); std::fclose(fp);
+    fp = std::fopen((filename + "_weights.bin").c_str(), "wb");
+    if (!fp) throw kt::Error("saveTsdfToDisk: cannot open " + filename + "_weights.bin");
+    std::fwrite(&weights[0], sizeof(short), weights.size(), fp); std::fclose(fp);
+}
+
+// ---- CloudSlice (CloudSlice.h:28-129): the record handed to the backend on every volume shift, without the PCL / Eigen types ----
+struct CloudSliceB200 {
+    enum Dimension { XPlus, XMinus, YPlus, YMinus, ZPlus, ZMinus, FIRST, FINAL, TSDF };      // CloudSlice.h:33-36
+    enum Odometry { ICP, GROUNDTRUTH, RGBD, FAIL };                                          // CloudSlice.h:38-41
+    std::vector<PointXYZRGB> cloud;            // pcl::PointCloud<pcl::PointXYZRGB>::points, same 32-byte layout
+    Dimension dimension; Odometry odometry;
+    float cameraTranslation[3]; float cameraRotation[9];        // Eigen::Vector3f / Matrix<float,3,3,RowMajor>
+    uint64_t utime;
+};
+
 // ---- KintinuousTracker facade (KintinuousTracker.h:85-172) without Eigen / cv / pcl / boost types ----
 class KintinuousTrackerB200 {
 public:
@@ -202,6 +311,20 @@ public:
         std::vector<PointXYZRGB> v(n);
         if (n) kt::check(kt_get_slice(ctx_, i, &v[0], n, &n, dimension, 0));
         return v;
+    }
+    // the whole CloudSlice record of slice i (cloud, dimension, odometry kind, camera pose at hand-over, timestamp)
+    CloudSliceB200 getCloudSliceRecord(int i) const
+    {
+        kt_slice_info info; kt::check(kt_get_slice_info(ctx_, i, &info));
+        CloudSliceB200 s;
+        s.cloud.resize(info.count);
+        size_t n = info.count;
+        if (n) kt::check(kt_get_slice(ctx_, i, &s.cloud[0], n, &n, 0, 0));
+        s.dimension = (CloudSliceB200::Dimension)info.dimension; s.odometry = (CloudSliceB200::Odometry)info.odometry;
+        for (int k = 0; k < 3; ++k) s.cameraTranslation[k] = info.camera_t[k];
+        for (int k = 0; k < 9; ++k) s.cameraRotation[k] = info.camera_R[k];
+        s.utime = info.utime;
+        return s;
     }
     kt_ctx* handle() { return ctx_; }
 private:

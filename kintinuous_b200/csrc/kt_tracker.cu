@@ -752,6 +752,19 @@ int kt_get_slice(kt_ctx* c, int idx, kt_point_xyzrgb* points, size_t max_points,
     return KT_OK;
 }
 
+int kt_get_slice_info(kt_ctx* c, int idx, kt_slice_info* info)
+{
+    if (!c || !info || idx < 0 || idx >= (int)c->slices.size()) { set_error("kt_get_slice_info: bad argument"); return KT_ERR_INVALID; }
+    const SliceRec& s = c->slices[idx];
+    info->dimension = s.dimension;
+    info->odometry = c->cfg.odometry == 0 ? 0 : 2;            // CloudSlice::ICP / CloudSlice::RGBD
+    for (int i = 0; i < 3; ++i) info->camera_t[i] = s.camera_t[i];
+    for (int i = 0; i < 9; ++i) info->camera_R[i] = s.camera_R[i];
+    info->utime = s.utime;
+    info->count = s.points.size();
+    return KT_OK;
+}
+
 int kt_get_trace(kt_ctx* c, float* dst, int max_iters, int* n_iters)
 {
     if (!c) return KT_ERR_INVALID;

@@ -18,6 +18,16 @@ int main()
         createVMap(Intr(132.f, 132.f, 80.f, 66.75f), f, vmap);
         createNMap(vmap, nmap);
         std::printf("shim ok: %d x %d -> %d x %d\n", f.rows(), f.cols(), p.rows(), p.cols());
+        // host classes of the volume (TSDFVolume.h / ColorVolume.h) on top of the operator API
+        TsdfVolume tsdf(64, 3.f);
+        ColorVolume color(tsdf);
+        tsdf.reset(color);
+        tsdf.setTsdfTruncDist(0.01f);                       // clamped to 2.1 voxels like the reference
+        DeviceArray<PointXYZRGB> buf; int3 wrap = make_int3(0, 0, 0);
+        DeviceArray<PointXYZRGB> got = tsdf.fetchCloud(buf, wrap, color.view(), 0, 64, 0, 64, 0, 64, wrap);
+        std::vector<float> v; std::vector<short> w;
+        tsdf.downloadTsdfAndWeighs(color, v, w);
+        std::printf("volume ok: trunc %.4f, %zu points, %zu voxels\n", tsdf.getTsdfTruncDist(), got.size(), v.size());
     } catch (const kt::Error& e) { std::printf("error: %s\n", e.what()); return 1; }
     return 0;
 }
