@@ -66,6 +66,11 @@ class Config(C.Structure):
         return c
 
 
+class SliceInfo(C.Structure):
+    _fields_ = [("dimension", C.c_int), ("odometry", C.c_int), ("camera_t", C.c_float * 3), ("camera_R", C.c_float * 9),
+                ("utime", C.c_uint64), ("count", C.c_size_t)]
+
+
 class Pose(C.Structure):
     _fields_ = [("R", C.c_float * 9), ("t", C.c_float * 3), ("global_t", C.c_float * 3), ("voxel_wrap", C.c_int * 3),
                 ("shifted", C.c_int), ("frame", C.c_int)]
@@ -159,6 +164,12 @@ class Tracker:
         if n.value:
             _check(self.lib.kt_get_slice(self.h, idx, _ptr(pts), C.c_size_t(n.value), C.byref(n), C.byref(dim), cam))
         return pts, dim.value, np.array(cam, dtype=np.float32)
+
+    def slice_info(self, idx):
+        """The rest of the CloudSlice record: dimension, odometry kind, camera pose at hand-over, timestamp, point count."""
+        info = SliceInfo()
+        _check(self.lib.kt_get_slice_info(self.h, idx, C.byref(info)))
+        return info
 
     def trace(self, max_iters=64):
         n = C.c_int(0)

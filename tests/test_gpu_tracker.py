@@ -53,8 +53,11 @@ def test_tracker_vs_golden_reference_cuda(built, frames, name, kw, nframes):
         gs = g["slices"]
         assert trk.num_slices() == len(gs)
         for i in range(len(gs)):
-            pts, dim, _ = trk.get_slice(i)
+            pts, dim, cam_t = trk.get_slice(i)
             assert dim == gs[i][0]
+            info = trk.slice_info(i)                                   # the full CloudSlice record
+            assert info.dimension == dim and info.count == len(pts) and info.odometry == (0 if kw.get("odometry", 0) == 0 else 2)
+            assert np.allclose(np.array(info.camera_t), cam_t) and abs(np.linalg.det(np.array(info.camera_R).reshape(3, 3)) - 1) < 1e-3
             # the reference's count of a full-volume extraction can be a few points short (its publication race)
             assert abs(len(pts) - gs[i][1]) <= max(5, 0.01 * gs[i][1]), (i, len(pts), gs[i])
     trk.close()
