@@ -14,10 +14,26 @@
 #include "kt_ops.h"
 #include <float.h>
 
+// The functions of this header also compile for the HOST (tests/cpp/solve_host.cu, run by `pytest -m "not gpu"` against numpy / cv2 / the
+// oracle): KT_HD = __host__ __device__, and the IEEE round-to-nearest intrinsics fall back to plain operators there (x86-64 SSE
+// arithmetic is IEEE and gcc does not contract without an FMA target).  Device code generation is unchanged by this.
+#define KT_HD __host__ __device__
+#ifdef __CUDA_ARCH__
+#define KT_FMUL(a, b) __fmul_rn((a), (b))
+#define KT_FADD(a, b) __fadd_rn((a), (b))
+#define KT_FSUB(a, b) __fsub_rn((a), (b))
+#define KT_FDIV(a, b) __fdiv_rn((a), (b))
+#else
+#define KT_FMUL(a, b) ((a) * (b))
+#define KT_FADD(a, b) ((a) + (b))
+#define KT_FSUB(a, b) ((a) - (b))
+#define KT_FDIV(a, b) ((a) / (b))
+#endif
+
 namespace kt {
 
 // sums: 27 upper-triangular products in the order aa ab ac ad ae af ag bb ... fg (cuda/internal.h:101-106)
-__device__ __forceinline__ void unpack_normal_equations(const float* sums, float* A, float* b)
+KT_HD __forceinline__ void unpack_normal_equations(const float* sums, float* A, float* b)
 {
     int shift = 0;
     for (int i = 0; i < 6; ++i)
@@ -33,7 +49,7 @@ __device__ __forceinline__ void unpack_normal_equations(const float* sums, float
 // thread; this one ~1 us).  Eigen::LDLT pivots on the largest diagonal entry; for an SPD matrix both orders are backward
 // stable and the solutions agree to ~cond(A) * 1e-16, far below the float pose they are rounded to.  A vanishing pivot
 // (degenerate geometry, e.g. no inliers) contributes 0 to the solution, which is what Eigen's solve does with its tolerance.
-__device__ __forceinline__ void ldlt6_solve(const double* Ain, const double* bin, double* x)
+KT_HD __forceinline__ void ldlt6_solve(const double* Ain, const double* bin, double* x)
 {
     double a[6][6];
 #pragma unroll
@@ -82,7 +98,7 @@ __device__ __forceinline__ void ldlt6_solve(const double* Ain, const double* bin
 }
 
 // cv::Rodrigues, rotation vector -> matrix, double (OpenCV 2.4.9 semantics)
-__device__ inline void rodrigues(const double* r, double* R)
+KT_HD inline void rodrigues(const double* r, double* R)
 {
     double rx = r[0], ry = r[1], rz = r[2];
     double theta = sqrt(rx * rx + ry * ry + rz * rz);
@@ -101,44 +117,48 @@ __device__ inline void rodrigues(const double* r, double* R)
     for (int k = 0; k < 9; ++k) R[k] = c * I[k] + c1 * rrt[k] + s * rx_[k];
 }
 
-__device__ __forceinline__ void mat3f_inverse(const float* m, float* r)   // Eigen 3x3 inverse (cofactors / det)
+KT_HD __forceinline__ void mat3f_inverse(const float* m, float* r)   // Eigen 3x3 inverse (cofactors / det)
 {
 #define KT_M(i, j) m[(i) * 3 + (j)]
 #define KT_COF(i, j) (KT_M(((i) + 1) % 3, ((j) + 1) % 3) * KT_M(((i) + 2) % 3, ((j) + 2) % 3) - KT_M(((i) + 1) % 3, ((j) + 2) % 3) * KT_M(((i) + 2) % 3, ((j) + 1) % 3))
-    float c00 = __fsub_rn(__fmul_rn(KT_M(1, 1), KT_M(2, 2)), __fmul_rn(KT_M(1, 2), KT_M(2, 1)));
-    float c10 = __fsub_rn(__fmul_rn(KT_M(2, 1), KT_M(0, 2)), __fmul_rn(KT_M(2, 2), KT_M(0, 1)));
-    float c20 = __fsub_rn(__fmul_rn(KT_M(0, 1), KT_M(1, 2)), __fmul_rn(KT_M(0, 2), KT_M(1, 1)));
-    float det = __fadd_rn(__fadd_rn(__fmul_rn(c00, KT_M(0, 0)), __fmul_rn(c10, KT_M(1, 0))), __fmul_rn(c20, KT_M(2, 0)));
-    float invdet = __fdiv_rn(1.0f, det);
-    float c01 = __fsub_rn(__fmul_rn(KT_M(1, 2), KT_M(2, 0)), __fmul_rn(KT_M(1, 0), KT_M(2, 2)));
-    float c11 = __fsub_rn(__fmul_rn(KT_M(2, 2), KT_M(0, 0)), __fmul_rn(KT_M(2, 0), KT_M(0, 2)));
-    float c21 = __fsub_rn(__fmul_rn(KT_M(0, 2), KT_M(1, 0)), __fmul_rn(KT_M(0, 0), KT_M(1, 2)));
-    float c02 = __fsub_rn(__fmul_rn(KT_M(1, 0), KT_M(2, 1)), __fmul_rn(KT_M(1, 1), KT_M(2, 0)));
-    float c12 = __fsub_rn(__fmul_rn(KT_M(2, 0), KT_M(0, 1)), __fmul_rn(KT_M(2, 1), KT_M(0, 0)));
-    float c22 = __fsub_rn(__fmul_rn(KT_M(0, 0), KT_M(1, 1)), __fmul_rn(KT_M(0, 1), KT_M(1, 0)));
-    r[0] = __fmul_rn(c00, invdet); r[1] = __fmul_rn(c10, invdet); r[2] = __fmul_rn(c20, invdet);
-    r[3] = __fmul_rn(c01, invdet); r[4] = __fmul_rn(c11, invdet); r[5] = __fmul_rn(c21, invdet);
-    r[6] = __fmul_rn(c02, invdet); r[7] = __fmul_rn(c12, invdet); r[8] = __fmul_rn(c22, invdet);
+    float c00 = KT_FSUB(KT_FMUL(KT_M(1, 1), KT_M(2, 2)), KT_FMUL(KT_M(1, 2), KT_M(2, 1)));
+    float c10 = KT_FSUB(KT_FMUL(KT_M(2, 1), KT_M(0, 2)), KT_FMUL(KT_M(2, 2), KT_M(0, 1)));
+    float c20 = KT_FSUB(KT_FMUL(KT_M(0, 1), KT_M(1, 2)), KT_FMUL(KT_M(0, 2), KT_M(1, 1)));
+    float det = KT_FADD(KT_FADD(KT_FMUL(c00, KT_M(0, 0)), KT_FMUL(c10, KT_M(1, 0))), KT_FMUL(c20, KT_M(2, 0)));
+    float invdet = KT_FDIV(1.0f, det);
+    float c01 = KT_FSUB(KT_FMUL(KT_M(1, 2), KT_M(2, 0)), KT_FMUL(KT_M(1, 0), KT_M(2, 2)));
+    float c11 = KT_FSUB(KT_FMUL(KT_M(2, 2), KT_M(0, 0)), KT_FMUL(KT_M(2, 0), KT_M(0, 2)));
+    float c21 = KT_FSUB(KT_FMUL(KT_M(0, 2), KT_M(1, 0)), KT_FMUL(KT_M(0, 0), KT_M(1, 2)));
+    float c02 = KT_FSUB(KT_FMUL(KT_M(1, 0), KT_M(2, 1)), KT_FMUL(KT_M(1, 1), KT_M(2, 0)));
+    float c12 = KT_FSUB(KT_FMUL(KT_M(2, 0), KT_M(0, 1)), KT_FMUL(KT_M(2, 1), KT_M(0, 0)));
+    float c22 = KT_FSUB(KT_FMUL(KT_M(0, 0), KT_M(1, 1)), KT_FMUL(KT_M(0, 1), KT_M(1, 0)));
+    r[0] = KT_FMUL(c00, invdet); r[1] = KT_FMUL(c10, invdet); r[2] = KT_FMUL(c20, invdet);
+    r[3] = KT_FMUL(c01, invdet); r[4] = KT_FMUL(c11, invdet); r[5] = KT_FMUL(c21, invdet);
+    r[6] = KT_FMUL(c02, invdet); r[7] = KT_FMUL(c12, invdet); r[8] = KT_FMUL(c22, invdet);
 #undef KT_COF
 #undef KT_M
 }
 
 // IEEE (non-contracted) float helpers: the reference does this part on the HOST CPU, without FMA.
-__device__ __forceinline__ float dot3_rn(float a0, float a1, float a2, float b0, float b1, float b2)
+KT_HD __forceinline__ float dot3_rn(float a0, float a1, float a2, float b0, float b1, float b2)
 {
-    return __fadd_rn(__fadd_rn(__fmul_rn(a0, b0), __fmul_rn(a1, b1)), __fmul_rn(a2, b2));
+    return KT_FADD(KT_FADD(KT_FMUL(a0, b0), KT_FMUL(a1, b1)), KT_FMUL(a2, b2));
 }
 
 // Solve for the increment and update resultRt (4x4 double) and the float pose (Rcurr, tcurr) given (Rprev, tprev).
-__device__ __forceinline__ void gauss_newton_update_p(const double* dA, const double* db, double* resultRt,
+KT_HD __forceinline__ void gauss_newton_update_p(const double* dA, const double* db, double* resultRt,
                                                       const float* Rp, const float* tprev, float* Rcurr, float* tcurr, long long* stamps = 0)
 {
     double x[6];
     ldlt6_solve(dA, db, x);
+#ifdef __CUDA_ARCH__
     if (stamps) stamps[0] = clock64();            // debug (tools/icp_prof.py)
+#endif
     double R[9];
     rodrigues(x + 3, R);
+#ifdef __CUDA_ARCH__
     if (stamps) stamps[1] = clock64();
+#endif
     const double cur[16] = {R[0], R[1], R[2], x[0], R[3], R[4], R[5], x[1], R[6], R[7], R[8], x[2], 0, 0, 0, 1};
     double res[16];
 #pragma unroll
@@ -168,11 +188,11 @@ __device__ __forceinline__ void gauss_newton_update_p(const double* dA, const do
 #pragma unroll
         for (int j = 0; j < 3; ++j)   // (Rprev * rot^T)(i,j) = sum_k Rprev(i,k) * rot(j,k)
             Rcurr[i * 3 + j] = dot3_rn(Rp[i * 3 + 0], Rp[i * 3 + 1], Rp[i * 3 + 2], rot[j * 3 + 0], rot[j * 3 + 1], rot[j * 3 + 2]);
-        tcurr[i] = __fadd_rn(dot3_rn(Rp[i * 3 + 0], Rp[i * 3 + 1], Rp[i * 3 + 2], tinv[0], tinv[1], tinv[2]), tprev[i]);
+        tcurr[i] = KT_FADD(dot3_rn(Rp[i * 3 + 0], Rp[i * 3 + 1], Rp[i * 3 + 2], tinv[0], tinv[1], tinv[2]), tprev[i]);
     }
 }
 
-__device__ __forceinline__ void gauss_newton_update(const double* dA, const double* db, OdomState* st)
+KT_HD __forceinline__ void gauss_newton_update(const double* dA, const double* db, OdomState* st)
 {
     gauss_newton_update_p(dA, db, st->resultRt, st->Rprev, st->tprev, st->Rcurr, st->tcurr);
 }
