@@ -11,6 +11,7 @@
 // copies; here: 5 pyramid launches, 1 + 19 odometry launches (solve on device), 3 fusion launches, 1 raycast
 // launch that also builds the model pyramid, one 200-byte D2H.
 #include "kt_ops.h"
+#include "kt_shift.hpp"
 #include <cstdlib>
 #include "../../include/kintinuous_b200.h"
 #include <vector>
@@ -131,8 +132,7 @@ template <class T> int dev_alloc(kt_ctx* c, T** p, size_t count)
 
 void vwrap_copy(const kt_ctx* c, int* w)       // KintinuousTracker::vWrapCopyUpdate (.cpp:1075-1085)
 {
-    const int V = c->cfg.vol;
-    for (int i = 0; i < 3; ++i) { w[i] = c->voxelWrap[i]; if (w[i] < 0) w[i] = V - ((-w[i]) % V); }
+    vwrap_nonneg(c->voxelWrap, c->cfg.vol, w);
 }
 
 int fetch_cloud(kt_ctx* c, const int* vWrapCopy, const int* lo, const int* hi)      // TsdfVolume::fetchCloud (TSDFVolume.cpp:131-172)
@@ -377,40 +377,24 @@ int process_frame_device(kt_ctx* c, uint64_t utime, kt_pose* out)
     c->current_utime = utime;
     c->rmats.push_back(Rcurr); c->tvecs.push_back(tcurr);                                // .cpp:578-579
 
-    for (int i = 0; i < 3; ++i) {                                                        // .cpp:581-596
-        float g = c->volumeBasis[i] - c->size * 0.5f;
-        g += c->voxelWrap[i] * c->voxel;
-        g += tcurr.v[i] - c->volumeBasis[i];
-        c->currentGlobalCamera[i] = g;
-    }
+    for (int i = 0; i < 3; ++i) c->currentGlobalCamera[i] = global_camera(c->volumeBasis[i], c->size, c->voxelWrap[i], c->voxel, tcurr.v[i]);   // .cpp:581-596
     M3 Rcurr_inv = m3_inverse(Rcurr);                                                    // .cpp:627
     float currentTranslation[3];
     for (int i = 0; i < 3; ++i) currentTranslation[i] = c->tvecs.back().v[i] - c->volumeBasis[i];
     const int thresh = c->parked ? INT_MAX : c->cfg.voxel_shift;                         // .cpp:636
     int trans[3];
-    for (int i = 0; i < 3; ++i) {                                                        // .cpp:642-667
-        int f = (int)std::floor(currentTranslation[i] / c->voxel);
-        trans[i] = (f < 0) ? std::max(-thresh, f) : std::min(thresh, f);
-    }
+    shift_steps(currentTranslation, c->voxel, thresh, trans);                            // .cpp:642-667
     int vWrapCopy[3];
     for (int axis = 0; axis < 3; ++axis) {                                               // x :675-723, y :729-777, z :783-831
         vwrap_copy(c, vWrapCopy);
         const int n = trans[axis];
-        int lo[3] = {0, 0, 0}, hi[3] = {V, V, V};
-        bool cycled = false;
-        if (n >= thresh) {
-            lo[axis] = 0; hi[axis] = n + 1 + c->overlap;
+        int lo[3], hi[3];
+        const int dir = shift_box(axis, n, thresh, c->overlap, V, lo, hi);              // kt_shift.hpp: which slab leaves the volume
+        const bool cycled = dir != 0;
+        if (cycled) {
             if ((r = fetch_cloud(c, vWrapCopy, lo, hi))) return r;
             if ((r = mg_barrier(c))) return r;                          // peers may still read my boundary plane for their extraction
-            if ((r = clear_volume_slab(axis, 0, c->tsdf, c->color, V, c->z_begin, c->z_end, c->voxelWrap[axis], c->voxelWrap[axis] + n, c->stream))) return r;
-            cycled = true;
-        } else if (n <= -thresh) {
-            if (axis < 2) { lo[axis] = V + (n - c->overlap); hi[axis] = V; }
-            else { lo[axis] = V + (n - c->overlap) - 1; hi[axis] = V - 1; }               // .cpp:805 (Q12)
-            if ((r = fetch_cloud(c, vWrapCopy, lo, hi))) return r;
-            if ((r = mg_barrier(c))) return r;
-            if ((r = clear_volume_slab(axis, 1, c->tsdf, c->color, V, c->z_begin, c->z_end, c->voxelWrap[axis], c->voxelWrap[axis] + n, c->stream))) return r;
-            cycled = true;
+            if ((r = clear_volume_slab(axis, dir < 0 ? 1 : 0, c->tsdf, c->color, V, c->z_begin, c->z_end, c->voxelWrap[axis], c->voxelWrap[axis] + n, c->stream))) return r;
         }
         if (cycled) {                                                                    // mutexOutCloudBuffer (.cpp:1156-1208)
             int vt[3] = {0, 0, 0}; vt[axis] = n;
@@ -418,7 +402,7 @@ int process_frame_device(kt_ctx* c, uint64_t utime, kt_pose* out)
             for (int i = 0; i < 3; ++i) voxelTransSize[i] = c->voxel * vt[i];
             // the slice is recorded before tvecs_.back() / voxelWrap move, with the camera of this frame
             for (int i = 0; i < 3; ++i) c->tvecs.back().v[i] -= voxelTransSize[i];
-            int dim = vt[0] > 0 ? 0 : vt[0] < 0 ? 1 : vt[1] > 0 ? 2 : vt[1] < 0 ? 3 : vt[2] > 0 ? 4 : 5;
+            const int dim = slice_dimension(vt);
             if ((r = push_slice(c, dim))) return r;
             for (int i = 0; i < 3; ++i) c->voxelWrap[i] += vt[i];
             for (int i = 0; i < 3; ++i) tcurr.v[i] -= voxelTransSize[i];
@@ -522,8 +506,7 @@ int kt_create(const kt_config* cfg, kt_ctx** out)
     c->overlap = cfg->overlap; c->parked = cfg->parked;
     c->size = cfg->volume_size;
     c->voxel = c->size / (float)cfg->vol;
-    float def = std::max(0.01f, c->size / 100.0f);                                              // KintinuousTracker.cpp:112
-    c->trunc = std::max(def, 2.1f * c->voxel);                                                  // TSDFVolume.cpp:96
+    c->trunc = trunc_dist_for(c->size, c->voxel);                                               // KintinuousTracker.cpp:112, TSDFVolume.cpp:96
     for (int i = 0; i < 3; ++i) c->volumeBasis[i] = c->size * 0.5f;                             // KintinuousTracker.cpp:109
     c->timing = false;
     {   // iteration schedules: ICPOdometry.cpp:42-55, RGBDOdometry.cpp:76-107
