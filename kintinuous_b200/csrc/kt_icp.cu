@@ -6,15 +6,18 @@
 //   struct JtJJtrSE3 (29 floats)                                         cuda/internal.h:98-149
 //   the host half of ICPOdometry::getIncrementalTransformation           ICPOdometry.cpp:86-180
 //
-// B200 design: the reference launches 64 CTAs x 128 threads (8 192 threads on
-// a 148-SM part), a second 1-CTA kernel, then cudaDeviceSynchronize + 116-byte D2H + host LDLT, 19x
-// per frame.  Here ONE launch per iteration covers the image with a grid sized to the SM count
-// (148 x k CTAs of 256 threads, grid-stride), reduces the 29 sums with warp shuffles -> shared memory ->
-// one 128-byte partial per CTA, and the LAST CTA to finish (ticket counter) sums the partials in a
-// fixed order (deterministic run to run), solves the 6x6 system in FP64 and writes the new pose into
-// device memory, where the next iteration's launch picks it up: no host round trip inside a frame.
-// Bound: L2-resident streaming (48 B/pixel: 24 streamed + 24 gathered) -- latency-, not HBM-bound at
-// 640x480 (14.7 MB per level-0 iteration).
+// B200 design: the reference launches 64 CTAs x 128 threads (8 192 threads on a 148-SM part), a second
+// 1-CTA kernel, then cudaDeviceSynchronize + 116-byte D2H + host LDLT, 19x per frame.  Two kernels here:
+//   icp_frame_kernel  the tracker's path: ONE persistent cooperative launch per FRAME (148 CTAs x 512 threads, one per SM) runs all
+//                     levels and iterations; the CTA's contiguous slice of the current maps is staged in shared memory by TMA bulk
+//                     copies once per level; per iteration: batched model-map gathers, warp transpose-reduce, one 128-byte partial
+//                     per CTA, ONE grid barrier, then every CTA sums the partials in the same fixed order and solves the 6x6
+//                     system redundantly in FP64 (kt_solve.cuh) -- no second barrier, no pose broadcast, bit-identical poses;
+//   icp_kernel        one launch per ITERATION (grid sized to the SM count, last-CTA tail solves): the operator API (kt_op_icp_step)
+//                     and the fallback of the per-iteration RGB-D path.
+// Reductions run in a fixed order (deterministic run to run); no host round trip inside a frame.
+// Bound: latency of the per-iteration tail (barrier, partial sum, FP64 solve); the main phase is issue-bound; 48 B/pixel/iteration
+// (24 streamed from the shared-memory stage + 24 gathered from L2), far from HBM-bound at 640x480.
 #include "kt_ops.h"
 #include "kt_solve.cuh"
 #include "kt_reduce.cuh"

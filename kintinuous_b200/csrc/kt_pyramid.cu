@@ -7,7 +7,7 @@
 //   createNMap / computeNmapKernel         maps.cu:83-121, :140-155
 //   tranformMaps / tranformMapsKernel      maps.cu:157-222
 //   resizeVMap/NMap / resizeMapKernel      maps.cu:225-308
-// B200 design: the bilateral filter stages a (16+12)x(32+12) depth tile in shared memory once per
+// B200 design: the bilateral filter stages a (4+12)x(32+12) depth tile (as float) in shared memory once per
 // CTA (169 taps/pixel come from smem, not L1); vertex and normal maps of ALL pyramid levels are
 // produced by ONE launch straight from the depth pyramid (the vertex map is never re-read to make
 // normals); per-pixel arithmetic keeps the reference's expression order (see kt_common.cuh).

@@ -12,13 +12,14 @@
 // B200 re-layout of the WORK, not of the bytes: threads are mapped to STORAGE coordinates (the
 // reference maps them to logical coordinates, so after a shift every warp straddles sector
 // boundaries); a warp always owns one aligned 64-B tsdf segment + one aligned 128-B colour line per z,
-// the z axis is split into slabs (grid.z) for 8x more CTAs than the reference's 1 024, whole columns
+// the z axis is split into 16 chunks (grid.z) for 16x more CTAs than the reference's 1 024, whole columns
 // and z-ranges outside the view frustum are skipped analytically (about 95 % of a centred 6 m cube),
 // and slab clears / init use 128-bit stores.
 // Exactness: the reference advances v_x, v_y, v_g_z, z_scaled by repeated float additions along z
 // (:565-574); rounding of those running sums decides which depth pixel a voxel reads, so the same
 // sequence of additions is replayed here (the z tables once per launch, v_x / v_y per thread).
-// Roofline: HBM; algorithmic bytes = 12 B per updated voxel + image-side gathers.
+// The colour update's per-pixel half (normal validity, view-angle weight, RGB as float) is prepared once per frame (color_prep_kernel).
+// Roofline: HBM by nature (12 B per updated voxel + image-side gathers), instruction-issue bound in practice.
 #include "kt_ops.h"
 
 namespace kt {
