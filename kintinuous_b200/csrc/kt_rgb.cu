@@ -14,7 +14,9 @@
 // B200 design: no per-call cudaMalloc/cudaFree (the reference allocates the 25-tap table and the reduce
 // scratch on every call); the warp (K R K^-1, K t) of each iteration is rebuilt on the
 // device from the running estimate; the sigma of the robust weight and the Gauss-Newton solve live in the
-// reduction tails, so an iteration is 2 launches (3 with ICP) and no host round trip.
+// reduction tails, so an iteration is 2 launches (3 with ICP) and no host round trip.  The tracker itself uses rgbd_frame_kernel:
+// the whole coarse-to-fine loop of -r / -ri in ONE cooperative launch (two grid barriers per iteration: count / sigma, then the sums),
+// correspondences kept in registers between the residual pass and the Jacobian pass.
 #include "kt_ops.h"
 #include "kt_solve.cuh"
 #include "kt_reduce.cuh"

@@ -8,8 +8,10 @@
 // B200 design: everything of a frame is enqueued on ONE stream with exactly one host
 // synchronisation -- after the odometry, because the shift decision and the slice hand-off are host logic in
 // the reference too.  The reference's frame has 59 launches, 26 cudaDeviceSynchronize and 19 blocking D2H
-// copies; here: 5 pyramid launches, 1 + 19 odometry launches (solve on device), 3 fusion launches, 1 raycast
-// launch that also builds the model pyramid, one 200-byte D2H.
+// copies; here: 6 front-end launches (bilateral, 3 pyrDown, maps, colour prep), ONE cooperative odometry launch (all levels and
+// iterations, solve on device), 3 fusion launches (scaleDepth, z table, integrate), 1 raycast launch that also builds the model
+// pyramid, one 48-byte D2H.  kt_prefetch_frame builds the NEXT frame's front end on a side stream into a spare buffer set while the
+// current frame is being fused.  The CUDA-free bookkeeping of the shifting volume lives in kt_shift.hpp (CPU-tested).
 #include "kt_ops.h"
 #include "kt_shift.hpp"
 #include <cstdlib>
