@@ -172,15 +172,19 @@ integrate_kernel(const IntegrateParams p)
     const float tranc_dist = p.trunc;
     const int cols = p.cols, rows = p.rows;
 
-    float v_g_x = (x + 0.5f) * cell_size.x - tcurr.x;
-    float v_g_y = (y + 0.5f) * cell_size.y - tcurr.y;
-    float v_g_z = (0 + 0.5f) * cell_size.z - tcurr.z;
+    // Parity-critical arithmetic is written with explicit round-to-nearest intrinsics in exactly the contraction nvcc chose for the
+    // reference's expressions (tsdf_volume.cu:549-563; read off the SASS of both builds): a*b + c*d compiles to fma(a, b, c*d).  Left to
+    // the compiler, an unrelated edit of this kernel can flip which product is fused and move a voxel's projection by one ulp.
+    float v_g_x = __fmaf_rn(x + 0.5f, cell_size.x, -tcurr.x);                            // (x + 0.5f) * cell_size.x - tcurr.x
+    float v_g_y = __fmaf_rn(y + 0.5f, cell_size.y, -tcurr.y);
+    float v_g_z = __fmaf_rn(0.5f, cell_size.z, -tcurr.z);                                // (0 + 0.5f) * cell_size.z - tcurr.z
 
-    float v_g_part_norm = v_g_x * v_g_x + v_g_y * v_g_y;
+    float v_g_part_norm = __fmaf_rn(v_g_x, v_g_x, __fmul_rn(v_g_y, v_g_y));              // v_g_x * v_g_x + v_g_y * v_g_y
 
-    float v_x = (Rcurr_inv.r0.x * v_g_x + Rcurr_inv.r0.y * v_g_y + Rcurr_inv.r0.z * v_g_z) * intr.fx;
-    float v_y = (Rcurr_inv.r1.x * v_g_x + Rcurr_inv.r1.y * v_g_y + Rcurr_inv.r1.z * v_g_z) * intr.fy;
-    float v_z = (Rcurr_inv.r2.x * v_g_x + Rcurr_inv.r2.y * v_g_y + Rcurr_inv.r2.z * v_g_z);
+    // (R.x * v_g_x + R.y * v_g_y + R.z * v_g_z) [* f]
+    float v_x = __fmul_rn(__fmaf_rn(Rcurr_inv.r0.z, v_g_z, __fmaf_rn(Rcurr_inv.r0.x, v_g_x, __fmul_rn(Rcurr_inv.r0.y, v_g_y))), intr.fx);
+    float v_y = __fmul_rn(__fmaf_rn(Rcurr_inv.r1.z, v_g_z, __fmaf_rn(Rcurr_inv.r1.x, v_g_x, __fmul_rn(Rcurr_inv.r1.y, v_g_y))), intr.fy);
+    float v_z = __fmaf_rn(Rcurr_inv.r2.z, v_g_z, __fmaf_rn(Rcurr_inv.r2.x, v_g_x, __fmul_rn(Rcurr_inv.r2.y, v_g_y)));
 
     float Rcurr_inv_0_z_scaled = Rcurr_inv.r0.z * cell_size.z * intr.fx;
     float Rcurr_inv_1_z_scaled = Rcurr_inv.r1.z * cell_size.z * intr.fy;
@@ -262,9 +266,9 @@ integrate_kernel(const IntegrateParams p)
             if (z < zhi) {
                 vgz[u] = zt[z];
                 const float z_scaled = zt[V + z];
-                float inv_z = 1.0f / (v_z + Rcurr_inv.r2.z * z_scaled);
+                float inv_z = 1.0f / __fmaf_rn(Rcurr_inv.r2.z, z_scaled, v_z);             // 1 / (v_z + Rcurr_inv.r2.z * z_scaled)
                 if (!(inv_z < 0)) {
-                    int2 coo = { __float2int_rn(v_x * inv_z + intr.cx), __float2int_rn(v_y * inv_z + intr.cy) };
+                    int2 coo = { __float2int_rn(__fmaf_rn(v_x, inv_z, intr.cx)), __float2int_rn(__fmaf_rn(v_y, inv_z, intr.cy)) };
                     if (coo.x >= 0 && coo.y >= 0 && coo.x < cols && coo.y < rows) {
                         int sz = z + p.wrap.z; if (sz >= V) sz -= V;
                         if (sz >= p.z_begin && sz < p.z_end) {             // this GPU's slab
@@ -288,7 +292,7 @@ integrate_kernel(const IntegrateParams p)
                 float Dp_scaled = Dp[u];
                 bool no_color = false;
                 if (Dp_scaled < 0.0) { Dp_scaled = -Dp_scaled; no_color = true; }
-                float sdf = Dp_scaled - sqrtf(vgz[u] * vgz[u] + v_g_part_norm);
+                float sdf = Dp_scaled - sqrtf(__fmaf_rn(vgz[u], vgz[u], v_g_part_norm));
                 if (Dp_scaled != 0 && sdf >= -tranc_dist) {
                     upd[u] = true; nocol[u] = no_color;
                     tsdf_new[u] = fmin(1.0f, sdf * tranc_dist_inv);
@@ -312,16 +316,16 @@ integrate_kernel(const IntegrateParams p)
             uchar4 c = cprev[u];
             float weight_prev = c.w;
             const float Wrk = 1;
-            p.tsdf[addr[u]] = pack_tsdf((tsdf_prev * weight_prev + Wrk * tsdf) / (weight_prev + Wrk));
+            p.tsdf[addr[u]] = pack_tsdf(__fmaf_rn(tsdf_prev, weight_prev, tsdf) / (weight_prev + Wrk));   // (F * W + Wrk * tsdf) / (W + Wrk), Wrk = 1
             c.w = min(weight_prev + Wrk, (float)KT_MAX_WEIGHT);
             if (PREP) {
                 const float cwv = nx[u];
                 if ((__float_as_int(cwv) >= 0 && !nocol[u]) || (c.x == 0 && c.y == 0 && c.z == 0)) {
                     const float Wrkc = fabsf(cwv);
                     const float4 rgb = rgbq[u];
-                    float new_x = (c.x * weight_prev + Wrkc * rgb.x) / (weight_prev + Wrkc);
-                    float new_y = (c.y * weight_prev + Wrkc * rgb.y) / (weight_prev + Wrkc);
-                    float new_z = (c.z * weight_prev + Wrkc * rgb.z) / (weight_prev + Wrkc);
+                    float new_x = __fmaf_rn(c.x, weight_prev, __fmul_rn(Wrkc, rgb.x)) / (weight_prev + Wrkc);   // (c * W + Wrkc * rgb) / (W + Wrkc)
+                    float new_y = __fmaf_rn(c.y, weight_prev, __fmul_rn(Wrkc, rgb.y)) / (weight_prev + Wrkc);
+                    float new_z = __fmaf_rn(c.z, weight_prev, __fmul_rn(Wrkc, rgb.z)) / (weight_prev + Wrkc);
                     c.x = sat_u8_rn(new_x);
                     c.y = sat_u8_rn(new_y);
                     c.z = sat_u8_rn(new_z);
@@ -332,9 +336,9 @@ integrate_kernel(const IntegrateParams p)
                 if ((!isnan(ncurr.x) && !nocol[u]) || (c.x == 0 && c.y == 0 && c.z == 0)) {
                     const float Wrkc = (p.angle_color ? min(1.0f, ncurr.z / KT_RGB_VIEW_ANGLE_WEIGHT) : 1.0f) * 2.0f;
                     uchar3 rgb = rgbv[u];
-                    float new_x = (c.x * weight_prev + Wrkc * rgb.x) / (weight_prev + Wrkc);
-                    float new_y = (c.y * weight_prev + Wrkc * rgb.y) / (weight_prev + Wrkc);
-                    float new_z = (c.z * weight_prev + Wrkc * rgb.z) / (weight_prev + Wrkc);
+                    float new_x = __fmaf_rn(c.x, weight_prev, __fmul_rn(Wrkc, rgb.x)) / (weight_prev + Wrkc);   // (c * W + Wrkc * rgb) / (W + Wrkc)
+                    float new_y = __fmaf_rn(c.y, weight_prev, __fmul_rn(Wrkc, rgb.y)) / (weight_prev + Wrkc);
+                    float new_z = __fmaf_rn(c.z, weight_prev, __fmul_rn(Wrkc, rgb.z)) / (weight_prev + Wrkc);
                     c.x = min(255, max(0, __float2int_rn(new_x)));
                     c.y = min(255, max(0, __float2int_rn(new_y)));
                     c.z = min(255, max(0, __float2int_rn(new_z)));
