@@ -23,10 +23,12 @@ __host__ __device__ __forceinline__ Intr intr_level(const Intr& k, int level)   
     return r;
 }
 
-__device__ __forceinline__ float dot3(const float3& a, const float3& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+// a.x * b.x + a.y * b.y + a.z * b.z in the contraction nvcc gives the reference's expressions: fma(a.z, b.z, fma(a.x, b.x, a.y * b.y));
+// a * b - c * d likewise is fma(a, b, -(c * d)).  Written out so that edits elsewhere cannot flip which product gets fused.
+__device__ __forceinline__ float dot3(const float3& a, const float3& b) { return __fmaf_rn(a.z, b.z, __fmaf_rn(a.x, b.x, __fmul_rn(a.y, b.y))); }
 __device__ __forceinline__ float3 cross3(const float3& a, const float3& b)
 {
-    return make_float3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+    return make_float3(__fmaf_rn(a.y, b.z, -__fmul_rn(a.z, b.y)), __fmaf_rn(a.z, b.x, -__fmul_rn(a.x, b.z)), __fmaf_rn(a.x, b.y, -__fmul_rn(a.y, b.x)));
 }
 __device__ __forceinline__ float3 sub3(const float3& a, const float3& b) { return make_float3(a.x - b.x, a.y - b.y, a.z - b.z); }
 __device__ __forceinline__ float3 add3(const float3& a, const float3& b) { return make_float3(a.x + b.x, a.y + b.y, a.z + b.z); }
