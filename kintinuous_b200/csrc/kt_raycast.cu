@@ -94,9 +94,9 @@ struct Caster {
         g.x = (point.x < vx) ? (g.x - 1) : g.x;
         g.y = (point.y < vy) ? (g.y - 1) : g.y;
         g.z = (point.z < vz) ? (g.z - 1) : g.z;
-        a = (point.x - (g.x + 0.5f) * p.cell_size.x) / p.cell_size.x;
-        b = (point.y - (g.y + 0.5f) * p.cell_size.y) / p.cell_size.y;
-        c = (point.z - (g.z + 0.5f) * p.cell_size.z) / p.cell_size.z;
+        a = __fmaf_rn(-(g.x + 0.5f), p.cell_size.x, point.x) / p.cell_size.x;        // (point.x - (g.x + 0.5f) * cell.x) / cell.x
+        b = __fmaf_rn(-(g.y + 0.5f), p.cell_size.y, point.y) / p.cell_size.y;
+        c = __fmaf_rn(-(g.z + 0.5f), p.cell_size.z, point.z) / p.cell_size.z;
         return true;
     }
 
@@ -104,14 +104,18 @@ struct Caster {
     {
         int3 g; float a, b, c;
         if (!trilinearSetup(point, g, a, b, c)) return qnan();
-        float res = readTsdf(g.x + 0, g.y + 0, g.z + 0) * (1 - a) * (1 - b) * (1 - c) +
-                    readTsdf(g.x + 0, g.y + 0, g.z + 1) * (1 - a) * (1 - b) * c +
-                    readTsdf(g.x + 0, g.y + 1, g.z + 0) * (1 - a) * b * (1 - c) +
-                    readTsdf(g.x + 0, g.y + 1, g.z + 1) * (1 - a) * b * c +
-                    readTsdf(g.x + 1, g.y + 0, g.z + 0) * a * (1 - b) * (1 - c) +
-                    readTsdf(g.x + 1, g.y + 0, g.z + 1) * a * (1 - b) * c +
-                    readTsdf(g.x + 1, g.y + 1, g.z + 0) * a * b * (1 - c) +
-                    readTsdf(g.x + 1, g.y + 1, g.z + 1) * a * b * c;
+        // readTsdf(000)*(1-a)*(1-b)*(1-c) + readTsdf(001)*(1-a)*(1-b)*c + ... + readTsdf(111)*a*b*c  (ray_caster.cu:155-171), written in the
+        // contraction nvcc gives that expression: every term's last multiply is fused into the running sum, except the second term,
+        // which is a plain product (fma(x0, w0, x1 * w1), then fma(xk, wk, sum)).
+        const float a1 = 1 - a, b1 = 1 - b, c1 = 1 - c;
+        float res = __fmaf_rn(__fmul_rn(__fmul_rn(readTsdf(g.x + 0, g.y + 0, g.z + 0), a1), b1), c1,
+                              __fmul_rn(__fmul_rn(__fmul_rn(readTsdf(g.x + 0, g.y + 0, g.z + 1), a1), b1), c));
+        res = __fmaf_rn(__fmul_rn(__fmul_rn(readTsdf(g.x + 0, g.y + 1, g.z + 0), a1), b), c1, res);
+        res = __fmaf_rn(__fmul_rn(__fmul_rn(readTsdf(g.x + 0, g.y + 1, g.z + 1), a1), b), c, res);
+        res = __fmaf_rn(__fmul_rn(__fmul_rn(readTsdf(g.x + 1, g.y + 0, g.z + 0), a), b1), c1, res);
+        res = __fmaf_rn(__fmul_rn(__fmul_rn(readTsdf(g.x + 1, g.y + 0, g.z + 1), a), b1), c, res);
+        res = __fmaf_rn(__fmul_rn(__fmul_rn(readTsdf(g.x + 1, g.y + 1, g.z + 0), a), b), c1, res);
+        res = __fmaf_rn(__fmul_rn(__fmul_rn(readTsdf(g.x + 1, g.y + 1, g.z + 1), a), b), c, res);
         return res;
     }
 
@@ -128,10 +132,16 @@ struct Caster {
         const uchar4 c010 = readColor(g.x + 0, g.y + 1, g.z + 0), c011 = readColor(g.x + 0, g.y + 1, g.z + 1);
         const uchar4 c100 = readColor(g.x + 1, g.y + 0, g.z + 0), c101 = readColor(g.x + 1, g.y + 0, g.z + 1);
         const uchar4 c110 = readColor(g.x + 1, g.y + 1, g.z + 0), c111 = readColor(g.x + 1, g.y + 1, g.z + 1);
-#define KT_TRI(f) ((float)c000.f * (1 - a) * (1 - b) * (1 - c) + (float)c001.f * (1 - a) * (1 - b) * c + \
-                   (float)c010.f * (1 - a) * b * (1 - c) + (float)c011.f * (1 - a) * b * c + \
-                   (float)c100.f * a * (1 - b) * (1 - c) + (float)c101.f * a * (1 - b) * c + \
-                   (float)c110.f * a * b * (1 - c) + (float)c111.f * a * b * c)
+        // same 8-term trilinear sum as interpolateTrilineary, same contraction
+        const float a1 = 1 - a, b1 = 1 - b, c1 = 1 - c;
+#define KT_TRI(f) __fmaf_rn(__fmul_rn(__fmul_rn((float)c111.f, a), b), c, \
+                  __fmaf_rn(__fmul_rn(__fmul_rn((float)c110.f, a), b), c1, \
+                  __fmaf_rn(__fmul_rn(__fmul_rn((float)c101.f, a), b1), c, \
+                  __fmaf_rn(__fmul_rn(__fmul_rn((float)c100.f, a), b1), c1, \
+                  __fmaf_rn(__fmul_rn(__fmul_rn((float)c011.f, a1), b), c, \
+                  __fmaf_rn(__fmul_rn(__fmul_rn((float)c010.f, a1), b), c1, \
+                  __fmaf_rn(__fmul_rn(__fmul_rn((float)c000.f, a1), b1), c1, \
+                            __fmul_rn(__fmul_rn(__fmul_rn((float)c001.f, a1), b1), c))))))))
         uchar4 r;
         r.x = KT_TRI(x); r.y = KT_TRI(y); r.z = KT_TRI(z);
         float heat = KT_TRI(w);
@@ -160,6 +170,12 @@ __device__ __forceinline__ float getMaxTime(const float3& volume_max, const floa
 // ~2 CTA rounds long (stage timer 72.8 -> 68.8 us against 32x8 tiles), and a 16x2 warp footprint keeps the rays of a warp closer.
 enum { RC_X = 16, RC_Y = 8 };
 
+// ray_start + ray_dir * t, as the fused multiply-add nvcc makes of the reference's expression (ray_caster.cu:337-411)
+__device__ __forceinline__ float3 ray_at(const float3& o, const float3& d, float t)
+{
+    return make_float3(__fmaf_rn(d.x, t, o.x), __fmaf_rn(d.y, t, o.y), __fmaf_rn(d.z, t, o.z));
+}
+
 // One ray.  Returns validity of vertex / normal; outputs by reference.
 template <bool POW2, typename IdxT, int RS, bool MG>
 __device__ __forceinline__ void cast_ray(const RayParams& p, int x, int y, bool& v_ok, float3& vtx, bool& n_ok, float3& nrm,
@@ -186,7 +202,7 @@ __device__ __forceinline__ void cast_ray(const RayParams& p, int x, int y, bool&
 
     const float time_step = p.time_step;
     float time_curr = time_start_volume;
-    int3 g = rc.getVoxel(add3(ray_start, scale3(ray_dir, time_curr)));
+    int3 g = rc.getVoxel(ray_at(ray_start, ray_dir, time_curr));
     g.x = max(0, min(g.x, p.V - 1));
     g.y = max(0, min(g.y, p.V - 1));
     g.z = max(0, min(g.z, p.V - 1));
@@ -204,7 +220,7 @@ __device__ __forceinline__ void cast_ray(const RayParams& p, int x, int y, bool&
 #pragma unroll
         for (int s = 0; s < RS; ++s) {
             tq[s] = t;
-            int3 gn = rc.getVoxel(add3(ray_start, scale3(ray_dir, (t + time_step))));
+            int3 gn = rc.getVoxel(ray_at(ray_start, ray_dir, (t + time_step)));
             inb[s] = rc.checkInds(gn);
             raw[s] = inb[s] ? rc.rawTsdf(gn.x, gn.y, gn.z) : (short)0;
             t += time_step;
@@ -220,16 +236,16 @@ __device__ __forceinline__ void cast_ray(const RayParams& p, int x, int y, bool&
             if (tsdf_prev < 0 && tsdf > 0) { done = true; break; }
             if (tsdf_prev > 0 && tsdf < 0) {
                 done = true;
-                float Ftdt = rc.interpolateTrilineary(add3(ray_start, scale3(ray_dir, (tc + time_step))));
+                float Ftdt = rc.interpolateTrilineary(ray_at(ray_start, ray_dir, (tc + time_step)));
                 if (isnan(Ftdt)) break;
-                float Ft = rc.interpolateTrilineary(add3(ray_start, scale3(ray_dir, tc)));
+                float Ft = rc.interpolateTrilineary(ray_at(ray_start, ray_dir, tc));
                 if (isnan(Ft)) break;
 
                 float Ts = tc - time_step * Ft / (Ftdt - Ft);
-                float3 vetex_found = add3(ray_start, scale3(ray_dir, Ts));
+                float3 vetex_found = ray_at(ray_start, ray_dir, Ts);
                 vtx = vetex_found; v_ok = true;
 
-                int3 gc = rc.getVoxel(add3(ray_start, scale3(ray_dir, tc)));
+                int3 gc = rc.getVoxel(ray_at(ray_start, ray_dir, tc));
                 col = rc.interpolateColorHeat(vetex_found); c_ok = true;
 
                 if (gc.x > 1 && gc.y > 1 && gc.z > 1 && gc.x < p.V - 2 && gc.y < p.V - 2 && gc.z < p.V - 2) {
