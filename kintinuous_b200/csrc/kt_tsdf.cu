@@ -84,7 +84,7 @@ scale_depth_kernel(const uint16_t* __restrict__ depth, float* __restrict__ scale
     int Dp = depth[(size_t)y * cols + x];
     float xl = (x - intr.cx) / intr.fx;
     float yl = (y - intr.cy) / intr.fy;
-    float lambda = sqrtf(xl * xl + yl * yl + 1);
+    float lambda = sqrtf(__fadd_rn(__fmaf_rn(xl, xl, __fmul_rn(yl, yl)), 1.f));     // sqrtf(xl * xl + yl * yl + 1), contraction pinned
     if (angleColor) {
         int STEP = 1, ky = 7, kx = 7;
         int ty = min(y - ky / 2 + ky, rows - 1);
