@@ -104,18 +104,14 @@ struct Caster {
     {
         int3 g; float a, b, c;
         if (!trilinearSetup(point, g, a, b, c)) return qnan();
-        // readTsdf(000)*(1-a)*(1-b)*(1-c) + readTsdf(001)*(1-a)*(1-b)*c + ... + readTsdf(111)*a*b*c  (ray_caster.cu:155-171), written in the
-        // contraction nvcc gives that expression: every term's last multiply is fused into the running sum, except the second term,
-        // which is a plain product (fma(x0, w0, x1 * w1), then fma(xk, wk, sum)).
-        const float a1 = 1 - a, b1 = 1 - b, c1 = 1 - c;
-        float res = __fmaf_rn(__fmul_rn(__fmul_rn(readTsdf(g.x + 0, g.y + 0, g.z + 0), a1), b1), c1,
-                              __fmul_rn(__fmul_rn(__fmul_rn(readTsdf(g.x + 0, g.y + 0, g.z + 1), a1), b1), c));
-        res = __fmaf_rn(__fmul_rn(__fmul_rn(readTsdf(g.x + 0, g.y + 1, g.z + 0), a1), b), c1, res);
-        res = __fmaf_rn(__fmul_rn(__fmul_rn(readTsdf(g.x + 0, g.y + 1, g.z + 1), a1), b), c, res);
-        res = __fmaf_rn(__fmul_rn(__fmul_rn(readTsdf(g.x + 1, g.y + 0, g.z + 0), a), b1), c1, res);
-        res = __fmaf_rn(__fmul_rn(__fmul_rn(readTsdf(g.x + 1, g.y + 0, g.z + 1), a), b1), c, res);
-        res = __fmaf_rn(__fmul_rn(__fmul_rn(readTsdf(g.x + 1, g.y + 1, g.z + 0), a), b), c1, res);
-        res = __fmaf_rn(__fmul_rn(__fmul_rn(readTsdf(g.x + 1, g.y + 1, g.z + 1), a), b), c, res);
+        float res = readTsdf(g.x + 0, g.y + 0, g.z + 0) * (1 - a) * (1 - b) * (1 - c) +
+                    readTsdf(g.x + 0, g.y + 0, g.z + 1) * (1 - a) * (1 - b) * c +
+                    readTsdf(g.x + 0, g.y + 1, g.z + 0) * (1 - a) * b * (1 - c) +
+                    readTsdf(g.x + 0, g.y + 1, g.z + 1) * (1 - a) * b * c +
+                    readTsdf(g.x + 1, g.y + 0, g.z + 0) * a * (1 - b) * (1 - c) +
+                    readTsdf(g.x + 1, g.y + 0, g.z + 1) * a * (1 - b) * c +
+                    readTsdf(g.x + 1, g.y + 1, g.z + 0) * a * b * (1 - c) +
+                    readTsdf(g.x + 1, g.y + 1, g.z + 1) * a * b * c;
         return res;
     }
 
@@ -132,16 +128,10 @@ struct Caster {
         const uchar4 c010 = readColor(g.x + 0, g.y + 1, g.z + 0), c011 = readColor(g.x + 0, g.y + 1, g.z + 1);
         const uchar4 c100 = readColor(g.x + 1, g.y + 0, g.z + 0), c101 = readColor(g.x + 1, g.y + 0, g.z + 1);
         const uchar4 c110 = readColor(g.x + 1, g.y + 1, g.z + 0), c111 = readColor(g.x + 1, g.y + 1, g.z + 1);
-        // same 8-term trilinear sum as interpolateTrilineary, same contraction
-        const float a1 = 1 - a, b1 = 1 - b, c1 = 1 - c;
-#define KT_TRI(f) __fmaf_rn(__fmul_rn(__fmul_rn((float)c111.f, a), b), c, \
-                  __fmaf_rn(__fmul_rn(__fmul_rn((float)c110.f, a), b), c1, \
-                  __fmaf_rn(__fmul_rn(__fmul_rn((float)c101.f, a), b1), c, \
-                  __fmaf_rn(__fmul_rn(__fmul_rn((float)c100.f, a), b1), c1, \
-                  __fmaf_rn(__fmul_rn(__fmul_rn((float)c011.f, a1), b), c, \
-                  __fmaf_rn(__fmul_rn(__fmul_rn((float)c010.f, a1), b), c1, \
-                  __fmaf_rn(__fmul_rn(__fmul_rn((float)c000.f, a1), b1), c1, \
-                            __fmul_rn(__fmul_rn(__fmul_rn((float)c001.f, a1), b1), c))))))))
+#define KT_TRI(f) ((float)c000.f * (1 - a) * (1 - b) * (1 - c) + (float)c001.f * (1 - a) * (1 - b) * c + \
+                   (float)c010.f * (1 - a) * b * (1 - c) + (float)c011.f * (1 - a) * b * c + \
+                   (float)c100.f * a * (1 - b) * (1 - c) + (float)c101.f * a * (1 - b) * c + \
+                   (float)c110.f * a * b * (1 - c) + (float)c111.f * a * b * c)
         uchar4 r;
         r.x = KT_TRI(x); r.y = KT_TRI(y); r.z = KT_TRI(z);
         float heat = KT_TRI(w);
