@@ -475,21 +475,16 @@ int integrate(const IntegrateArgs& a, float* ztable_dev, cudaStream_t s)
         p.lz_lo = lo[i]; p.lz_hi = hi[i];
         dim3 block(32, 8), grid(div_up(V, 32), div_up(V, 8), div_up(hi[i] - lo[i], p.zchunk));
         if (idx32) {
-            // batch depth / CTAs per SM (KT_INT_ZU overrides).  Measured (tools/stage_ab.py, 640x480): 512^3 2-voxel batches at 4 CTAs/SM
-            // 78 us vs 81 us for 1-voxel steps at 6 CTAs/SM; 1024^3 395 vs 351 us: once the updated region outgrows L2, occupancy wins
+            // batch depth / CTAs per SM (KT_INT_ZU = 1 or 2 overrides).  Measured (tools/stage_ab.py, 640x480): 512^3 2-voxel batches at 4
+            // CTAs/SM 78 us vs 81 us for 1-voxel steps at 6 CTAs/SM; 1024^3 395 vs 351 us: once the updated region outgrows L2, occupancy
+            // wins.  Also measured and dropped: 3- and 4-voxel batches (82 / 93 us), 2-voxel batches at 5 or 6 CTAs/SM (81 / 91 us, spills)
             const int variant = zu ? zu : (V >= 1024 ? 1 : 2);
             if (prep && (variant == 1 || variant == 2)) {
                 if (variant == 1) integrate_kernel<unsigned int, 1, 6, true><<<grid, block, 0, s>>>(p);
                 else integrate_kernel<unsigned int, 2, 4, true><<<grid, block, 0, s>>>(p);
             } else
-            switch (variant) {
-            case 4: integrate_kernel<unsigned int, 4, 3><<<grid, block, 0, s>>>(p); break;
-            case 5: integrate_kernel<unsigned int, 2, 5><<<grid, block, 0, s>>>(p); break;
-            case 6: integrate_kernel<unsigned int, 2, 6><<<grid, block, 0, s>>>(p); break;
-            case 3: integrate_kernel<unsigned int, 3, 4><<<grid, block, 0, s>>>(p); break;
-            case 1: integrate_kernel<unsigned int, 1, 6><<<grid, block, 0, s>>>(p); break;
-            default: integrate_kernel<unsigned int, 2, 4><<<grid, block, 0, s>>>(p); break;
-            }
+            if (variant == 1) integrate_kernel<unsigned int, 1, 6><<<grid, block, 0, s>>>(p);
+            else integrate_kernel<unsigned int, 2, 4><<<grid, block, 0, s>>>(p);
         }
         else if (prep) integrate_kernel<size_t, 1, 6, true><<<grid, block, 0, s>>>(p);
         else if (zu == 2) integrate_kernel<size_t, 2, 4><<<grid, block, 0, s>>>(p);

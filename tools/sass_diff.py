@@ -22,12 +22,13 @@ def kernels(path):
 
 
 a, b = kernels(sys.argv[1]), kernels(sys.argv[2])
-bad = 0
+diff = only = 0
 for k in sorted(set(a) | set(b)):
     if k not in a or k not in b:
-        print("ONLY IN", "before" if k in a else "after", k); bad += 1
+        print("ONLY IN", "before" if k in a else "after", k); only += 1
     elif a[k] != b[k]:
         n = sum(1 for x, y in zip(a[k], b[k]) if x != y) + abs(len(a[k]) - len(b[k]))
-        print(f"DIFF  {k}: {len(a[k])} -> {len(b[k])} instructions, {n} positions differ"); bad += 1
-print(f"{len(set(a) & set(b)) - bad if bad else len(a)} of {len(set(a) | set(b))} kernels identical")
-sys.exit(1 if bad else 0)
+        print(f"DIFF  {k}: {len(a[k])} -> {len(b[k])} instructions, {n} positions differ"); diff += 1
+common = len(set(a) & set(b))
+print(f"{common - diff} of {common} common kernels identical, {only} present in one build only")
+sys.exit(1 if diff else 0)
