@@ -119,7 +119,7 @@ class ClockSampler:
                 self.rows.append((mhz, mask))
             except Exception:
                 pass
-            time.sleep(0.01)
+            time.sleep(0.002)
 
     def start(self):
         self.run = True
@@ -132,7 +132,7 @@ class ClockSampler:
             self.t.join(timeout=1.0)
             sm = [r[0] for r in self.rows]
             reasons = sorted({name for r in self.rows for bit, name in self.REASONS.items() if r[1] & bit})
-            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(sm), "source": "nvml, 10 ms poll"}
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(sm), "source": "nvml, 2 ms poll"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml and nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -207,11 +207,15 @@ def run_reference(args, world, rank, local):
     from oracle import refbind
     import kintinuous_b200 as kb
     cfg = kb.Config.default(rows=ROWS, cols=COLS, vol=args.vol, odometry=args.odometry)
-    n_frames = min(N_INPUT_FRAMES, max(8, args.steps + args.warmup + 1))
+    n_frames = N_INPUT_FRAMES                         # the same frame set as the b200 arm (same_config)
     frames = make_stream(n_frames)
-    line = {"metric": f"frames/s {COLS}x{ROWS} into {args.vol}^3 TSDF ({METRIC_TAGS[args.odometry]} tracker)", "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+    PREWARM = int(os.environ.get("KT_BENCH_PREWARM", "150"))
+    warmup = max(3, args.warmup)
+    # n_gpus is what this arm USED: the reference has no multi-GPU path, rank 0 runs it on one GPU whatever --gpus says
+    line = {"metric": f"frames/s {COLS}x{ROWS} into {args.vol}^3 TSDF ({METRIC_TAGS[args.odometry]} tracker)", "unit": "frames/s", "n_gpus": 1, "requested_gpus": args.gpus, "steps": args.steps, "warmup": warmup,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": {"workload": f"synthetic {COLS}x{ROWS} RGB-D stream, {args.vol}^3 volume (6 m), {TRACKER_NAMES[args.odometry]} {{10,5,4}}, shifting on (-t 14)", "frames_cycled": n_frames}}
+            "config": {"workload": f"synthetic {COLS}x{ROWS} RGB-D stream, {args.vol}^3 volume (6 m), {TRACKER_NAMES[args.odometry]} {{10,5,4}}, shifting on (-t 14)", "frames_cycled": n_frames,
+                       "prewarm_frames": PREWARM, "untimed_frames_before_region": PREWARM + warmup + 1}}
     use_cuda = False
     try:
         import torch
@@ -234,10 +238,11 @@ def run_reference(args, world, rank, local):
         sync = lambda: None
         kind = "port"
         sample = f"oracle/_ref unavailable: CPU oracle port on {cores} threads"
-        args.steps = min(args.steps, 8); args.warmup = min(args.warmup, 1)
-        line["steps"], line["warmup"] = args.steps, args.warmup
+        args.steps = min(args.steps, 8); warmup = 1; PREWARM = 0
+        line["steps"], line["warmup"] = args.steps, warmup
+        line["config"]["prewarm_frames"] = 0; line["config"]["untimed_frames_before_region"] = 2
     i = 0
-    for _ in range(args.warmup + 1):
+    for _ in range(PREWARM + warmup + 1):             # the same untimed lead-in as the b200 arm (GPU clocks, allocator, first shifts)
         d, c = frames[pingpong(i, n_frames)]; t.process(d, c, i); i += 1
     sync(); t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -387,9 +392,13 @@ def main():
     icp_ms = results.get("icp_kernel_ms", 0.0) or st[1]
     ach = icp_bytes / (icp_ms * 1e-3) / 1e9 if icp_ms > 0 else None
     traffic = None
+    traffic_file = None
     try:                                                      # dram__bytes_read.sum + dram__bytes_write.sum of the committed ncu capture
-        import csv
-        rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "r1_ncu_full_v10_icp_frame_kernel.csv" if args.odometry == 0 else "r1_ncu_full_v10_rgbd_frame_kernel.csv"))))
+        import csv, glob
+        kname = "icp_frame_kernel" if args.odometry == 0 else "rgbd_frame_kernel"
+        cands = sorted(glob.glob(os.path.join(ROOT, "profiles", f"r2_ncu_full_*{kname}*.csv"))) or sorted(glob.glob(os.path.join(ROOT, "profiles", f"r1_ncu_full_v10_{kname}.csv")))
+        traffic_file = os.path.relpath(cands[-1], ROOT)
+        rows = list(csv.reader(open(cands[-1])))
         H, U, Vv = rows[0], rows[1], rows[2]
         def val(name):
             i = H.index(name); x = float(Vv[i]); u = U[i].lower()
@@ -397,8 +406,12 @@ def main():
         traffic = val("dram__bytes_read.sum") + val("dram__bytes_write.sum")
     except Exception:
         traffic = None
+    # compulsory DRAM bytes of the launch: the four map sets of the levels in use, read once (48 B/pixel; later iterations hit L2 / smem)
+    compulsory = sum(per_px * P_LEVELS[l] for l in range(4) if ICP_ITERS[l] > 0)
     roofline = {"kernel": kernel_name, "bound": "hbm",
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None, "traffic": traffic,
+                "traffic_source": f"ncu --set full capture {traffic_file} (dram__bytes_read.sum + dram__bytes_write.sum, one launch); not re-measured in this run" if traffic else None,
+                "compulsory_dram_bytes": compulsory, "frac_compulsory_dram": (compulsory / (icp_ms * 1e-3) / 1e9 / peak) if icp_ms > 0 else None,
                 "peak_source": peak_src, "bytes_per_launch": icp_bytes, "avg_launch_ms": icp_ms,
                 "note": "algorithmic bytes / CUDA-event time of that launch; the kernel is latency-bound by design at 640x480 (19 sequential reduce+solve steps separated by grid barriers, inputs L2-resident so DRAM traffic is far below the algorithmic bytes); see DESIGN.md section 4 and profiles/r1_ncu_summary.md",
                 "dominant_stage": dom}
@@ -409,7 +422,7 @@ def main():
     line = {"metric": f"frames/s {COLS}x{ROWS} into {args.vol}^3 TSDF ({METRIC_TAGS[args.odometry]} tracker)", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
             "ms_per_step": 1e3 * dt / args.steps, "wall_ms_per_step": 1e3 * results["device"]["wall"] / args.steps, "timing": "CUDA events on the tracker stream, max over ranks", "higher_is_better": True, "scaling": "strong" if zslab else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"synthetic {COLS}x{ROWS} RGB-D stream, {args.vol}^3 volume (6 m), {tracker_name} {{10,5,4}}, shifting on (-t 14)", "parallelism": (f"one stream, volume z-slab sharded over {world} GPUs (P2P raycast, replicated ICP)" if zslab else f"{world} independent streams"), "vol": args.vol, "odometry": args.odometry,
-                       "prewarm_frames": PREWARM, "l2": f"inputs larger than L2: {n} frames x {ROWS * COLS * 5 / 1e6:.2f} MB = {n * ROWS * COLS * 5 / 1e6:.0f} MB cycled (ping-pong)"},
+                       "prewarm_frames": PREWARM, "untimed_frames_before_region": PREWARM + warmup + 1, "prefetch_hint": not args.no_prefetch, "l2": f"inputs larger than L2: {n} frames x {ROWS * COLS * 5 / 1e6:.2f} MB = {n * ROWS * COLS * 5 / 1e6:.0f} MB cycled (ping-pong)"},
             "e2e": {"value": e2e_v, "unit": "frames/s", "h2d_bytes_per_step": ROWS * COLS * 5, "d2h_bytes_per_step": 48},
             "gpu_launches": int(results["device"]["launches"]), "clocks": clocks, "roofline": roofline, "stages": stages}
     if not args.no_cpu_baseline:

@@ -146,6 +146,10 @@ KT_API int kt_mgpu_info(kt_ctx* ctx, int* info5);
 KT_API long long kt_launch_count(kt_ctx* ctx);
 /* debug: 64 x 5 clock64() stamps of the last whole-frame ICP launch (recorded only while stage timing is enabled) */
 KT_API int kt_debug_icp_profile(kt_ctx* ctx, long long* out512);
+/* debug / parity tap: the arguments of the last integrateTsdfVolume call of the tracker (KintinuousTracker.cpp:864-876): Rcurr^-1
+ * (9, row-major), tcurr after the shift adjustment (3), vWrapCopy (3).  Lets a test replay the frame with the reference's own
+ * operators on the tracker's own poses and demand a bit-identical volume. */
+KT_API int kt_debug_last_integrate(kt_ctx* ctx, float* Rinv9, float* t3, int* wrap3);
 KT_API int kt_alloc_pinned(void** ptr, size_t bytes);
 KT_API int kt_free_pinned(void* ptr);
 

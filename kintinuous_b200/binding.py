@@ -195,6 +195,12 @@ class Tracker:
         _check(self.lib.kt_download_map(self.h, which, level, _ptr(out)))
         return out
 
+    def last_integrate(self):
+        """(Rinv 3x3, t 3, wrap 3) of the last integration (kt_debug_last_integrate)."""
+        R = np.zeros(9, np.float32); t = np.zeros(3, np.float32); w = np.zeros(3, np.int32)
+        _check(self.lib.kt_debug_last_integrate(self.h, _ptr(R), _ptr(t), _ptr(w)))
+        return R.reshape(3, 3), t, w
+
     def set_stage_timing(self, on=True):
         _check(self.lib.kt_set_stage_timing(self.h, int(on)))
 

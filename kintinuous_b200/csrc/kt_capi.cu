@@ -5,6 +5,7 @@
 #include "../../include/kintinuous_b200.h"
 #include <cstring>
 #include <cstddef>
+#include <mutex>
 
 using namespace kt;
 
@@ -14,9 +15,22 @@ Intr intr4(const float* k) { Intr r = {k[0], k[1], k[2], k[3]}; return r; }
 Mat33 mat33(const float* m) { Mat33 r; r.r0 = make_float3(m[0], m[1], m[2]); r.r1 = make_float3(m[3], m[4], m[5]); r.r2 = make_float3(m[6], m[7], m[8]); return r; }
 cudaStream_t st(void* s) { return (cudaStream_t)s; }
 
-// scratch shared by the stateless operator calls (the reference keeps sumDataSE3 / outDataSE3 in its odometry objects)
+// Scratch of the stateless operator calls (the reference keeps sumDataSE3 / outDataSE3 in its odometry objects and is not thread-safe
+// either: internal.h:299-536 has static state in computeDerivativeImages and __device__ globals in extract.cu).  One set PER DEVICE
+// (the device current at the call), and the calls that use it are serialised by a process-wide mutex, so operator calls from several
+// host threads / on several devices are safe, just not concurrent.
 struct OpScratch { OdomState* state; float* partials; int* ipartials; float* ztable; int ztable_n; unsigned int* counter; OdomState* host_state; };
-OpScratch g_ops = {0, 0, 0, 0, 0, 0, 0};
+enum { KT_MAX_DEVICES = 64 };
+OpScratch g_ops_dev[KT_MAX_DEVICES];
+std::mutex g_ops_mu;
+OpScratch& ops_scratch()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= KT_MAX_DEVICES) dev = 0;
+    return g_ops_dev[dev];
+}
+#define g_ops (ops_scratch())
+#define KT_OPS_LOCK() std::lock_guard<std::mutex> _ops_lock(g_ops_mu)
 
 int ensure_scratch()
 {
@@ -85,6 +99,7 @@ int kt_op_icp_step(const float* Rcurr, const float* tcurr, const float* vmap_cur
                    const float* vmap_g_prev, const float* nmap_g_prev, int rows, int cols,
                    float dist_thres, float angle_thres, float* A_host, float* b_host, float* residual_host, void* s)
 {
+    KT_OPS_LOCK();
     int r = ensure_scratch(); if (r) return r;
     OdomState* h = g_ops.host_state;
     std::memset(h, 0, sizeof(OdomState));
@@ -103,6 +118,7 @@ int kt_op_integrate(const uint16_t* depth_raw, int rows, int cols, const float* 
                     const float* Rinv, const float* t, float trunc, int16_t* tsdf, uint8_t* color, int vol,
                     const int* wrap, const uint8_t* rgb, const float* nmap_curr, int angle_color, float* depth_scaled, void* s)
 {
+    KT_OPS_LOCK();
     int r = ensure_ztable(vol); if (r) return r;
     r = scale_depth(depth_raw, depth_scaled, rows, cols, intr4(k), angle_color != 0, st(s)); if (r) return r;
     IntegrateArgs a; a.cw = 0; a.rgbf = 0;
@@ -133,6 +149,7 @@ int kt_op_extract_slice(const int16_t* tsdf, const float* vs, int vol, kt_point_
                         const int* wrap, const uint8_t* color, int minX, int maxX, int minY, int maxY, int minZ, int maxZ,
                         int subsample, const int* real_wrap, size_t* count, void* s)
 {
+    KT_OPS_LOCK();
     int r = ensure_scratch(); if (r) return r;
     KT_CUDA(cudaMemsetAsync(g_ops.counter, 0, sizeof(unsigned int), st(s)));
     r = extract_slice(tsdf, make_float3(vs[0], vs[1], vs[2]), vol, out, capacity, make_int3(wrap[0], wrap[1], wrap[2]), color,
@@ -172,6 +189,7 @@ int kt_op_rgb_residual(float min_scale, const int16_t* dIdx, const int16_t* dIdy
                        const uint8_t* last_image, const uint8_t* next_image, void* corres, int rows, int cols,
                        float max_depth_delta, const float* kt3, const float* krkinv9, int* sigma_sum, int* count, void* s)
 {
+    KT_OPS_LOCK();
     int r = ensure_scratch(); if (r) return r;
     OdomState* h = g_ops.host_state;
     std::memset(h, 0, sizeof(OdomState));
@@ -191,6 +209,7 @@ int kt_op_rgb_residual(float min_scale, const int16_t* dIdx, const int16_t* dIdy
 int kt_op_rgb_step(const void* corres, float sigma, const float* cloud, float fx, float fy, const int16_t* dIdx, const int16_t* dIdy,
                    float sobel_scale, int rows, int cols, float* A_host, float* b_host, void* s)
 {
+    KT_OPS_LOCK();
     int r = ensure_scratch(); if (r) return r;
     RgbLevelArgs a; std::memset(&a, 0, sizeof(a));
     a.corres = const_cast<void*>(corres); a.cloud = cloud; a.fx = fx; a.fy = fy; a.dIdx = dIdx; a.dIdy = dIdy; a.sobel_scale = sobel_scale; a.rows = rows; a.cols = cols;

@@ -42,6 +42,13 @@ __device__ __forceinline__ float3 mul33(const Mat33& m, const float3& v)
 
 __host__ __device__ __forceinline__ int div_up(int a, int b) { return (a + b - 1) / b; }
 
+// Cyclic volume offset reduced to [0, V).  The reference's kernels take the tracker's vWrapCopy -- non-negative but unbounded: it grows by
+// `thresh` voxels per +shift (KintinuousTracker.cpp:1075-1085) -- and reduce it with % VOLUME per access (tsdf_volume.cu:612,
+// ray_caster.cu:98-110, extract.cu:139).  The kernels here wrap by compare-subtract or mask, so every host wrapper reduces the offset
+// once per launch; congruent offsets address the same storage, so results are unchanged.
+__host__ __device__ __forceinline__ int wrap_mod(int w, int V) { int r = w % V; return r < 0 ? r + V : r; }
+__host__ __device__ __forceinline__ int3 wrap_mod3(const int3& w, int V) { return make_int3(wrap_mod(w.x, V), wrap_mod(w.y, V), wrap_mod(w.z, V)); }
+
 // TSDF fixed point (cuda/device.hpp:67-83, cuda/internal.h:237)
 #define KT_DIVISOR 32767
 __device__ __forceinline__ short pack_tsdf(float tsdf)
@@ -58,6 +65,10 @@ __device__ __forceinline__ float qnan() { return __int_as_float(0x7fffffff); }
 namespace kt {
 void set_error(const char* fmt, ...);
 int cuda_check(cudaError_t e, const char* what, const char* file, int line);
+// Per-device facts and one-time kernel attribute configuration, cached per device ordinal (kt_config.device lets one process own
+// trackers on several GPUs; cudaFuncSetAttribute is per device).
+struct DeviceInfo { int sm_count; int smem_optin; unsigned int configured; };
+DeviceInfo& device_info();                      // of the CURRENT device
 extern std::atomic<long long> g_launches;      // kernels launched by this library (bench.py: gpu_launches); contexts may live on several host threads
 }
 #define KT_CUDA(expr) do { int _s = kt::cuda_check((expr), #expr, __FILE__, __LINE__); if (_s) return _s; } while (0)

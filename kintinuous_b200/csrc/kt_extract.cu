@@ -158,7 +158,7 @@ int extract_slice(const int16_t* tsdf, const float3& volume_size, int vol, void*
 {
     if (maxX <= minX || maxY <= minY || maxZ <= minZ) return 0;
     ExtractParams p;
-    p.tsdf = tsdf; p.color = (const uchar4*)color; p.V = vol; p.wrap = wrap; p.real_wrap = real_wrap;
+    p.tsdf = tsdf; p.color = (const uchar4*)color; p.V = vol; p.wrap = wrap_mod3(wrap, vol); p.real_wrap = real_wrap;
     p.multi = 0; p.z_begin = 0; p.z_end = vol;
     p.cell = make_float3(volume_size.x / vol, volume_size.y / vol, volume_size.z / vol);
     p.minX = minX; p.maxX = maxX; p.minY = minY; p.maxY = maxY; p.minZ = minZ; p.maxZ = maxZ; p.subsample = subsample < 1 ? 1 : subsample;
@@ -177,7 +177,7 @@ int extract_slice_mg(const VolumeView& vv, const float3& volume_size, int vol, v
 {
     if (maxX <= minX || maxY <= minY || maxZ <= minZ) return 0;
     ExtractParams p;
-    p.tsdf = vv.tsdf[vv.rank]; p.color = (const uchar4*)vv.color[vv.rank]; p.V = vol; p.wrap = wrap; p.real_wrap = real_wrap;
+    p.tsdf = vv.tsdf[vv.rank]; p.color = (const uchar4*)vv.color[vv.rank]; p.V = vol; p.wrap = wrap_mod3(wrap, vol); p.real_wrap = real_wrap;
     p.cell = make_float3(volume_size.x / vol, volume_size.y / vol, volume_size.z / vol);
     p.minX = minX; p.maxX = maxX; p.minY = minY; p.maxY = maxY; p.minZ = minZ; p.maxZ = maxZ; p.subsample = subsample < 1 ? 1 : subsample;
     p.out = (uint4*)out; p.capacity = (unsigned int)capacity; p.counter = counter_dev;

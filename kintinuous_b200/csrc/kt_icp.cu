@@ -350,16 +350,7 @@ __global__ void odom_begin_kernel(OdomState* st, const float* pose12)
 
 } // namespace
 
-static int g_sm_count = 0;
-static int sm_count()
-{
-    if (!g_sm_count) {
-        int dev = 0; cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-        if (g_sm_count <= 0) g_sm_count = 148;
-    }
-    return g_sm_count;
-}
+static int sm_count() { return device_info().sm_count; }
 
 int reduce_grid_for(int n_items)
 {
@@ -404,11 +395,11 @@ int icp_frame(const IcpLevelArgs* levels, const int* iters, const float* pose12_
     int need_k = 0;
     for (int l = 0; l < LEVELS; ++l)
         if (iters[l] > 0) { int q = (div_up(levels[l].rows * levels[l].cols, grid) + 3) & ~3; int k = div_up(q, FRAME_THREADS); if (k > need_k) need_k = k; }
-    static int smem_optin = -1;
-    if (smem_optin < 0) {
-        int dev = 0; cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    DeviceInfo& di = device_info();
+    const int smem_optin = di.smem_optin;
+    if (!(di.configured & 1u)) {
         if (smem_optin > 0) cudaFuncSetAttribute((const void*)icp_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - 4096);
+        di.configured |= 1u;
     }
     const size_t stage_bytes = (size_t)6 * need_k * FRAME_THREADS * sizeof(float);
     const bool can_stage = need_k > 0 && need_k <= STAGE_MAX_K && smem_optin > 0 && stage_bytes <= (size_t)(smem_optin - 4096);

@@ -386,7 +386,7 @@ int raycast(const RaycastArgs& a, cudaStream_t s)
     RayParams p;
     p.intr = a.k; p.Rcurr = a.R; p.tcurr = a.t; p.time_step = a.trunc * 0.8f; p.volume_size = a.volume_size;
     p.cell_size = make_float3(a.volume_size.x / a.vol, a.volume_size.y / a.vol, a.volume_size.z / a.vol);
-    p.volume = a.tsdf; p.color_volume = (const uchar4*)a.color; p.V = a.vol; p.wrap = a.wrap;
+    p.volume = a.tsdf; p.color_volume = (const uchar4*)a.color; p.V = a.vol; p.wrap = wrap_mod3(a.wrap, a.vol);
     for (int l = 0; l < LEVELS; ++l) { p.vmap[l] = a.vmap[l]; p.nmap[l] = a.nmap[l]; }
     p.vmap_color = (uchar4*)a.vmap_color; p.rows = a.rows; p.cols = a.cols;
     p.n_levels = a.n_levels; p.z_begin = 0; p.tile_row_begin = 0; p.n_out = 1;

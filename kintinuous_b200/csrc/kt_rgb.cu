@@ -680,13 +680,8 @@ int rgbd_frame(const IcpLevelArgs* icp_levels, const RgbLevelArgs* rgb_levels, c
     for (int l = 0; l < LEVELS; ++l) { p.icp[l] = icp_levels[l]; p.rgb[l] = rgb_levels[l]; p.iters[l] = iters[l]; total += iters[l]; }
     for (int k = 0; k < 12; ++k) p.pose12[k] = pose12_host[k];
     p.st = state; p.partials = partials; p.trace = trace; p.bar = bar_dev; p.bar_base = *bar_count; p.with_icp = with_icp;
-    static int sms = 0, smem_optin = 0;                      // one device per process (one process per GPU)
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    }
+    DeviceInfo& di = device_info();
+    const int sms = di.sm_count, smem_optin = di.smem_optin;
     int grid = sms > 0 ? sms : 148;
     if (grid * 64 * 2 > MAX_PARTIALS * 32) grid = MAX_PARTIALS * 32 / 128;
     int need_k = 0;
@@ -695,11 +690,10 @@ int rgbd_frame(const IcpLevelArgs* icp_levels, const RgbLevelArgs* rgb_levels, c
     if (need_k > RGBD_MAX_K) return 1;
     const size_t bytes = (size_t)need_k * FRAME_THREADS * ((with_icp ? 6 * 4 : 0) + 12);
     if (smem_optin <= 0 || bytes > (size_t)(smem_optin - 8192)) return 1;
-    static bool configured = false;
-    if (!configured) {
+    if (!(di.configured & 2u)) {
         cudaFuncSetAttribute((const void*)rgbd_frame_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - 8192);
         cudaFuncSetAttribute((const void*)rgbd_frame_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - 8192);
-        configured = true;
+        di.configured |= 2u;
     }
     p.stage_k = need_k;
     void* args[] = {&p};

@@ -41,6 +41,24 @@ int cuda_check(cudaError_t e, const char* what, const char* file, int line)
     return KT_ERR_CUDA;
 }
 
+DeviceInfo& device_info()
+{
+    enum { MAXD = 64 };
+    static DeviceInfo info[MAXD];
+    static std::atomic<int> ready[MAXD];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAXD) dev = 0;
+    if (!ready[dev].load(std::memory_order_acquire)) {
+        DeviceInfo d; d.sm_count = 0; d.smem_optin = 0; d.configured = 0;
+        cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&d.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        if (d.sm_count <= 0) d.sm_count = 148;
+        info[dev] = d;
+        ready[dev].store(1, std::memory_order_release);
+    }
+    return info[dev];
+}
+
 // ---- small host math (what the reference takes from Eigen) ---------------------------------------
 struct M3 { float m[9]; };
 struct V3 { float v[3]; };
@@ -93,7 +111,7 @@ struct kt_ctx {
     bool pf_built;             // the prefetched set holds the finished front end
     bool color_prepared;       // cw_scratch / rgbf_scratch hold this frame's per-pixel colour inputs
     bool frontend_ready;       // set for the duration of one process_frame_device call
-    cudaStream_t stream_copy; cudaEvent_t ev_prefetch, ev_done[2]; int last_parity;
+    cudaStream_t stream_copy; cudaEvent_t ev_prefetch, ev_done[2], ev_maps; int last_parity; bool maps_on_stream;   // ev_maps: this frame's front end (on `stream`) has written the current maps
     uint16_t* depths_curr[LEVELS];
     float* vmaps_g_prev[LEVELS]; float* nmaps_g_prev[LEVELS]; float* vmaps_curr[LEVELS]; float* nmaps_curr[LEVELS];
     uint8_t* vmap_curr_color; float* depth_scaled; float* ztable; float* cw_scratch; float* rgbf_scratch; float* cw_alt; float* rgbf_alt;
@@ -116,6 +134,7 @@ struct kt_ctx {
     uint8_t* peer_arena[MAX_GPUS]; bool connected;
     unsigned int** peer_flags_dev; unsigned int epoch; int* mg_error_dev; int* mg_error_host;
     VolumeView vv;
+    float last_int_Rinv[9], last_int_t[3]; int last_int_wrap[3];       // arguments of the last integration (kt_debug_last_integrate)
 };
 
 namespace {
@@ -198,6 +217,8 @@ int do_integrate(kt_ctx* c, const M3& Rinv, const V3& t, const int* wrap)
     a.Rinv = to_mat33(Rinv.m); a.t = make_float3(t.v[0], t.v[1], t.v[2]); a.trunc = c->trunc;
     a.tsdf = c->tsdf; a.color = c->color; a.vol = c->cfg.vol; a.wrap = make_int3(wrap[0], wrap[1], wrap[2]);
     a.rgb = c->rgb; a.nmap_curr = c->nmaps_curr[0]; a.angle_color = c->cfg.angle_color != 0;
+    for (int k = 0; k < 9; ++k) c->last_int_Rinv[k] = Rinv.m[k];
+    for (int k = 0; k < 3; ++k) { c->last_int_t[k] = t.v[k]; c->last_int_wrap[k] = wrap[k]; }
     a.z_begin = c->z_begin; a.z_end = c->z_end; a.cw = c->color_prepared ? c->cw_scratch : 0; a.rgbf = c->color_prepared ? (float4*)c->rgbf_scratch : 0;
     return integrate(a, c->ztable, c->stream);
 }
@@ -216,7 +237,10 @@ int run_odometry(kt_ctx* c, const M3& Rprev, const V3& tprev, M3* Rcurr, V3* tcu
         if (!c->frontend_ready && (r = rgbd_frontend(c, c->depth_raw, c->rgb, c->stream))) return r;
     }
     int total_iters = 0;
-    if (mode == 0) {
+    // KT_FORCE_PER_ITERATION (test hook): take the per-iteration kernels -- the path of images too large for the whole-frame kernels'
+    // shared-memory stage -- on an image that would fit, so that it can be compared against the whole-frame path and the reference
+    static const bool force_per_iteration = getenv("KT_FORCE_PER_ITERATION") != nullptr;
+    if (mode == 0 && !force_per_iteration) {
         // ICP-only: the whole coarse-to-fine loop is ONE cooperative launch (kt_icp.cu, icp_frame_kernel)
         IcpLevelArgs la[LEVELS];
         for (int level = 0; level < LEVELS; ++level) {
@@ -231,8 +255,11 @@ int run_odometry(kt_ctx* c, const M3& Rprev, const V3& tprev, M3* Rcurr, V3* tcu
     }
     const double SOBEL_SCALE = 1.0 / std::pow(2.0, 3);
     const int minimumGradientMagnitudes[4] = {12, 5, 3, 1};
-    bool per_iteration_path = (mode != 0);
-    if (mode != 0) {
+    bool per_iteration_path = (mode != 0) || force_per_iteration;
+    if (force_per_iteration) {
+        KT_CUDA(cudaMemcpyAsync(c->pose12_dev, c->pose12_host, 12 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        if ((r = odom_begin_frame(c->state, c->pose12_dev, c->stream))) return r;
+    } else if (mode != 0) {
         // whole-frame RGB-D / ICP+RGB-D kernel (kt_rgb.cu, rgbd_frame_kernel): ONE cooperative launch for all levels and iterations
         IcpLevelArgs la[LEVELS]; RgbLevelArgs ra4[LEVELS];
         for (int level = 0; level < LEVELS; ++level) {
@@ -351,7 +378,10 @@ int process_frame_device(kt_ctx* c, uint64_t utime, kt_pose* out)
         KT_CUDA(cudaStreamWaitEvent(c->stream2, c->ev_input, 0));
         if ((r = build_frontend(c, c->depth_raw, c->rgb, c->depth_scaled, c->depths_curr, c->vmaps_curr, c->nmaps_curr, 0, 0, c->cw_scratch, c->rgbf_scratch, c->stream2, c->stream))) return r;
         KT_CUDA(cudaEventRecord(c->ev_scaled, c->stream2));
-    }
+        // the look-ahead front end of the NEXT frame (kt_prefetch_frame, side stream) reads these maps as its stale-plane source (Q7)
+        KT_CUDA(cudaEventRecord(c->ev_maps, c->stream));
+        c->maps_on_stream = true;
+    } else c->maps_on_stream = false;          // adopted set: it was produced on stream_copy itself, stream order covers it
     mark(c, 1);
 
     if (c->global_time == 0) {                                                           // .cpp:481-557
@@ -470,8 +500,9 @@ int kt_reset(kt_ctx* c)
     for (int i = 0; i < 3; ++i) { c->voxelWrap[i] = 0; c->currentGlobalCamera[i] = c->volumeBasis[i] - c->size * 0.5f; }
     c->slices.clear();
     c->trace_iters = 0; c->shifted_last = 0; c->cloud_count = 0;
-    c->pf_valid = false; c->pf_built = false; c->frontend_ready = false;
+    c->pf_valid = false; c->pf_built = false; c->frontend_ready = false; c->maps_on_stream = false;
     if (c->stream_copy) cudaStreamSynchronize(c->stream_copy);
+    if (c->mg_error_dev) { KT_CUDA(cudaMemsetAsync(c->mg_error_dev, 0, sizeof(int), c->stream)); *c->mg_error_host = 0; }      // a timed-out cross-GPU barrier is not sticky across resets
     int r = init_slab(c->tsdf, c->color, c->cfg.vol, c->slab_z, c->stream);
     if (r) return r;
     // Q7: stale y/z planes of invalid pixels start from a defined state (zeros)
@@ -553,6 +584,7 @@ int kt_create(const kt_config* cfg, kt_ctx** out)
     KT_TRY(kt::cuda_check(cudaStreamCreateWithFlags(&c->stream_copy, cudaStreamNonBlocking), "stream_copy", __FILE__, __LINE__));
     KT_TRY(kt::cuda_check(cudaEventCreateWithFlags(&c->ev_prefetch, cudaEventDisableTiming), "event", __FILE__, __LINE__));
     for (int i = 0; i < 2; ++i) KT_TRY(kt::cuda_check(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming), "event", __FILE__, __LINE__));
+    KT_TRY(kt::cuda_check(cudaEventCreateWithFlags(&c->ev_maps, cudaEventDisableTiming), "event", __FILE__, __LINE__)); c->maps_on_stream = false;
     c->last_parity = 0;
     for (int l = 0; l < LEVELS; ++l) {
         size_t Pl = P >> (2 * l);
@@ -610,6 +642,7 @@ int kt_destroy(kt_ctx* c)
     if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
     if (c->stream_copy) { cudaStreamSynchronize(c->stream_copy); cudaStreamDestroy(c->stream_copy); }
     if (c->ev_prefetch) cudaEventDestroy(c->ev_prefetch);
+    if (c->ev_maps) cudaEventDestroy(c->ev_maps);
     for (int i = 0; i < 2; ++i) if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
     if (c->ev_input) cudaEventDestroy(c->ev_input);
     if (c->ev_scaled) cudaEventDestroy(c->ev_scaled);
@@ -683,7 +716,9 @@ int kt_prefetch_frame(kt_ctx* c, const uint16_t* depth, const uint8_t* rgb)
     c->pf_built = false;
     static const bool lookahead = getenv("KT_NO_LOOKAHEAD") == nullptr;       // A/B knob: copy only
     if (lookahead && c->global_time > 0) {
-        // invalid pixels keep the y/z planes of the previous frame's maps = the set that is current now (Q7)
+        // invalid pixels keep the y/z planes of the previous frame's maps = the set that is current now (Q7); if that set was built on the
+        // compute stream (frame not prefetched, e.g. frame 0), wait for its front end -- not for the whole frame
+        if (c->maps_on_stream) KT_CUDA(cudaStreamWaitEvent(c->stream_copy, c->ev_maps, 0));
         int r = build_frontend(c, c->depth_alt, c->rgb_alt, c->depth_scaled_alt, c->depths_alt, c->vmaps_alt, c->nmaps_alt, c->vmaps_curr, c->nmaps_curr,
                                c->cw_alt, c->rgbf_alt, c->stream_copy, c->stream_copy);
         if (r) return r;
@@ -874,6 +909,14 @@ float kt_span_elapsed_ms(kt_ctx* c)
     float t = 0.f;
     if (cudaEventSynchronize(c->ev_span[1]) != cudaSuccess || cudaEventElapsedTime(&t, c->ev_span[0], c->ev_span[1]) != cudaSuccess) { cudaGetLastError(); return -1.f; }
     return t;
+}
+
+int kt_debug_last_integrate(kt_ctx* c, float* Rinv9, float* t3, int* wrap3)
+{
+    if (!c || !Rinv9 || !t3 || !wrap3) return KT_ERR_INVALID;
+    for (int k = 0; k < 9; ++k) Rinv9[k] = c->last_int_Rinv[k];
+    for (int k = 0; k < 3; ++k) { t3[k] = c->last_int_t[k]; wrap3[k] = c->last_int_wrap[k]; }
+    return KT_OK;
 }
 
 long long kt_launch_count(kt_ctx* c) { return c ? g_launches.load() - c->launches_at_create : g_launches.load(); }

@@ -443,7 +443,7 @@ int integrate(const IntegrateArgs& a, float* ztable_dev, cudaStream_t s)
     KT_LAUNCH_CHECK();
     IntegrateParams p;
     p.depth_scaled = a.depth_scaled; p.rows = a.rows; p.cols = a.cols; p.k = a.k; p.cell = cell; p.Rinv = a.Rinv; p.t = a.t; p.trunc = a.trunc;
-    p.tsdf = a.tsdf; p.color = (uchar4*)a.color; p.V = V; p.wrap = a.wrap; p.rgb = a.rgb; p.nmap = a.nmap_curr; p.angle_color = a.angle_color;
+    p.tsdf = a.tsdf; p.color = (uchar4*)a.color; p.V = V; p.wrap = wrap_mod3(a.wrap, V); p.rgb = a.rgb; p.nmap = a.nmap_curr; p.angle_color = a.angle_color;
     static int n_chunks = -1, order = -1;          // tuning knobs: KT_INT_ZCHUNKS (default 16), KT_INT_ORDER (0 near-first = default, 1 far-first)
     if (n_chunks < 0) { const char* e = getenv("KT_INT_ZCHUNKS"); n_chunks = e ? atoi(e) : 16; if (n_chunks < 1) n_chunks = 1; }
     if (order < 0) { const char* e = getenv("KT_INT_ORDER"); order = e ? atoi(e) : 0; }
@@ -464,7 +464,7 @@ int integrate(const IntegrateArgs& a, float* ztable_dev, cudaStream_t s)
     int lo[2], hi[2], n = 0;
     if (slab >= V) { lo[0] = 0; hi[0] = V; n = 1; }
     else {
-        const int ls = ((a.z_begin - a.wrap.z) % V + V) % V;
+        const int ls = wrap_mod(a.z_begin - p.wrap.z, V);
         lo[0] = ls; hi[0] = ls + slab < V ? ls + slab : V; n = 1;
         if (ls + slab > V) { lo[1] = 0; hi[1] = ls + slab - V; n = 2; }
     }

@@ -52,7 +52,8 @@ def test_nonnegative_wrap_alias_addresses_the_same_storage_plane(lib):
             for i in range(3):
                 want = w[i] if w[i] >= 0 else V - ((-w[i]) % V)                     # .cpp:1075-1085 as written (V, not 0, for multiples of V)
                 assert o[i] == want and o[i] >= 0
-                assert (o[i] - w[i]) % V == 0                                        # same plane modulo V: what the kernels need
+                assert (o[i] - w[i]) % V == 0                                        # congruent modulo V; it is NOT bounded: positive wraps pass through unchanged,
+                # so every kernel wrapper reduces it with wrap_mod() before launch (kt_common.cuh; GPU test test_wrap_beyond_one_volume_length)
 
 
 def test_shift_steps_clamp_and_floor(lib):
