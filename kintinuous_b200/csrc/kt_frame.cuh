@@ -20,6 +20,62 @@ __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int tar
     __syncthreads();
 }
 
+// ---- grid-wide sum of the CTAs' 29 partial sums without a barrier, a fence or a second pass over per-CTA partials ----
+// One 64-bit word per component (two sets, by iteration parity; XW_STRIDE 8-byte units apart so that the words live in different L2
+// slices).  Every CTA adds  round(partial * 2^32) with the low 8 bits cleared, plus 1  to the word with ONE fire-and-forget atomic: the
+// low byte of (word now - word when this set was last complete) therefore counts the CTAs that have arrived, and the rest is the exact
+// integer sum of their partials.  Integer addition commutes, so the total is bit-identical in every CTA and from run to run whatever
+// the arrival order; its resolution (2^-24 absolute per CTA) is finer than the float partials' own rounding for every entry that
+// matters to the solve.  Latency: one atomic to L2 plus one poll round trip after the LAST CTA arrived
+// (measured with tools/tail_bench.cu against the counter barrier + partial re-read it replaces).
+// Requirements: gridDim.x <= 255; the words are zero when the launch starts (the host keeps them so, kt_tracker.cu).
+enum { XW_STRIDE = 32, XW_WORDS = 2 * 32 * XW_STRIDE };
+
+__device__ __forceinline__ void red_add_u64(unsigned long long* p, unsigned long long v)
+{ asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p)
+{ unsigned long long v; asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
+
+struct GridSumState { unsigned long long prev[2]; };          // per lane: the word's value when its set was last complete
+
+// Called by ALL 32 lanes of ONE warp per CTA.  Lanes with active == true contribute q (an integer whose low 8 bits are zero) to their
+// word and get the grid total of their word back; `ex` = exchange counter of the launch (its parity selects the word set; a CTA can be
+// at most one exchange ahead of another, so two sets suffice).  A lost peer would spin forever: the poll is bounded (~2 s at 2 GHz) and
+// reports through *timeout instead of hanging the GPU.
+__device__ __forceinline__ long long grid_sum_fixed(unsigned long long* words, int ex, int lane, bool active, long long q, GridSumState& st, unsigned int G, int* timeout)
+{
+    long long total = 0;
+    if (active) {
+        const int par = ex & 1;
+        unsigned long long* w = words + ((size_t)par * 32 + lane) * XW_STRIDE;
+        red_add_u64(w, (unsigned long long)(q + 1));
+        const unsigned long long prev = par ? st.prev[1] : st.prev[0];
+        unsigned long long now, d;
+        unsigned int spins = 0; long long t0 = 0;
+        for (;;) {
+            now = ld_relaxed_u64(w); d = now - prev;
+            if ((unsigned int)(d & 0xFFull) == G) break;
+            if ((++spins & 0x3FFFu) == 0) {
+                const long long t = clock64();
+                if (t0 == 0) t0 = t;
+                else if (t - t0 > 4000000000LL) { if (timeout) *timeout = 1; break; }
+            }
+        }
+        if (par) st.prev[1] = now; else st.prev[0] = now;
+        total = (long long)(d - (unsigned long long)G);
+    }
+    return total;
+}
+__device__ __forceinline__ long long to_fixed32(float v) { return __double2ll_rn((double)v * 4294967296.0) & ~0xFFll; }
+__device__ __forceinline__ double from_fixed32(long long t) { return (double)t * (1.0 / 4294967296.0); }
+
+// The usual case: lane l < 29 passes the CTA's partial of component l and gets the grid total of component l back (as a double: the
+// exact integer sum scaled by 2^-32).
+__device__ __forceinline__ double grid_sum_words(unsigned long long* words, int ex, int lane, float partial, GridSumState& st, unsigned int G, int* timeout)
+{
+    return from_fixed32(grid_sum_fixed(words, ex, lane, lane < NSUM, to_fixed32(partial), st, G, timeout));
+}
+
 // ---- TMA (bulk async copy engine) helpers: global -> shared 1-D bulk copies completing on an mbarrier ----
 __device__ __forceinline__ unsigned int smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned int count)
@@ -143,5 +199,42 @@ __device__ __forceinline__ void icp_pixel_finish(const float3& vcurr, const floa
     sum[28] += 1.f;
 }
 
+// The same split with the projection's intermediates handed over in registers instead of being recomputed: vcurr_g (volume frame) and
+// vcurr_cp (previous camera frame; it IS s_cp of reduce.cu:268 -- the same expression).  Bit-identical sums to icp_pixel_staged.
+__device__ __forceinline__ int icp_pixel_project2(const float3& vcurr, int cols, int rows, const Intr& intr,
+                                                  const Mat33& Rcurr, const float3& tcurr, const Mat33& Rprev_inv, const float3& tprev,
+                                                  float3& vcurr_g, float3& vcurr_cp)
+{
+    if (isnan(vcurr.x)) return -1;
+    vcurr_g = add3(mul33(Rcurr, vcurr), tcurr);
+    vcurr_cp = mul33(Rprev_inv, sub3(vcurr_g, tprev));
+    int2 ukr;
+    ukr.x = __float2int_rn(vcurr_cp.x * intr.fx / vcurr_cp.z + intr.cx);
+    ukr.y = __float2int_rn(vcurr_cp.y * intr.fy / vcurr_cp.z + intr.cy);
+    if (ukr.x < 0 || ukr.y < 0 || ukr.x >= cols || ukr.y >= rows || vcurr_cp.z < 0) return -1;
+    return ukr.y * cols + ukr.x;
+}
+
+__device__ __forceinline__ void icp_pixel_finish2(const float3& vcurr_g, const float3& s_cp, const float3& ncurr, const float3& vprev_g, const float3& nprev_g,
+                                                  const Mat33& Rcurr, const Mat33& Rprev_inv, const float3& tprev,
+                                                  float dist_thres, float angle_thres, float (&sum)[32])
+{
+    if (isnan(vprev_g.x) || isnan(nprev_g.x) || isnan(ncurr.x)) return;
+    float3 ncurr_g = mul33(Rcurr, ncurr);
+    float dist = norm3(sub3(vprev_g, vcurr_g));
+    float sine = norm3(cross3(ncurr_g, nprev_g));
+    if (!(sine < angle_thres && dist <= dist_thres)) return;
+    float3 d_cp = mul33(Rprev_inv, sub3(vprev_g, tprev));
+    float3 n_cp = mul33(Rprev_inv, nprev_g);
+    float3 sxn = cross3(s_cp, n_cp);
+    const float row[7] = {n_cp.x, n_cp.y, n_cp.z, sxn.x, sxn.y, sxn.z, dot3(n_cp, sub3(s_cp, d_cp))};
+    int k = 0;
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int b = a; b < 7; ++b) sum[k++] += row[a] * row[b];
+    sum[27] += row[6] * row[6];
+    sum[28] += 1.f;
+}
 
 } // namespace kt

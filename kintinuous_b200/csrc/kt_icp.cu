@@ -137,22 +137,26 @@ icp_kernel(const IcpParams p)
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Whole-frame ICP: all levels and iterations in ONE cooperative launch (one CTA per SM).  Per iteration: every CTA reduces
-// its pixels to a 29-float partial, ONE grid barrier, then EVERY CTA sums the per-CTA partials in the same fixed order and
-// performs the same FP64 solve redundantly, so that no second barrier / broadcast of the pose is needed (the result is
-// bit-identical in all CTAs because the instruction sequence and inputs are identical).
-enum { ICP_BATCH = 5 };          // pixels per thread whose model-map gathers are issued together (640x480 level 0 has 5 chunks)
+// Whole-frame ICP: all levels and iterations in ONE cooperative launch (one CTA per SM).  Per iteration:
+//   main     every thread's pixels in batches of ICP_BATCH: project all, issue all model-map gathers, finish all (the projected point and
+//            the current vertex stay in registers between the two halves); 29 sums per thread;
+//   reduce   warp transpose-sum (lane l ends with component l) -> shared memory -> warp 0 adds the 16 warps in a fixed order;
+//   exchange warp 0: ONE fire-and-forget 64-bit atomic per component into self-counting fixed-point words, poll until all CTAs are
+//            in (grid_sum_words, kt_frame.cuh): no grid barrier, no fence, no re-read of 148 partials;
+//   solve    lane 0 of warp 0 of EVERY CTA: the same FP64 LDL^T + Rodrigues + pose composition on the same bit-identical totals
+//            (kt_solve.cuh, latency-trimmed form), so no pose broadcast is needed and all CTAs hold identical poses.
+// Two __syncthreads per iteration.  The totals are exact integer sums => deterministic run to run.
+enum { ICP_BATCH = 4 };          // pixels per thread whose model-map gathers are in flight together
 
 struct IcpFrameParams {
     IcpLevelArgs lv[LEVELS];
     int iters[LEVELS];
     float pose12[12];          // Rprev (9), tprev (3)
     OdomState* st;
-    float* partials;           // [2][32][grid]  (double-buffered by iteration parity; component-major)
+    unsigned long long* xwords;    // grid_sum_words exchange words (XW_WORDS), zero at launch
     float* trace;
-    unsigned int* bar;         // monotonically increasing arrival counter
-    unsigned int bar_base;     // value of the counter when this launch starts
-    long long* prof;           // optional: 5 clock64() stamps per iteration from CTA 0 (debug)
+    int* timeout;              // set to 1 if a peer CTA never arrived (bounded poll)
+    long long* prof;           // optional: clock64() stamps per iteration from CTA 0 (debug)
     int stage_k;               // passes of FRAME_THREADS pixels per CTA that fit the shared-memory stage (0 = no staging)
 };
 
@@ -163,8 +167,7 @@ icp_frame_kernel(const IcpFrameParams p)
     __shared__ float s_Rp[9], s_tp[3], s_Rpi[9], s_R[9], s_t[3];
     __shared__ double s_Rt[16];
     __shared__ float s_red[FRAME_THREADS / 32][32];
-    __shared__ float s_sum[32];
-    __shared__ double s_sumd[32];          // the same totals widened by the lanes that produced them (thread 0's solve reads doubles)
+    __shared__ double s_sumd[32];
     __shared__ __align__(8) unsigned long long s_mbar;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int G = gridDim.x;
@@ -180,8 +183,8 @@ icp_frame_kernel(const IcpFrameParams p)
     Rprev_inv.r0 = make_float3(s_Rpi[0], s_Rpi[1], s_Rpi[2]); Rprev_inv.r1 = make_float3(s_Rpi[3], s_Rpi[4], s_Rpi[5]); Rprev_inv.r2 = make_float3(s_Rpi[6], s_Rpi[7], s_Rpi[8]);
     tprev = make_float3(s_tp[0], s_tp[1], s_tp[2]);
 
+    GridSumState gs; gs.prev[0] = 0ull; gs.prev[1] = 0ull;
     int it = 0;
-    unsigned int target = p.bar_base;
     unsigned int stage_parity = 0;
     for (int level = LEVELS - 1; level >= 0; --level) {
         if (p.iters[level] == 0) continue;
@@ -194,7 +197,7 @@ icp_frame_kernel(const IcpFrameParams p)
         const Intr intr = a.k;
         const float dist_thres = a.dist_thres, angle_thres = a.angle_thres;
         // pixels of this CTA: ONE contiguous range of q = ceil(N / G) pixels (rounded up to the 16-byte TMA granule), so that every SM
-        // gets the same share (chunks of FRAME_THREADS pixels dealt round-robin left 8 CTAs with a fifth pass at 640x480)
+        // gets the same share
         const int q = (((N + G - 1) / G) + 3) & ~3;
         const int i_begin = min(N, (int)blockIdx.x * q), cnt = min(N, i_begin + q) - i_begin;
         const int n_pass = (q + FRAME_THREADS - 1) / FRAME_THREADS;
@@ -229,15 +232,15 @@ icp_frame_kernel(const IcpFrameParams p)
 #pragma unroll
             for (int k = 0; k < 32; ++k) sum[k] = 0.f;
             if (staged) {
-                // batches of ICP_BATCH pixels per thread: project all, gather all (independent loads in flight together), finish all
                 for (int k0 = 0; k0 < n_pass; k0 += ICP_BATCH) {
-                    int j[ICP_BATCH]; float g[ICP_BATCH][6];
+                    if (k0 * FRAME_THREADS + wid * 32 >= cnt) break;              // warp-uniform: this warp has no pixel in this batch
+                    int j[ICP_BATCH]; float g[ICP_BATCH][6]; float3 vg[ICP_BATCH], vcp[ICP_BATCH];
 #pragma unroll
                     for (int b = 0; b < ICP_BATCH; ++b) {
                         const int o = (k0 + b) * FRAME_THREADS + tid;
                         j[b] = -1;
-                        if (o < cnt)
-                            j[b] = icp_pixel_project(make_float3(s_stage[o], s_stage[ps + o], s_stage[2 * ps + o]), cols, rows, intr, Rcurr, tcurr, Rprev_inv, tprev);
+                        if (k0 + b < n_pass && o < cnt)
+                            j[b] = icp_pixel_project2(make_float3(s_stage[o], s_stage[ps + o], s_stage[2 * ps + o]), cols, rows, intr, Rcurr, tcurr, Rprev_inv, tprev, vg[b], vcp[b]);
                     }
 #pragma unroll
                     for (int b = 0; b < ICP_BATCH; ++b) {
@@ -249,10 +252,9 @@ icp_frame_kernel(const IcpFrameParams p)
                     for (int b = 0; b < ICP_BATCH; ++b) {
                         if (j[b] >= 0) {
                             const int o = (k0 + b) * FRAME_THREADS + tid;
-                            icp_pixel_finish(make_float3(s_stage[o], s_stage[ps + o], s_stage[2 * ps + o]),
-                                             make_float3(s_stage[3 * ps + o], s_stage[4 * ps + o], s_stage[5 * ps + o]),
-                                             make_float3(g[b][0], g[b][1], g[b][2]), make_float3(g[b][3], g[b][4], g[b][5]),
-                                             Rcurr, tcurr, Rprev_inv, tprev, dist_thres, angle_thres, sum);
+                            icp_pixel_finish2(vg[b], vcp[b], make_float3(s_stage[3 * ps + o], s_stage[4 * ps + o], s_stage[5 * ps + o]),
+                                              make_float3(g[b][0], g[b][1], g[b][2]), make_float3(g[b][3], g[b][4], g[b][5]),
+                                              Rcurr, Rprev_inv, tprev, dist_thres, angle_thres, sum);
                         }
                     }
                 }
@@ -263,68 +265,52 @@ icp_frame_kernel(const IcpFrameParams p)
                     icp_pixel_staged(vc, nc, N, cols, rows, vmap_g_prev, nmap_g_prev, intr, Rcurr, tcurr, Rprev_inv, tprev, dist_thres, angle_thres, sum);
                 }
             }
-            // CTA reduction: warp transpose-sum (lane l ends with component l), then a fixed-order sum over the 16 warps
+            // CTA reduction: warp transpose-sum (lane l ends with component l), then warp 0 adds the 16 warps in a fixed order
             {
                 const float v = warp_transpose_sum(sum, lane);
                 s_red[wid][lane] = v;
             }
             __syncthreads();
-            float* part = p.partials + (size_t)(it & 1) * 32 * G;
-            if (tid < NSUM) {
+            if (wid == 0) {
                 float v = 0.f;
 #pragma unroll
-                for (int w = 0; w < FRAME_THREADS / 32; ++w) v += s_red[w][tid];
-                part[(size_t)tid * G + blockIdx.x] = v;
-            }
-            target += (unsigned int)G;
-            if (prof) p.prof[it * 8 + 1] = clock64();
-            grid_barrier(p.bar, target);
-            if (prof) p.prof[it * 8 + 2] = clock64();
-            // every CTA: fixed-order total of the G partials of each component (16 lanes per component, loads issued together)
-            {
-                const int comp = tid >> 4, sub = tid & 15;
-                float x[10];
+                for (int w = 0; w < FRAME_THREADS / 32; ++w) v += s_red[w][lane];
+                if (prof) p.prof[it * 8 + 1] = clock64();
+                const double total = grid_sum_words(p.xwords, it, lane, v, gs, (unsigned int)G, p.timeout);
+                s_sumd[lane] = total;
+                __syncwarp();
+                if (prof) p.prof[it * 8 + 2] = clock64();
+                if (lane == 0) {
+                    // unpack 27 sums -> symmetric A (row-major) and b, constant indices only (registers, no local memory)
+                    double dA[36], db[6];
+                    {
+                        int shift = 0;
 #pragma unroll
-                for (int q = 0; q < 10; ++q) {
-                    const int b = sub + 16 * q;
-                    x[q] = (comp < NSUM && b < G) ? __ldcg(&part[(size_t)comp * G + b]) : 0.f;
-                }
-                float v = 0.f;
+                        for (int i = 0; i < 6; ++i)
 #pragma unroll
-                for (int q = 0; q < 10; ++q) v += x[q];
-                for (int b = sub + 160; b < G; b += 16) v += (comp < NSUM) ? __ldcg(&part[(size_t)comp * G + b]) : 0.f;
-                v += __shfl_xor_sync(0xffffffffu, v, 8);
-                v += __shfl_xor_sync(0xffffffffu, v, 4);
-                v += __shfl_xor_sync(0xffffffffu, v, 2);
-                v += __shfl_xor_sync(0xffffffffu, v, 1);
-                if (sub == 0 && comp < NSUM) { s_sum[comp] = v; s_sumd[comp] = (double)v; }
-            }
-            __syncthreads();
-            if (prof) p.prof[it * 8 + 3] = clock64();
-            if (tid == 0) {
-                // unpack 27 sums -> symmetric A (row-major) and b, constant indices only (registers, no local memory)
-                double dA[36], db[6];
-                {
-                    int shift = 0;
-#pragma unroll
-                    for (int i = 0; i < 6; ++i)
-#pragma unroll
-                        for (int j = i; j < 7; ++j) {
-                            const double value = s_sumd[shift++];
-                            if (j == 6) db[i] = value; else { dA[j * 6 + i] = value; dA[i * 6 + j] = value; }
-                        }
+                            for (int jx = i; jx < 7; ++jx) {
+                                const double value = s_sumd[shift++];
+                                if (jx == 6) db[i] = value; else { dA[jx * 6 + i] = value; dA[i * 6 + jx] = value; }
+                            }
+                    }
+                    gauss_newton_update_fast(dA, db, s_Rt, s_Rp, s_tp, s_R, s_t);
+                    if (prof) p.prof[it * 8 + 3] = clock64();
                 }
                 if (p.trace && blockIdx.x == 0 && it < 64) {
+                    // the iteration's normal equations as the reference hands them to the host (reduce.cu:404-418), written after the
+                    // solve was issued so that the stores are off the critical path
                     float* t = p.trace + (size_t)it * TRACE_STRIDE;
-#pragma unroll
-                    for (int k = 0; k < 36; ++k) t[k] = (float)dA[k];
-#pragma unroll
-                    for (int k = 0; k < 6; ++k) t[36 + k] = (float)db[k];
-                    t[42] = s_sum[27]; t[43] = s_sum[28];
+                    if (lane < NSUM) {
+                        const float value = (float)total;
+                        // component index -> (i, j) of the upper triangle with the b column: rows of 7, 6, 5, ... entries
+                        int i = 0, base = 0;
+                        while (lane >= base + (7 - i) && i < 6) { base += 7 - i; ++i; }
+                        if (lane < 27) {
+                            const int jx = i + (lane - base);
+                            if (jx == 6) t[36 + i] = value; else { t[jx * 6 + i] = value; t[i * 6 + jx] = value; }
+                        } else t[42 + (lane - 27)] = value;
+                    }
                 }
-                if (prof) p.prof[it * 8 + 5] = clock64();
-                gauss_newton_update_p(dA, db, s_Rt, s_Rp, s_tp, s_R, s_t, prof ? p.prof + it * 8 + 6 : (long long*)0);
-                if (prof) p.prof[it * 8 + 4] = clock64();
             }
             __syncthreads();
         }
@@ -379,18 +365,17 @@ int odom_begin_frame(OdomState* state, const float* pose12_dev, cudaStream_t s)
 
 
 // Whole-frame ICP (ICP-only odometry).  pose12 = Rprev (9) + tprev (3) on the host; the result lands in state->Rcurr/tcurr.
-// bar_dev: one unsigned int, zeroed once at allocation; *bar_count (host) tracks its value across launches.
-int icp_frame(const IcpLevelArgs* levels, const int* iters, const float* pose12_host, OdomState* state, float* partials,
-              float* trace, unsigned int* bar_dev, unsigned int* bar_count, long long* prof_dev, cudaStream_t s)
+// xwords_dev: XW_WORDS 64-bit exchange words, ZERO when the launch starts (the tracker resets them once per frame, kt_tracker.cu).
+int icp_frame(const IcpLevelArgs* levels, const int* iters, const float* pose12_host, OdomState* state, unsigned long long* xwords_dev,
+              float* trace, int* timeout_dev, long long* prof_dev, cudaStream_t s)
 {
     IcpFrameParams p;
     p.prof = prof_dev;
-    int total = 0;
-    for (int l = 0; l < LEVELS; ++l) { p.lv[l] = levels[l]; p.iters[l] = iters[l]; total += iters[l]; }
+    for (int l = 0; l < LEVELS; ++l) { p.lv[l] = levels[l]; p.iters[l] = iters[l]; }
     for (int k = 0; k < 12; ++k) p.pose12[k] = pose12_host[k];
-    p.st = state; p.partials = partials; p.trace = trace; p.bar = bar_dev; p.bar_base = *bar_count;
+    p.st = state; p.xwords = xwords_dev; p.trace = trace; p.timeout = timeout_dev;
     int grid = sm_count();
-    if (grid * 32 * 2 > MAX_PARTIALS * 32) grid = MAX_PARTIALS / 2;
+    if (grid > 255) grid = 255;                  // the exchange words count arrivals in 8 bits
     // shared-memory stage for the current maps: 6 planes x stage_k x 2 KB (one contiguous pixel range per CTA), sized for the largest level in use
     int need_k = 0;
     for (int l = 0; l < LEVELS; ++l)
@@ -408,7 +393,17 @@ int icp_frame(const IcpLevelArgs* levels, const int* iters, const float* pose12_
     cudaError_t e = cudaLaunchCooperativeKernel((const void*)icp_frame_kernel, dim3(grid), dim3(FRAME_THREADS), args, can_stage ? stage_bytes : 0, s);
     ++g_launches;
     if (e != cudaSuccess) return cuda_check(e, "cudaLaunchCooperativeKernel(icp_frame_kernel)", __FILE__, __LINE__);
-    *bar_count += (unsigned int)(grid * total);
+    return 0;
+}
+
+namespace { __global__ void __launch_bounds__(256) zero_words_kernel(unsigned long long* w, int n) { for (int i = threadIdx.x; i < n; i += blockDim.x) w[i] = 0ull; } }
+
+size_t odom_exchange_words() { return (size_t)XW_WORDS; }
+
+int odom_exchange_reset(unsigned long long* xwords_dev, cudaStream_t s)
+{
+    zero_words_kernel<<<1, 256, 0, s>>>(xwords_dev, (int)XW_WORDS);
+    KT_LAUNCH_CHECK();
     return 0;
 }
 

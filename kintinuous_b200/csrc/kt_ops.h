@@ -35,6 +35,21 @@ struct TransformLevel { const float* vs; const float* ns; float* vd; float* nd; 
 int transform_maps_pyramid(const TransformLevel* levels, int n_levels, const Mat33& R, const float3& t, cudaStream_t s);
 int resize_map(const float* in, float* out, int in_rows, int in_cols, bool normalize, cudaStream_t s);
 
+// ---- fused front end (kt_frontend.cu): depth pyramid, vertex / normal maps of all levels, colour prep, photometric pyramids + gradients ----
+struct FrontendArgs {
+    const uint16_t* depth_f;       // bilateral-filtered depth, level 0 (null: no depth pyramid / maps, photometric set only)
+    const uint16_t* depth_raw;     // raw depth (photometric set)
+    const uint8_t* rgb;            // colour prep + intensity
+    int rows, cols; Intr k;
+    uint16_t* const* depths;       // [LEVELS]; [0] is depth_f itself (not written)
+    float* const* vmaps; float* const* nmaps; float* const* vstale; float* const* nstale;      // [LEVELS] each; stale may be null
+    float* cw; float4* rgbf; bool angle_color;                                                   // colour prep outputs (null: skip)
+    int cut_off; float* const* depth_m; uint8_t* const* intensity; int16_t* const* dIdx; int16_t* const* dIdy;   // photometric set (null: skip)
+};
+int frontend_pyramid(const FrontendArgs& a, cudaStream_t s);
+// bilateralFilter + scaleDepth in one launch (they share the raw-depth tile); either output may be null
+int bilateral_scale(const uint16_t* src, uint16_t* dst, float* scaled, int rows, int cols, const Intr& k, bool angle_color, cudaStream_t s);
+
 // ---- RGB-D preprocessing (kt_rgb.cu) ----
 int short_depth_to_metres(const uint16_t* src, float* dst, int rows, int cols, int cut_off, cudaStream_t s);
 int pyrdown_gauss_f(const float* src, float* dst, int src_rows, int src_cols, cudaStream_t s);
@@ -50,6 +65,7 @@ struct OdomState {
     float Rprev[9], tprev[3], Rprev_inv[9];
     // running estimate (ICPOdometry.cpp:73-74,177-178)
     float Rcurr[9], tcurr[3];
+    int odo_timeout;                        // set by a whole-frame kernel whose exchange poll gave up (a peer CTA never arrived); read back with the pose
     double resultRt[16];                    // cv::Mat resultRt (ICPOdometry.cpp:83)
     // photometric warp of the current iteration (RGBDOdometry.cpp:209-231)
     float krkinv[9], kt[3];
@@ -71,8 +87,12 @@ struct IcpLevelArgs {
 //   mode 1: reduce + LDLT solve + pose update on device (ICP-only odometry)
 int icp_iteration(const IcpLevelArgs& a, OdomState* state, float* partials, float* trace, int mode, cudaStream_t s);
 
-int icp_frame(const IcpLevelArgs* levels, const int* iters, const float* pose12_host, OdomState* state, float* partials,
-              float* trace, unsigned int* bar_dev, unsigned int* bar_count, long long* prof_dev, cudaStream_t s);
+int icp_frame(const IcpLevelArgs* levels, const int* iters, const float* pose12_host, OdomState* state, unsigned long long* xwords_dev,
+              float* trace, int* timeout_dev, long long* prof_dev, cudaStream_t s);
+// exchange words of the whole-frame odometry kernels (grid_sum_words, kt_frame.cuh): their count, and the reset (zero) of a word array --
+// stream-ordered, once per frame between two odometry launches
+size_t odom_exchange_words();
+int odom_exchange_reset(unsigned long long* xwords_dev, cudaStream_t s);
 
 struct RgbLevelArgs {
     const int16_t* dIdx; const int16_t* dIdy; const float* last_depth; const float* next_depth;
@@ -82,8 +102,9 @@ struct RgbLevelArgs {
 // use_state_warp 1: (K R K^-1, K t) rebuilt on the device from state->resultRt; 0: taken from state->krkinv / kt
 int rgb_residual(const RgbLevelArgs& a, OdomState* state, int* partials, int use_state_warp, cudaStream_t s);
 // mode 0: reduce only; 1: solve RGB-only; 2: solve A_rgb + 100 A_icp (RGBDOdometry.cpp:316-321)
+// Returns 1 (and launches nothing) when the image does not fit the kernel's shared-memory stage.  xwords_dev: zero at launch (see icp_frame).
 int rgbd_frame(const IcpLevelArgs* icp_levels, const RgbLevelArgs* rgb_levels, const int* iters, int with_icp, const float* pose12_host, OdomState* state,
-               float* partials, float* trace, unsigned int* bar_dev, unsigned int* bar_count, cudaStream_t s);
+               unsigned long long* xwords_dev, float* trace, int* timeout_dev, cudaStream_t s);
 int rgb_iteration(const RgbLevelArgs& a, OdomState* state, float* partials, float* trace, int mode, float sigma_override, cudaStream_t s);
 // pose12_dev: Rprev (9) + tprev (3) in device memory
 int odom_begin_frame(OdomState* state, const float* pose12_dev, cudaStream_t s);
@@ -101,6 +122,7 @@ struct IntegrateArgs {
     int16_t* tsdf; uint8_t* color; int vol; int3 wrap; const uint8_t* rgb; const float* nmap_curr; bool angle_color;
     int z_begin, z_end;          // storage-z slab owned by this GPU ([0, vol) on a single GPU)
     float* cw; float4* rgbf;     // optional per-pixel scratch (rows*cols each): colour weight + float RGB prepared once per frame
+    unsigned long long* reset_words; int reset_count;   // optional: 64-bit words the launch's prologue kernel zeroes (the odometry's exchange words)
 };
 int integrate(const IntegrateArgs& a, float* ztable_dev /* 2*vol floats */, cudaStream_t s);
 // per-pixel colour weight (sign = normal invalid) + float RGB for IntegrateArgs::cw / rgbf; once per frame, after the normal map exists

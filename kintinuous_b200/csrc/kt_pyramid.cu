@@ -65,9 +65,38 @@ __device__ __forceinline__ float bilateral_window(const float (*tile)[BIL_W + 1]
     return sum1 / sum2;
 }
 
+// scaleDepth (tsdf_volume.cu:491-538) for the pixel at tile position (ly, lx): the depth along the ray, D * |((x - cx) / fx, (y - cy) / fy, 1)| / 1000,
+// negated ("do not fuse colour here") when more than 5 pixels of its 7x7 window -- clipped like every window of the reference, exclusive and
+// to cols-1 / rows-1 (Q1) -- differ by more than 200 mm or the pixel itself is empty.  Depths and their differences are exact in float.
+__device__ __forceinline__ float scale_depth_px(const float (*tile)[BIL_W + 1], int ly, int lx, int x, int y, int rows, int cols, const Intr& intr, bool angleColor)
+{
+    const float Df = tile[ly + BIL_R][lx + BIL_R];
+    const int Dp = (int)Df;
+    const float xl = (x - intr.cx) / intr.fx;
+    const float yl = (y - intr.cy) / intr.fy;
+    const float lambda = sqrtf(__fadd_rn(__fmaf_rn(xl, xl, __fmul_rn(yl, yl)), 1.f));     // sqrtf(xl * xl + yl * yl + 1), contraction pinned
+    if (angleColor) {
+        const int dx_lo = max(-3, -x), dx_hi = min(4, cols - 1 - x), dy_lo = max(-3, -y), dy_hi = min(4, rows - 1 - y);
+        int count = 0;
+        if (Dp == 0) count = max(0, dx_hi - dx_lo) * max(0, dy_hi - dy_lo);
+        else {
+#pragma unroll
+            for (int dy = -3; dy <= 3; ++dy)
+#pragma unroll
+                for (int dx = -3; dx <= 3; ++dx)
+                    if (dy >= dy_lo && dy < dy_hi && dx >= dx_lo && dx < dx_hi && fabsf(Df - tile[ly + BIL_R + dy][lx + BIL_R + dx]) > 200.f) ++count;
+        }
+        if (count > 5) return -Dp * lambda / 1000.f;
+    }
+    return Dp * lambda / 1000.f;
+}
+
+// bilateralFilter and scaleDepth share the raw-depth tile: one launch produces the filtered depth (dst) and / or the ray-scaled depth
+// for the integration (scaled).
+template <bool BIL, bool SCALE>
 __global__ void __launch_bounds__(BIL_TX * BIL_TY)
-bilateral_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst, int rows, int cols,
-                 float sigma_space2_inv_half, float sigma_color2_inv_half)
+bilateral_scale_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst, float* __restrict__ scaled, int rows, int cols,
+                       float sigma_space2_inv_half, float sigma_color2_inv_half, const Intr intr, bool angleColor)
 {
     __shared__ float tile[BIL_H][BIL_W + 1];
     const int x0 = blockIdx.x * BIL_TX, y0 = blockIdx.y * BIL_TY;
@@ -82,6 +111,8 @@ bilateral_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst, i
     const int any_big = __syncthreads_or(big);
     const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
     if (x >= cols || y >= rows) return;
+    if (SCALE) scaled[(size_t)y * cols + x] = scale_depth_px(tile, threadIdx.y, threadIdx.x, x, y, rows, cols, intr, angleColor);
+    if (!BIL) return;
 
     const int D = BIL_R * 2 + 1;
     const float value_f = tile[threadIdx.y + BIL_R][threadIdx.x + BIL_R];
@@ -96,18 +127,18 @@ bilateral_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst, i
         dst[(size_t)y * cols + x] = (uint16_t)max(0, min(res, 32767));
         return;
     }
-    // a depth above 46 340 mm in the tile: (value - tmp)^2 can overflow int32 in the reference; keep its integer arithmetic
+    // a depth above 46 340 mm in the tile: (value - tmp)^2 overflows int32 in the reference; this CTA reproduces its integer arithmetic,
+    // overflow included, on the same tile
     const int value = (int)value_f;
-    const int tx = min(x - D / 2 + D, cols - 1);
-    const int ty = min(y - D / 2 + D, rows - 1);
     float sum1 = 0, sum2 = 0;
-    for (int cy = max(y - D / 2, 0); cy < ty; ++cy) {
+    const int cy0 = max(y - D / 2, 0), cy1 = min(y - D / 2 + D, rows - 1), cx0 = max(x - D / 2, 0), cx1 = min(x - D / 2 + D, cols - 1);
+    for (int cy = cy0; cy < cy1; ++cy) {
         const float* trow = tile[cy - y0 + BIL_R];
-        for (int cx = max(x - D / 2, 0); cx < tx; ++cx) {
-            int tmp = (int)trow[cx - x0 + BIL_R];
-            float space2 = (x - cx) * (x - cx) + (y - cy) * (y - cy);
-            float color2 = (value - tmp) * (value - tmp);
-            float weight = __expf(-(space2 * sigma_space2_inv_half + color2 * sigma_color2_inv_half));
+        for (int cx = cx0; cx < cx1; ++cx) {
+            const int tmp = (int)trow[cx - x0 + BIL_R];
+            const float space2 = (x - cx) * (x - cx) + (y - cy) * (y - cy);
+            const float color2 = (value - tmp) * (value - tmp);
+            const float weight = __expf(-(space2 * sigma_space2_inv_half + color2 * sigma_color2_inv_half));
             sum1 += tmp * weight;
             sum2 += weight;
         }
@@ -297,12 +328,27 @@ resize_map_kernel(int drows, int dcols, int srows, int scols, const float* __res
 
 } // namespace
 
-int bilateral(const uint16_t* src, uint16_t* dst, int rows, int cols, cudaStream_t s)
+int bilateral_scale(const uint16_t* src, uint16_t* dst, float* scaled, int rows, int cols, const Intr& k, bool angle_color, cudaStream_t s)
 {
     dim3 block(BIL_TX, BIL_TY), grid(div_up(cols, BIL_TX), div_up(rows, BIL_TY));
-    bilateral_kernel<<<grid, block, 0, s>>>(src, dst, rows, cols, 0.5f / (SIGMA_SPACE * SIGMA_SPACE), 0.5f / (SIGMA_COLOR * SIGMA_COLOR));
+    const float ks = 0.5f / (SIGMA_SPACE * SIGMA_SPACE), kc = 0.5f / (SIGMA_COLOR * SIGMA_COLOR);
+    if (dst && scaled) bilateral_scale_kernel<true, true><<<grid, block, 0, s>>>(src, dst, scaled, rows, cols, ks, kc, k, angle_color);
+    else if (dst) bilateral_scale_kernel<true, false><<<grid, block, 0, s>>>(src, dst, scaled, rows, cols, ks, kc, k, angle_color);
+    else if (scaled) bilateral_scale_kernel<false, true><<<grid, block, 0, s>>>(src, dst, scaled, rows, cols, ks, kc, k, angle_color);
+    else return 0;
     KT_LAUNCH_CHECK();
     return 0;
+}
+
+int bilateral(const uint16_t* src, uint16_t* dst, int rows, int cols, cudaStream_t s)
+{
+    Intr k = {1.f, 1.f, 0.f, 0.f};
+    return bilateral_scale(src, dst, 0, rows, cols, k, false, s);
+}
+
+int scale_depth(const uint16_t* depth, float* scaled, int rows, int cols, const Intr& k, bool angle_color, cudaStream_t s)
+{
+    return bilateral_scale(depth, 0, scaled, rows, cols, k, angle_color, s);
 }
 
 int pyrdown(const uint16_t* src, uint16_t* dst, int srows, int scols, cudaStream_t s)

@@ -334,9 +334,9 @@ struct RgbdFrameParams {
     int iters[LEVELS];
     float pose12[12];
     OdomState* st;
-    float* partials;           // [2][64][grid]
+    unsigned long long* xwords;    // grid_sum_fixed exchange words (kt_frame.cuh), zero at launch
     float* trace;
-    unsigned int* bar; unsigned int bar_base;
+    int* timeout;
     int stage_k;               // chunks of FRAME_THREADS pixels per CTA (<= RGBD_MAX_K)
     int with_icp;
 };
@@ -352,7 +352,6 @@ rgbd_frame_kernel(const RgbdFrameParams p)
     __shared__ float s_Rp[9], s_tp[3], s_Rpi[9], s_R[9], s_t[3], s_w[12];
     __shared__ double s_Rt[16];
     __shared__ float s_red[FRAME_THREADS / 32][32];
-    __shared__ float s_sum[32], s_sum_icp[32];
     __shared__ double s_sumd[32];          // merged normal equations in double, written by the lanes that own the components
     __shared__ int s_cnt[FRAME_THREADS / 32][2];
     __shared__ int s_tot[2];
@@ -376,8 +375,9 @@ rgbd_frame_kernel(const RgbdFrameParams p)
     Rprev_inv.r0 = make_float3(s_Rpi[0], s_Rpi[1], s_Rpi[2]); Rprev_inv.r1 = make_float3(s_Rpi[3], s_Rpi[4], s_Rpi[5]); Rprev_inv.r2 = make_float3(s_Rpi[6], s_Rpi[7], s_Rpi[8]);
     tprev = make_float3(s_tp[0], s_tp[1], s_tp[2]);
 
-    int it = 0;
-    unsigned int target = p.bar_base;
+    int it = 0, ex = 0;                      // iteration / exchange counters (two exchanges per iteration)
+    GridSumState gs; gs.prev[0] = 0ull; gs.prev[1] = 0ull;
+    double icp_total = 0.0;                  // warp 0, lane l: grid total of ICP component l of this iteration
     unsigned int stage_parity = 0;
     for (int level = LEVELS - 1; level >= 0; --level) {
         if (p.iters[level] == 0) continue;
@@ -482,38 +482,29 @@ rgbd_frame_kernel(const RgbdFrameParams p)
                     }
                 }
             }
-            // reduce pass A: ints (count, sigma) and, with ICP, the 29 float sums
+            // reduce pass A: ints (count, sigma) and, with ICP, the 29 float sums -> exchange 1 (lanes 0..28: ICP sums, 29 / 30: count / sigma)
             for (int o = 16; o > 0; o >>= 1) { cnt += __shfl_down_sync(0xffffffffu, cnt, o); sig += __shfl_down_sync(0xffffffffu, sig, o); }
             if (lane == 0) { s_cnt[wid][0] = cnt; s_cnt[wid][1] = sig; }
             if (WITH_ICP) { const float v = warp_transpose_sum(sum, lane); s_red[wid][lane] = v; }
             __syncthreads();
-            float* partA = p.partials + (size_t)(it & 1) * 64 * G;             // rows 0..31: ICP floats, 32..33: count / sigma (as int bits)
-            if (WITH_ICP && tid < NSUM) {
-                float v = 0.f;
-#pragma unroll
-                for (int w = 0; w < FRAME_THREADS / 32; ++w) v += s_red[w][tid];
-                partA[(size_t)tid * G + blockIdx.x] = v;
-            }
-            if (tid == 32) { int c = 0; for (int w = 0; w < FRAME_THREADS / 32; ++w) c += s_cnt[w][0]; partA[(size_t)32 * G + blockIdx.x] = __int_as_float(c); }
-            if (tid == 33) { int c = 0; for (int w = 0; w < FRAME_THREADS / 32; ++w) c += s_cnt[w][1]; partA[(size_t)33 * G + blockIdx.x] = __int_as_float(c); }
-            target += (unsigned int)G;
-            grid_barrier(p.bar, target);
-            {
-                const int comp = tid >> 4, sub = tid & 15;
-                if (comp < 32) {
+            if (wid == 0) {
+                long long q = 0;
+                if (WITH_ICP && lane < NSUM) {
                     float v = 0.f;
-                    if (WITH_ICP && comp < NSUM) for (int b = sub; b < G; b += 16) v += __ldcg(&partA[(size_t)comp * G + b]);
-                    v += __shfl_xor_sync(0xffffffffu, v, 8); v += __shfl_xor_sync(0xffffffffu, v, 4);
-                    v += __shfl_xor_sync(0xffffffffu, v, 2); v += __shfl_xor_sync(0xffffffffu, v, 1);
-                    if (sub == 0) s_sum_icp[comp] = v;
+#pragma unroll
+                    for (int w = 0; w < FRAME_THREADS / 32; ++w) v += s_red[w][lane];
+                    q = to_fixed32(v);
+                } else if (lane == 29 || lane == 30) {
+                    int c = 0;
+                    for (int w = 0; w < FRAME_THREADS / 32; ++w) c += s_cnt[w][lane - 29];
+                    q = (long long)c << 8;
                 }
-                if (wid == 0) {       // integer totals (order-independent)
-                    int c = 0, g2 = 0;
-                    for (int b = lane; b < G; b += 32) { c += __float_as_int(__ldcg(&partA[(size_t)32 * G + b])); g2 += __float_as_int(__ldcg(&partA[(size_t)33 * G + b])); }
-                    for (int o = 16; o > 0; o >>= 1) { c += __shfl_down_sync(0xffffffffu, c, o); g2 += __shfl_down_sync(0xffffffffu, g2, o); }
-                    if (lane == 0) { s_tot[0] = c; s_tot[1] = g2; }
-                }
+                const bool active = (WITH_ICP && lane < NSUM) || lane == 29 || lane == 30;
+                const long long tot = grid_sum_fixed(p.xwords, ex, lane, active, q, gs, (unsigned int)G, p.timeout);
+                if (WITH_ICP && lane < NSUM) icp_total = from_fixed32(tot);
+                if (lane == 29 || lane == 30) s_tot[lane - 29] = (int)(tot >> 8);
             }
+            ++ex;
             __syncthreads();
             // Q3: sigmaVal = sqrt((float)sigma / rgbSize == 0 ? 1 : rgbSize)   (RGBDOdometry.cpp:253)
             const int rgb_count = s_tot[0], rgb_sigma = s_tot[1];
@@ -559,61 +550,50 @@ rgbd_frame_kernel(const RgbdFrameParams p)
             }
             { const float v = warp_transpose_sum(sum, lane); s_red[wid][lane] = v; }
             __syncthreads();
-            float* partB = partA + (size_t)34 * G;
-            if (tid < NSUM) {
+            if (wid == 0) {
                 float v = 0.f;
 #pragma unroll
-                for (int w = 0; w < FRAME_THREADS / 32; ++w) v += s_red[w][tid];
-                partB[(size_t)tid * G + blockIdx.x] = v;
-            }
-            target += (unsigned int)G;
-            grid_barrier(p.bar, target);
-            {
-                const int comp = tid >> 4, sub = tid & 15;
-                float v = 0.f;
-                if (comp < NSUM) for (int b = sub; b < G; b += 16) v += __ldcg(&partB[(size_t)comp * G + b]);
-                v += __shfl_xor_sync(0xffffffffu, v, 8); v += __shfl_xor_sync(0xffffffffu, v, 4);
-                v += __shfl_xor_sync(0xffffffffu, v, 2); v += __shfl_xor_sync(0xffffffffu, v, 1);
-                if (sub == 0 && comp < NSUM) {
-                    s_sum[comp] = v;
-                    // A = A_rgb + 100 A_icp, b = b_rgb + 10 b_icp in double (RGBDOdometry.cpp:316-321); the b sums are components
-                    // 6, 12, 17, 21, 24, 26 of the 27 (internal.h:101-106 order)
-                    double m = (double)v;
-                    if (WITH_ICP) {
-                        const bool is_b = (comp == 6) || (comp == 12) || (comp == 17) || (comp == 21) || (comp == 24) || (comp == 26);
-                        m = fma(is_b ? 10.0 : 100.0, (double)s_sum_icp[comp], m);
-                    }
-                    s_sumd[comp] = m;
+                for (int w = 0; w < FRAME_THREADS / 32; ++w) v += s_red[w][lane];
+                const double total = grid_sum_words(p.xwords, ex, lane, v, gs, (unsigned int)G, p.timeout);      // exchange 2: the photometric sums
+                // A = A_rgb + 100 A_icp, b = b_rgb + 10 b_icp in double (RGBDOdometry.cpp:316-321); the b sums are components
+                // 6, 12, 17, 21, 24, 26 of the 27 (internal.h:101-106 order)
+                double m = total;
+                if (WITH_ICP) {
+                    const bool is_b = (lane == 6) || (lane == 12) || (lane == 17) || (lane == 21) || (lane == 24) || (lane == 26);
+                    m = fma(is_b ? 10.0 : 100.0, icp_total, m);
                 }
-            }
-            __syncthreads();
-            if (tid == 0) {
-                // unpack 27 sums -> symmetric A (row-major) and b, constant indices only (registers, no local memory)
-                double dA[36], db[6];
-                {
-                    int shift = 0;
+                s_sumd[lane] = m;
+                __syncwarp();
+                if (lane == 0) {
+                    // unpack 27 sums -> symmetric A (row-major) and b, constant indices only (registers, no local memory)
+                    double dA[36], db[6];
+                    {
+                        int shift = 0;
 #pragma unroll
-                    for (int i = 0; i < 6; ++i)
+                        for (int i = 0; i < 6; ++i)
 #pragma unroll
-                        for (int j = i; j < 7; ++j) {
-                            const double value = s_sumd[shift++];
-                            if (j == 6) db[i] = value; else { dA[j * 6 + i] = value; dA[i * 6 + j] = value; }
-                        }
+                            for (int j = i; j < 7; ++j) {
+                                const double value = s_sumd[shift++];
+                                if (j == 6) db[i] = value; else { dA[j * 6 + i] = value; dA[i * 6 + j] = value; }
+                            }
+                    }
+                    gauss_newton_update_fast(dA, db, s_Rt, s_Rp, s_tp, s_R, s_t);
                 }
                 if (p.trace && blockIdx.x == 0 && it < 64) {            // the photometric part alone, like the reference's A_rgb / b_rgb
                     float* t = p.trace + (size_t)it * TRACE_STRIDE;
-                    int shift = 0;
-#pragma unroll
-                    for (int i = 0; i < 6; ++i)
-#pragma unroll
-                        for (int j = i; j < 7; ++j) {
-                            const float value = s_sum[shift++];
+                    if (lane < NSUM) {
+                        const float value = (float)total;
+                        int i = 0, base = 0;
+                        while (lane >= base + (7 - i) && i < 6) { base += 7 - i; ++i; }
+                        if (lane < 27) {
+                            const int j = i + (lane - base);
                             if (j == 6) t[36 + i] = value; else { t[j * 6 + i] = value; t[i * 6 + j] = value; }
                         }
-                    t[42] = (float)rgb_sigma; t[43] = (float)rgb_count;
+                    }
+                    if (lane == 0) { t[42] = (float)rgb_sigma; t[43] = (float)rgb_count; }
                 }
-                gauss_newton_update_p(dA, db, s_Rt, s_Rp, s_tp, s_R, s_t);
             }
+            ++ex;
             __syncthreads();
         }
     }
@@ -673,17 +653,17 @@ int rgb_iteration(const RgbLevelArgs& a, OdomState* state, float* partials, floa
 // Whole-frame RGB-D / ICP+RGB-D odometry.  Returns 1 (and launches nothing) when the image does not fit the shared-memory stage,
 // in which case the caller falls back to the per-iteration kernels above.
 int rgbd_frame(const IcpLevelArgs* icp_levels, const RgbLevelArgs* rgb_levels, const int* iters, int with_icp, const float* pose12_host, OdomState* state,
-               float* partials, float* trace, unsigned int* bar_dev, unsigned int* bar_count, cudaStream_t s)
+               unsigned long long* xwords_dev, float* trace, int* timeout_dev, cudaStream_t s)
 {
     RgbdFrameParams p;
     int total = 0;
     for (int l = 0; l < LEVELS; ++l) { p.icp[l] = icp_levels[l]; p.rgb[l] = rgb_levels[l]; p.iters[l] = iters[l]; total += iters[l]; }
     for (int k = 0; k < 12; ++k) p.pose12[k] = pose12_host[k];
-    p.st = state; p.partials = partials; p.trace = trace; p.bar = bar_dev; p.bar_base = *bar_count; p.with_icp = with_icp;
+    p.st = state; p.xwords = xwords_dev; p.trace = trace; p.timeout = timeout_dev; p.with_icp = with_icp;
     DeviceInfo& di = device_info();
     const int sms = di.sm_count, smem_optin = di.smem_optin;
     int grid = sms > 0 ? sms : 148;
-    if (grid * 64 * 2 > MAX_PARTIALS * 32) grid = MAX_PARTIALS * 32 / 128;
+    if (grid > 255) grid = 255;                  // the exchange words count arrivals in 8 bits
     int need_k = 0;
     for (int l = 0; l < LEVELS; ++l)
         if (iters[l] > 0) { int k = div_up(rgb_levels[l].rows * rgb_levels[l].cols, grid * FRAME_THREADS); if (k > need_k) need_k = k; }
@@ -701,7 +681,7 @@ int rgbd_frame(const IcpLevelArgs* icp_levels, const RgbLevelArgs* rgb_levels, c
                              : cudaLaunchCooperativeKernel((const void*)rgbd_frame_kernel<false>, dim3(grid), dim3(FRAME_THREADS), args, bytes, s);
     ++g_launches;
     if (e != cudaSuccess) return cuda_check(e, "cudaLaunchCooperativeKernel(rgbd_frame_kernel)", __FILE__, __LINE__);
-    *bar_count += (unsigned int)(grid * total * 2);
+    (void)total;
     return 0;
 }
 

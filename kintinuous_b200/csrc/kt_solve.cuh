@@ -192,6 +192,142 @@ KT_HD __forceinline__ void gauss_newton_update_p(const double* dA, const double*
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Latency-trimmed form of the same step, used inside the whole-frame kernels where ONE thread's dependent FP64 chain sits on the
+// critical path of every Gauss-Newton iteration (19 per frame).  Same mathematics, same FP64 precision class:
+//   * 1/d_k of the LDL^T pivots: hardware reciprocal seed (rcp.approx.ftz.f64, ~2^-20) + three Newton steps (error squares each
+//     step: below 2^-53 after two; the third makes it robust) instead of the IEEE division subroutine -- on the device only; the
+//     host build keeps the plain division;
+//   * Rodrigues for |r|^2 <= 0.25 (|r| <= 0.5 rad = 28 degrees per ITERATION; tracking increments are < 0.05): the series of
+//     sin(t)/t and (1 - cos t)/t^2 in t^2 (terms to t^18 / 19!, truncation < 1e-19) -- no sqrt, no division, no sincos; larger
+//     rotations take the closed form above;
+//   * the 4x4 product keeps only the three rows that are not (0 0 0 1).
+// tests/test_device_solve_on_host.py runs both forms against numpy / cv2.Rodrigues.
+KT_HD __forceinline__ double fast_rcp(double d)
+{
+#ifdef __CUDA_ARCH__
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    r = fma(r, fma(-d, r, 1.0), r);
+    r = fma(r, fma(-d, r, 1.0), r);
+    r = fma(r, fma(-d, r, 1.0), r);
+    return r;
+#else
+    return 1.0 / d;
+#endif
+}
+
+KT_HD __forceinline__ void ldlt6_solve_fast(const double* Ain, const double* bin, double* x)
+{
+    double a[6][6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j < 6; ++j) a[i][j] = Ain[i * 6 + j];
+    double dinv[6];
+    double scale = 0.0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) scale = fmax(scale, fabs(a[i][i]));
+    const double tiny = scale * 1e-30 + DBL_MIN;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        const double d = a[k][k];
+        const double inv = (fabs(d) > tiny) ? fast_rcp(d) : 0.0;
+        dinv[k] = inv;
+        double col[6], l[6];
+#pragma unroll
+        for (int i = k + 1; i < 6; ++i) { col[i] = a[i][k]; l[i] = col[i] * inv; }
+#pragma unroll
+        for (int i = k + 1; i < 6; ++i)
+#pragma unroll
+            for (int j = k + 1; j <= i; ++j) a[i][j] -= l[i] * col[j];
+#pragma unroll
+        for (int i = k + 1; i < 6; ++i) a[i][k] = l[i];
+    }
+    double y[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        double v = bin[i];
+#pragma unroll
+        for (int j = 0; j < i; ++j) v -= a[i][j] * y[j];
+        y[i] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) y[i] *= dinv[i];
+#pragma unroll
+    for (int i = 5; i >= 0; --i) {
+        double v = y[i];
+#pragma unroll
+        for (int j = i + 1; j < 6; ++j) v -= a[j][i] * y[j];
+        y[i] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) x[i] = y[i];
+}
+
+KT_HD __forceinline__ void rodrigues_fast(const double* r, double* R)
+{
+    const double rx = r[0], ry = r[1], rz = r[2];
+    const double t2 = rx * rx + ry * ry + rz * rz;
+    if (!(t2 <= 0.25)) { rodrigues(r, R); return; }
+    // A = sin(t)/t = sum (-1)^k t2^k / (2k+1)!,  B = (1 - cos t)/t^2 = sum (-1)^k t2^k / (2k+2)!
+    double A = -1.0 / 121645100408832000.0;        // -1/19!
+    double B = -1.0 / 2432902008176640000.0;       // -1/20!
+    A = fma(A, t2, 1.0 / 355687428096000.0);   B = fma(B, t2, 1.0 / 6402373705728000.0);      // 17!, 18!
+    A = fma(A, t2, -1.0 / 1307674368000.0);    B = fma(B, t2, -1.0 / 20922789888000.0);       // 15!, 16!
+    A = fma(A, t2, 1.0 / 6227020800.0);        B = fma(B, t2, 1.0 / 87178291200.0);           // 13!, 14!
+    A = fma(A, t2, -1.0 / 39916800.0);         B = fma(B, t2, -1.0 / 479001600.0);            // 11!, 12!
+    A = fma(A, t2, 1.0 / 362880.0);            B = fma(B, t2, 1.0 / 3628800.0);               // 9!, 10!
+    A = fma(A, t2, -1.0 / 5040.0);             B = fma(B, t2, -1.0 / 40320.0);                // 7!, 8!
+    A = fma(A, t2, 1.0 / 120.0);               B = fma(B, t2, 1.0 / 720.0);                   // 5!, 6!
+    A = fma(A, t2, -1.0 / 6.0);                B = fma(B, t2, -1.0 / 24.0);                   // 3!, 4!
+    A = fma(A, t2, 1.0);                       B = fma(B, t2, 0.5);
+    const double c = fma(-t2, B, 1.0);             // cos t
+    R[0] = fma(B, rx * rx, c); R[1] = fma(B, rx * ry, -A * rz); R[2] = fma(B, rx * rz, A * ry);
+    R[3] = fma(B, rx * ry, A * rz); R[4] = fma(B, ry * ry, c); R[5] = fma(B, ry * rz, -A * rx);
+    R[6] = fma(B, rx * rz, -A * ry); R[7] = fma(B, ry * rz, A * rx); R[8] = fma(B, rz * rz, c);
+}
+
+KT_HD __forceinline__ void gauss_newton_update_fast(const double* dA, const double* db, double* resultRt,
+                                                    const float* Rp, const float* tprev, float* Rcurr, float* tcurr)
+{
+    double x[6];
+    ldlt6_solve_fast(dA, db, x);
+    double R[9];
+    rodrigues_fast(x + 3, R);
+    // resultRt <- [R | x0..2; 0 0 0 1] * resultRt: rows 0..2 only (row 3 of both factors is 0 0 0 1)
+    double res[12];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            double s = (j == 3) ? x[i] : 0.0;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) s = fma(R[i * 3 + k], resultRt[k * 4 + j], s);
+            res[i * 4 + j] = s;
+        }
+#pragma unroll
+    for (int k = 0; k < 12; ++k) resultRt[k] = res[k];
+    float rot[9], tr[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) rot[i * 3 + j] = (float)res[i * 4 + j];
+        tr[i] = (float)res[i * 4 + 3];
+    }
+    float tinv[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) tinv[i] = -dot3_rn(rot[0 * 3 + i], rot[1 * 3 + i], rot[2 * 3 + i], tr[0], tr[1], tr[2]);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            Rcurr[i * 3 + j] = dot3_rn(Rp[i * 3 + 0], Rp[i * 3 + 1], Rp[i * 3 + 2], rot[j * 3 + 0], rot[j * 3 + 1], rot[j * 3 + 2]);
+        tcurr[i] = KT_FADD(dot3_rn(Rp[i * 3 + 0], Rp[i * 3 + 1], Rp[i * 3 + 2], tinv[0], tinv[1], tinv[2]), tprev[i]);
+    }
+}
+
 KT_HD __forceinline__ void gauss_newton_update(const double* dA, const double* db, OdomState* st)
 {
     gauss_newton_update_p(dA, db, st->resultRt, st->Rprev, st->tprev, st->Rcurr, st->tcurr);

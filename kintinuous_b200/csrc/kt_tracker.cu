@@ -82,7 +82,7 @@ static Mat33 to_mat33(const float* m) { Mat33 r; r.r0 = make_float3(m[0], m[1], 
 struct SliceRec { int dimension; std::vector<kt_point_xyzrgb> points; float camera_t[3]; float camera_R[9]; uint64_t utime; };
 
 // what the host reads back after the odometry of a frame
-struct OdomResult { float Rcurr[9]; float tcurr[3]; int iter; int rgb_count; int rgb_sigma; };
+struct OdomResult { float Rcurr[9]; float tcurr[3]; int timeout; int pad[3]; };
 
 } // namespace kt
 
@@ -115,6 +115,7 @@ struct kt_ctx {
     uint16_t* depths_curr[LEVELS];
     float* vmaps_g_prev[LEVELS]; float* nmaps_g_prev[LEVELS]; float* vmaps_curr[LEVELS]; float* nmaps_curr[LEVELS];
     uint8_t* vmap_curr_color; float* depth_scaled; float* ztable; float* cw_scratch; float* rgbf_scratch; float* cw_alt; float* rgbf_alt;
+    unsigned long long* xwords_dev; bool xwords_clean;      // exchange words of the whole-frame odometry kernels; zero between frames
     OdomState* state; float* partials; int* ipartials; float* trace_dev; float* pose12_dev; unsigned int* bar_dev; unsigned int bar_count; long long* prof_dev;
     kt_point_xyzrgb* cloud_dev; unsigned int* counter_dev; size_t cloud_capacity; size_t cloud_count;
     // RGB-D
@@ -184,34 +185,10 @@ int push_slice(kt_ctx* c, int dimension)
     return 0;
 }
 
-int populate_rgbd(kt_ctx* c, const uint16_t* depth_raw, const uint8_t* rgb, float** destDepths, uint8_t** destImages, cudaStream_t s)   // RGBDOdometry::populateRGBDData (.cpp:140-158)
-{
-    const int rows = c->cfg.rows, cols = c->cfg.cols;
-    int r;
-    if ((r = short_depth_to_metres(depth_raw, destDepths[0], rows, cols, (int)(6.0 * 1000), s))) return r;
-    for (int i = 0; i + 1 < LEVELS; ++i) if ((r = pyrdown_gauss_f(destDepths[i], destDepths[i + 1], rows >> i, cols >> i, s))) return r;
-    if ((r = bgr_to_intensity(rgb, destImages[0], rows, cols, s))) return r;
-    for (int i = 0; i + 1 < LEVELS; ++i) if ((r = pyrdown_uchar_gauss(destImages[i], destImages[i + 1], rows >> i, cols >> i, s))) return r;
-    return 0;
-}
-
-// Photometric front end of a frame (pose-independent): float depth + intensity pyramids and the image gradients of all levels
-// (RGBDOdometry.cpp:140-158 + computeDerivativeImages, :172-175), into the "next" buffers.
-int rgbd_frontend(kt_ctx* c, const uint16_t* depth_raw, const uint8_t* rgb, cudaStream_t s)
-{
-    const int rows = c->cfg.rows, cols = c->cfg.cols;
-    int r;
-    if ((r = populate_rgbd(c, depth_raw, rgb, c->nextDepth, c->nextImage, s))) return r;
-    for (int i = 0; i < LEVELS; ++i)
-        if ((r = derivative_images(c->nextImage[i], c->nextdIdx[i], c->nextdIdy[i], rows >> i, cols >> i, s))) return r;
-    return 0;
-}
-
 int do_integrate(kt_ctx* c, const M3& Rinv, const V3& t, const int* wrap)
 {
     const int rows = c->cfg.rows, cols = c->cfg.cols;
     Intr k = {c->cfg.fx, c->cfg.fy, c->cfg.cx, c->cfg.cy};
-    KT_CUDA(cudaStreamWaitEvent(c->stream, c->ev_scaled, 0));       // scaleDepth ran on stream2 since the frame arrived
     IntegrateArgs a;
     a.depth_scaled = c->depth_scaled; a.rows = rows; a.cols = cols; a.k = k; a.volume_size = make_float3(c->size, c->size, c->size);
     a.Rinv = to_mat33(Rinv.m); a.t = make_float3(t.v[0], t.v[1], t.v[2]); a.trunc = c->trunc;
@@ -219,6 +196,7 @@ int do_integrate(kt_ctx* c, const M3& Rinv, const V3& t, const int* wrap)
     a.rgb = c->rgb; a.nmap_curr = c->nmaps_curr[0]; a.angle_color = c->cfg.angle_color != 0;
     for (int k = 0; k < 9; ++k) c->last_int_Rinv[k] = Rinv.m[k];
     for (int k = 0; k < 3; ++k) { c->last_int_t[k] = t.v[k]; c->last_int_wrap[k] = wrap[k]; }
+    a.reset_words = c->xwords_dev; a.reset_count = (int)odom_exchange_words(); c->xwords_clean = true;       // the prologue launch of integrate() zeroes them
     a.z_begin = c->z_begin; a.z_end = c->z_end; a.cw = c->color_prepared ? c->cw_scratch : 0; a.rgbf = c->color_prepared ? (float4*)c->rgbf_scratch : 0;
     return integrate(a, c->ztable, c->stream);
 }
@@ -232,10 +210,6 @@ int run_odometry(kt_ctx* c, const M3& Rprev, const V3& tprev, M3* Rcurr, V3* tcu
     for (int k = 0; k < 3; ++k) c->pose12_host[9 + k] = tprev.v[k];
     const float distThres = 0.10f, angleThres = sinf(20.f * 3.14159254f / 180.f);      // ICPOdometry.h:35-36
     Intr K = {c->cfg.fx, c->cfg.fy, c->cfg.cx, c->cfg.cy};
-    if (mode != 0) {
-        // built ahead of time by kt_prefetch_frame when the frame was prefetched (the "next" buffers are free between two frames)
-        if (!c->frontend_ready && (r = rgbd_frontend(c, c->depth_raw, c->rgb, c->stream))) return r;
-    }
     int total_iters = 0;
     // KT_FORCE_PER_ITERATION (test hook): take the per-iteration kernels -- the path of images too large for the whole-frame kernels'
     // shared-memory stage -- on an image that would fit, so that it can be compared against the whole-frame path and the reference
@@ -250,7 +224,9 @@ int run_odometry(kt_ctx* c, const M3& Rprev, const V3& tprev, M3* Rcurr, V3* tcu
             total_iters += c->iterations[level];
         }
         if (c->timing) cudaEventRecord(c->ev_icp[0], c->stream);
-        if ((r = icp_frame(la, c->iterations, c->pose12_host, c->state, c->partials, c->trace_dev, c->bar_dev, &c->bar_count, c->timing ? c->prof_dev : 0, c->stream))) return r;
+        if (!c->xwords_clean && (r = odom_exchange_reset(c->xwords_dev, c->stream))) return r;
+        c->xwords_clean = false;
+        if ((r = icp_frame(la, c->iterations, c->pose12_host, c->state, c->xwords_dev, c->trace_dev, &c->state->odo_timeout, c->timing ? c->prof_dev : 0, c->stream))) return r;
         if (c->timing) cudaEventRecord(c->ev_icp[1], c->stream);
     }
     const double SOBEL_SCALE = 1.0 / std::pow(2.0, 3);
@@ -276,7 +252,9 @@ int run_odometry(kt_ctx* c, const M3& Rprev, const V3& tprev, M3* Rcurr, V3* tcu
             ra.max_depth_delta = 0.07f; ra.fx = kl.fx; ra.fy = kl.fy; ra.sobel_scale = (float)SOBEL_SCALE;
             ra.Kfx = (double)K.fx / div; ra.Kfy = (double)K.fy / div; ra.Kcx = (double)K.cx / div; ra.Kcy = (double)K.cy / div;
         }
-        r = rgbd_frame(la, ra4, c->iterations, mode == 2 ? 1 : 0, c->pose12_host, c->state, c->partials, c->trace_dev, c->bar_dev, &c->bar_count, c->stream);
+        if (!c->xwords_clean && (r = odom_exchange_reset(c->xwords_dev, c->stream))) return r;
+        r = rgbd_frame(la, ra4, c->iterations, mode == 2 ? 1 : 0, c->pose12_host, c->state, c->xwords_dev, c->trace_dev, &c->state->odo_timeout, c->stream);
+        if (r == 0) c->xwords_clean = false;
         if (r < 0) return r;
         if (r == 0) { per_iteration_path = false; for (int level = 0; level < LEVELS; ++level) total_iters += c->iterations[level]; }
         else {       // image too large for the shared-memory stage: per-iteration kernels
@@ -315,10 +293,15 @@ int run_odometry(kt_ctx* c, const M3& Rprev, const V3& tprev, M3* Rcurr, V3* tcu
     }
     c->trace_iters = std::min(total_iters, MAX_TRACE_ITERS);
     // one 64-byte read-back of the estimate (+ the trace when someone asked for it later: it stays on the device)
-    KT_CUDA(cudaMemcpyAsync(c->result_host->Rcurr, (char*)c->state + offsetof(OdomState, Rcurr), 12 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    static_assert(offsetof(OdomState, odo_timeout) == offsetof(OdomState, Rcurr) + 12 * sizeof(float), "the time-out flag travels with the pose");
+    KT_CUDA(cudaMemcpyAsync(c->result_host->Rcurr, (char*)c->state + offsetof(OdomState, Rcurr), 13 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     if (c->world > 1) KT_CUDA(cudaMemcpyAsync(c->mg_error_host, c->mg_error_dev, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     KT_CUDA(cudaStreamSynchronize(c->stream));
     if (c->world > 1 && *c->mg_error_host) { set_error("cross-GPU barrier timed out waiting for rank %d", *c->mg_error_host - 1); return KT_ERR_STATE; }
+    if (c->result_host->timeout) {
+        cudaMemsetAsync(&c->state->odo_timeout, 0, sizeof(int), c->stream);
+        set_error("odometry kernel: a CTA never arrived at the grid-wide sum (bounded poll gave up)"); return KT_ERR_STATE;
+    }
     for (int k = 0; k < 9; ++k) Rcurr->m[k] = c->result_host->Rcurr[k];
     for (int k = 0; k < 3; ++k) tcurr->v[k] = c->result_host->tcurr[k];
     if (mode != 0) {
@@ -337,29 +320,26 @@ int mg_barrier(kt_ctx* c)
     return xgpu_barrier(c->peer_flags_dev, (unsigned int*)(c->arena + c->off_flags), c->rank, c->world, c->epoch, c->mg_error_dev, c->stream);
 }
 
-// Pose-independent front end of one frame: scaleDepth (for integrate) on s_scale, bilateral + pyrDown + vertex / normal maps of all
-// levels on s_pyr.  vstale / nstale: the previous frame's maps when the outputs are a spare set (Q7 staleness), else null.
+// Pose-independent front end of one frame in TWO launches (kt_frontend.cu): bilateral filter + scaleDepth, then the depth pyramid, the
+// vertex / normal maps of all levels, the colour-integration inputs and -- for -r / -ri -- the photometric pyramids and gradients
+// (RGBDOdometry::populateRGBDData / firstRun + computeDerivativeImages, RGBDOdometry.cpp:140-175) into depth_m / intensity.
+// vstale / nstale: the previous frame's maps when the outputs are a spare set (Q7 staleness), else null.
 int build_frontend(kt_ctx* c, const uint16_t* depth_raw, const uint8_t* rgb, float* depth_scaled, uint16_t* const* depths, float* const* vmaps, float* const* nmaps,
-                   float* const* vstale, float* const* nstale, float* cw, float* rgbf, cudaStream_t s_scale, cudaStream_t s_pyr)
+                   float* const* vstale, float* const* nstale, float* cw, float* rgbf, float* const* depth_m, uint8_t* const* intensity, cudaStream_t s)
 {
     const int rows = c->cfg.rows, cols = c->cfg.cols, mode = c->cfg.odometry;
     int r;
     Intr K = {c->cfg.fx, c->cfg.fy, c->cfg.cx, c->cfg.cy};
-    if ((r = scale_depth(depth_raw, depth_scaled, rows, cols, K, c->cfg.angle_color != 0, s_scale))) return r;
     const bool use_icp_maps = (mode == 0) || (mode == 2) || c->cfg.angle_color;        // KintinuousTracker.cpp:465 (Q10)
-    if (use_icp_maps) {
-        if ((r = bilateral(depth_raw, depths[0], rows, cols, s_pyr))) return r;
-        for (int i = 1; i < LEVELS; ++i) if ((r = pyrdown(depths[i - 1], depths[i], rows >> (i - 1), cols >> (i - 1), s_pyr))) return r;
-        MapsLevel ml[LEVELS];
-        for (int i = 0; i < LEVELS; ++i) {
-            ml[i].depth = depths[i]; ml[i].vmap = vmaps[i]; ml[i].nmap = nmaps[i]; ml[i].rows = rows >> i; ml[i].cols = cols >> i; ml[i].k = intr_level(K, i);
-            ml[i].vstale = vstale ? vstale[i] : 0; ml[i].nstale = nstale ? nstale[i] : 0;
-        }
-        if ((r = create_maps_pyramid(ml, LEVELS, s_pyr))) return r;
-        // colour integration inputs that depend only on the pixel (normal validity, view-angle weight, RGB as float)
-        if ((r = color_prep(nmaps[0], rgb, rows, cols, c->cfg.angle_color != 0, cw, (float4*)rgbf, s_pyr))) return r;
-        c->color_prepared = true;
-    } else c->color_prepared = false;
+    if ((r = bilateral_scale(depth_raw, use_icp_maps ? depths[0] : 0, depth_scaled, rows, cols, K, c->cfg.angle_color != 0, s))) return r;
+    FrontendArgs fa;
+    fa.depth_f = use_icp_maps ? depths[0] : 0; fa.depth_raw = depth_raw; fa.rgb = rgb; fa.rows = rows; fa.cols = cols; fa.k = K;
+    fa.depths = depths; fa.vmaps = use_icp_maps ? vmaps : 0; fa.nmaps = use_icp_maps ? nmaps : 0; fa.vstale = vstale; fa.nstale = nstale;
+    fa.cw = use_icp_maps ? cw : 0; fa.rgbf = use_icp_maps ? (float4*)rgbf : 0; fa.angle_color = c->cfg.angle_color != 0;
+    fa.cut_off = (int)(6.0 * 1000);                                                      // RGBDOdometry.cpp:147
+    fa.depth_m = depth_m; fa.intensity = intensity; fa.dIdx = depth_m ? c->nextdIdx : 0; fa.dIdy = depth_m ? c->nextdIdy : 0;
+    if (use_icp_maps || depth_m) { if ((r = frontend_pyramid(fa, s))) return r; }
+    c->color_prepared = use_icp_maps;
     return 0;
 }
 
@@ -373,11 +353,10 @@ int process_frame_device(kt_ctx* c, uint64_t utime, kt_pose* out)
     c->shifted_last = 0;
     mark(c, 0);
     if (!c->frontend_ready) {
-        // fork: scaleDepth (tsdf_volume.cu:491-538) only needs the raw depth; it overlaps the pyramid on a second stream
-        KT_CUDA(cudaEventRecord(c->ev_input, c->stream));
-        KT_CUDA(cudaStreamWaitEvent(c->stream2, c->ev_input, 0));
-        if ((r = build_frontend(c, c->depth_raw, c->rgb, c->depth_scaled, c->depths_curr, c->vmaps_curr, c->nmaps_curr, 0, 0, c->cw_scratch, c->rgbf_scratch, c->stream2, c->stream))) return r;
-        KT_CUDA(cudaEventRecord(c->ev_scaled, c->stream2));
+        // the first frame's photometric pyramids are the "last" set (RGBDOdometry::firstRun), every later frame's the "next" set
+        float* const* dm = mode != 0 ? (c->global_time == 0 ? c->lastDepth : c->nextDepth) : 0;
+        uint8_t* const* im = mode != 0 ? (c->global_time == 0 ? c->lastImage : c->nextImage) : 0;
+        if ((r = build_frontend(c, c->depth_raw, c->rgb, c->depth_scaled, c->depths_curr, c->vmaps_curr, c->nmaps_curr, 0, 0, c->cw_scratch, c->rgbf_scratch, dm, im, c->stream))) return r;
         // the look-ahead front end of the NEXT frame (kt_prefetch_frame, side stream) reads these maps as its stale-plane source (Q7)
         KT_CUDA(cudaEventRecord(c->ev_maps, c->stream));
         c->maps_on_stream = true;
@@ -388,7 +367,6 @@ int process_frame_device(kt_ctx* c, uint64_t utime, kt_pose* out)
         M3 Rcam = c->rmats.back(); V3 tcam = c->tvecs.back();
         M3 Rcam_inv = m3_inverse(Rcam);
         int emptyVoxel[3] = {0, 0, 0};
-        if (mode != 0 && (r = populate_rgbd(c, c->depth_raw, c->rgb, c->lastDepth, c->lastImage, c->stream))) return r;    // rgbd->firstRun
         mark(c, 2); mark(c, 3);
         if ((r = do_integrate(c, Rcam_inv, tcam, emptyVoxel))) return r;
         mark(c, 4);
@@ -603,6 +581,8 @@ int kt_create(const kt_config* cfg, kt_ctx** out)
     }
     c->vmap_curr_color = c->arena + c->off_vcol; KT_TRY(dev_alloc(c, &c->depth_scaled, P)); KT_TRY(dev_alloc(c, &c->depth_scaled_alt, P)); c->pf_built = false; c->frontend_ready = false;
     KT_TRY(dev_alloc(c, &c->ztable, (size_t)2 * cfg->vol)); KT_TRY(dev_alloc(c, &c->cw_scratch, P)); KT_TRY(dev_alloc(c, &c->rgbf_scratch, P * 4)); KT_TRY(dev_alloc(c, &c->cw_alt, P)); KT_TRY(dev_alloc(c, &c->rgbf_alt, P * 4));
+    KT_TRY(dev_alloc(c, &c->xwords_dev, odom_exchange_words()));
+    KT_TRY(kt::cuda_check(cudaMemset(c->xwords_dev, 0, odom_exchange_words() * sizeof(unsigned long long)), "memset", __FILE__, __LINE__)); c->xwords_clean = true;
     KT_TRY(dev_alloc(c, &c->state, 1)); KT_TRY(dev_alloc(c, &c->partials, (size_t)MAX_PARTIALS * 32));
     KT_TRY(kt::cuda_check(cudaMemset(c->partials, 0, (size_t)MAX_PARTIALS * 32 * sizeof(float)), "memset", __FILE__, __LINE__));   // tags start at 0
     KT_TRY(dev_alloc(c, &c->bar_dev, 1)); KT_TRY(kt::cuda_check(cudaMemset(c->bar_dev, 0, sizeof(unsigned int)), "memset", __FILE__, __LINE__)); c->bar_count = 0;
@@ -719,12 +699,12 @@ int kt_prefetch_frame(kt_ctx* c, const uint16_t* depth, const uint8_t* rgb)
         // invalid pixels keep the y/z planes of the previous frame's maps = the set that is current now (Q7); if that set was built on the
         // compute stream (frame not prefetched, e.g. frame 0), wait for its front end -- not for the whole frame
         if (c->maps_on_stream) KT_CUDA(cudaStreamWaitEvent(c->stream_copy, c->ev_maps, 0));
-        int r = build_frontend(c, c->depth_alt, c->rgb_alt, c->depth_scaled_alt, c->depths_alt, c->vmaps_alt, c->nmaps_alt, c->vmaps_curr, c->nmaps_curr,
-                               c->cw_alt, c->rgbf_alt, c->stream_copy, c->stream_copy);
-        if (r) return r;
         // photometric odometry: its "next" pyramids were swapped to "last" when the previous frame's odometry finished, so the
         // buffers now called next are free until the coming frame
-        if (c->cfg.odometry != 0 && (r = rgbd_frontend(c, c->depth_alt, c->rgb_alt, c->stream_copy))) return r;
+        const bool ph = c->cfg.odometry != 0;
+        int r = build_frontend(c, c->depth_alt, c->rgb_alt, c->depth_scaled_alt, c->depths_alt, c->vmaps_alt, c->nmaps_alt, c->vmaps_curr, c->nmaps_curr,
+                               c->cw_alt, c->rgbf_alt, ph ? c->nextDepth : 0, ph ? c->nextImage : 0, c->stream_copy);
+        if (r) return r;
         c->pf_built = true;
     }
     KT_CUDA(cudaEventRecord(c->ev_prefetch, c->stream_copy));

@@ -3,7 +3,7 @@
 // Replaces (reference, src/frontend/cuda/tsdf_volume.cu):
 //   initVolume / initColorVolume                         :452-479, :57-86
 //   clearVolume{X,Y,Z}[Back][c] (12 wrappers, 6 kernels) :88-448
-//   scaleDepth                                           :491-538
+//   scaleDepth                                           :491-538   (fused with the bilateral filter: kt_pyramid.cu, bilateral_scale_kernel)
 //   tsdf23 / integrateTsdfVolume                         :541-674
 // Volume layout: two planes in HBM, exactly the reference's encoding so that
 // kt_volume_export_reference_layout is a plain copy: tsdf short[V^3] (value * 32767, round toward zero)
@@ -21,6 +21,7 @@
 // The colour update's per-pixel half (normal validity, view-angle weight, RGB as float) is prepared once per frame (color_prep_kernel).
 // Roofline: HBM by nature (12 B per updated voxel + image-side gathers), instruction-issue bound in practice.
 #include "kt_ops.h"
+#include "kt_replay.cuh"
 
 namespace kt {
 
@@ -75,36 +76,14 @@ clear_planes_x_kernel(int16_t* __restrict__ tsdf, uchar4* __restrict__ color, in
 }
 
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-scale_depth_kernel(const uint16_t* __restrict__ depth, float* __restrict__ scaled, int rows, int cols, const Intr intr, bool angleColor)
-{
-    int x = threadIdx.x + blockIdx.x * blockDim.x;
-    int y = threadIdx.y + blockIdx.y * blockDim.y;
-    if (x >= cols || y >= rows) return;
-    int Dp = depth[(size_t)y * cols + x];
-    float xl = (x - intr.cx) / intr.fx;
-    float yl = (y - intr.cy) / intr.fy;
-    float lambda = sqrtf(__fadd_rn(__fmaf_rn(xl, xl, __fmul_rn(yl, yl)), 1.f));     // sqrtf(xl * xl + yl * yl + 1), contraction pinned
-    if (angleColor) {
-        int STEP = 1, ky = 7, kx = 7;
-        int ty = min(y - ky / 2 + ky, rows - 1);
-        int tx = min(x - kx / 2 + kx, cols - 1);
-        int count = 0;
-        for (int cy = max(y - ky / 2, 0); cy < ty; cy += STEP)
-            for (int cx = max(x - kx / 2, 0); cx < tx; cx += STEP)
-                if (abs(Dp - depth[(size_t)cy * cols + cx]) > 200 || Dp == 0) count++;
-        if (count > 5) scaled[(size_t)y * cols + x] = -Dp * lambda / 1000.f;
-        else scaled[(size_t)y * cols + x] = Dp * lambda / 1000.f;
-    } else {
-        scaled[(size_t)y * cols + x] = Dp * lambda / 1000.f;
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
 // z tables: v_g_z(z) and z_scaled(z) as the reference's running sums produce them (tsdf_volume.cu:555,563,570-571)
-__global__ void ztable_kernel(float* __restrict__ table, int V, float cell_z, float t_z)
+// Prologue of the integration, one small launch: the z tables (thread 0: the running sums are serial by definition) and, with the other
+// threads, the reset of the odometry kernels' exchange words for the next frame (grid_sum_words, kt_frame.cuh) -- this launch sits
+// between two odometry launches on the tracker's stream anyway, so the reset costs no launch of its own.
+__global__ void __launch_bounds__(256) ztable_kernel(float* __restrict__ table, int V, float cell_z, float t_z, unsigned long long* __restrict__ reset_words, int reset_count)
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    for (int i = threadIdx.x; i < reset_count; i += blockDim.x) reset_words[i] = 0ull;
+    if (threadIdx.x != 0) return;
     float v_g_z = (0 + 0.5f) * cell_z - t_z;
     float z_scaled = 0;
     for (int z = 0; z < V; ++z) {
@@ -236,11 +215,10 @@ integrate_kernel(const IntegrateParams p)
         if (zlo >= zhi) return;
     }
 
-    // replay the running sums up to zlo (exactly the additions the reference performs)
-    for (int z = 0; z < zlo; ++z) {
-        v_x += Rcurr_inv_0_z_scaled;
-        v_y += Rcurr_inv_1_z_scaled;
-    }
+    // the running sums at zlo: exactly the bits the reference reaches after zlo additions, in O(binades crossed) instead of O(zlo)
+    // dependent FADDs (kt_replay.cuh; the one-by-one replay was about a quarter of this kernel's issued instructions)
+    v_x = replay_add(v_x, Rcurr_inv_0_z_scaled, zlo);
+    v_y = replay_add(v_y, Rcurr_inv_1_z_scaled, zlo);
 
     const float* __restrict__ zt = p.ztable;
     const float* __restrict__ depthScaled = p.depth_scaled;
@@ -427,19 +405,11 @@ int color_prep(const float* nmap, const uint8_t* rgb, int rows, int cols, bool a
     return 0;
 }
 
-int scale_depth(const uint16_t* depth, float* scaled, int rows, int cols, const Intr& k, bool angle_color, cudaStream_t s)
-{
-    dim3 block(32, 8), grid(div_up(cols, 32), div_up(rows, 8));
-    scale_depth_kernel<<<grid, block, 0, s>>>(depth, scaled, rows, cols, k, angle_color);
-    KT_LAUNCH_CHECK();
-    return 0;
-}
-
 int integrate(const IntegrateArgs& a, float* ztable_dev, cudaStream_t s)
 {
     const int V = a.vol;
     float3 cell = make_float3(a.volume_size.x / V, a.volume_size.y / V, a.volume_size.z / V);   // host division, tsdf_volume.cu:659-661
-    ztable_kernel<<<1, 32, 0, s>>>(ztable_dev, V, cell.z, a.t.z);
+    ztable_kernel<<<1, 256, 0, s>>>(ztable_dev, V, cell.z, a.t.z, a.reset_words, a.reset_words ? a.reset_count : 0);
     KT_LAUNCH_CHECK();
     IntegrateParams p;
     p.depth_scaled = a.depth_scaled; p.rows = a.rows; p.cols = a.cols; p.k = a.k; p.cell = cell; p.Rinv = a.Rinv; p.t = a.t; p.trunc = a.trunc;

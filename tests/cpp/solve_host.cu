@@ -11,4 +11,9 @@ void kts_unpack(const float* sums27, float* A36, float* b6) { kt::unpack_normal_
 // one Gauss-Newton update: resultRt (4x4 double, in/out), previous pose -> current pose
 void kts_update(const double* A, const double* b, double* resultRt, const float* Rprev, const float* tprev, float* Rcurr, float* tcurr)
 { kt::gauss_newton_update_p(A, b, resultRt, Rprev, tprev, Rcurr, tcurr); }
+// the latency-trimmed forms the whole-frame kernels use (series Rodrigues, 3-row product; the reciprocal seed is device-only)
+void kts_ldlt6_solve_fast(const double* A, const double* b, double* x) { kt::ldlt6_solve_fast(A, b, x); }
+void kts_rodrigues_fast(const double* r, double* R) { kt::rodrigues_fast(r, R); }
+void kts_update_fast(const double* A, const double* b, double* resultRt, const float* Rprev, const float* tprev, float* Rcurr, float* tcurr)
+{ kt::gauss_newton_update_fast(A, b, resultRt, Rprev, tprev, Rcurr, tcurr); }
 }

@@ -127,3 +127,37 @@ def test_pose_update_follows_the_reference_formulas(solve_lib):
         inv = np.linalg.inv(want)
         assert np.abs(Rc.reshape(3, 3) - Rprev.astype(np.float64) @ inv[:3, :3]).max() < 1e-6
         assert np.abs(tc - (Rprev.astype(np.float64) @ inv[:3, 3] + tprev)).max() < 1e-6
+
+
+def test_trimmed_forms_agree_with_the_closed_forms(solve_lib):
+    """The whole-frame kernels run the latency-trimmed step (kt_solve.cuh: gauss_newton_update_fast): series Rodrigues below 0.5 rad
+    (closed form above), three-row product.  Against cv2.Rodrigues: 2 ulp of the matrix entries; against the plain step: the float pose
+    may differ in its last bit only where the double intermediate sits on a rounding boundary."""
+    cv2 = pytest.importorskip("cv2")
+    from scipy.spatial.transform import Rotation
+    rng = np.random.default_rng(9)
+    for scale in (0.0, 1e-17, 1e-9, 1e-4, 1e-2, 0.1, 0.28, 0.29, 0.5, 1.0, 3.0):       # 0.28 / 0.29: either side of |r|^2 = 0.25 for unit-ish directions
+        for _ in range(20):
+            r = rng.standard_normal(3); r = r / np.linalg.norm(r) * scale * (1.0 + 0.5 * rng.random())
+            R = np.zeros(9)
+            solve_lib.kts_rodrigues_fast(_p(r), _p(R))
+            Rcv, _ = cv2.Rodrigues(r.reshape(3, 1))
+            assert np.abs(R.reshape(3, 3) - Rcv).max() < 5e-16, (scale, np.abs(R.reshape(3, 3) - Rcv).max())
+    worst = 0.0
+    for _ in range(200):
+        A = _normal_matrix(rng, rng.choice([1.0, 1e3, 1e5]))
+        xt = rng.standard_normal(6) * np.array([0.02, 0.02, 0.02, 0.01, 0.01, 0.01]) * rng.choice([1.0, 1e-3])
+        b = A @ xt
+        Rt = np.eye(4)
+        Rt[:3, :3] = Rotation.from_rotvec(rng.standard_normal(3) * 0.02).as_matrix(); Rt[:3, 3] = rng.standard_normal(3) * 0.01
+        Rprev = Rotation.from_rotvec(rng.standard_normal(3)).as_matrix().astype(np.float32)
+        tprev = (rng.standard_normal(3) + 3).astype(np.float32)
+        out = []
+        for fn in (solve_lib.kts_update, solve_lib.kts_update_fast):
+            res = Rt.copy().reshape(-1); Rc = np.zeros(9, np.float32); tc = np.zeros(3, np.float32)
+            fn(_p(np.ascontiguousarray(A)), _p(b), _p(res), _p(np.ascontiguousarray(Rprev)), _p(tprev), _p(Rc), _p(tc))
+            out.append((res.copy(), Rc.copy(), tc.copy()))
+        assert np.abs(out[0][0][:12] - out[1][0][:12]).max() < 1e-15
+        assert (out[1][0][12:] == np.array([0, 0, 0, 1.0])).all()
+        worst = max(worst, np.abs(out[0][1] - out[1][1]).max(), np.abs(out[0][2] - out[1][2]).max())
+    assert worst <= 2.4e-7 * 4                     # at most one float ulp of a pose entry (|t| < 4)

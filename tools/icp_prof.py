@@ -13,13 +13,11 @@ for k in range(6):
 buf = np.zeros(512, np.int64)
 kb.load().kt_debug_icp_profile(t.h, buf.ctypes.data_as(C.c_void_p))
 full = buf.reshape(64, 8)[:19]
-st = full[:, :5]
-names = ["main+cta_reduce", "barrier", "sum_partials", "solve"]
+st = full[:, :4]
+names = ["main+cta_reduce", "exchange", "solve"]
 d = np.diff(st, axis=1)
 print("iter  " + "  ".join(f"{n:>16s}" for n in names) + "   total   gap_to_next")
 for i in range(19):
-    gap = st[i + 1, 0] - st[i, 4] if i < 18 else 0
-    print(f"{i:3d}   " + "  ".join(f"{int(x):16d}" for x in d[i]) + f"  {int(st[i,4]-st[i,0]):7d}  {int(gap):6d}")
-sol = np.stack([full[:, 5] - full[:, 3], full[:, 6] - full[:, 5], full[:, 7] - full[:, 6], full[:, 4] - full[:, 7]], 1)
-print("solve split (unpack, ldlt+subst, rodrigues, matmul+pose), mean cycles:", sol.mean(0).astype(int).tolist())
-print("sum cycles", int(st[18, 4] - st[0, 0]), "stage_ms", t.stage_ms())
+    gap = st[i + 1, 0] - st[i, 3] if i < 18 else 0
+    print(f"{i:3d}   " + "  ".join(f"{int(x):16d}" for x in d[i]) + f"  {int(st[i,3]-st[i,0]):7d}  {int(gap):6d}")
+print("sum cycles", int(st[18, 3] - st[0, 0]), "stage_ms", t.stage_ms(), "icp_kernel_ms", t.icp_kernel_ms())

@@ -45,6 +45,19 @@ __device__ __forceinline__ void do_solve(const float* s_sum, double* s_Rt, float
         }
     gauss_newton_update_p(dA, db, s_Rt, s_Rp, s_tp, s_R, s_t);
 }
+__device__ __forceinline__ void do_solve_fast(const float* s_sum, double* s_Rt, float* s_Rp, float* s_tp, float* s_R, float* s_t)
+{
+    double dA[36], db[6];
+    int shift = 0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = i; j < 7; ++j) {
+            double value = (double)s_sum[shift++];
+            if (j == 6) db[i] = value * 1e-6; else { if (i == j) value += 1e4; dA[j * 6 + i] = value; dA[i * 6 + j] = value; }
+        }
+    gauss_newton_update_fast(dA, db, s_Rt, s_Rp, s_tp, s_R, s_t);
+}
 
 // ---- V0: what icp_frame_kernel does today -------------------------------------------------------------------------------
 __global__ void __launch_bounds__(T, 1) v0_kernel(P p)
@@ -296,8 +309,46 @@ __global__ void __launch_bounds__(T, 1) v5_kernel(P p)
     if (tid == 0 && blockIdx.x == 0) p.out[0] = chk;
 }
 
+
+// ---- V6: self-counting fixed-point words.  Every CTA adds (fixed-point value with the low 8 bits cleared) + 1 to 29 64-bit words; the
+// low byte of (word_now - word_at_the_previous_use) therefore counts arrivals and the rest is the exact integer sum: no counter, no
+// fence, no zeroing (two word sets by iteration parity, persistent).  STRIDE = distance between the 29 words in 8-byte units. --------
+template <int STRIDE, int FASTSOLVE>
+__global__ void __launch_bounds__(T, 1) v6_kernel(P p)
+{
+    __shared__ float s_sum[32]; __shared__ double s_Rt[16]; __shared__ float s_Rp[9], s_tp[3], s_R[9], s_t[3];
+    const int tid = threadIdx.x, G = gridDim.x;
+    if (tid == 0) { for (int k = 0; k < 16; ++k) s_Rt[k] = (k % 5 == 0); for (int k = 0; k < 9; ++k) { s_Rp[k] = (k % 4 == 0); s_R[k] = s_Rp[k]; } for (int k = 0; k < 3; ++k) { s_tp[k] = 3.f; s_t[k] = 3.f; } }
+    __syncthreads();
+    float chk = 0.f;
+    unsigned long long prev[2] = {0ull, 0ull};
+    unsigned long long* w0 = p.ll;                                   // [2][32 * STRIDE]
+    if (tid < NS) { prev[0] = ld_relaxed_u64(&w0[(size_t)tid * STRIDE]); prev[1] = ld_relaxed_u64(&w0[(size_t)(32 + tid) * STRIDE]); }
+    for (int it = 0; it < p.iters; ++it) {
+        long long t0 = clock64();
+        if (tid < 32) {
+            unsigned long long* w = w0 + (size_t)(it & 1) * 32 * STRIDE + (size_t)tid * STRIDE;
+            if (tid < NS) {
+                const float v = my_value(tid, it) + s_t[0] * 1e-9f;
+                const long long q = __double2ll_rn((double)v * 4294967296.0) & ~0xFFll;
+                red_add_u64(w, (unsigned long long)(q + 1));
+                unsigned long long now, d;
+                do { now = ld_relaxed_u64(w); d = now - prev[it & 1]; } while ((unsigned int)(d & 0xFFull) != (unsigned int)G);
+                prev[it & 1] = now;
+                s_sum[tid] = (float)((double)(long long)(d - (unsigned long long)G) * (1.0 / 4294967296.0));
+            }
+        }
+        __syncthreads();
+        if (tid == 0 && p.solve) do_solve(s_sum, s_Rt, s_Rp, s_tp, s_R, s_t);
+        __syncthreads();
+        chk += s_sum[5] + s_t[1];
+        if (blockIdx.x == 0 && tid == 0) p.cycles[it] = clock64() - t0;
+    }
+    if (tid == 0 && blockIdx.x == 0) p.out[0] = chk;
+}
+
 // ---- the solve alone, on one thread of one CTA, sums in shared memory ---------------------------------------------------
-__global__ void solve_only_kernel(P p)
+template <int FAST> __global__ void solve_only_kernel(P p)
 {
     __shared__ float s_sum[32]; __shared__ double s_Rt[16]; __shared__ float s_Rp[9], s_tp[3], s_R[9], s_t[3];
     const int tid = threadIdx.x;
@@ -306,13 +357,26 @@ __global__ void solve_only_kernel(P p)
     __syncthreads();
     for (int it = 0; it < p.iters; ++it) {
         long long t0 = clock64();
-        if (tid == 0) do_solve(s_sum, s_Rt, s_Rp, s_tp, s_R, s_t);
+        if (tid == 0) { if (FAST) do_solve_fast(s_sum, s_Rt, s_Rp, s_tp, s_R, s_t); else do_solve(s_sum, s_Rt, s_Rp, s_tp, s_R, s_t); }
         __syncthreads();
         if (tid < NS) s_sum[tid] += s_t[tid % 3] * 1e-3f;
         __syncthreads();
         if (tid == 0) p.cycles[it] = clock64() - t0;
     }
     if (tid == 0) p.out[0] = s_t[0] + s_R[1];
+}
+
+// accuracy of the device-only reciprocal path: x from ldlt6_solve_fast vs ldlt6_solve on the same systems
+__global__ void solve_check_kernel(const double* A, const double* b, int n, double* maxrel)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double x0[6], x1[6];
+    ldlt6_solve(A + (size_t)i * 36, b + (size_t)i * 6, x0);
+    ldlt6_solve_fast(A + (size_t)i * 36, b + (size_t)i * 6, x1);
+    double num = 0, den = 1e-300;
+    for (int k = 0; k < 6; ++k) { num = fmax(num, fabs(x0[k] - x1[k])); den = fmax(den, fabs(x0[k])); }
+    maxrel[i] = num / den;
 }
 
 template <class K> static void run(const char* name, K kernel, P p, int grid, int cluster, bool coop)
@@ -357,6 +421,12 @@ int main()
         run("V3 cluster 4 DSMEM + LL leaders", v3_kernel<4>, p, sms, 4, true);
         run("V3 cluster 8 DSMEM + LL leaders", v3_kernel<8>, p, 144, 8, true);
         run("V3 cluster 16 DSMEM + LL leaders", v3_kernel<16>, p, 128, 16, true);
+        run("V6 self-counting words, packed", v6_kernel<1, 0>, p, sms, 1, true);
+        run("V6 self-counting words, stride 256 B", v6_kernel<32, 0>, p, sms, 1, true);
+        run("V6 self-counting words, stride 1280 B", v6_kernel<160, 0>, p, sms, 1, true);
+        run("V6 stride 256 B, 16 CTAs", v6_kernel<32, 0>, p, 16, 1, true);
+        run("V6 stride 256 B, 32 CTAs", v6_kernel<32, 0>, p, 32, 1, true);
+        run("V6 stride 256 B, 74 CTAs", v6_kernel<32, 0>, p, 74, 1, true);
         run("V4 two-level LL, 4 reducers", v4_kernel<4>, p, sms, 1, true);
         run("V4 two-level LL, 8 reducers", v4_kernel<8>, p, sms, 1, true);
         run("V4 two-level LL, 12 reducers", v4_kernel<12>, p, sms, 1, true);
@@ -366,6 +436,25 @@ int main()
         run("V2 flat LL, 16 CTAs", v2_kernel, p, 16, 1, true);
         run("V2 flat LL, 37 CTAs", v2_kernel, p, 37, 1, true);
     }
-    run("solve only (thread 0, sums in smem)", solve_only_kernel, p, 1, 1, false);
+    {
+        const int n = 4096;
+        std::vector<double> hA((size_t)n * 36), hb((size_t)n * 6), hr(n);
+        srand(7);
+        for (int i = 0; i < n; ++i) {
+            double J[40][6];
+            const double sc = (i % 3 == 0) ? 300.0 : (i % 3 == 1 ? 1.0 : 1e-2);
+            for (int r = 0; r < 40; ++r) for (int c = 0; c < 6; ++c) J[r][c] = sc * ((rand() / (double)RAND_MAX) - 0.5) * (c < 3 ? 1.0 : 0.3);
+            for (int a = 0; a < 6; ++a) for (int c = 0; c < 6; ++c) { double s = 0; for (int r = 0; r < 40; ++r) s += J[r][a] * J[r][c]; hA[(size_t)i * 36 + a * 6 + c] = s; }
+            for (int c = 0; c < 6; ++c) hb[(size_t)i * 6 + c] = (rand() / (double)RAND_MAX) - 0.5;
+        }
+        double *dA, *db, *dr; CK(cudaMalloc(&dA, hA.size() * 8)); CK(cudaMalloc(&db, hb.size() * 8)); CK(cudaMalloc(&dr, n * 8));
+        CK(cudaMemcpy(dA, hA.data(), hA.size() * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(db, hb.data(), hb.size() * 8, cudaMemcpyHostToDevice));
+        solve_check_kernel<<<(n + 127) / 128, 128>>>(dA, db, n, dr); CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(hr.data(), dr, n * 8, cudaMemcpyDeviceToHost));
+        double w = 0; for (int i = 0; i < n; ++i) w = hr[i] > w ? hr[i] : w;
+        printf("ldlt6_solve_fast vs ldlt6_solve on %d random SPD systems: max relative difference of x = %.3e\n", n, w);
+    }
+    run("solve only (thread 0, sums in smem)", solve_only_kernel<0>, p, 1, 1, false);
+    run("solve only, trimmed (rcp+Newton, series Rodrigues)", solve_only_kernel<1>, p, 1, 1, false);
     return 0;
 }
