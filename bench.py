@@ -200,6 +200,59 @@ def cpu_baseline_leg(frames, n_sample):
             "sample": f"{n_sample} frames of the same 640x480 -> 512^3 ICP workload, oracle/kt_oracle_cpu.cpp on {cores} std::threads ({dt:.1f} s)"}
 
 
+def shared_volume_leg(kb, torch, args, world, rank, local, device, dev_depth, dev_rgb, n, warmup):
+    """One RGB-D stream fused into ONE volume (BASELINE configs[3]: 1024^3) by all `world` GPUs: TSDF replicated (owner stores changed
+    voxels into every replica over NVLink from inside integrate_kernel), colour / weight planes block-cyclic, ray casting split into
+    image bands with the model-map all-gather as P2P stores in the kernel epilogue, ICP replicated; no collective library call on the
+    data path.  Strong scaling of one stream: frames/s of THE stream, max over ranks, CUDA events on the tracker stream."""
+    V = args.shared_vol
+    cfg = kb.Config.default(rows=ROWS, cols=COLS, vol=V, odometry=args.odometry, device=local, rank=rank if world > 1 else 0, world=world)
+    trk = kb.Tracker(cfg)
+    if world > 1:
+        from kintinuous_b200 import mgpu
+        mgpu.connect(trk)
+    steps = max(20, min(args.steps, 100))
+    prewarm = 40
+
+    def run(k, i):
+        for _ in range(k):
+            j = pingpong(i, n); jn = pingpong(i + 1, n)
+            trk.process_frame_device(dev_depth[j], dev_rgb[j], i)
+            if not args.no_prefetch:
+                trk.prefetch_frame(dev_depth[jn], dev_rgb[jn])
+            i += 1
+        return i
+    i = run(prewarm + warmup + 1, 0)
+    torch.cuda.synchronize(); barrier(world)
+    trk.span_mark(0)
+    i = run(steps, i)
+    trk.span_mark(1)
+    dt = trk.span_elapsed_ms() * 1e-3
+    torch.cuda.synchronize(); barrier(world)
+    dt = max_over_ranks(dt, world, device)
+    trk.set_stage_timing(True)
+    acc = np.zeros(6); m = 0
+    for _ in range(12):
+        j = pingpong(i, n); p = trk.process_frame_device(dev_depth[j], dev_rgb[j], i); i += 1
+        if p.shifted == 0:
+            acc += np.array(trk.stage_ms()); m += 1
+    st = (acc / max(1, m)).tolist()
+    info = trk.mgpu_info()
+    trk.close()
+    barrier(world)
+    P0 = ROWS * COLS
+    maps_bytes = sum((P0 >> (2 * l)) * 24 for l in range(4)) + P0 * 4
+    return {"value": steps / dt, "unit": "frames/s", "n_gpus": world, "vol": V, "steps": steps, "ms_per_step": 1e3 * dt / steps, "scaling": "strong",
+            "workload": f"ONE synthetic {COLS}x{ROWS} RGB-D stream into ONE {V}^3 volume (6 m) shared by {world} GPU(s), {TRACKER_NAMES[args.odometry]}",
+            "parallelism": ("single GPU" if world == 1 else
+                            f"TSDF plane replicated on {world} GPUs (owner stores changed voxels into every replica: NVLink P2P stores inside integrate_kernel), colour/weight planes block-cyclic "
+                            f"(blocks of {info['block']} storage z planes), ray cast split into {world} image bands with the model-map all-gather as P2P stores in the kernel epilogue, "
+                            "flag barriers in peer memory, ICP replicated; no NCCL call on the data path"),
+            "stages_ms_rank0": {nm: st[k] for k, nm in enumerate(["pyramid", "odometry", "shift", "integrate", "raycast"])},
+            "p2p_model_map_bytes_per_frame": int(maps_bytes * (world - 1)) if world > 1 else 0,
+            "arena_mb_per_gpu": info["arena_mb"]}
+
+
 def run_reference(args, world, rank, local):
     """--impl reference: the reference's own CUDA kernels behind the restated host loop (rank 0 only)."""
     if rank != 0:
@@ -265,6 +318,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=48)
     ap.add_argument("--no-prefetch", action="store_true", help="do not give the kt_prefetch_frame hint (A/B)")
+    ap.add_argument("--no-shared-volume", action="store_true", help="skip the extra one-stream / one-shared-1024^3-volume leg (the zslab sub-record)")
+    ap.add_argument("--shared-vol", type=int, default=1024)
     ap.add_argument("--vol", type=int, default=VOL)
     ap.add_argument("--scale", type=int, default=1, help="image scale: 1 = 640x480 (configs 1-3), 2 = 1280x960 (configs[4])")
     ap.add_argument("--odometry", type=int, default=0, help="0 ICP (configs[1]), 2 ICP+RGB-D (configs[2])")
@@ -363,6 +418,14 @@ def main():
             results["icp_kernel_ms"] = icp_ms / max(1, m)
         trk.close()
 
+    # ---- BASELINE configs[3]: ONE stream into ONE 1024^3 volume shared by all `world` GPUs (the north_star's multi-GPU design): a
+    # sub-record of the same JSON line at every N (N = 1: the single-GPU figure it is compared with) ----
+    shared = None
+    if args.mode == "streams" and not args.no_shared_volume and args.scale == 1:
+        try:
+            shared = shared_volume_leg(kb, torch, args, world, rank, local, device, dev_depth, dev_rgb, n, warmup)
+        except Exception as e:  # the headline number must survive a failure of the extra leg
+            shared = {"value": None, "error": str(e)[:300]}
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
@@ -425,6 +488,8 @@ def main():
                        "prewarm_frames": PREWARM, "untimed_frames_before_region": PREWARM + warmup + 1, "prefetch_hint": not args.no_prefetch, "l2": f"inputs larger than L2: {n} frames x {ROWS * COLS * 5 / 1e6:.2f} MB = {n * ROWS * COLS * 5 / 1e6:.0f} MB cycled (ping-pong)"},
             "e2e": {"value": e2e_v, "unit": "frames/s", "h2d_bytes_per_step": ROWS * COLS * 5, "d2h_bytes_per_step": 48},
             "gpu_launches": int(results["device"]["launches"]), "clocks": clocks, "roofline": roofline, "stages": stages}
+    if shared is not None:
+        line["zslab"] = shared
     if not args.no_cpu_baseline:
         try:
             line["cpu_baseline"] = cpu_baseline_leg(frames, args.cpu_sample)

@@ -134,18 +134,28 @@ KT_API float kt_get_icp_kernel_ms(kt_ctx* ctx);
  * marks (ms, synchronises on mark 1; < 0 on error).  bench.py times its region with this, not with the host clock. */
 KT_API int kt_span_mark(kt_ctx* ctx, int which);
 KT_API float kt_span_elapsed_ms(kt_ctx* ctx);
-/* ---- z-slab sharding of ONE volume over `world` GPUs, one process per GPU (no counterpart in the reference) ----
- * Every rank creates its context with kt_config.rank / world, exports the CUDA-IPC handle (64 bytes) of its shared arena
- * (volume slab, model maps, barrier flags), the host exchanges the handles (torch.distributed / MPI / anything) and every rank
- * calls kt_mgpu_connect with all `world` handles in rank order.  After that kt_process_frame must be called by all ranks with
- * the same frame; results (poses, model maps) are bit-identical on every rank and to the single-GPU run.  With world > 1,
- * kt_volume_export_reference_layout and the slices cover this rank's storage planes [rank*vol/world, (rank+1)*vol/world). */
+/* ---- ONE volume shared by `world` GPUs, one process per GPU (no counterpart in the reference) ----
+ * The TSDF plane is replicated on every GPU (the owner of a voxel stores its changed value into all replicas over NVLink, inside the
+ * integration kernel), the colour / weight plane is sharded by storage z plane, block-cyclically.  Every rank creates its context with
+ * kt_config.rank / world, exports the CUDA-IPC handle (64 bytes) of its shared arena (TSDF replica, colour planes, model maps, barrier
+ * flags), the host exchanges the handles (torch.distributed / MPI / anything) and every rank calls kt_mgpu_connect with all `world`
+ * handles in rank order.  After that kt_process_frame must be called by all ranks with the same frame; results (poses, model maps,
+ * TSDF replicas) are bit-identical on every rank and to the single-GPU run.  With world > 1, kt_volume_export_reference_layout and
+ * the slices cover the storage planes this rank owns (kt_mgpu_info: info5 = world, rank, planes owned, planes per ownership block,
+ * arena MB; local plane l is storage plane (l / B * world + rank) * B + l % B). */
 KT_API int kt_mgpu_arena_handle(kt_ctx* ctx, void* handle64);
 KT_API int kt_mgpu_connect(kt_ctx* ctx, const void* handles /* world x 64 bytes */, int world);
 KT_API int kt_mgpu_info(kt_ctx* ctx, int* info5);
+KT_API int kt_mgpu_export_tsdf_replica(kt_ctx* ctx, int16_t* tsdf_host /* vol^3 */);
 KT_API long long kt_launch_count(kt_ctx* ctx);
 /* debug: 64 x 5 clock64() stamps of the last whole-frame ICP launch (recorded only while stage timing is enabled) */
 KT_API int kt_debug_icp_profile(kt_ctx* ctx, long long* out512);
+/* getLiveImage (KintinuousTracker.cpp:835-862, 960-981, 1125-1154): shaded weight image (uchar3), colour image (uchar3) and model depth
+ * (u16 mm) of the surface predicted at the last pose; host buffers of rows*cols pixels, any may be NULL. */
+KT_API int kt_get_live_image(kt_ctx* ctx, uint8_t* shaded_rgb_host, uint8_t* color_rgb_host, uint16_t* model_depth_host);
+/* getLiveTsdf (.cpp:835-850, 1087-1123): surface points of the whole volume at this moment, without recording a slice.
+ * *count = points found (clamped to the cloud buffer capacity); up to max_points are copied. */
+KT_API int kt_get_live_tsdf(kt_ctx* ctx, kt_point_xyzrgb* points_host, size_t max_points, size_t* count);
 /* debug / parity tap: the arguments of the last integrateTsdfVolume call of the tracker (KintinuousTracker.cpp:864-876): Rcurr^-1
  * (9, row-major), tcurr after the shift adjustment (3), vWrapCopy (3).  Lets a test replay the frame with the reference's own
  * operators on the tracker's own poses and demand a bit-identical volume. */
@@ -160,6 +170,14 @@ KT_API int kt_op_create_vmap(const float* intr4, const uint16_t* depth_dev, floa
 KT_API int kt_op_create_nmap(const float* vmap_dev, float* nmap_dev, int rows, int cols, void* stream);                     /* createNMap (maps.cu:140) */
 /* fused createVMap + createNMap for one level (the product's own path) */
 KT_API int kt_op_create_maps(const float* intr4, const uint16_t* depth_dev, float* vmap_dev, float* nmap_dev, int rows, int cols, void* stream);
+/* The fused front end the tracker runs per frame, on caller buffers (2 launches): bilateralFilter + scaleDepth, then pyrDown x3,
+ * createVMap / createNMap x4, the per-pixel colour-integration inputs (cw: view-angle weight, sign = normal invalid; rgbf: float4 RGB)
+ * and -- when depth_m4 is not NULL -- shortDepthToMetres (cut-off 6 m), imageBGRToIntensity, pyrDownGaussF / pyrDownUcharGauss x3 and
+ * computeDerivativeImages x4 (bilateral_pyrdown.cu:60-420, maps.cu:57-155, tsdf_volume.cu:491-538,601-622).  Every *4 argument is an
+ * array of 4 device pointers (pyramid levels); depths4[0] receives the filtered depth.  cw / rgbf / depth_scaled may be NULL. */
+KT_API int kt_op_frontend(const uint16_t* depth_raw_dev, const uint8_t* rgb_dev, int rows, int cols, const float* intr4, int angle_color,
+                   uint16_t* const* depths4, float* const* vmaps4, float* const* nmaps4, float* depth_scaled_dev, float* cw_dev, float* rgbf_dev,
+                   float* const* depth_m4, uint8_t* const* intensity4, int16_t* const* dIdx4, int16_t* const* dIdy4, void* stream);
 KT_API int kt_op_transform_maps(const float* vmap_src, const float* nmap_src, const float* R9, const float* t3,
                          float* vmap_dst, float* nmap_dst, int rows, int cols, void* stream);                        /* tranformMaps (maps.cu:204) */
 KT_API int kt_op_resize_vmap(const float* in_dev, float* out_dev, int in_rows, int in_cols, void* stream);                  /* resizeVMap (maps.cu:299) */
@@ -198,6 +216,14 @@ KT_API int kt_op_rgb_residual(float min_scale, const int16_t* dIdx, const int16_
                        float max_depth_delta, const float* kt3, const float* krkinv9, int* sigma_sum, int* count, void* stream);
 KT_API int kt_op_rgb_step(const void* corres_dev, float sigma, const float* cloud_dev, float fx, float fy, const int16_t* dIdx, const int16_t* dIdy,
                    float sobel_scale, int rows, int cols, float* A_host, float* b_host, void* stream);
+
+/* generateImage (image_generator.cu:161-186): shaded weight heat-map image (dst) and colour image (dstColor) of the predicted surface,
+ * uchar3 each, either may be NULL; light = LightSource {pos[1], number}.  generateDepth (:187-230): model depth in mm from the model
+ * vertex map, row 3 of R^-1 and t (max_depth is unused there as well). */
+KT_API int kt_op_generate_image(const float* vmap_dev, const float* nmap_dev, const uint8_t* vmap_curr_color_dev, const float* light_pos3, int n_lights,
+                         uint8_t* dst_rgb_dev, uint8_t* dst_color_rgb_dev, int rows, int cols, void* stream);
+KT_API int kt_op_generate_depth(const float* Rcurr_inv9, const float* tcurr3, const float* vmap_dev, const float* nmap_dev, uint16_t* dst_dev,
+                         int rows, int cols, float max_depth, void* stream);
 
 #ifdef __cplusplus
 }

@@ -195,6 +195,20 @@ class Tracker:
         _check(self.lib.kt_download_map(self.h, which, level, _ptr(out)))
         return out
 
+    def live_image(self):
+        """getLiveImage: (shaded uint8 [rows, cols, 3], colour uint8 [rows, cols, 3], model depth uint16 [rows, cols])."""
+        r, c = self.cfg.rows, self.cfg.cols
+        a = np.zeros((r, c, 3), np.uint8); b = np.zeros((r, c, 3), np.uint8); d = np.zeros((r, c), np.uint16)
+        _check(self.lib.kt_get_live_image(self.h, _ptr(a), _ptr(b), _ptr(d)))
+        return a, b, d
+
+    def live_tsdf(self, max_points=None):
+        n = C.c_size_t(0)
+        cap = max_points if max_points is not None else 3 * self.cfg.rows * self.cfg.cols
+        pts = np.zeros(cap, dtype=POINT_DTYPE)
+        _check(self.lib.kt_get_live_tsdf(self.h, _ptr(pts), C.c_size_t(cap), C.byref(n)))
+        return pts[:min(cap, n.value)]
+
     def last_integrate(self):
         """(Rinv 3x3, t 3, wrap 3) of the last integration (kt_debug_last_integrate)."""
         R = np.zeros(9, np.float32); t = np.zeros(3, np.float32); w = np.zeros(3, np.int32)
@@ -235,14 +249,22 @@ class Tracker:
     def mgpu_info(self):
         info = (C.c_int * 5)()
         _check(self.lib.kt_mgpu_info(self.h, info))
-        return dict(world=info[0], rank=info[1], slab_planes=info[2], first_plane=info[3], arena_mb=info[4])
+        return dict(world=info[0], rank=info[1], planes=info[2], block=info[3], arena_mb=info[4])
 
-    def export_slab(self):
-        """This rank's storage planes of both volume planes (the whole volume when world == 1)."""
+    def export_owned(self):
+        """The storage planes this rank owns (the whole volume when world == 1), in local plane order: TSDF gathered out of the local
+        replica, colour / weight planes as stored.  mgpu.owned_planes() gives their storage z."""
         i = self.mgpu_info(); V = self.cfg.vol
-        t = np.empty((i["slab_planes"], V, V), dtype=np.int16); c = np.empty((i["slab_planes"], V, V, 4), dtype=np.uint8)
+        t = np.empty((i["planes"], V, V), dtype=np.int16); c = np.empty((i["planes"], V, V, 4), dtype=np.uint8)
         _check(self.lib.kt_volume_export_reference_layout(self.h, _ptr(t), _ptr(c)))
         return t, c
+
+    def export_tsdf_replica(self):
+        """The full local TSDF replica (world > 1: every rank holds all planes)."""
+        V = self.cfg.vol
+        t = np.empty((V, V, V), dtype=np.int16)
+        _check(self.lib.kt_mgpu_export_tsdf_replica(self.h, _ptr(t)))
+        return t
 
 
 class _Ops:
@@ -266,6 +288,17 @@ class _Ops:
 
     def create_maps(self, intr, depth, vmap, nmap, rows, cols):
         k = _f(intr); _check(self._l().kt_op_create_maps(_ptr(k), _ptr(depth), _ptr(vmap), _ptr(nmap), rows, cols, None))
+
+    def frontend(self, depth_raw, rgb, rows, cols, intr, angle_color, depths, vmaps, nmaps, depth_scaled=None, cw=None, rgbf=None,
+                 depth_m=None, intensity=None, dIdx=None, dIdy=None):
+        """The fused per-frame front end (2 launches) on caller buffers; every pyramid argument is a list of 4 CUDA tensors."""
+        k = _f(intr)
+        def arr(lst):
+            if lst is None:
+                return None
+            return (C.c_void_p * 4)(*[x.data_ptr() for x in lst])
+        _check(self._l().kt_op_frontend(_ptr(depth_raw), _ptr(rgb), rows, cols, _ptr(k), int(angle_color), arr(depths), arr(vmaps), arr(nmaps),
+                                        _ptr(depth_scaled), _ptr(cw), _ptr(rgbf), arr(depth_m), arr(intensity), arr(dIdx), arr(dIdy), None))
 
     def transform_maps(self, vs, ns, R, t, vd, nd, rows, cols):
         R = _f(R); t = _f(t)
@@ -337,6 +370,14 @@ class _Ops:
         _check(self._l().kt_op_rgb_residual(C.c_float(min_scale), _ptr(dIdx), _ptr(dIdy), _ptr(last_depth), _ptr(next_depth), _ptr(last_image), _ptr(next_image),
                                             _ptr(corres), rows, cols, C.c_float(max_depth_delta), _ptr(ktf), _ptr(kk), C.byref(sigma), C.byref(count), None))
         return sigma.value, count.value
+
+    def generate_image(self, vmap, nmap, vmap_color, light_pos, n_lights, dst, dst_color, rows, cols):
+        lp = _f(light_pos)
+        _check(self._l().kt_op_generate_image(_ptr(vmap), _ptr(nmap), _ptr(vmap_color), _ptr(lp), n_lights, _ptr(dst), _ptr(dst_color), rows, cols, None))
+
+    def generate_depth(self, Rinv, t, vmap, nmap, dst, rows, cols, max_depth=6.0):
+        Ri, tt = _f(Rinv), _f(t)
+        _check(self._l().kt_op_generate_depth(_ptr(Ri), _ptr(tt), _ptr(vmap), _ptr(nmap), _ptr(dst), rows, cols, C.c_float(max_depth), None))
 
     def rgb_step(self, corres, sigma, cloud, fx, fy, dIdx, dIdy, sobel_scale, rows, cols):
         A = np.zeros(36, np.float32); b = np.zeros(6, np.float32)

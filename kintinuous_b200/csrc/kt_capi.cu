@@ -85,6 +85,23 @@ int kt_op_create_maps(const float* k, const uint16_t* depth, float* vmap, float*
     KT_CUDA(cudaStreamSynchronize(st(s))); return KT_OK;
 }
 
+// the product's fused front end (bilateral_scale_kernel + frontend_pyramid_kernel) on caller buffers: what the tracker runs per frame
+int kt_op_frontend(const uint16_t* depth_raw, const uint8_t* rgb, int rows, int cols, const float* k, int angle_color,
+                   uint16_t* const* depths4, float* const* vmaps4, float* const* nmaps4, float* depth_scaled, float* cw, float* rgbf,
+                   float* const* depth_m4, uint8_t* const* intensity4, int16_t* const* dIdx4, int16_t* const* dIdy4, void* s)
+{
+    if (!depth_raw || !rgb || !depths4 || !vmaps4 || !nmaps4) { set_error("kt_op_frontend: null argument"); return KT_ERR_INVALID; }
+    int r = bilateral_scale(depth_raw, depths4[0], depth_scaled, rows, cols, intr4(k), angle_color != 0, st(s)); if (r) return r;
+    FrontendArgs fa;
+    fa.depth_f = depths4[0]; fa.depth_raw = depth_raw; fa.rgb = rgb; fa.rows = rows; fa.cols = cols; fa.k = intr4(k);
+    fa.depths = depths4; fa.vmaps = vmaps4; fa.nmaps = nmaps4; fa.vstale = 0; fa.nstale = 0;
+    fa.cw = cw; fa.rgbf = (float4*)rgbf; fa.angle_color = angle_color != 0; fa.cut_off = 6000;
+    fa.depth_m = depth_m4; fa.intensity = intensity4; fa.dIdx = dIdx4; fa.dIdy = dIdy4;
+    r = frontend_pyramid(fa, st(s)); if (r) return r;
+    KT_CUDA(cudaStreamSynchronize(st(s)));
+    return KT_OK;
+}
+
 int kt_op_transform_maps(const float* vs, const float* ns, const float* R, const float* t, float* vd, float* nd, int rows, int cols, void* s)
 { int r = transform_maps(vs, ns, mat33(R), make_float3(t[0], t[1], t[2]), vd, nd, rows, cols, st(s)); if (r) return r; KT_CUDA(cudaStreamSynchronize(st(s))); return KT_OK; }
 
@@ -121,11 +138,11 @@ int kt_op_integrate(const uint16_t* depth_raw, int rows, int cols, const float* 
     KT_OPS_LOCK();
     int r = ensure_ztable(vol); if (r) return r;
     r = scale_depth(depth_raw, depth_scaled, rows, cols, intr4(k), angle_color != 0, st(s)); if (r) return r;
-    IntegrateArgs a; a.cw = 0; a.rgbf = 0; a.reset_words = 0; a.reset_count = 0;
+    IntegrateArgs a; a.cw = 0; a.rgbf = 0; a.reset_words = 0; a.reset_count = 0; a.reset_stride = 1;
     a.depth_scaled = depth_scaled; a.rows = rows; a.cols = cols; a.k = intr4(k); a.volume_size = make_float3(vs[0], vs[1], vs[2]);
     a.Rinv = mat33(Rinv); a.t = make_float3(t[0], t[1], t[2]); a.trunc = trunc; a.tsdf = tsdf; a.color = color; a.vol = vol;
     a.wrap = make_int3(wrap[0], wrap[1], wrap[2]); a.rgb = rgb; a.nmap_curr = nmap_curr; a.angle_color = angle_color != 0;
-    a.z_begin = 0; a.z_end = vol;
+    a.multi = 0; a.vv = single_volume(tsdf, color, vol);
     r = integrate(a, g_ops.ztable, st(s)); if (r) return r;
     KT_CUDA(cudaStreamSynchronize(st(s)));
     return KT_OK;
@@ -204,6 +221,20 @@ int kt_op_rgb_residual(float min_scale, const int16_t* dIdx, const int16_t* dIdy
     KT_CUDA(cudaStreamSynchronize(st(s)));
     *count = res[0]; *sigma_sum = res[1];
     return KT_OK;
+}
+
+int kt_op_generate_image(const float* vmap, const float* nmap, const uint8_t* vmap_curr_color, const float* light_pos3, int n_lights,
+                         uint8_t* dst_rgb, uint8_t* dst_color_rgb, int rows, int cols, void* s)
+{
+    int r = generate_views(vmap, nmap, vmap_curr_color, rows, cols, light_pos3, n_lights, dst_rgb, dst_color_rgb, 0, 0, 0, st(s)); if (r) return r;
+    KT_CUDA(cudaStreamSynchronize(st(s))); return KT_OK;
+}
+
+int kt_op_generate_depth(const float* Rinv9, const float* t3, const float* vmap, const float* nmap, uint16_t* dst, int rows, int cols, float max_depth, void* s)
+{
+    (void)max_depth;                               // unused by the reference kernel too (image_generator.cu:187-211)
+    int r = generate_views(vmap, nmap, 0, rows, cols, 0, 0, 0, 0, Rinv9, t3, dst, st(s)); if (r) return r;
+    KT_CUDA(cudaStreamSynchronize(st(s))); return KT_OK;
 }
 
 int kt_op_rgb_step(const void* corres, float sigma, const float* cloud, float fx, float fy, const int16_t* dIdx, const int16_t* dIdy,

@@ -19,7 +19,7 @@ namespace {
 
 struct ExtractParams {
     const int16_t* tsdf; const uchar4* color; int V; int3 wrap; int3 real_wrap; float3 cell;
-    VolumeView vv; int multi; int z_begin, z_end;          // sharded volume: emit only for voxels of the local slab
+    VolumeView vv; int multi;                              // shared volume: emit only for voxels of the storage planes this rank owns
     int minX, maxX, minY, maxY, minZ, maxZ, subsample;
     uint4* out; unsigned int capacity; unsigned int* counter;
 };
@@ -33,11 +33,11 @@ __device__ __forceinline__ size_t vox_addr(const ExtractParams& p, int x, int y,
 __device__ __forceinline__ float fetch(const ExtractParams& p, int x, int y, int z, int& weight, uchar4& c)
 {
     if (p.multi) {
+        // TSDF from the local replica; colour / weight from the plane's owner (local memory or NVLink peer)
         const int sx = (x + p.wrap.x) % p.V, sy = (y + p.wrap.y) % p.V, sz = (z + p.wrap.z) % p.V;
-        const int owner = sz >> p.vv.slab_shift, lz = sz & (p.vv.slab_z - 1);
-        const size_t a = ((size_t)lz * p.V + sy) * p.V + sx;
-        float tsdf = unpack_tsdf(__ldg(p.vv.tsdf[owner] + a));
-        c = __ldg(reinterpret_cast<const uchar4*>(p.vv.color[owner]) + a);
+        float tsdf = unpack_tsdf(__ldg(&p.tsdf[((size_t)sz * p.V + sy) * p.V + sx]));
+        const size_t a = ((size_t)vv_local_plane(p.vv, sz) * p.V + sy) * p.V + sx;
+        c = __ldg(reinterpret_cast<const uchar4*>(p.vv.color[vv_owner(p.vv, sz)]) + a);
         weight = c.w;
         return tsdf;
     }
@@ -87,7 +87,7 @@ extract_kernel(const ExtractParams p)
             const int y = p.minY + (int)(r % ny);
             const int z = p.minZ + (int)(r / ny);
             bool mine = true;
-            if (p.multi) { const int sz = (z + p.wrap.z) % p.V; mine = (sz >= p.z_begin && sz < p.z_end); }
+            if (p.multi) { const int sz = (z + p.wrap.z) % p.V; mine = vv_owner(p.vv, sz) == p.vv.rank; }
             if (mine && x < p.V && y < p.V && x % p.subsample == 0 && y % p.subsample == 0 && (z - p.minZ) % p.subsample == 0) {
                 uchar4 c;
                 float F = fetch(p, x, y, z, W, c);
@@ -159,7 +159,7 @@ int extract_slice(const int16_t* tsdf, const float3& volume_size, int vol, void*
     if (maxX <= minX || maxY <= minY || maxZ <= minZ) return 0;
     ExtractParams p;
     p.tsdf = tsdf; p.color = (const uchar4*)color; p.V = vol; p.wrap = wrap_mod3(wrap, vol); p.real_wrap = real_wrap;
-    p.multi = 0; p.z_begin = 0; p.z_end = vol;
+    p.multi = 0; p.vv = single_volume(const_cast<int16_t*>(tsdf), const_cast<uint8_t*>(color), vol);
     p.cell = make_float3(volume_size.x / vol, volume_size.y / vol, volume_size.z / vol);
     p.minX = minX; p.maxX = maxX; p.minY = minY; p.maxY = maxY; p.minZ = minZ; p.maxZ = maxZ; p.subsample = subsample < 1 ? 1 : subsample;
     p.out = (uint4*)out; p.capacity = (unsigned int)capacity; p.counter = counter_dev;
@@ -181,7 +181,7 @@ int extract_slice_mg(const VolumeView& vv, const float3& volume_size, int vol, v
     p.cell = make_float3(volume_size.x / vol, volume_size.y / vol, volume_size.z / vol);
     p.minX = minX; p.maxX = maxX; p.minY = minY; p.maxY = maxY; p.minZ = minZ; p.maxZ = maxZ; p.subsample = subsample < 1 ? 1 : subsample;
     p.out = (uint4*)out; p.capacity = (unsigned int)capacity; p.counter = counter_dev;
-    p.vv = vv; p.multi = 1; p.z_begin = vv.rank * vv.slab_z; p.z_end = p.z_begin + vv.slab_z;
+    p.vv = vv; p.multi = 1;
     size_t total = (size_t)(maxX - minX) * (maxY - minY) * (maxZ - minZ);
     size_t blocks = (total + 255) / 256;
     int grid = (int)(blocks < (size_t)148 * 16 ? blocks : (size_t)148 * 16);

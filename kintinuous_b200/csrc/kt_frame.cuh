@@ -22,14 +22,14 @@ __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int tar
 
 // ---- grid-wide sum of the CTAs' 29 partial sums without a barrier, a fence or a second pass over per-CTA partials ----
 // One 64-bit word per component (two sets, by iteration parity; XW_STRIDE 8-byte units apart so that the words live in different L2
-// slices).  Every CTA adds  round(partial * 2^32) with the low 8 bits cleared, plus 1  to the word with ONE fire-and-forget atomic: the
+// slices: 2400 cycles per exchange at 1280 B against 3700 with the words packed).  Every CTA adds  round(partial * 2^32) with the low 8 bits cleared, plus 1  to the word with ONE fire-and-forget atomic: the
 // low byte of (word now - word when this set was last complete) therefore counts the CTAs that have arrived, and the rest is the exact
 // integer sum of their partials.  Integer addition commutes, so the total is bit-identical in every CTA and from run to run whatever
 // the arrival order; its resolution (2^-24 absolute per CTA) is finer than the float partials' own rounding for every entry that
 // matters to the solve.  Latency: one atomic to L2 plus one poll round trip after the LAST CTA arrived
 // (measured with tools/tail_bench.cu against the counter barrier + partial re-read it replaces).
 // Requirements: gridDim.x <= 255; the words are zero when the launch starts (the host keeps them so, kt_tracker.cu).
-enum { XW_STRIDE = 32, XW_WORDS = 2 * 32 * XW_STRIDE };
+enum { XW_STRIDE = 160, XW_WORDS = 2 * 32 * XW_STRIDE };     // 1280 B apart: measured best of 8 / 256 / 1280 / 2304 / 4352 / 16640 B (tools/tail_bench.cu)
 
 __device__ __forceinline__ void red_add_u64(unsigned long long* p, unsigned long long v)
 { asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory"); }

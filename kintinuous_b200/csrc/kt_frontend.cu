@@ -20,12 +20,13 @@
 // Bound: HBM streaming of the outputs (51 B per level-0 pixel ICP-only, 74 B with the photometric set), latency of three
 // dependent in-CTA levels.
 #include "kt_ops.h"
+#include "kt_frontend.cuh"
 
 namespace kt {
 
 namespace {
 
-enum { FE_TW = 64, FE_TH = 32, FE_THREADS = 256 };
+enum { FE_TW = 64, FE_TH = 32, FE_THREADS = 512 };
 
 // geometry of the computed region per level (in that level's pixels): owned tile + HL pixels left / top + HR pixels right / bottom
 template <bool RGBD, int L> struct FeL {
@@ -47,122 +48,6 @@ struct FrontendParams {
 };
 
 #define KT_RGB_VIEW_ANGLE_WEIGHT 0.75f
-
-// pyrDownGaussKernel (bilateral_pyrdown.cu:102-136): edge-aware 5x5 {.375, .25, .0625} decimation of the filtered depth.
-// src(y, x): the finer level; (x, y): destination pixel; all products are exact in float (dyadic weights x 16-bit integers).
-template <class Src>
-__device__ __forceinline__ uint16_t pyrdown_depth_px(const Src& src, int x, int y, int srows, int scols)
-{
-    const float sigma_color3 = 3 * 30.f;                   // 3 * sigma_color (bilateral_pyrdown.cu:56,121)
-    const int center = src(2 * y, 2 * x);
-    const int x_mi = max(0, 2 * x - 2) - 2 * x, y_mi = max(0, 2 * y - 2) - 2 * y;
-    const int x_ma = min(scols, 2 * x + 3) - 2 * x, y_ma = min(srows, 2 * y + 3) - 2 * y;
-    const float weights[3] = {0.375f, 0.25f, 0.0625f};
-    float sum = 0, wall = 0;
-#pragma unroll
-    for (int yi = -2; yi <= 2; ++yi)
-#pragma unroll
-        for (int xi = -2; xi <= 2; ++xi) {
-            if (yi < y_mi || yi >= y_ma || xi < x_mi || xi >= x_ma) continue;
-            const int val = src(2 * y + yi, 2 * x + xi);
-            if (abs(val - center) < sigma_color3) {
-                const float w = weights[xi < 0 ? -xi : xi] * weights[yi < 0 ? -yi : yi];
-                sum += val * w;
-                wall += w;
-            }
-        }
-    return (uint16_t)static_cast<int>(sum / wall);
-}
-
-// pyrDownKernelGaussF / pyrDownKernelIntensityGauss (bilateral_pyrdown.cu:172-233): {1,4,6,4,1}^2 decimation whose window
-// [max(0, 2x-2), min(2x+3, scols-1)) excludes the last column / row (Q1), whose weight index runs from the clipped END of the window,
-// and whose weight sum is accumulated in an int (Q2).
-__device__ __forceinline__ int gauss5(int r, int c)
-{
-    const int g[5] = {1, 4, 6, 4, 1};
-    return g[r] * g[c];
-}
-template <class Src>
-__device__ __forceinline__ float pyrdown_float_px(const Src& src, int x, int y, int srows, int scols)
-{
-    const int tx = min(2 * x + 3, scols - 1), ty = min(2 * y + 3, srows - 1);
-    const int cx0 = max(0, 2 * x - 2), cy0 = max(0, 2 * y - 2);
-    float sum = 0; int count = 0;
-#pragma unroll
-    for (int dy = 0; dy < 5; ++dy)
-#pragma unroll
-        for (int dx = 0; dx < 5; ++dx) {
-            const int cy = cy0 + dy, cxx = cx0 + dx;
-            if (cy >= ty || cxx >= tx) continue;
-            const float v = src(cy, cxx);
-            if (!isnan(v)) {
-                const int g = gauss5(ty - cy - 1, tx - cxx - 1);
-                sum = __fmaf_rn(v, (float)g, sum);
-                count += g;
-            }
-        }
-    return (float)(sum / (float)count);
-}
-template <class Src>
-__device__ __forceinline__ uint8_t pyrdown_uchar_px(const Src& src, int x, int y, int srows, int scols)
-{
-    const int tx = min(2 * x + 3, scols - 1), ty = min(2 * y + 3, srows - 1);
-    const int cx0 = max(0, 2 * x - 2), cy0 = max(0, 2 * y - 2);
-    float sum = 0; int count = 0;
-#pragma unroll
-    for (int dy = 0; dy < 5; ++dy)
-#pragma unroll
-        for (int dx = 0; dx < 5; ++dx) {
-            const int cy = cy0 + dy, cxx = cx0 + dx;
-            if (cy >= ty || cxx >= tx) continue;
-            const int g = gauss5(ty - cy - 1, tx - cxx - 1);
-            sum += (float)((int)src(cy, cxx) * g);                   // <= 255 * 36: exact
-            count += g;
-        }
-    return (uint8_t)(sum / (float)count);
-}
-
-// applyKernel (bilateral_pyrdown.cu:274-298): the 3x3 gradient pair; the tap index walks 8..0 over the taps actually visited
-__device__ __forceinline__ float gsx_tap(int k) { const float t[9] = {0.52201f, 0.00000f, -0.52201f, 0.79451f, -0.00000f, -0.79451f, 0.52201f, 0.00000f, -0.52201f}; return t[k]; }
-__device__ __forceinline__ float gsy_tap(int k) { const float t[9] = {0.52201f, 0.79451f, 0.52201f, 0.00000f, 0.00000f, 0.00000f, -0.52201f, -0.79451f, -0.52201f}; return t[k]; }
-template <class Src>
-__device__ __forceinline__ void gradient_px(const Src& src, int x, int y, int rows, int cols, int16_t& gx, int16_t& gy)
-{
-    float dxVal = 0, dyVal = 0;
-    const int j0 = max(y - 1, 0), j1 = min(y + 1, rows - 1), i0 = max(x - 1, 0), i1 = min(x + 1, cols - 1);
-    if (j0 == y - 1 && j1 == y + 1 && i0 == x - 1 && i1 == x + 1) {
-        int k = 8;
-#pragma unroll
-        for (int j = -1; j <= 1; ++j)
-#pragma unroll
-            for (int i = -1; i <= 1; ++i) {
-                const float v = (float)src(y + j, x + i);
-                dxVal = __fmaf_rn(v, gsx_tap(k), dxVal);
-                dyVal = __fmaf_rn(v, gsy_tap(k), dyVal);
-                --k;
-            }
-    } else {
-        const float tx9[9] = {0.52201f, 0.00000f, -0.52201f, 0.79451f, -0.00000f, -0.79451f, 0.52201f, 0.00000f, -0.52201f};
-        const float ty9[9] = {0.52201f, 0.79451f, 0.52201f, 0.00000f, 0.00000f, 0.00000f, -0.52201f, -0.79451f, -0.52201f};
-        int k = 8;
-        for (int j = j0; j <= j1; ++j)
-            for (int i = i0; i <= i1; ++i) {
-                const float v = (float)src(j, i);
-                dxVal = __fmaf_rn(v, tx9[k], dxVal);
-                dyVal = __fmaf_rn(v, ty9[k], dyVal);
-                --k;
-            }
-    }
-    gx = (int16_t)dxVal; gy = (int16_t)dyVal;
-}
-
-// computeVmapKernel's vertex (maps.cu:57-80) from a depth value
-__device__ __forceinline__ bool vertex_of(int d, int u, int v, float fx_inv, float fy_inv, float cx, float cy, float3& out)
-{
-    const float z = d / 1000.f;
-    if (z != 0) { out.x = z * (u - cx) * fx_inv; out.y = z * (v - cy) * fy_inv; out.z = z; return true; }
-    return false;
-}
 
 // a level's shared-memory tile addressed in that level's GLOBAL pixel coordinates
 template <class T> struct Tile {
@@ -228,7 +113,7 @@ __device__ __forceinline__ void fe_level(const FrontendParams& p, const FeSmem& 
                 const bool ok01 = vertex_of(td(v, u + 1), u + 1, v, fx_inv, fy_inv, cx, cy, v01);
                 const bool ok10 = vertex_of(td(v + 1, u), u, v + 1, fx_inv, fy_inv, cx, cy, v10);
                 if (ok01 && ok10) {
-                    const float3 n = normalized3(cross3(sub3(v01, v00), sub3(v10, v00)));
+                    const float3 n = normalized3(cross3(diff3(v01, v00), diff3(v10, v00)));
                     nm[gi] = n.x; nm[gi + P] = n.y; nm[gi + 2 * P] = n.z;
                     okn = true; nx_seen = n.x; nz_seen = n.z;
                 }
@@ -286,14 +171,8 @@ frontend_pyramid_kernel(const FrontendParams p)
             sm.sd[0][i] = (in && p.depth_f) ? p.depth_f[gi] : (uint16_t)0;
             if (RGBD) {
                 const int raw = in ? (int)p.depth_raw[gi] : 0;
-                sm.sf[0][i] = (raw > p.cut_off || raw <= 0) ? qnan() : ((float)raw) / 1000.0f;     // short2FloatKernel, bilateral_pyrdown.cu:235-245
-                uint8_t iv = 0;
-                if (in) {                                                                             // bgr2IntensityKernel, :247-259 (PixelRGB {r,g,b})
-                    const uchar3 c = p.rgb[gi];
-                    const int value = __fmaf_rn((float)c.y, 0.587f, __fmaf_rn((float)c.x, 0.114f, __fmul_rn((float)c.z, 0.299f)));
-                    iv = (uint8_t)value;
-                }
-                sm.si[0][i] = iv;
+                sm.sf[0][i] = depth_to_metres(raw, p.cut_off);
+                sm.si[0][i] = in ? rgb_to_intensity(p.rgb[gi]) : (uint8_t)0;
             }
         }
     }

@@ -8,17 +8,28 @@ namespace kt {
 static const int LEVELS = 4;                 // ICPOdometry.h:52 / RGBDOdometry.h:96
 static const int MAX_GPUS = 8;
 
-// How a kernel reaches any voxel of the (possibly z-slab sharded) volume: rank g owns the storage planes
-// [g * slab_z, (g + 1) * slab_z); tsdf[g] / color[g] point at the first voxel of that slab -- local memory for g == rank,
-// CUDA-IPC mapped peer memory (NVLink P2P) otherwise.  Single GPU: world = 1, slab_z = V.
+// How the kernels reach the volume when it is shared by `world` GPUs (one process per GPU, peers mapped through CUDA IPC / NVLink).
+//   * the TSDF plane (2 B / voxel) is REPLICATED: every rank holds all V^3 shorts; the owner of a voxel computes its update and stores a
+//     CHANGED value into every replica (P2P stores inside integrate_kernel), so ray casting -- ~100 dependent scattered TSDF reads per
+//     ray -- never leaves local HBM;
+//   * the colour / weight plane (4 B / voxel, the weight in .w) is SHARDED by storage z plane, block-cyclically: planes are dealt to the
+//     ranks in blocks of 2^bshift (owner = (sz >> bshift) mod world), so that whatever part of the volume the camera looks at, every
+//     rank owns an equal share of the voxels to integrate; it is read remotely only for the trilinear colour tap of a ray's hit point
+//     and for the neighbour voxels of an extraction at block edges.
+// Ownership is a property of the STORAGE plane, hence invariant under volume shifting.  Single GPU: world = 1 (owner 0, local plane = sz).
 struct VolumeView {
-    int16_t* tsdf[MAX_GPUS]; uint8_t* color[MAX_GPUS];
-    int world, rank, slab_z, slab_shift;
+    int16_t* tsdf[MAX_GPUS];      // every rank's full replica (V^3 shorts); [rank] is local memory
+    uint8_t* color[MAX_GPUS];     // every rank's own colour planes (V^2 * V / world uchar4), local plane order
+    int world, rank, bshift, nshift;
 };
+__host__ __device__ __forceinline__ int vv_owner(const VolumeView& v, int sz) { return (sz >> v.bshift) & (v.world - 1); }
+__host__ __device__ __forceinline__ int vv_local_plane(const VolumeView& v, int sz)
+{ return ((sz >> (v.bshift + v.nshift)) << v.bshift) | (sz & ((1 << v.bshift) - 1)); }
 inline VolumeView single_volume(int16_t* tsdf, uint8_t* color, int V)
 {
+    (void)V;
     VolumeView v; for (int g = 0; g < MAX_GPUS; ++g) { v.tsdf[g] = tsdf; v.color[g] = color; }
-    v.world = 1; v.rank = 0; v.slab_z = V; v.slab_shift = 0; int t = V; while (t > 1) { t >>= 1; ++v.slab_shift; }
+    v.world = 1; v.rank = 0; v.bshift = 0; v.nshift = 0;
     return v;
 }
 
@@ -49,6 +60,10 @@ struct FrontendArgs {
 int frontend_pyramid(const FrontendArgs& a, cudaStream_t s);
 // bilateralFilter + scaleDepth in one launch (they share the raw-depth tile); either output may be null
 int bilateral_scale(const uint16_t* src, uint16_t* dst, float* scaled, int rows, int cols, const Intr& k, bool angle_color, cudaStream_t s);
+
+// ---- GUI taps (kt_views.cu): generateImage + generateDepth in one launch; any of the three outputs may be null ----
+int generate_views(const float* vmap, const float* nmap, const uint8_t* vmap_color, int rows, int cols, const float* light_pos3, int n_lights,
+                   uint8_t* dst_rgb, uint8_t* dst_color_rgb, const float* Rinv9, const float* t3, uint16_t* depth, cudaStream_t s);
 
 // ---- RGB-D preprocessing (kt_rgb.cu) ----
 int short_depth_to_metres(const uint16_t* src, float* dst, int rows, int cols, int cut_off, cudaStream_t s);
@@ -91,7 +106,8 @@ int icp_frame(const IcpLevelArgs* levels, const int* iters, const float* pose12_
               float* trace, int* timeout_dev, long long* prof_dev, cudaStream_t s);
 // exchange words of the whole-frame odometry kernels (grid_sum_words, kt_frame.cuh): their count, and the reset (zero) of a word array --
 // stream-ordered, once per frame between two odometry launches
-size_t odom_exchange_words();
+size_t odom_exchange_words();          // allocation size (64-bit words)
+int odom_exchange_used(int* stride);   // number of words actually used, and their spacing
 int odom_exchange_reset(unsigned long long* xwords_dev, cudaStream_t s);
 
 struct RgbLevelArgs {
@@ -112,17 +128,17 @@ int reduce_grid_for(int n_items);
 
 // ---- volume (kt_tsdf.cu, kt_raycast.cu, kt_extract.cu) ----
 int init_volume(int16_t* tsdf, uint8_t* color, int vol, cudaStream_t s);                  // whole volume
-int init_slab(int16_t* tsdf_local, uint8_t* color_local, int vol, int slab_z, cudaStream_t s);
+int init_shared(const VolumeView& vv, int vol, cudaStream_t s);       // this rank's TSDF replica and colour planes
 int clear_volume(int axis, int back, int16_t* tsdf, uint8_t* color, int vol, int current_wrap, int delta_wrap, cudaStream_t s);
-// sharded: tsdf_local / color_local are this rank's slab (storage planes [z_begin, z_end))
-int clear_volume_slab(int axis, int back, int16_t* tsdf_local, uint8_t* color_local, int vol, int z_begin, int z_end, int current_wrap, int delta_wrap, cudaStream_t s);
+// shared volume: the TSDF planes of the local replica and the colour planes this rank owns
+int clear_volume_shared(int axis, int back, const VolumeView& vv, int vol, int current_wrap, int delta_wrap, cudaStream_t s);
 int scale_depth(const uint16_t* depth, float* scaled, int rows, int cols, const Intr& k, bool angle_color, cudaStream_t s);
 struct IntegrateArgs {
     const float* depth_scaled; int rows, cols; Intr k; float3 volume_size; Mat33 Rinv; float3 t; float trunc;
     int16_t* tsdf; uint8_t* color; int vol; int3 wrap; const uint8_t* rgb; const float* nmap_curr; bool angle_color;
-    int z_begin, z_end;          // storage-z slab owned by this GPU ([0, vol) on a single GPU)
+    int multi; VolumeView vv;    // multi != 0: the volume is shared by vv.world GPUs (tsdf / color above are vv.tsdf[rank] / vv.color[rank])
     float* cw; float4* rgbf;     // optional per-pixel scratch (rows*cols each): colour weight + float RGB prepared once per frame
-    unsigned long long* reset_words; int reset_count;   // optional: 64-bit words the launch's prologue kernel zeroes (the odometry's exchange words)
+    unsigned long long* reset_words; int reset_count, reset_stride;   // optional: reset_count 64-bit words, reset_stride apart, that the launch's prologue kernel zeroes (the odometry's exchange words)
 };
 int integrate(const IntegrateArgs& a, float* ztable_dev /* 2*vol floats */, cudaStream_t s);
 // per-pixel colour weight (sign = normal invalid) + float RGB for IntegrateArgs::cw / rgbf; once per frame, after the normal map exists
@@ -139,7 +155,7 @@ int raycast(const RaycastArgs& a, cudaStream_t s);
 int extract_slice(const int16_t* tsdf, const float3& volume_size, int vol, void* out, size_t capacity, const int3& wrap,
                   const uint8_t* color, int minX, int maxX, int minY, int maxY, int minZ, int maxZ, int subsample,
                   const int3& real_wrap, unsigned int* counter_dev, cudaStream_t s);
-// sharded: only voxels whose storage plane lies in this rank's slab emit points; neighbours are read through vv (P2P at slab edges)
+// shared volume: only voxels whose storage plane this rank owns emit points; colours of foreign planes are read through vv (P2P)
 int extract_slice_mg(const VolumeView& vv, const float3& volume_size, int vol, void* out, size_t capacity, const int3& wrap,
                      int minX, int maxX, int minY, int maxY, int minZ, int maxZ, int subsample,
                      const int3& real_wrap, unsigned int* counter_dev, cudaStream_t s);

@@ -14,6 +14,7 @@
 // Roofline: HBM-bound streaming except the bilateral filter, which is instruction-issue / MUFU(ex2)-bound
 // (169 __expf per pixel, 9 instructions per tap); algorithmic bytes: DESIGN.md section 4.
 #include "kt_ops.h"
+#include "kt_frontend.cuh"
 
 namespace kt {
 
@@ -147,50 +148,15 @@ bilateral_scale_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ 
     dst[(size_t)y * cols + x] = (uint16_t)max(0, min(res, 32767));
 }
 
+// pyrDown (bilateral_pyrdown.cu:102-136, :345-354) at operator level: one thread per output pixel around pyrdown_depth_px
+// (kt_frontend.cuh), the function the tracker's fused front end evaluates on shared-memory tiles.
 __global__ void __launch_bounds__(256)
-pyrdown_gauss_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst, int srows, int scols, int drows, int dcols, float sigma_color)
+pyrdown_gauss_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst, int srows, int scols, int drows, int dcols)
 {
-    int x = blockIdx.x * blockDim.x + threadIdx.x;
-    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= dcols || y >= drows) return;
-    const int D = 5;
-    int center = src[(size_t)(2 * y) * scols + 2 * x];
-    int x_mi = max(0, 2 * x - D / 2) - 2 * x;
-    int y_mi = max(0, 2 * y - D / 2) - 2 * y;
-    int x_ma = min(scols, 2 * x - D / 2 + D) - 2 * x;
-    int y_ma = min(srows, 2 * y - D / 2 + D) - 2 * y;
-    float sum = 0, wall = 0;
-    const float weights[3] = {0.375f, 0.25f, 0.0625f};
-    if (x_mi == -2 && y_mi == -2 && x_ma == 3 && y_ma == 3) {
-        // interior: the 25 loads are issued together; same taps in the same order (all products of these dyadic weights with
-        // a 16-bit integer are exact in float, so the accumulation is bit-identical to the general loop)
-        int vals[25];
-#pragma unroll
-        for (int yi = -2; yi <= 2; ++yi)
-#pragma unroll
-            for (int xi = -2; xi <= 2; ++xi) vals[(yi + 2) * 5 + xi + 2] = src[(size_t)(2 * y + yi) * scols + 2 * x + xi];
-#pragma unroll
-        for (int yi = -2; yi <= 2; ++yi)
-#pragma unroll
-            for (int xi = -2; xi <= 2; ++xi) {
-                const int val = vals[(yi + 2) * 5 + xi + 2];
-                if (abs(val - center) < 3 * sigma_color) {
-                    sum += val * weights[xi < 0 ? -xi : xi] * weights[yi < 0 ? -yi : yi];
-                    wall += weights[xi < 0 ? -xi : xi] * weights[yi < 0 ? -yi : yi];
-                }
-            }
-        dst[(size_t)y * dcols + x] = (uint16_t)static_cast<int>(sum / wall);
-        return;
-    }
-    for (int yi = y_mi; yi < y_ma; ++yi)
-        for (int xi = x_mi; xi < x_ma; ++xi) {
-            int val = src[(size_t)(2 * y + yi) * scols + 2 * x + xi];
-            if (abs(val - center) < 3 * sigma_color) {
-                sum += val * weights[abs(xi)] * weights[abs(yi)];
-                wall += weights[abs(xi)] * weights[abs(yi)];
-            }
-        }
-    dst[(size_t)y * dcols + x] = (uint16_t)static_cast<int>(sum / wall);
+    const GlobalSrc<uint16_t> s = {src, scols};
+    dst[(size_t)y * dcols + x] = pyrdown_depth_px(s, x, y, srows, scols);
 }
 
 __device__ __forceinline__ bool vertex_from_depth(const uint16_t* __restrict__ depth, int cols, int u, int v,
@@ -198,8 +164,8 @@ __device__ __forceinline__ bool vertex_from_depth(const uint16_t* __restrict__ d
 {
     float z = depth[(size_t)v * cols + u] / 1000.f;        // mm -> m
     if (z != 0) {
-        out.x = z * (u - cx) * fx_inv;
-        out.y = z * (v - cy) * fy_inv;
+        out.x = __fmul_rn(__fmul_rn(z, (u - cx)), fx_inv);        // rounded products: never fused with the normal's differences (kt_frontend.cuh)
+        out.y = __fmul_rn(__fmul_rn(z, (v - cy)), fy_inv);
         out.z = z;
         return true;
     }
@@ -231,7 +197,7 @@ nmap_kernel(const float* __restrict__ vmap, float* __restrict__ nmap, int rows, 
     if (!isnan(v00.x) && !isnan(v01.x) && !isnan(v10.x)) {
         v00.y = vmap[i + P]; v01.y = vmap[i + 1 + P]; v10.y = vmap[i + cols + P];
         v00.z = vmap[i + 2 * P]; v01.z = vmap[i + 1 + 2 * P]; v10.z = vmap[i + cols + 2 * P];
-        float3 r = normalized3(cross3(sub3(v01, v00), sub3(v10, v00)));
+        float3 r = normalized3(cross3(diff3(v01, v00), diff3(v10, v00)));
         nmap[i] = r.x; nmap[i + P] = r.y; nmap[i + 2 * P] = r.z;
     } else nmap[i] = qnan();
 }
@@ -265,7 +231,7 @@ maps_pyramid_kernel(const MapsParams p)
         bool ok01 = vertex_from_depth(L.depth, cols, u + 1, v, fx_inv, fy_inv, cx, cy, v01);
         bool ok10 = vertex_from_depth(L.depth, cols, u, v + 1, fx_inv, fy_inv, cx, cy, v10);
         if (ok01 && ok10) {
-            float3 n = normalized3(cross3(sub3(v01, v00), sub3(v10, v00)));
+            float3 n = normalized3(cross3(diff3(v01, v00), diff3(v10, v00)));
             nm[i] = n.x; nm[i + P] = n.y; nm[i + 2 * P] = n.z;
             okn = true;
         }
@@ -355,7 +321,7 @@ int pyrdown(const uint16_t* src, uint16_t* dst, int srows, int scols, cudaStream
 {
     int drows = srows / 2, dcols = scols / 2;
     dim3 block(32, 8), grid(div_up(dcols, 32), div_up(drows, 8));
-    pyrdown_gauss_kernel<<<grid, block, 0, s>>>(src, dst, srows, scols, drows, dcols, SIGMA_COLOR);
+    pyrdown_gauss_kernel<<<grid, block, 0, s>>>(src, dst, srows, scols, drows, dcols);
     KT_LAUNCH_CHECK();
     return 0;
 }

@@ -46,15 +46,10 @@ struct Caster {
         int sz = z + p.wrap.z; if (sz >= p.V) sz -= p.V;
         return ((IdxT)sz * p.V + sy) * p.V + sx;
     }
-    // sharded volume: slab owner = storage z >> slab_shift; the pointer table holds local or NVLink-peer (CUDA IPC) addresses
+    // shared volume (MG): the TSDF is replicated, so the march and every trilinear TSDF tap read LOCAL memory exactly as on one GPU; only
+    // the colour / weight planes are sharded (block-cyclic by storage z): local memory or an NVLink peer (CUDA IPC) through the table
     __device__ __forceinline__ short rawTsdf(int x, int y, int z) const
     {
-        if (MG) {
-            const int m = p.V - 1;
-            const unsigned int sx = (x + p.wrap.x) & m, sy = (y + p.wrap.y) & m, sz = (z + p.wrap.z) & m;
-            const unsigned int lz = sz & (p.vv.slab_z - 1);
-            return __ldg(p.vv.tsdf[sz >> p.vv.slab_shift] + ((((size_t)lz << shift) | sy) << shift | sx));
-        }
         return __ldg(&p.volume[addr(x, y, z)]);
     }
     __device__ __forceinline__ float readTsdf(int x, int y, int z) const { return unpack_tsdf(rawTsdf(x, y, z)); }
@@ -63,8 +58,8 @@ struct Caster {
         if (MG) {
             const int m = p.V - 1;
             const unsigned int sx = (x + p.wrap.x) & m, sy = (y + p.wrap.y) & m, sz = (z + p.wrap.z) & m;
-            const unsigned int lz = sz & (p.vv.slab_z - 1);
-            return __ldg(reinterpret_cast<const uchar4*>(p.vv.color[sz >> p.vv.slab_shift]) + ((((size_t)lz << shift) | sy) << shift | sx));
+            const unsigned int lz = (unsigned int)vv_local_plane(p.vv, (int)sz);
+            return __ldg(reinterpret_cast<const uchar4*>(p.vv.color[vv_owner(p.vv, (int)sz)]) + ((((size_t)lz << shift) | sy) << shift | sx));
         }
         return __ldg(&p.color_volume[addr(x, y, z)]);
     }
@@ -397,11 +392,15 @@ int raycast(const RaycastArgs& a, cudaStream_t s)
     static const bool force64 = getenv("KT_FORCE_IDX64") != nullptr;     // test hook, see kt_tsdf.cu
     const bool idx32 = !force64 && (size_t)a.vol * a.vol * a.vol <= ((size_t)1 << 31);
     if (a.multi) {
-        if (!pow2 || (a.vv.slab_z & (a.vv.slab_z - 1))) { set_error("raycast: the sharded volume needs power-of-two V and slab"); return -1; }
+        if (!pow2) { set_error("raycast: the shared volume needs a power-of-two resolution"); return -1; }
         p.vv = a.vv; p.tile_row_begin = a.tile_row_begin; p.n_out = a.vv.world;
+        p.volume = a.vv.tsdf[a.vv.rank];                      // the local TSDF replica
         for (int g = 0; g < MAX_GPUS; ++g) { for (int l = 0; l < LEVELS; ++l) { p.peer_vmap[g][l] = a.peer_vmap[g][l]; p.peer_nmap[g][l] = a.peer_nmap[g][l]; } p.peer_vcol[g] = (uchar4*)a.peer_vcol[g]; }
         grid.y = a.tile_row_end - a.tile_row_begin;
-        if (grid.y > 0) raycast_kernel<true, size_t, 8, 8, true><<<grid, block, 0, s>>>(p);
+        if (grid.y > 0) {
+            if (idx32) raycast_kernel<true, unsigned int, 8, 8, true><<<grid, block, 0, s>>>(p);
+            else raycast_kernel<true, size_t, 8, 8, true><<<grid, block, 0, s>>>(p);
+        }
     }
     else if (pow2 && idx32) {
         // 8 speculative steps per batch at 8 CTAs/SM; measured and dropped: 4 steps per batch (72.3 vs 68.2 us), 10 CTAs/SM (73.2 us, spills)

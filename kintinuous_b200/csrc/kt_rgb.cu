@@ -21,113 +21,47 @@
 #include "kt_solve.cuh"
 #include "kt_reduce.cuh"
 #include "kt_frame.cuh"
+#include "kt_frontend.cuh"
 
 namespace kt {
 
 namespace {
 
+// Operator-level pre-processing kernels (kt_op_short_depth_to_metres / _bgr_to_intensity / _pyrdown_gauss_f / _pyrdown_uchar_gauss /
+// _derivative_images / _project_to_point_cloud): one thread per output pixel around the per-pixel functions of kt_frontend.cuh -- the
+// same functions the tracker's fused front end evaluates on shared-memory tiles (tests/test_gpu_ops.py holds the two bit-identical).
+enum PreOp { PRE_METRES, PRE_INTENSITY, PRE_DOWN_F, PRE_DOWN_U8, PRE_GRADIENT };
+struct PreParams { const void* src; void* dst; void* dst2; int rows, cols, srows, scols, cut_off; };
+
+template <int OP>
 __global__ void __launch_bounds__(256)
-short2float_kernel(const uint16_t* __restrict__ src, float* __restrict__ dst, int rows, int cols, int cutOff)
+preprocess_kernel(const PreParams p)
 {
-    int x = blockIdx.x * blockDim.x + threadIdx.x;
-    int y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= cols || y >= rows) return;
-    size_t i = (size_t)y * cols + x;
-    dst[i] = src[i] > cutOff || src[i] <= 0 ? qnan() : ((float)src[i]) / 1000.0f;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= p.cols || y >= p.rows) return;
+    const size_t i = (size_t)y * p.cols + x;
+    if (OP == PRE_METRES) ((float*)p.dst)[i] = depth_to_metres((int)((const uint16_t*)p.src)[i], p.cut_off);
+    else if (OP == PRE_INTENSITY) ((uint8_t*)p.dst)[i] = rgb_to_intensity(((const uchar3*)p.src)[i]);
+    else if (OP == PRE_DOWN_F) { const GlobalSrc<float> s = {(const float*)p.src, p.scols}; ((float*)p.dst)[i] = pyrdown_float_px(s, x, y, p.srows, p.scols); }
+    else if (OP == PRE_DOWN_U8) { const GlobalSrc<uint8_t> s = {(const uint8_t*)p.src, p.scols}; ((uint8_t*)p.dst)[i] = pyrdown_uchar_px(s, x, y, p.srows, p.scols); }
+    else {
+        const GlobalSrc<uint8_t> s = {(const uint8_t*)p.src, p.cols};
+        int16_t gx, gy;
+        gradient_px(s, x, y, p.rows, p.cols, gx, gy);
+        ((int16_t*)p.dst)[i] = gx; ((int16_t*)p.dst2)[i] = gy;
+    }
 }
 
-__global__ void __launch_bounds__(256)
-bgr2intensity_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int rows, int cols)
-{
-    int x = blockIdx.x * blockDim.x + threadIdx.x;
-    int y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= cols || y >= rows) return;
-    size_t i = (size_t)y * cols + x;
-    const uint8_t r = src[i * 3 + 0], g = src[i * 3 + 1], b = src[i * 3 + 2];     // PixelRGB {r,g,b}
-    int value = (float)r * 0.114f + (float)b * 0.299f + (float)g * 0.587f;
-    dst[i] = value;
-}
-
-__constant__ float c_gauss5[25] = {1, 4, 6, 4, 1, 4, 16, 24, 16, 4, 6, 24, 36, 24, 6, 4, 16, 24, 16, 4, 1, 4, 6, 4, 1};
-
-__global__ void __launch_bounds__(256)
-pyrdown_gauss_f_kernel(const float* __restrict__ src, float* __restrict__ dst, int srows, int scols, int drows, int dcols)
-{
-    int x = blockIdx.x * blockDim.x + threadIdx.x;
-    int y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= dcols || y >= drows) return;
-    const int D = 5;
-    int tx = min(2 * x - D / 2 + D, scols - 1);
-    int ty = min(2 * y - D / 2 + D, srows - 1);
-    int cy = max(0, 2 * y - D / 2);
-    float sum = 0;
-    int count = 0;                                             // Q2: float weights accumulate into an int
-    for (; cy < ty; ++cy)
-        for (int cx = max(0, 2 * x - D / 2); cx < tx; ++cx) {
-            float v = src[(size_t)cy * scols + cx];
-            if (!isnan(v)) {
-                sum += v * c_gauss5[(ty - cy - 1) * 5 + (tx - cx - 1)];
-                count += c_gauss5[(ty - cy - 1) * 5 + (tx - cx - 1)];
-            }
-        }
-    dst[(size_t)y * dcols + x] = (float)(sum / (float)count);
-}
-
-__global__ void __launch_bounds__(256)
-pyrdown_uchar_gauss_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int srows, int scols, int drows, int dcols)
-{
-    int x = blockIdx.x * blockDim.x + threadIdx.x;
-    int y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= dcols || y >= drows) return;
-    const int D = 5;
-    int tx = min(2 * x - D / 2 + D, scols - 1);
-    int ty = min(2 * y - D / 2 + D, srows - 1);
-    int cy = max(0, 2 * y - D / 2);
-    float sum = 0;
-    int count = 0;
-    for (; cy < ty; ++cy)
-        for (int cx = max(0, 2 * x - D / 2); cx < tx; ++cx) {
-            sum += src[(size_t)cy * scols + cx] * c_gauss5[(ty - cy - 1) * 5 + (tx - cx - 1)];
-            count += c_gauss5[(ty - cy - 1) * 5 + (tx - cx - 1)];
-        }
-    dst[(size_t)y * dcols + x] = (sum / (float)count);
-}
-
-__constant__ float c_gsx[9] = {0.52201f, 0.00000f, -0.52201f, 0.79451f, -0.00000f, -0.79451f, 0.52201f, 0.00000f, -0.52201f};
-__constant__ float c_gsy[9] = {0.52201f, 0.79451f, 0.52201f, 0.00000f, 0.00000f, 0.00000f, -0.52201f, -0.79451f, -0.52201f};
-
-__global__ void __launch_bounds__(256)
-derivative_kernel(const uint8_t* __restrict__ src, int16_t* __restrict__ dx, int16_t* __restrict__ dy, int rows, int cols)
-{
-    int x = threadIdx.x + blockIdx.x * blockDim.x;
-    int y = threadIdx.y + blockIdx.y * blockDim.y;
-    if (x >= cols || y >= rows) return;
-    float dxVal = 0, dyVal = 0;
-    int kernelIndex = 8;                                        // walks 8..0 over the taps actually visited (border quirk kept)
-    for (int j = max(y - 1, 0); j <= min(y + 1, rows - 1); j++)
-        for (int i = max(x - 1, 0); i <= min(x + 1, cols - 1); i++) {
-            dxVal += (float)src[(size_t)j * cols + i] * c_gsx[kernelIndex];
-            dyVal += (float)src[(size_t)j * cols + i] * c_gsy[kernelIndex];
-            --kernelIndex;
-        }
-    dx[(size_t)y * cols + x] = dxVal;
-    dy[(size_t)y * cols + x] = dyVal;
-}
-
+// projectToPointCloud (maps.cu:311-345): last-frame depth -> float3 point, intrinsics in double
 __global__ void __launch_bounds__(256)
 project_points_kernel(const float* __restrict__ depth, float3* __restrict__ cloud, int rows, int cols,
                       const double invFx, const double invFy, const double cx, const double cy)
 {
-    int x = blockIdx.x * blockDim.x + threadIdx.x;
-    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= cols || y >= rows) return;
-    size_t i = (size_t)y * cols + x;
-    float z = depth[i];
-    float3 c;
-    c.x = (float)((x - cx) * z * invFx);
-    c.y = (float)((y - cy) * z * invFy);
-    c.z = z;
-    cloud[i] = c;
+    const size_t i = (size_t)y * cols + x;
+    const float z = depth[i];
+    cloud[i] = make_float3((float)((x - cx) * z * invFx), (float)((y - cy) * z * invFy), z);
 }
 
 // 16-byte correspondence record, byte-compatible with the reference's DataTerm (cuda/internal.h:90-96)
@@ -608,19 +542,19 @@ rgbd_frame_kernel(const RgbdFrameParams p)
 #define KT_GRID2D(cols, rows) dim3 block(32, 8), grid(div_up(cols, 32), div_up(rows, 8))
 
 int short_depth_to_metres(const uint16_t* src, float* dst, int rows, int cols, int cut_off, cudaStream_t s)
-{ KT_GRID2D(cols, rows); short2float_kernel<<<grid, block, 0, s>>>(src, dst, rows, cols, cut_off); KT_LAUNCH_CHECK(); return 0; }
+{ KT_GRID2D(cols, rows); PreParams p = {src, dst, 0, rows, cols, rows, cols, cut_off}; preprocess_kernel<PRE_METRES><<<grid, block, 0, s>>>(p); KT_LAUNCH_CHECK(); return 0; }
 
 int bgr_to_intensity(const uint8_t* rgb, uint8_t* dst, int rows, int cols, cudaStream_t s)
-{ KT_GRID2D(cols, rows); bgr2intensity_kernel<<<grid, block, 0, s>>>(rgb, dst, rows, cols); KT_LAUNCH_CHECK(); return 0; }
+{ KT_GRID2D(cols, rows); PreParams p = {rgb, dst, 0, rows, cols, rows, cols, 0}; preprocess_kernel<PRE_INTENSITY><<<grid, block, 0, s>>>(p); KT_LAUNCH_CHECK(); return 0; }
 
 int pyrdown_gauss_f(const float* src, float* dst, int srows, int scols, cudaStream_t s)
-{ int dr = srows / 2, dc = scols / 2; KT_GRID2D(dc, dr); pyrdown_gauss_f_kernel<<<grid, block, 0, s>>>(src, dst, srows, scols, dr, dc); KT_LAUNCH_CHECK(); return 0; }
+{ int dr = srows / 2, dc = scols / 2; KT_GRID2D(dc, dr); PreParams p = {src, dst, 0, dr, dc, srows, scols, 0}; preprocess_kernel<PRE_DOWN_F><<<grid, block, 0, s>>>(p); KT_LAUNCH_CHECK(); return 0; }
 
 int pyrdown_uchar_gauss(const uint8_t* src, uint8_t* dst, int srows, int scols, cudaStream_t s)
-{ int dr = srows / 2, dc = scols / 2; KT_GRID2D(dc, dr); pyrdown_uchar_gauss_kernel<<<grid, block, 0, s>>>(src, dst, srows, scols, dr, dc); KT_LAUNCH_CHECK(); return 0; }
+{ int dr = srows / 2, dc = scols / 2; KT_GRID2D(dc, dr); PreParams p = {src, dst, 0, dr, dc, srows, scols, 0}; preprocess_kernel<PRE_DOWN_U8><<<grid, block, 0, s>>>(p); KT_LAUNCH_CHECK(); return 0; }
 
 int derivative_images(const uint8_t* src, int16_t* dx, int16_t* dy, int rows, int cols, cudaStream_t s)
-{ KT_GRID2D(cols, rows); derivative_kernel<<<grid, block, 0, s>>>(src, dx, dy, rows, cols); KT_LAUNCH_CHECK(); return 0; }
+{ KT_GRID2D(cols, rows); PreParams p = {src, dx, dy, rows, cols, rows, cols, 0}; preprocess_kernel<PRE_GRADIENT><<<grid, block, 0, s>>>(p); KT_LAUNCH_CHECK(); return 0; }
 
 int project_to_point_cloud(const float* depth, float* cloud, int rows, int cols, double fx, double fy, double cx, double cy, cudaStream_t s)
 {

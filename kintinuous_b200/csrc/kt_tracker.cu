@@ -128,14 +128,16 @@ struct kt_ctx {
     bool timing; cudaEvent_t ev[7]; float stage_ms[6]; cudaEvent_t ev_icp[2]; cudaEvent_t ev_span[2];
     long long launches_at_create;
     std::vector<void*> allocs;
-    // z-slab sharding over `world` GPUs (one process per GPU; peers' arenas are mapped through CUDA IPC)
-    int world, rank, slab_z, z_begin, z_end;
+    // ONE volume shared by `world` GPUs (one process per GPU; peers' arenas are mapped through CUDA IPC): TSDF plane replicated, colour /
+    // weight plane sharded block-cyclically by storage z (VolumeView, kt_ops.h)
+    int world, rank, local_planes, mg_block;
     uint8_t* arena; size_t arena_bytes;
     size_t off_tsdf, off_color, off_vmap[LEVELS], off_nmap[LEVELS], off_vcol, off_flags;
     uint8_t* peer_arena[MAX_GPUS]; bool connected;
     unsigned int** peer_flags_dev; unsigned int epoch; int* mg_error_dev; int* mg_error_host;
     VolumeView vv;
     float last_int_Rinv[9], last_int_t[3]; int last_int_wrap[3];       // arguments of the last integration (kt_debug_last_integrate)
+    uint8_t* view_dev;                                                  // GUI taps: shaded image, colour image, model depth (allocated on first use)
 };
 
 namespace {
@@ -196,8 +198,8 @@ int do_integrate(kt_ctx* c, const M3& Rinv, const V3& t, const int* wrap)
     a.rgb = c->rgb; a.nmap_curr = c->nmaps_curr[0]; a.angle_color = c->cfg.angle_color != 0;
     for (int k = 0; k < 9; ++k) c->last_int_Rinv[k] = Rinv.m[k];
     for (int k = 0; k < 3; ++k) { c->last_int_t[k] = t.v[k]; c->last_int_wrap[k] = wrap[k]; }
-    a.reset_words = c->xwords_dev; a.reset_count = (int)odom_exchange_words(); c->xwords_clean = true;       // the prologue launch of integrate() zeroes them
-    a.z_begin = c->z_begin; a.z_end = c->z_end; a.cw = c->color_prepared ? c->cw_scratch : 0; a.rgbf = c->color_prepared ? (float4*)c->rgbf_scratch : 0;
+    a.reset_words = c->xwords_dev; a.reset_count = odom_exchange_used(&a.reset_stride); c->xwords_clean = true;       // the prologue launch of integrate() zeroes them
+    a.multi = c->world > 1 ? 1 : 0; a.vv = c->vv; a.cw = c->color_prepared ? c->cw_scratch : 0; a.rgbf = c->color_prepared ? (float4*)c->rgbf_scratch : 0;
     return integrate(a, c->ztable, c->stream);
 }
 
@@ -404,7 +406,7 @@ int process_frame_device(kt_ctx* c, uint64_t utime, kt_pose* out)
         if (cycled) {
             if ((r = fetch_cloud(c, vWrapCopy, lo, hi))) return r;
             if ((r = mg_barrier(c))) return r;                          // peers may still read my boundary plane for their extraction
-            if ((r = clear_volume_slab(axis, dir < 0 ? 1 : 0, c->tsdf, c->color, V, c->z_begin, c->z_end, c->voxelWrap[axis], c->voxelWrap[axis] + n, c->stream))) return r;
+            if ((r = clear_volume_shared(axis, dir < 0 ? 1 : 0, c->vv, V, c->voxelWrap[axis], c->voxelWrap[axis] + n, c->stream))) return r;
         }
         if (cycled) {                                                                    // mutexOutCloudBuffer (.cpp:1156-1208)
             int vt[3] = {0, 0, 0}; vt[axis] = n;
@@ -420,6 +422,8 @@ int process_frame_device(kt_ctx* c, uint64_t utime, kt_pose* out)
         }
     }
     vwrap_copy(c, vWrapCopy);
+    // shared volume: every rank has cleared the leaving planes of ITS TSDF replica before any peer's integration stores into it
+    if (c->shifted_last && (r = mg_barrier(c))) return r;
     mark(c, 3);
 
     if ((r = do_integrate(c, Rcurr_inv, tcurr, vWrapCopy))) return r;                    // .cpp:864-876
@@ -481,7 +485,7 @@ int kt_reset(kt_ctx* c)
     c->pf_valid = false; c->pf_built = false; c->frontend_ready = false; c->maps_on_stream = false;
     if (c->stream_copy) cudaStreamSynchronize(c->stream_copy);
     if (c->mg_error_dev) { KT_CUDA(cudaMemsetAsync(c->mg_error_dev, 0, sizeof(int), c->stream)); *c->mg_error_host = 0; }      // a timed-out cross-GPU barrier is not sticky across resets
-    int r = init_slab(c->tsdf, c->color, c->cfg.vol, c->slab_z, c->stream);
+    int r = init_shared(c->vv, c->cfg.vol, c->stream);
     if (r) return r;
     // Q7: stale y/z planes of invalid pixels start from a defined state (zeros)
     const size_t P = (size_t)c->cfg.rows * c->cfg.cols;
@@ -506,7 +510,7 @@ int kt_create(const kt_config* cfg, kt_ctx** out)
     if (cfg->world > 1) {
         const int w = cfg->world;
         if (w > MAX_GPUS || (w & (w - 1)) || cfg->rank < 0 || cfg->rank >= w || (cfg->vol & (cfg->vol - 1)) || cfg->vol / w < 2) {
-            set_error("kt_create: z-slab sharding needs world in {2,4,8}, 0 <= rank < world and a power-of-two vol"); return KT_ERR_INVALID; }
+            set_error("kt_create: a shared volume needs world in {2,4,8}, 0 <= rank < world and a power-of-two vol"); return KT_ERR_INVALID; }
     }
     if (!kt_cuda_available()) { set_error("kt_create: no CUDA device (this library has no CPU path)"); return KT_ERR_CUDA; }
     KT_CUDA(cudaSetDevice(cfg->device));
@@ -535,12 +539,18 @@ int kt_create(const kt_config* cfg, kt_ctx** out)
     const size_t P = (size_t)cfg->rows * cfg->cols;
     {   // shared arena: local volume slab, model maps, raycast colour, barrier flags -- one allocation, one IPC handle
         c->world = cfg->world > 1 ? cfg->world : 1; c->rank = cfg->world > 1 ? cfg->rank : 0;
-        c->slab_z = cfg->vol / c->world; c->z_begin = c->rank * c->slab_z; c->z_end = c->z_begin + c->slab_z;
+        c->local_planes = cfg->vol / c->world;
+        // colour planes are dealt to the ranks in blocks of mg_block storage planes (KT_MG_BLOCK, default 8): small enough that any
+        // viewing frustum spreads evenly over the ranks, large enough to amortise the jump over the foreign blocks in integrate_kernel
+        c->mg_block = 8;
+        if (const char* e = getenv("KT_MG_BLOCK")) { int b = atoi(e); if (b >= 1 && (b & (b - 1)) == 0) c->mg_block = b; }
+        while (c->mg_block > 1 && c->mg_block * c->world > cfg->vol) c->mg_block >>= 1;
+        if (c->world == 1) c->mg_block = 1;
         auto al = [](size_t x) { return (x + 255) / 256 * 256; };
         size_t off = 0;
-        const size_t slab_vox = (size_t)cfg->vol * cfg->vol * c->slab_z;
-        c->off_tsdf = off; off = al(off + slab_vox * 2);
-        c->off_color = off; off = al(off + slab_vox * 4);
+        const size_t plane_vox = (size_t)cfg->vol * cfg->vol;
+        c->off_tsdf = off; off = al(off + plane_vox * cfg->vol * 2);                   // full replica
+        c->off_color = off; off = al(off + plane_vox * c->local_planes * 4);            // this rank's planes
         for (int l = 0; l < LEVELS; ++l) { size_t Pl = P >> (2 * l); c->off_vmap[l] = off; off = al(off + Pl * 12); c->off_nmap[l] = off; off = al(off + Pl * 12); }
         c->off_vcol = off; off = al(off + P * 4);
         c->off_flags = off; off = al(off + 256);
@@ -552,7 +562,9 @@ int kt_create(const kt_config* cfg, kt_ctx** out)
         c->connected = (c->world == 1);
         c->epoch = 0;
         c->vv = single_volume(c->tsdf, c->color, cfg->vol);
-        c->vv.world = c->world; c->vv.rank = c->rank; c->vv.slab_z = c->slab_z; c->vv.slab_shift = 0; { int t = c->slab_z; while (t > 1) { t >>= 1; ++c->vv.slab_shift; } }
+        c->vv.world = c->world; c->vv.rank = c->rank;
+        c->vv.bshift = 0; { int t = c->mg_block; while (t > 1) { t >>= 1; ++c->vv.bshift; } }
+        c->vv.nshift = 0; { int t = c->world; while (t > 1) { t >>= 1; ++c->vv.nshift; } }
         KT_TRY(dev_alloc(c, &c->peer_flags_dev, (size_t)MAX_GPUS)); KT_TRY(dev_alloc(c, &c->mg_error_dev, 1));
         KT_TRY(kt::cuda_check(cudaMemset(c->mg_error_dev, 0, sizeof(int)), "memset", __FILE__, __LINE__));
         KT_TRY(kt::cuda_check(cudaMallocHost((void**)&c->mg_error_host, sizeof(int)), "pinned", __FILE__, __LINE__)); *c->mg_error_host = 0;
@@ -784,9 +796,22 @@ int kt_volume_export_reference_layout(kt_ctx* c, int16_t* tsdf_host, uint8_t* co
     if (!c) return KT_ERR_INVALID;
     KT_CUDA(cudaSetDevice(c->cfg.device));
     KT_CUDA(cudaStreamSynchronize(c->stream));
-    const size_t n = (size_t)c->cfg.vol * c->cfg.vol * c->slab_z;       // sharded: this rank's slab (storage planes [rank*V/world, ...))
-    if (tsdf_host) KT_CUDA(cudaMemcpy(tsdf_host, c->tsdf, n * 2, cudaMemcpyDeviceToHost));
-    if (color_host) KT_CUDA(cudaMemcpy(color_host, c->color, n * 4, cudaMemcpyDeviceToHost));
+    const size_t plane = (size_t)c->cfg.vol * c->cfg.vol;
+    if (c->world == 1) {
+        if (tsdf_host) KT_CUDA(cudaMemcpy(tsdf_host, c->tsdf, plane * c->cfg.vol * 2, cudaMemcpyDeviceToHost));
+        if (color_host) KT_CUDA(cudaMemcpy(color_host, c->color, plane * c->cfg.vol * 4, cudaMemcpyDeviceToHost));
+        return KT_OK;
+    }
+    // shared volume: the storage planes this rank OWNS, in local plane order (kt_mgpu_info gives the block size; local plane l is storage
+    // plane ((l / B * world + rank) * B + l % B); the TSDF planes are gathered out of the local replica
+    if (color_host) KT_CUDA(cudaMemcpy(color_host, c->color, plane * c->local_planes * 4, cudaMemcpyDeviceToHost));
+    if (tsdf_host) {
+        const int B = c->mg_block;
+        for (int l0 = 0; l0 < c->local_planes; l0 += B) {
+            const size_t sz0 = (size_t)((l0 / B) * c->world + c->rank) * B;
+            KT_CUDA(cudaMemcpy(tsdf_host + (size_t)l0 * plane, c->tsdf + sz0 * plane, plane * B * 2, cudaMemcpyDeviceToHost));
+        }
+    }
     return KT_OK;
 }
 
@@ -859,10 +884,19 @@ int kt_mgpu_connect(kt_ctx* c, const void* handles, int n)
     return KT_OK;
 }
 
-int kt_mgpu_info(kt_ctx* c, int* info5)       // world, rank, slab planes, first storage plane, arena bytes (MB)
+int kt_mgpu_info(kt_ctx* c, int* info5)       // world, rank, colour planes owned, planes per ownership block, arena bytes (MB)
 {
     if (!c || !info5) return KT_ERR_INVALID;
-    info5[0] = c->world; info5[1] = c->rank; info5[2] = c->slab_z; info5[3] = c->z_begin; info5[4] = (int)(c->arena_bytes >> 20);
+    info5[0] = c->world; info5[1] = c->rank; info5[2] = c->local_planes; info5[3] = c->mg_block; info5[4] = (int)(c->arena_bytes >> 20);
+    return KT_OK;
+}
+
+int kt_mgpu_export_tsdf_replica(kt_ctx* c, int16_t* tsdf_host)      // the full local TSDF replica, storage order (test tap)
+{
+    if (!c || !tsdf_host) return KT_ERR_INVALID;
+    KT_CUDA(cudaSetDevice(c->cfg.device));
+    KT_CUDA(cudaStreamSynchronize(c->stream));
+    KT_CUDA(cudaMemcpy(tsdf_host, c->tsdf, (size_t)c->cfg.vol * c->cfg.vol * c->cfg.vol * 2, cudaMemcpyDeviceToHost));
     return KT_OK;
 }
 
@@ -889,6 +923,43 @@ float kt_span_elapsed_ms(kt_ctx* c)
     float t = 0.f;
     if (cudaEventSynchronize(c->ev_span[1]) != cudaSuccess || cudaEventElapsedTime(&t, c->ev_span[0], c->ev_span[1]) != cudaSuccess) { cudaGetLastError(); return -1.f; }
     return t;
+}
+
+// getLiveImage (KintinuousTracker.cpp:835-862, 960-981, 1125-1154): shaded weight image, colour image and model depth of the predicted
+// surface at the last pose.  One launch on the tracker's stream + one copy; any output may be NULL.
+int kt_get_live_image(kt_ctx* c, uint8_t* shaded_rgb_host, uint8_t* color_rgb_host, uint16_t* model_depth_host)
+{
+    if (!c) return KT_ERR_INVALID;
+    KT_CUDA(cudaSetDevice(c->cfg.device));
+    const size_t P = (size_t)c->cfg.rows * c->cfg.cols;
+    if (!c->view_dev) { int r = dev_alloc(c, &c->view_dev, P * 8); if (r) return r; }
+    uint8_t* shaded = c->view_dev; uint8_t* col = c->view_dev + P * 3; uint16_t* dep = (uint16_t*)(c->view_dev + P * 6);
+    const float light[3] = {c->size * -3.f, c->size * -3.f, c->size * -3.f};
+    const M3 Rinv = m3_inverse(c->rmats.back());
+    int r = generate_views(c->vmaps_g_prev[0], c->nmaps_g_prev[0], c->vmap_curr_color, c->cfg.rows, c->cfg.cols, light, 1,
+                           shaded_rgb_host ? shaded : 0, color_rgb_host ? col : 0, Rinv.m, c->tvecs.back().v, model_depth_host ? dep : 0, c->stream);
+    if (r) return r;
+    if (shaded_rgb_host) KT_CUDA(cudaMemcpyAsync(shaded_rgb_host, shaded, P * 3, cudaMemcpyDeviceToHost, c->stream));
+    if (color_rgb_host) KT_CUDA(cudaMemcpyAsync(color_rgb_host, col, P * 3, cudaMemcpyDeviceToHost, c->stream));
+    if (model_depth_host) KT_CUDA(cudaMemcpyAsync(model_depth_host, dep, P * 2, cudaMemcpyDeviceToHost, c->stream));
+    KT_CUDA(cudaStreamSynchronize(c->stream));
+    return KT_OK;
+}
+
+// getLiveTsdf (KintinuousTracker.cpp:835-850, 1087-1123): the whole volume's surface points without recording a slice.
+int kt_get_live_tsdf(kt_ctx* c, kt_point_xyzrgb* points, size_t max_points, size_t* count)
+{
+    if (!c) return KT_ERR_INVALID;
+    KT_CUDA(cudaSetDevice(c->cfg.device));
+    int vWrapCopy[3]; vwrap_copy(c, vWrapCopy);
+    const int V = c->cfg.vol;
+    int lo[3] = {0, 0, 0}, hi[3] = {V, V, V};
+    int r = fetch_cloud(c, vWrapCopy, lo, hi);
+    if (r) return r;
+    if (count) *count = c->cloud_count;
+    const size_t n = std::min(max_points, c->cloud_count);
+    if (points && n) KT_CUDA(cudaMemcpy(points, c->cloud_dev, n * sizeof(kt_point_xyzrgb), cudaMemcpyDeviceToHost));
+    return KT_OK;
 }
 
 int kt_debug_last_integrate(kt_ctx* c, float* Rinv9, float* t3, int* wrap3)

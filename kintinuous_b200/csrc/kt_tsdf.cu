@@ -37,8 +37,10 @@ __global__ void __launch_bounds__(256) fill_zero_u4(uint4* __restrict__ p, size_
 
 // Clear `count` consecutive storage planes [p0, p0+count) (mod V) along `axis` in both volumes.
 // Work item = 8 consecutive x voxels (16 B of tsdf, 32 B of colour) for the y / z axes.
+// Shared volume (vv.world > 1): the TSDF planes of the local replica are all cleared here (every rank clears its own replica, no
+// traffic), the colour planes only where this rank owns the storage z plane.
 __global__ void __launch_bounds__(256)
-clear_planes_yz_kernel(int16_t* __restrict__ tsdf, uint8_t* __restrict__ color, int V, int axis, int p0, int count, int zb, int ze)
+clear_planes_yz_kernel(int16_t* __restrict__ tsdf, uint8_t* __restrict__ color, int V, int axis, int p0, int count, const VolumeView vv)
 {
     const int xg = V / 8;                                   // groups of 8 voxels per row
     const size_t total = (size_t)count * V * xg;
@@ -51,27 +53,26 @@ clear_planes_yz_kernel(int16_t* __restrict__ tsdf, uint8_t* __restrict__ color, 
         int plane = p0 + i; if (plane >= V) plane -= V;
         int sy = axis == 1 ? plane : other;
         int sz = axis == 1 ? other : plane;
-        if (sz < zb || sz >= ze) continue;                    // not this rank's slab
-        size_t base = ((size_t)(sz - zb) * V + sy) * V + (size_t)g * 8;
-        *reinterpret_cast<uint4*>(tsdf + base) = z4;
+        *reinterpret_cast<uint4*>(tsdf + ((size_t)sz * V + sy) * V + (size_t)g * 8) = z4;
+        if (vv_owner(vv, sz) != vv.rank) continue;            // not this rank's colour plane
+        size_t base = ((size_t)vv_local_plane(vv, sz) * V + sy) * V + (size_t)g * 8;
         uint4* c = reinterpret_cast<uint4*>(color + base * 4);
         c[0] = z4; c[1] = z4;
     }
 }
 
 __global__ void __launch_bounds__(256)
-clear_planes_x_kernel(int16_t* __restrict__ tsdf, uchar4* __restrict__ color, int V, int p0, int count, int zb, int ze)
+clear_planes_x_kernel(int16_t* __restrict__ tsdf, uchar4* __restrict__ color, int V, int p0, int count, const VolumeView vv)
 {
     const size_t total = (size_t)count * V * V;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         int i = (int)(idx % count);
         size_t r = idx / count;                              // r = sz * V + sy
         int sx = p0 + i; if (sx >= V) sx -= V;
-        const int sz = (int)(r / V);
-        if (sz < zb || sz >= ze) continue;
-        size_t a = (r - (size_t)zb * V) * V + sx;
-        tsdf[a] = 0;
-        color[a] = make_uchar4(0, 0, 0, 0);
+        const int sz = (int)(r / V), sy = (int)(r - (size_t)sz * V);
+        tsdf[r * V + sx] = 0;
+        if (vv_owner(vv, sz) != vv.rank) continue;
+        color[((size_t)vv_local_plane(vv, sz) * V + sy) * V + sx] = make_uchar4(0, 0, 0, 0);
     }
 }
 
@@ -80,9 +81,9 @@ clear_planes_x_kernel(int16_t* __restrict__ tsdf, uchar4* __restrict__ color, in
 // Prologue of the integration, one small launch: the z tables (thread 0: the running sums are serial by definition) and, with the other
 // threads, the reset of the odometry kernels' exchange words for the next frame (grid_sum_words, kt_frame.cuh) -- this launch sits
 // between two odometry launches on the tracker's stream anyway, so the reset costs no launch of its own.
-__global__ void __launch_bounds__(256) ztable_kernel(float* __restrict__ table, int V, float cell_z, float t_z, unsigned long long* __restrict__ reset_words, int reset_count)
+__global__ void __launch_bounds__(256) ztable_kernel(float* __restrict__ table, int V, float cell_z, float t_z, unsigned long long* __restrict__ reset_words, int reset_count, int reset_stride)
 {
-    for (int i = threadIdx.x; i < reset_count; i += blockDim.x) reset_words[i] = 0ull;
+    for (int i = threadIdx.x; i < reset_count; i += blockDim.x) reset_words[(size_t)i * reset_stride] = 0ull;
     if (threadIdx.x != 0) return;
     float v_g_z = (0 + 0.5f) * cell_z - t_z;
     float z_scaled = 0;
@@ -99,9 +100,9 @@ struct IntegrateParams {
     int16_t* tsdf; uchar4* color; int V; int3 wrap; const uint8_t* rgb; const float* nmap; bool angle_color;
     const float* ztable; int zchunk;
     const float* cw; const float4* rgbf;   // PREP: per-pixel colour weight (sign bit = normal invalid) and RGB as floats
-    int lz_lo, lz_hi;          // LOGICAL z range walked by this launch (a slab is one or two such ranges)
+    int lz_lo, lz_hi;          // LOGICAL z range walked by this launch
     int z_far_first;           // schedule the z chunks from high z to low z (see integrate())
-    int z_begin, z_end;        // storage-z range owned here; volume pointers are indexed with (sz - z_begin)
+    VolumeView vv;             // shared volume (MG instances): plane ownership and the peers' TSDF replicas
 };
 
 #define KT_MAX_WEIGHT 128          // Tsdf::MAX_WEIGHT (tsdf_volume.cu:486)
@@ -131,7 +132,10 @@ __device__ __forceinline__ unsigned int sat_u8_rn(float x)       // == min(255, 
     return r;
 }
 
-template <typename IdxT, int ZU, int MINB, bool PREP = false>
+// MG: the volume is shared by vv.world GPUs (VolumeView, kt_ops.h): this launch updates only the voxels of storage planes this rank owns
+// -- it jumps over the foreign blocks of planes, fast-forwarding the running sums exactly (replay_add) -- and stores every CHANGED
+// TSDF value into all ranks' replicas.
+template <typename IdxT, int ZU, int MINB, bool PREP = false, bool MG = false>
 __global__ void __launch_bounds__(256, MINB)
 integrate_kernel(const IntegrateParams p)
 {
@@ -232,8 +236,23 @@ integrate_kernel(const IntegrateParams p)
     // blend + stores) so that ZU independent memory round trips are in flight per thread; the per-voxel arithmetic and the
     // running sums are exactly the reference's (storage addresses of different z never alias, which the compiler cannot know).
     for (int zb = zlo; zb < zhi; zb += ZU) {
+        if (MG) {
+            // storage plane of this logical z; if it is not mine, jump to my next block (the block pattern has period B * world, which
+            // divides V, so it continues across the cyclic wrap)
+            int sz = zb + p.wrap.z; if (sz >= V) sz -= V;
+            if (vv_owner(p.vv, sz) != p.vv.rank) {
+                const int blk = sz >> p.vv.bshift;
+                const int foreign = (p.vv.rank - blk - 1) & (p.vv.world - 1);          // whole foreign blocks between this one and mine
+                int skip = (((blk + 1) << p.vv.bshift) - sz) + (foreign << p.vv.bshift);
+                skip = min(skip, zhi - zb);
+                v_x = replay_add(v_x, Rcurr_inv_0_z_scaled, skip);
+                v_y = replay_add(v_y, Rcurr_inv_1_z_scaled, skip);
+                zb += skip - ZU;
+                continue;
+            }
+        }
         float vgz[ZU], Dp[ZU];
-        IdxT pix[ZU], addr[ZU];
+        IdxT pix[ZU], addr[ZU], caddr[ZU];
         bool ok[ZU];
         float nx[ZU], nz[ZU];
         int16_t tprev[ZU]; uchar4 cprev[ZU]; uchar3 rgbv[ZU]; float4 rgbq[ZU];
@@ -249,12 +268,11 @@ integrate_kernel(const IntegrateParams p)
                     int2 coo = { __float2int_rn(__fmaf_rn(v_x, inv_z, intr.cx)), __float2int_rn(__fmaf_rn(v_y, inv_z, intr.cy)) };
                     if (coo.x >= 0 && coo.y >= 0 && coo.x < cols && coo.y < rows) {
                         int sz = z + p.wrap.z; if (sz >= V) sz -= V;
-                        if (sz >= p.z_begin && sz < p.z_end) {             // this GPU's slab
-                            ok[u] = true;
-                            pix[u] = (IdxT)coo.y * cols + coo.x;
-                            addr[u] = (IdxT)(sz - p.z_begin) * plane + col_off;
-                            Dp[u] = depthScaled[pix[u]];
-                        }
+                        ok[u] = true;
+                        pix[u] = (IdxT)coo.y * cols + coo.x;
+                        addr[u] = (IdxT)sz * plane + col_off;
+                        caddr[u] = MG ? (IdxT)vv_local_plane(p.vv, sz) * plane + col_off : addr[u];      // colour planes are sharded, local order
+                        Dp[u] = depthScaled[pix[u]];
                     }
                 }
                 v_x += Rcurr_inv_0_z_scaled;
@@ -276,7 +294,7 @@ integrate_kernel(const IntegrateParams p)
                     tsdf_new[u] = fmin(1.0f, sdf * tranc_dist_inv);
                     // (issuing these loads together with the depth gather, before the test, was slower: 78 -> 88 us at 512^3)
                     tprev[u] = p.tsdf[addr[u]];
-                    cprev[u] = p.color[addr[u]];
+                    cprev[u] = p.color[caddr[u]];
                     if (PREP) { nx[u] = p.cw[pix[u]]; rgbq[u] = p.rgbf[pix[u]]; }
                     else {
                         nx[u] = nmap_curr[pix[u]];
@@ -294,7 +312,12 @@ integrate_kernel(const IntegrateParams p)
             uchar4 c = cprev[u];
             float weight_prev = c.w;
             const float Wrk = 1;
-            p.tsdf[addr[u]] = pack_tsdf(__fmaf_rn(tsdf_prev, weight_prev, tsdf) / (weight_prev + Wrk));   // (F * W + Wrk * tsdf) / (W + Wrk), Wrk = 1
+            const short tnew = pack_tsdf(__fmaf_rn(tsdf_prev, weight_prev, tsdf) / (weight_prev + Wrk));   // (F * W + Wrk * tsdf) / (W + Wrk), Wrk = 1
+            p.tsdf[addr[u]] = tnew;
+            if (MG && tnew != tprev[u]) {
+                // the owner publishes a changed value to every replica (free-space voxels that stay at 32767 cause no traffic)
+                for (int g = 0; g < p.vv.world; ++g) if (g != p.vv.rank) p.vv.tsdf[g][addr[u]] = tnew;
+            }
             c.w = min(weight_prev + Wrk, (float)KT_MAX_WEIGHT);
             if (PREP) {
                 const float cwv = nx[u];
@@ -322,7 +345,7 @@ integrate_kernel(const IntegrateParams p)
                     c.z = min(255, max(0, __float2int_rn(new_z)));
                 }
             }
-            p.color[addr[u]] = c;
+            p.color[caddr[u]] = c;
         }
     }
 }
@@ -360,17 +383,17 @@ int init_volume(int16_t* tsdf, uint8_t* color, int vol, cudaStream_t s)
 //   which drops the last plane exactly when |n| is a multiple of 16.
 int clear_volume(int axis, int back, int16_t* tsdf, uint8_t* color, int vol, int current, int delta, cudaStream_t s)
 {
-    return clear_volume_slab(axis, back, tsdf, color, vol, 0, vol, current, delta, s);
+    return clear_volume_shared(axis, back, single_volume(tsdf, color, vol), vol, current, delta, s);
 }
 
-int init_slab(int16_t* tsdf_local, uint8_t* color_local, int vol, int slab_z, cudaStream_t s)
+int init_shared(const VolumeView& vv, int vol, cudaStream_t s)
 {
-    size_t n = (size_t)vol * vol * slab_z;
-    int r = fill_zero(tsdf_local, n * 2, s); if (r) return r;
-    return fill_zero(color_local, n * 4, s);
+    const size_t plane = (size_t)vol * vol;
+    int r = fill_zero(vv.tsdf[vv.rank], plane * vol * 2, s); if (r) return r;
+    return fill_zero(vv.color[vv.rank], plane * (vol / vv.world) * 4, s);
 }
 
-int clear_volume_slab(int axis, int back, int16_t* tsdf, uint8_t* color, int vol, int zb, int ze, int current, int delta, cudaStream_t s)
+int clear_volume_shared(int axis, int back, const VolumeView& vv, int vol, int current, int delta, cudaStream_t s)
 {
     const int V = vol;
     const int n = delta - current;
@@ -384,14 +407,15 @@ int clear_volume_slab(int axis, int back, int16_t* tsdf, uint8_t* color, int vol
     }
     if (count <= 0) return 0;
     if (count > V) count = V;
+    int16_t* tsdf = vv.tsdf[vv.rank]; uint8_t* color = vv.color[vv.rank];
     if (axis == 0) {
         size_t total = (size_t)count * V * V;
         int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-        clear_planes_x_kernel<<<grid, 256, 0, s>>>(tsdf, (uchar4*)color, V, p0, count, zb, ze);
+        clear_planes_x_kernel<<<grid, 256, 0, s>>>(tsdf, (uchar4*)color, V, p0, count, vv);
     } else {
         size_t total = (size_t)count * V * (V / 8);
         int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-        clear_planes_yz_kernel<<<grid, 256, 0, s>>>(tsdf, color, V, axis, p0, count, zb, ze);
+        clear_planes_yz_kernel<<<grid, 256, 0, s>>>(tsdf, color, V, axis, p0, count, vv);
     }
     KT_LAUNCH_CHECK();
     return 0;
@@ -409,7 +433,7 @@ int integrate(const IntegrateArgs& a, float* ztable_dev, cudaStream_t s)
 {
     const int V = a.vol;
     float3 cell = make_float3(a.volume_size.x / V, a.volume_size.y / V, a.volume_size.z / V);   // host division, tsdf_volume.cu:659-661
-    ztable_kernel<<<1, 256, 0, s>>>(ztable_dev, V, cell.z, a.t.z, a.reset_words, a.reset_words ? a.reset_count : 0);
+    ztable_kernel<<<1, 256, 0, s>>>(ztable_dev, V, cell.z, a.t.z, a.reset_words, a.reset_words ? a.reset_count : 0, a.reset_stride);
     KT_LAUNCH_CHECK();
     IntegrateParams p;
     p.depth_scaled = a.depth_scaled; p.rows = a.rows; p.cols = a.cols; p.k = a.k; p.cell = cell; p.Rinv = a.Rinv; p.t = a.t; p.trunc = a.trunc;
@@ -424,43 +448,38 @@ int integrate(const IntegrateArgs& a, float* ztable_dev, cudaStream_t s)
     const bool prep = prep_knob != 0 && a.cw && a.rgbf;      // the caller ran color_prep() on this frame's normal map and image
     p.cw = a.cw; p.rgbf = a.rgbf;
     p.ztable = ztable_dev; p.zchunk = V >= 64 ? (V + n_chunks - 1) / n_chunks : V;
-    p.z_begin = a.z_begin; p.z_end = a.z_end;
     // z chunks: a warp walks its columns' voxels serially, so a chunk's length is the scheduling quantum of the launch.  Measured on
-    // B200 (640x480 into 512^3, tools/stage_ab.py): 8 chunks 100 us, 16 chunks 78 us, 32 chunks 96 us (per-chunk column setup and the
-    // replay of the running sums grow); dispatching the far chunks first was slower at every chunk count (89-109 us).
+    // B200 (640x480 into 512^3, tools/stage_ab.py): 8 chunks 100 us, 16 chunks 78 us, 32 chunks 96 us (per-chunk column setup);
+    // dispatching the far chunks first was slower at every chunk count (89-109 us).
     p.z_far_first = (a.Rinv.r2.z > 0.f) == (order != 0) ? 1 : 0;          // z component of the camera's viewing axis in the volume frame
-    // logical z ranges of the owned storage planes [z_begin, z_end): storage = (logical + wrap.z) mod V
-    const int slab = a.z_end - a.z_begin;
-    int lo[2], hi[2], n = 0;
-    if (slab >= V) { lo[0] = 0; hi[0] = V; n = 1; }
-    else {
-        const int ls = wrap_mod(a.z_begin - p.wrap.z, V);
-        lo[0] = ls; hi[0] = ls + slab < V ? ls + slab : V; n = 1;
-        if (ls + slab > V) { lo[1] = 0; hi[1] = ls + slab - V; n = 2; }
-    }
+    const bool multi = a.multi && a.vv.world > 1;
+    p.vv = multi ? a.vv : single_volume(a.tsdf, a.color, V);
     // KT_FORCE_IDX64 (test hook): take the 64-bit index path the 2048^3 volume needs on a volume small enough to check against the reference
     static const bool force64 = getenv("KT_FORCE_IDX64") != nullptr;
-    const bool idx32 = !force64 && (size_t)slab * V * V <= ((size_t)1 << 31);
-    for (int i = 0; i < n; ++i) {
-        p.lz_lo = lo[i]; p.lz_hi = hi[i];
-        dim3 block(32, 8), grid(div_up(V, 32), div_up(V, 8), div_up(hi[i] - lo[i], p.zchunk));
-        if (idx32) {
-            // batch depth / CTAs per SM (KT_INT_ZU = 1 or 2 overrides).  Measured (tools/stage_ab.py, 640x480): 512^3 2-voxel batches at 4
-            // CTAs/SM 78 us vs 81 us for 1-voxel steps at 6 CTAs/SM; 1024^3 395 vs 351 us: once the updated region outgrows L2, occupancy
-            // wins.  Also measured and dropped: 3- and 4-voxel batches (82 / 93 us), 2-voxel batches at 5 or 6 CTAs/SM (81 / 91 us, spills)
-            const int variant = zu ? zu : (V >= 1024 ? 1 : 2);
-            if (prep && (variant == 1 || variant == 2)) {
-                if (variant == 1) integrate_kernel<unsigned int, 1, 6, true><<<grid, block, 0, s>>>(p);
-                else integrate_kernel<unsigned int, 2, 4, true><<<grid, block, 0, s>>>(p);
-            } else
-            if (variant == 1) integrate_kernel<unsigned int, 1, 6><<<grid, block, 0, s>>>(p);
-            else integrate_kernel<unsigned int, 2, 4><<<grid, block, 0, s>>>(p);
-        }
-        else if (prep) integrate_kernel<size_t, 1, 6, true><<<grid, block, 0, s>>>(p);
-        else if (zu == 2) integrate_kernel<size_t, 2, 4><<<grid, block, 0, s>>>(p);
-        else integrate_kernel<size_t, 1, 6><<<grid, block, 0, s>>>(p);
-        KT_LAUNCH_CHECK();
+    const bool idx32 = !force64 && (size_t)V * V * V <= ((size_t)1 << 31);
+    p.lz_lo = 0; p.lz_hi = V;
+    dim3 block(32, 8), grid(div_up(V, 32), div_up(V, 8), div_up(V, p.zchunk));
+    if (multi) {
+        if (V & (V - 1)) { set_error("integrate: the shared volume needs a power-of-two resolution"); return -1; }
+        // one voxel per step: the walk alternates between owned blocks and exact jumps over foreign ones
+        if (idx32) { if (prep) integrate_kernel<unsigned int, 1, 6, true, true><<<grid, block, 0, s>>>(p); else integrate_kernel<unsigned int, 1, 6, false, true><<<grid, block, 0, s>>>(p); }
+        else { if (prep) integrate_kernel<size_t, 1, 6, true, true><<<grid, block, 0, s>>>(p); else integrate_kernel<size_t, 1, 6, false, true><<<grid, block, 0, s>>>(p); }
+    } else if (idx32) {
+        // batch depth / CTAs per SM (KT_INT_ZU = 1 or 2 overrides).  Measured (tools/stage_ab.py, 640x480): 512^3 2-voxel batches at 4
+        // CTAs/SM 78 us vs 81 us for 1-voxel steps at 6 CTAs/SM; 1024^3 395 vs 351 us: once the updated region outgrows L2, occupancy
+        // wins.  Also measured and dropped: 3- and 4-voxel batches (82 / 93 us), 2-voxel batches at 5 or 6 CTAs/SM (81 / 91 us, spills)
+        const int variant = zu ? zu : (V >= 1024 ? 1 : 2);
+        if (prep && (variant == 1 || variant == 2)) {
+            if (variant == 1) integrate_kernel<unsigned int, 1, 6, true><<<grid, block, 0, s>>>(p);
+            else integrate_kernel<unsigned int, 2, 4, true><<<grid, block, 0, s>>>(p);
+        } else
+        if (variant == 1) integrate_kernel<unsigned int, 1, 6><<<grid, block, 0, s>>>(p);
+        else integrate_kernel<unsigned int, 2, 4><<<grid, block, 0, s>>>(p);
     }
+    else if (prep) integrate_kernel<size_t, 1, 6, true><<<grid, block, 0, s>>>(p);
+    else if (zu == 2) integrate_kernel<size_t, 2, 4><<<grid, block, 0, s>>>(p);
+    else integrate_kernel<size_t, 1, 6><<<grid, block, 0, s>>>(p);
+    KT_LAUNCH_CHECK();
     return 0;
 }
 

@@ -1,28 +1,36 @@
-"""Host-side plumbing of the z-slab mode (one process per GPU, `torch.distributed` for the control plane only).
+"""Host-side plumbing of the shared-volume mode (ONE stream, `world` GPUs, one process per GPU; `torch.distributed` for the control
+plane only).
 
-The data path has no collective library call: slabs and model maps are reached through CUDA-IPC mapped peer memory over NVLink,
-the predicted-surface all-gather is P2P stores inside the ray-cast kernel, synchronisation is a flag barrier in peer memory
-(kintinuous_b200/csrc/kt_tsdf.cu, xgpu_barrier_kernel).  `torch.distributed` (NCCL on GPUs, gloo in the CPU tests) only carries
-the 64-byte IPC handles at start-up and the final timing reduction.
+The data path has no collective library call.  The TSDF plane is replicated: the owner of a voxel stores its changed value into every
+rank's replica from inside the integration kernel (NVLink P2P stores to CUDA-IPC mapped peer memory), so ray casting reads local HBM
+only.  The colour / weight plane is sharded by storage z plane, block-cyclically (blocks of `block` planes dealt round-robin), which
+spreads any viewing frustum evenly over the ranks.  The predicted-surface all-gather is P2P stores inside the ray-cast kernel,
+synchronisation is a flag barrier in peer memory (kintinuous_b200/csrc/kt_tsdf.cu, xgpu_barrier_kernel).  `torch.distributed` (NCCL on
+GPUs, gloo in the CPU tests) only carries the 64-byte IPC handles at start-up and the final timing reduction.
 """
 from __future__ import annotations
 
 
-def slab_range(rank: int, world: int, vol: int):
-    """Storage z planes owned by `rank`: contiguous, equal, invariant under volume shifting."""
-    assert vol % world == 0
-    s = vol // world
-    return rank * s, (rank + 1) * s
+def owner_of_plane(storage_z: int, world: int, block: int) -> int:
+    """Rank that owns the colour / weight data (and performs the integration) of a storage z plane; invariant under volume shifting."""
+    return (storage_z // block) % world
+
+
+def local_plane(storage_z: int, world: int, block: int) -> int:
+    """Index of an owned storage plane in its owner's local plane order."""
+    return (storage_z // (block * world)) * block + storage_z % block
+
+
+def owned_planes(rank: int, world: int, vol: int, block: int):
+    """Storage z planes owned by `rank`, in local plane order (kt_volume_export_reference_layout / Tracker.export_owned order)."""
+    n = vol // world
+    return [((l // block) * world + rank) * block + l % block for l in range(n)]
 
 
 def tile_rows(rank: int, world: int, rows: int, tile: int = 8):
     """Rows of 32x8 ray-cast tiles cast by `rank` (contiguous bands; every tile row belongs to exactly one rank)."""
     tiles = rows // tile
     return rank * tiles // world, (rank + 1) * tiles // world
-
-
-def owner_of_plane(storage_z: int, world: int, vol: int) -> int:
-    return storage_z // (vol // world)
 
 
 def exchange(obj, group=None):

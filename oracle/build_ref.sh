@@ -27,7 +27,7 @@ FLAGS="-std=c++14 -O3 -gencode arch=compute_100,code=sm_100 --ftz=true --prec-di
 for V in $VOLS; do
   B=$TMP/build_$V; mkdir -p $B
   pids=()
-  for f in bilateral_pyrdown maps reduce tsdf_volume ray_caster extract; do
+  for f in bilateral_pyrdown maps reduce tsdf_volume ray_caster extract image_generator; do
     $NVCC $FLAGS -DVOL=$V -I"$TMP/cuda" -c "$TMP/cuda/$f.cu" -o $B/$f.o & pids+=($!)
   done
   $NVCC $FLAGS -DVOL=$V -I"$TMP/cuda" -I"$HERE" -Xcompiler -ffp-contract=off -c "$HERE/ref_harness.cu" -o $B/ref_harness.o & pids+=($!)

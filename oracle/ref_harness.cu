@@ -133,6 +133,24 @@ void ktref_raycast(const float* intr, const float* Rcurr, const float* tcurr, fl
     cudaSafeCall(cudaDeviceSynchronize());
 }
 
+// GUI taps: generateImage / generateDepth (image_generator.cu:161-230)
+void ktref_generate_image(const float* vmap, const float* nmap, const unsigned char* vmap_color, const float* light_pos3, int n_lights,
+                          unsigned char* dst_rgb, unsigned char* dst_color_rgb, int rows, int cols)
+{
+    DeviceArray2D<float> v = wrap2<float>(vmap, rows * 3, cols), n = wrap2<float>(nmap, rows * 3, cols);
+    DeviceArray2D<uchar4> vc = wrap2<uchar4>(vmap_color, rows, cols);
+    LightSource light; light.number = n_lights; light.pos[0] = make_float3(light_pos3[0], light_pos3[1], light_pos3[2]);
+    PtrStepSz<uchar3> d(rows, cols, (uchar3*)dst_rgb, (size_t)cols * 3), dc(rows, cols, (uchar3*)dst_color_rgb, (size_t)cols * 3);
+    generateImage(v, n, vc, light, d, dc);
+}
+void ktref_generate_depth(const float* Rinv, const float* t, const float* vmap, const float* nmap, u16* dst, int rows, int cols, float max_depth)
+{
+    DeviceArray2D<float> v = wrap2<float>(vmap, rows * 3, cols), n = wrap2<float>(nmap, rows * 3, cols);
+    DeviceArray2D<u16> d = wrap2<u16>(dst, rows, cols);
+    generateDepth(toMat33(Rinv), toF3(t), v, n, d, max_depth);
+    cudaSafeCall(cudaDeviceSynchronize());
+}
+
 size_t ktref_extract(const short* tsdf, const float* volume_size, void* out, size_t out_cap, const int* voxelWrap,
                      const unsigned char* color, int minX, int maxX, int minY, int maxY, int minZ, int maxZ, int subsample,
                      const int* realVoxelWrap)

@@ -177,6 +177,12 @@ class RefCuda:
         return int(self.lib.ktref_extract(_ptr(tsdf), _ptr(vs), _ptr(out), C.c_size_t(capacity), _ptr(w), _ptr(color),
                                           box[0], box[1], box[2], box[3], box[4], box[5], subsample, _ptr(rw)))
 
+    def generate_image(self, vmap, nmap, vmap_color, light_pos, n_lights, dst, dst_color, rows, cols):
+        lp = _f(light_pos); self.lib.ktref_generate_image(_ptr(vmap), _ptr(nmap), _ptr(vmap_color), _ptr(lp), n_lights, _ptr(dst), _ptr(dst_color), rows, cols)
+
+    def generate_depth(self, Rinv, t, vmap, nmap, dst, rows, cols, max_depth=6.0):
+        Ri, tt = _f(Rinv), _f(t); self.lib.ktref_generate_depth(_ptr(Ri), _ptr(tt), _ptr(vmap), _ptr(nmap), _ptr(dst), rows, cols, C.c_float(max_depth))
+
     def clear(self, axis, back, tsdf, color, current, delta): self.lib.ktref_clear(axis, back, _ptr(tsdf), _ptr(color), current, delta)
     def init_volume(self, tsdf, color): self.lib.ktref_init_volume(_ptr(tsdf), _ptr(color))
     def short_depth_to_metres(self, s, d, rows, cols, cut): self.lib.ktref_short_depth_to_metres(_ptr(s), _ptr(d), rows, cols, cut)

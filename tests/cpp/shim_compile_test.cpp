@@ -35,7 +35,7 @@ int main()
         for (int i = 0; i < rows * cols; ++i) bad += (fh[i] != 1500);                    // bilateral of a constant image is the constant
         std::vector<float> vh(3 * rows * cols);
         vmap.download(&vh[0], cols * 4);
-        for (int i = 0; i < rows * cols; ++i) bad += (vh[2 * rows * cols + i] != 1.5f);  // vertex z = depth / 1000
+        for (int i = 0; i < rows * cols; ++i) { const float dz = vh[2 * rows * cols + i] - 1.5f; bad += (dz > 1e-6f || dz < -1e-6f); }  // vertex z = depth / 1000 (1500 * 0.001f)
         // integrate the wall into the 64^3 volume (camera at the volume centre, looking along +z), then extract and ray cast it
         std::vector<unsigned char> rgbh(rows * cols * 3, 200);
         DeviceArray2D<PixelRGB> colors; colors.upload(&rgbh[0], cols * 3, rows, cols);

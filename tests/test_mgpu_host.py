@@ -13,12 +13,20 @@ def test_partitions_cover_exactly_once():
     from kintinuous_b200 import mgpu
     for vol in (256, 512, 1024):
         for world in (1, 2, 4, 8):
-            owned = np.zeros(vol, int)
-            for r in range(world):
-                a, b = mgpu.slab_range(r, world, vol)
-                owned[a:b] += 1
-                assert all(mgpu.owner_of_plane(z, world, vol) == r for z in (a, b - 1))
-            assert (owned == 1).all()
+            for block in (1, 4, 8, 16):
+                owned = np.zeros(vol, int)
+                for r in range(world):
+                    planes = mgpu.owned_planes(r, world, vol, block)
+                    assert len(planes) == vol // world
+                    for l, z in enumerate(planes):
+                        owned[z] += 1
+                        assert mgpu.owner_of_plane(z, world, block) == r and mgpu.local_plane(z, world, block) == l
+                assert (owned == 1).all()
+                # balance: any window of block * world consecutive storage planes holds exactly `block` planes of every rank
+                for r in range(world):
+                    mine = np.zeros(vol, int); mine[mgpu.owned_planes(r, world, vol, block)] = 1
+                    w = block * world
+                    assert all(mine[s:s + w].sum() == block for s in range(0, vol, w))
     for rows in (480, 960, 120):
         for world in (1, 2, 4, 8):
             cover = np.zeros(rows // 8, int)
@@ -38,9 +46,9 @@ rank, world = dist.get_rank(), dist.get_world_size()
 handle = bytes([rank]) * 64                      # stands in for the 64-byte cudaIpcMemHandle_t
 got = mgpu.exchange(handle)
 assert len(got) == world and all(got[r] == bytes([r]) * 64 for r in range(world)), got
-a, b = mgpu.slab_range(rank, world, 512)
+n_mine = len(mgpu.owned_planes(rank, world, 512, 8))
 import torch
-t = torch.tensor([b - a], dtype=torch.int64)
+t = torch.tensor([n_mine], dtype=torch.int64)
 dist.all_reduce(t)
 assert int(t.item()) == 512
 dist.barrier()

@@ -6,7 +6,17 @@ mkdir -p gpurun_out
 for step in "$@"; do
   case $step in
     tail)  timeout 300 tools/bin/tail_bench > gpurun_out/${TAG}_tail_bench.txt 2>&1; tail -40 gpurun_out/${TAG}_tail_bench.txt ;;
-    tests) timeout 2400 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 | tee gpurun_out/${TAG}_pytest.log ;;
+    tests) timeout 2400 python -m pytest tests -m gpu -x -q --tb=short > gpurun_out/${TAG}_pytest_full.log 2>&1; grep -E "^E |Error|passed|failed" gpurun_out/${TAG}_pytest_full.log | head -40 | tee gpurun_out/${TAG}_pytest.log ;;
+    tests_all) timeout 3000 python -m pytest tests -m gpu -q --tb=short > gpurun_out/${TAG}_pytest_full.log 2>&1; grep -E "^E  +(Assert|assert)|Error|passed|failed|FAILED|^cfg odometry|colour mismatches" gpurun_out/${TAG}_pytest_full.log | cut -c1-400 | head -60 | tee gpurun_out/${TAG}_pytest.log ;;
+    mg2) timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/mgpu_check.py --vol 256 --frames 10 --voxel-shift 2 2>&1 | grep -E "MGPU_CHECK|mismatch|Error|error|slice" | cut -c1-400 | tee gpurun_out/${TAG}_mg2.log
+         timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 tools/mgpu_check.py --vol 256 --frames 8 --voxel-shift 2 --odometry 2 2>&1 | grep -E "MGPU_CHECK|mismatch|Error|error|slice" | cut -c1-400 | tee -a gpurun_out/${TAG}_mg2.log ;;
+    mgbench) NG=${NG:-2}; timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus $NG --steps 100 --warmup 10 --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/${TAG}_bench_${NG}gpu.json
+         python - <<PY
+import json
+d = json.load(open("gpurun_out/${TAG}_bench_${NG}gpu.json"))
+print("streams value", round(d["value"], 1), "zslab", json.dumps(d.get("zslab"))[:900])
+PY
+         ;;
     newtests) timeout 2400 python -m pytest tests/test_gpu_baseline_configs.py tests/test_shim_builds.py -m gpu -x -q -s 2>&1 | tail -25 | tee gpurun_out/${TAG}_pytest_new.log ;;
     smoke) python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2 | tee gpurun_out/${TAG}_smoke.log ;;
     bench) python bench.py --steps 200 --warmup 20 2>&1 | tail -1 > gpurun_out/${TAG}_bench_cfg2.json

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Multi-GPU equivalence check (run under torchrun, one rank per GPU): the z-slab tracker over `world` GPUs must reproduce the
-single-GPU tracker bit for bit (poses, model maps, volume slabs, shift events, extracted slices as a multiset).
+"""Multi-GPU equivalence check (run under torchrun, one rank per GPU): ONE volume shared by `world` GPUs (replicated TSDF, block-cyclic
+colour planes) must reproduce the single-GPU tracker bit for bit: poses, model maps, every rank's TSDF replica, the colour / weight planes
+each rank owns, shift events, extracted slices as a multiset.
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/mgpu_check.py --vol 256
 """
 import argparse, os, sys, time
@@ -33,9 +34,10 @@ for k, (d, c) in enumerate(frames):
     same = list(p.R) == list(q.R) and list(p.t) == list(q.t) and list(p.voxel_wrap) == list(q.voxel_wrap) and p.shifted == q.shifted
     if not same: ok = False; print(f"[rank {rank}] frame {k}: pose mismatch", np.abs(np.array(p.t) - np.array(q.t)).max(), list(p.voxel_wrap), list(q.voxel_wrap), flush=True)
 torch.cuda.synchronize(); dist.barrier()
-zb, ze = mgpu.slab_range(rank, world, args.vol)
-ts, cs = trk.export_slab(); tf, cf = single.export_volume()
-vol_ok = bool((ts == tf[zb:ze]).all() and (cs == cf[zb:ze]).all())
+info = trk.mgpu_info()
+planes = mgpu.owned_planes(rank, world, args.vol, info["block"])
+ts, cs = trk.export_owned(); tf, cf = single.export_volume()
+vol_ok = bool((ts == tf[planes]).all() and (cs == cf[planes]).all()) and bool((trk.export_tsdf_replica() == tf).all())
 maps_ok = all(bool(np.array_equal(trk.download_map(w, l), single.download_map(w, l), equal_nan=True)) for w in (2, 3) for l in range(3))
 trk.finalise(); single.finalise()
 def canon(pts):

@@ -98,8 +98,6 @@ __global__ void __launch_bounds__(T, 1) v0_kernel(P p)
 // ---- V1: fixed-point 64-bit atomic accumulators (order-independent => deterministic) + release counter ------------------
 __device__ __forceinline__ unsigned int ld_acquire(const unsigned int* p) { unsigned int v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 __device__ __forceinline__ void red_release_add(unsigned int* p, unsigned int v) { asm volatile("red.release.gpu.global.add.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
-__device__ __forceinline__ void red_add_u64(unsigned long long* p, unsigned long long v) { asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory"); }
-__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) { unsigned long long v; asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
 
 __global__ void __launch_bounds__(T, 1) v1_kernel(P p)
 {
@@ -381,7 +379,7 @@ __global__ void solve_check_kernel(const double* A, const double* b, int n, doub
 
 template <class K> static void run(const char* name, K kernel, P p, int grid, int cluster, bool coop)
 {
-    CK(cudaMemset(p.bar, 0, 4)); CK(cudaMemset(p.acc, 0, 4 * 32 * 8)); CK(cudaMemset(p.ll, 0, (size_t)2 * 1024 * 32 * 8)); CK(cudaMemset(p.ll2, 0, (size_t)2 * 64 * 32 * 8));
+    CK(cudaMemset(p.bar, 0, 4)); CK(cudaMemset(p.acc, 0, 4 * 32 * 8)); CK(cudaMemset(p.ll, 0, (size_t)2 * 4096 * 32 * 8)); CK(cudaMemset(p.ll2, 0, (size_t)2 * 64 * 32 * 8));
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(T); cfg.dynamicSmemBytes = 0; cfg.stream = 0;
@@ -407,7 +405,7 @@ int main()
     int sms = 0; CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
     P p; p.iters = 2000;
     CK(cudaMalloc(&p.partials, 2 * 32 * 1024 * 4)); CK(cudaMalloc(&p.bar, 4)); CK(cudaMalloc(&p.acc, 4 * 32 * 8));
-    CK(cudaMalloc(&p.ll, (size_t)2 * 1024 * 32 * 8)); CK(cudaMalloc(&p.ll2, (size_t)2 * 64 * 32 * 8));
+    CK(cudaMalloc(&p.ll, (size_t)2 * 4096 * 32 * 8)); CK(cudaMalloc(&p.ll2, (size_t)2 * 64 * 32 * 8));
     CK(cudaMalloc(&p.cycles, p.iters * 8)); CK(cudaMalloc(&p.out, 128));
     printf("SMs %d\n", sms);
     for (int solve = 0; solve < 2; ++solve) {
@@ -424,6 +422,10 @@ int main()
         run("V6 self-counting words, packed", v6_kernel<1, 0>, p, sms, 1, true);
         run("V6 self-counting words, stride 256 B", v6_kernel<32, 0>, p, sms, 1, true);
         run("V6 self-counting words, stride 1280 B", v6_kernel<160, 0>, p, sms, 1, true);
+        run("V6 self-counting words, stride 2304 B", v6_kernel<288, 0>, p, sms, 1, true);
+        run("V6 self-counting words, stride 4352 B", v6_kernel<544, 0>, p, sms, 1, true);
+        run("V6 self-counting words, stride 5376 B", v6_kernel<672, 0>, p, sms, 1, true);
+        run("V6 self-counting words, stride 16640 B", v6_kernel<2080, 0>, p, sms, 1, true);
         run("V6 stride 256 B, 16 CTAs", v6_kernel<32, 0>, p, 16, 1, true);
         run("V6 stride 256 B, 32 CTAs", v6_kernel<32, 0>, p, 32, 1, true);
         run("V6 stride 256 B, 74 CTAs", v6_kernel<32, 0>, p, 74, 1, true);
