@@ -123,7 +123,8 @@ KT_API int kt_get_trace(kt_ctx* ctx, float* dst, int max_iters, int* n_iters);
  * storage (cyclic) order.  Either pointer may be NULL.  (TSDFVolume.h:154, ColorVolume.h:93) */
 KT_API int kt_volume_export_reference_layout(kt_ctx* ctx, int16_t* tsdf_host, uint8_t* color_host);
 /* which: 0 vmap_curr, 1 nmap_curr, 2 vmap_g_prev, 3 nmap_g_prev (3*rows_l*cols_l floats), 4 depth_curr (u16),
- * 5 raycast colour (uchar4, level 0).  Test / GUI tap (getLiveImage inputs). */
+ * 5 raycast colour (uchar4, level 0); 6 scaled depth (float), 7 colour weight (float), 8 float RGB (float4): the integration's per-pixel
+ * inputs, level 0.  Test / GUI tap (getLiveImage inputs). */
 KT_API int kt_download_map(kt_ctx* ctx, int which, int level, void* dst_host);
 /* Stage timers (CUDA events) of the last frame, milliseconds: pyramid, odometry, shift, integrate, raycast, total. */
 KT_API int kt_get_stage_ms(kt_ctx* ctx, float* ms6);
@@ -150,6 +151,17 @@ KT_API int kt_mgpu_export_tsdf_replica(kt_ctx* ctx, int16_t* tsdf_host /* vol^3 
 KT_API long long kt_launch_count(kt_ctx* ctx);
 /* debug: 64 x 5 clock64() stamps of the last whole-frame ICP launch (recorded only while stage timing is enabled) */
 KT_API int kt_debug_icp_profile(kt_ctx* ctx, long long* out512);
+/* ---- OdometryProvider level (OdometryProvider.h:42-52) ----
+ * One call = ICPOdometry / RGBDOdometry::getIncrementalTransformation (ICPOdometry.cpp:68-186, RGBDOdometry.cpp:165-393) for a caller that
+ * owns the pose history (Rprev / tprev in, Rcurr / tcurr out, camera-to-volume) and the maps: the model maps vmaps_g_prev / nmaps_g_prev
+ * (volume frame) and optionally the current maps (NULL: built from the depth frame by the fused front end), 4 pyramid levels each,
+ * device pointers, SoA x 3 like the reference's DeviceArray2D<float>(3 * rows, cols).  The context (kt_create with the odometry mode and
+ * the image geometry; its volume is not touched) lends the kernels' scratch and keeps the photometric last / next pyramids between
+ * calls; kt_odometry_first_run = RGBDOdometry::firstRun on the first frame.  The 0.3 m jump guard (RGBDOdometry.cpp:383) applies. */
+KT_API int kt_odometry_first_run(kt_ctx* ctx, const uint16_t* depth_dev, const uint8_t* rgb_dev);
+KT_API int kt_odometry_increment(kt_ctx* ctx, const uint16_t* depth_dev, const uint8_t* rgb_dev, const float* Rprev9, const float* tprev3,
+                          const float* const* vmaps_g_prev4, const float* const* nmaps_g_prev4,
+                          const float* const* vmaps_curr4, const float* const* nmaps_curr4, float* Rcurr9, float* tcurr3);
 /* getLiveImage (KintinuousTracker.cpp:835-862, 960-981, 1125-1154): shaded weight image (uchar3), colour image (uchar3) and model depth
  * (u16 mm) of the surface predicted at the last pose; host buffers of rows*cols pixels, any may be NULL. */
 KT_API int kt_get_live_image(kt_ctx* ctx, uint8_t* shaded_rgb_host, uint8_t* color_rgb_host, uint16_t* model_depth_host);

@@ -190,8 +190,12 @@ class Tracker:
             out = np.empty((3, rows, cols), dtype=np.float32)
         elif which == 4:
             out = np.empty((rows, cols), dtype=np.uint16)
-        else:
+        elif which == 5:
             out = np.empty((rows, cols, 4), dtype=np.uint8)
+        elif which == 8:
+            out = np.empty((rows, cols, 4), dtype=np.float32)
+        else:
+            out = np.empty((rows, cols), dtype=np.float32)
         _check(self.lib.kt_download_map(self.h, which, level, _ptr(out)))
         return out
 

@@ -158,6 +158,7 @@ struct IcpFrameParams {
     int* timeout;              // set to 1 if a peer CTA never arrived (bounded poll)
     long long* prof;           // optional: clock64() stamps per iteration from CTA 0 (debug)
     int stage_k;               // passes of FRAME_THREADS pixels per CTA that fit the shared-memory stage (0 = no staging)
+    float* host_pose; unsigned int host_seq;      // optional mapped host record: pose (12), time-out (1), sequence number (1)
 };
 
 __global__ void __launch_bounds__(FRAME_THREADS, 1)
@@ -318,6 +319,18 @@ icp_frame_kernel(const IcpFrameParams p)
     if (blockIdx.x == 0 && tid < 12) {
         if (tid < 9) p.st->Rcurr[tid] = s_R[tid]; else p.st->tcurr[tid - 9] = s_t[tid - 9];
         if (tid == 0) p.st->iter = it;
+        if (p.host_pose) {
+            // the estimate also goes straight to mapped, pinned HOST memory (12 floats, the time-out flag, then a sequence number behind a
+            // system-scope fence): the host polls the sequence number instead of paying a D2H copy + stream synchronisation per frame
+            if (tid == 0) {
+                volatile float* hp = p.host_pose;
+                for (int k = 0; k < 9; ++k) hp[k] = s_R[k];
+                for (int k = 0; k < 3; ++k) hp[9 + k] = s_t[k];
+                ((volatile int*)p.host_pose)[12] = p.timeout ? *(volatile int*)p.timeout : 0;
+                __threadfence_system();
+                ((volatile unsigned int*)p.host_pose)[13] = p.host_seq;
+            }
+        }
     }
 }
 
@@ -367,9 +380,10 @@ int odom_begin_frame(OdomState* state, const float* pose12_dev, cudaStream_t s)
 // Whole-frame ICP (ICP-only odometry).  pose12 = Rprev (9) + tprev (3) on the host; the result lands in state->Rcurr/tcurr.
 // xwords_dev: XW_WORDS 64-bit exchange words, ZERO when the launch starts (the tracker resets them once per frame, kt_tracker.cu).
 int icp_frame(const IcpLevelArgs* levels, const int* iters, const float* pose12_host, OdomState* state, unsigned long long* xwords_dev,
-              float* trace, int* timeout_dev, long long* prof_dev, cudaStream_t s)
+              float* trace, int* timeout_dev, long long* prof_dev, float* host_pose, unsigned int host_seq, cudaStream_t s)
 {
     IcpFrameParams p;
+    p.host_pose = host_pose; p.host_seq = host_seq;
     p.prof = prof_dev;
     for (int l = 0; l < LEVELS; ++l) { p.lv[l] = levels[l]; p.iters[l] = iters[l]; }
     for (int k = 0; k < 12; ++k) p.pose12[k] = pose12_host[k];

@@ -103,7 +103,7 @@ struct IcpLevelArgs {
 int icp_iteration(const IcpLevelArgs& a, OdomState* state, float* partials, float* trace, int mode, cudaStream_t s);
 
 int icp_frame(const IcpLevelArgs* levels, const int* iters, const float* pose12_host, OdomState* state, unsigned long long* xwords_dev,
-              float* trace, int* timeout_dev, long long* prof_dev, cudaStream_t s);
+              float* trace, int* timeout_dev, long long* prof_dev, float* host_pose, unsigned int host_seq, cudaStream_t s);
 // exchange words of the whole-frame odometry kernels (grid_sum_words, kt_frame.cuh): their count, and the reset (zero) of a word array --
 // stream-ordered, once per frame between two odometry launches
 size_t odom_exchange_words();          // allocation size (64-bit words)
@@ -120,7 +120,7 @@ int rgb_residual(const RgbLevelArgs& a, OdomState* state, int* partials, int use
 // mode 0: reduce only; 1: solve RGB-only; 2: solve A_rgb + 100 A_icp (RGBDOdometry.cpp:316-321)
 // Returns 1 (and launches nothing) when the image does not fit the kernel's shared-memory stage.  xwords_dev: zero at launch (see icp_frame).
 int rgbd_frame(const IcpLevelArgs* icp_levels, const RgbLevelArgs* rgb_levels, const int* iters, int with_icp, const float* pose12_host, OdomState* state,
-               unsigned long long* xwords_dev, float* trace, int* timeout_dev, cudaStream_t s);
+               unsigned long long* xwords_dev, float* trace, int* timeout_dev, float* host_pose, unsigned int host_seq, cudaStream_t s);
 int rgb_iteration(const RgbLevelArgs& a, OdomState* state, float* partials, float* trace, int mode, float sigma_override, cudaStream_t s);
 // pose12_dev: Rprev (9) + tprev (3) in device memory
 int odom_begin_frame(OdomState* state, const float* pose12_dev, cudaStream_t s);

@@ -12,6 +12,7 @@
 #pragma once
 #include <stdint.h>
 #include <string.h>
+#include <math.h>
 
 #ifndef KT_HD
 #define KT_HD __host__ __device__
@@ -77,6 +78,73 @@ KT_HD inline float replay_add(float x, float a, int k)
         {   // the step that leaves the binade / a tie / |x| < |a| / zero / inf / nan
             const float xn = rp_add(x, a);
             if (rp_bits(xn) == rp_bits(x)) return x;           // a fixed point stays one
+            x = xn;
+            --k;
+        }
+    }
+    return x;
+}
+
+
+// The reference's tsdf23 as COMPILED does not add a float increment: nvcc contracts  v_x += Rcurr_inv.z * cell_size.z * intr.fx  into
+//   v_x = fma(R_z * cell, f, v_x)          (SASS of the reference build: FMUL R4 = cell * R_z once, FFMA R9 = R4 * fx + R9 per z step)
+// i.e. the addend is the EXACT 48-bit product P = m * f, not its float rounding.  The two differ only when a running sum sits within a
+// fraction of an ulp of a rounding boundary -- a handful of voxels per million pick the neighbouring depth pixel -- which is exactly what a
+// bit-exact replay against the reference at 512^3 exposed.  replay_fma(x, m, f, k) returns the bits of k steps x <- fma(m, f, x): same closed
+// form as replay_add with P kept exact in double (24 x 24 bits fit 53), A = round(P / u) and the remainder compared with u/2 exactly.
+KT_HD __forceinline__ float rp_fma(float m, float f, float x) {
+#ifdef __CUDA_ARCH__
+    return __fmaf_rn(m, f, x);
+#else
+    return fmaf(m, f, x);
+#endif
+}
+
+KT_HD inline float replay_fma(float x, float m, float f, int k)
+{
+    if (k <= 0) return x;
+    const double P = (double)m * (double)f;                     // exact
+    if (P == 0.0 || !(P == P) || P - P != 0.0) {                // zero / nan / inf addend: a real step decides, and it is a fixed point afterwards
+        const float x1 = rp_fma(m, f, x);
+        return (k == 1 || rp_bits(rp_fma(m, f, x1)) == rp_bits(x1)) ? x1 : rp_fma(m, f, x1);
+    }
+    while (k > 0) {
+        const uint32_t xb = rp_bits(x);
+        const int ex = (int)((xb >> 23) & 0xffu);
+        if (ex != 0 && ex != 255) {
+            // q = P / u scaled into the magnitude direction of x: positive q_m grows |x|.  u = 2^(ex - 150).
+            const double scale = ex >= 150 ? 1.0 / (double)(1ull << (ex - 150 < 63 ? ex - 150 : 62)) : (double)(1ull << (150 - ex < 63 ? 150 - ex : 62));
+            if (ex > 150 - 62 && ex < 150 + 62) {
+                double q = P * scale;                           // exact (power-of-two scaling, no overflow in these ranges)
+                if (xb >> 31) q = -q;
+                if (q < 16777216.0 && q > -16777216.0) {
+                    const double A = rint(q);                   // nearest integer, ties to even (irrelevant: ties are excluded below)
+                    const double r = q - A;                     // exact
+                    if (r != 0.5 && r != -0.5) {
+                        const uint32_t X = (xb & 0x7fffffu) | 0x800000u;
+                        if (A == 0.0) {
+                            // |P| < u/2: x is a fixed point -- unless x sits on its binade's lower edge and shrinks (finer ulp below)
+                            if (q >= 0.0 || X != 0x800000u) return x;
+                        } else {
+                            const long long Ai = (long long)A;
+                            long long n;
+                            if (Ai > 0) n = (long long)(0xffffffu - X) / Ai;
+                            else n = X > 0x800000u ? (long long)(X - 0x800001u) / (-Ai) : 0;
+                            if (n > k) n = k;
+                            if (n > 0) {
+                                const uint32_t Xn = (uint32_t)((long long)X + n * Ai);
+                                x = rp_float((xb & 0xff800000u) | (Xn & 0x7fffffu));
+                                k -= (int)n;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        if (k == 0) break;
+        {   // the step that leaves the binade / a tie / |x| below the addend / zero / inf / nan
+            const float xn = rp_fma(m, f, x);
+            if (rp_bits(xn) == rp_bits(x)) return x;
             x = xn;
             --k;
         }

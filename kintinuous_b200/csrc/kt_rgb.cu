@@ -271,6 +271,7 @@ struct RgbdFrameParams {
     unsigned long long* xwords;    // grid_sum_fixed exchange words (kt_frame.cuh), zero at launch
     float* trace;
     int* timeout;
+    float* host_pose; unsigned int host_seq;      // optional mapped host record: pose (12), time-out (1), sequence number (1)
     int stage_k;               // chunks of FRAME_THREADS pixels per CTA (<= RGBD_MAX_K)
     int with_icp;
 };
@@ -534,6 +535,18 @@ rgbd_frame_kernel(const RgbdFrameParams p)
     if (blockIdx.x == 0 && tid < 12) {
         if (tid < 9) p.st->Rcurr[tid] = s_R[tid]; else p.st->tcurr[tid - 9] = s_t[tid - 9];
         if (tid == 0) p.st->iter = it;
+        if (p.host_pose) {
+            // the estimate also goes straight to mapped, pinned HOST memory (12 floats, the time-out flag, then a sequence number behind a
+            // system-scope fence): the host polls the sequence number instead of paying a D2H copy + stream synchronisation per frame
+            if (tid == 0) {
+                volatile float* hp = p.host_pose;
+                for (int k = 0; k < 9; ++k) hp[k] = s_R[k];
+                for (int k = 0; k < 3; ++k) hp[9 + k] = s_t[k];
+                ((volatile int*)p.host_pose)[12] = p.timeout ? *(volatile int*)p.timeout : 0;
+                __threadfence_system();
+                ((volatile unsigned int*)p.host_pose)[13] = p.host_seq;
+            }
+        }
     }
 }
 
@@ -587,9 +600,10 @@ int rgb_iteration(const RgbLevelArgs& a, OdomState* state, float* partials, floa
 // Whole-frame RGB-D / ICP+RGB-D odometry.  Returns 1 (and launches nothing) when the image does not fit the shared-memory stage,
 // in which case the caller falls back to the per-iteration kernels above.
 int rgbd_frame(const IcpLevelArgs* icp_levels, const RgbLevelArgs* rgb_levels, const int* iters, int with_icp, const float* pose12_host, OdomState* state,
-               unsigned long long* xwords_dev, float* trace, int* timeout_dev, cudaStream_t s)
+               unsigned long long* xwords_dev, float* trace, int* timeout_dev, float* host_pose, unsigned int host_seq, cudaStream_t s)
 {
     RgbdFrameParams p;
+    p.host_pose = host_pose; p.host_seq = host_seq;
     int total = 0;
     for (int l = 0; l < LEVELS; ++l) { p.icp[l] = icp_levels[l]; p.rgb[l] = rgb_levels[l]; p.iters[l] = iters[l]; total += iters[l]; }
     for (int k = 0; k < 12; ++k) p.pose12[k] = pose12_host[k];

@@ -82,7 +82,7 @@ static Mat33 to_mat33(const float* m) { Mat33 r; r.r0 = make_float3(m[0], m[1], 
 struct SliceRec { int dimension; std::vector<kt_point_xyzrgb> points; float camera_t[3]; float camera_R[9]; uint64_t utime; };
 
 // what the host reads back after the odometry of a frame
-struct OdomResult { float Rcurr[9]; float tcurr[3]; int timeout; int pad[3]; };
+struct OdomResult { float Rcurr[9]; float tcurr[3]; int timeout; unsigned int seq; int pad[2]; };     // seq: written last by the odometry kernel (mapped host memory)
 
 } // namespace kt
 
@@ -122,7 +122,7 @@ struct kt_ctx {
     float* lastDepth[LEVELS]; float* nextDepth[LEVELS]; uint8_t* lastImage[LEVELS]; uint8_t* nextImage[LEVELS];
     int16_t* nextdIdx[LEVELS]; int16_t* nextdIdy[LEVELS]; float* pointClouds[LEVELS]; void* corresImg[LEVELS];
     // pinned host staging
-    float* pose12_host; OdomResult* result_host; float* trace_host; unsigned int* counter_host;
+    float* pose12_host; OdomResult* result_host; float* result_dev_alias; unsigned int pose_seq; bool pose_spin; float* trace_host; unsigned int* counter_host;
     int trace_iters; int shifted_last;
     // timing
     bool timing; cudaEvent_t ev[7]; float stage_ms[6]; cudaEvent_t ev_icp[2]; cudaEvent_t ev_span[2];
@@ -228,7 +228,9 @@ int run_odometry(kt_ctx* c, const M3& Rprev, const V3& tprev, M3* Rcurr, V3* tcu
         if (c->timing) cudaEventRecord(c->ev_icp[0], c->stream);
         if (!c->xwords_clean && (r = odom_exchange_reset(c->xwords_dev, c->stream))) return r;
         c->xwords_clean = false;
-        if ((r = icp_frame(la, c->iterations, c->pose12_host, c->state, c->xwords_dev, c->trace_dev, &c->state->odo_timeout, c->timing ? c->prof_dev : 0, c->stream))) return r;
+        ++c->pose_seq;
+        if ((r = icp_frame(la, c->iterations, c->pose12_host, c->state, c->xwords_dev, c->trace_dev, &c->state->odo_timeout, c->timing ? c->prof_dev : 0,
+                           c->pose_spin ? c->result_dev_alias : 0, c->pose_seq, c->stream))) return r;
         if (c->timing) cudaEventRecord(c->ev_icp[1], c->stream);
     }
     const double SOBEL_SCALE = 1.0 / std::pow(2.0, 3);
@@ -255,7 +257,9 @@ int run_odometry(kt_ctx* c, const M3& Rprev, const V3& tprev, M3* Rcurr, V3* tcu
             ra.Kfx = (double)K.fx / div; ra.Kfy = (double)K.fy / div; ra.Kcx = (double)K.cx / div; ra.Kcy = (double)K.cy / div;
         }
         if (!c->xwords_clean && (r = odom_exchange_reset(c->xwords_dev, c->stream))) return r;
-        r = rgbd_frame(la, ra4, c->iterations, mode == 2 ? 1 : 0, c->pose12_host, c->state, c->xwords_dev, c->trace_dev, &c->state->odo_timeout, c->stream);
+        ++c->pose_seq;
+        r = rgbd_frame(la, ra4, c->iterations, mode == 2 ? 1 : 0, c->pose12_host, c->state, c->xwords_dev, c->trace_dev, &c->state->odo_timeout,
+                       c->pose_spin ? c->result_dev_alias : 0, c->pose_seq, c->stream);
         if (r == 0) c->xwords_clean = false;
         if (r < 0) return r;
         if (r == 0) { per_iteration_path = false; for (int level = 0; level < LEVELS; ++level) total_iters += c->iterations[level]; }
@@ -296,9 +300,19 @@ int run_odometry(kt_ctx* c, const M3& Rprev, const V3& tprev, M3* Rcurr, V3* tcu
     c->trace_iters = std::min(total_iters, MAX_TRACE_ITERS);
     // one 64-byte read-back of the estimate (+ the trace when someone asked for it later: it stays on the device)
     static_assert(offsetof(OdomState, odo_timeout) == offsetof(OdomState, Rcurr) + 12 * sizeof(float), "the time-out flag travels with the pose");
-    KT_CUDA(cudaMemcpyAsync(c->result_host->Rcurr, (char*)c->state + offsetof(OdomState, Rcurr), 13 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-    if (c->world > 1) KT_CUDA(cudaMemcpyAsync(c->mg_error_host, c->mg_error_dev, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    KT_CUDA(cudaStreamSynchronize(c->stream));
+    bool got = false;
+    if (c->pose_spin && !per_iteration_path && c->world == 1 && !c->timing) {
+        // the whole-frame kernel wrote the estimate into mapped host memory and then its sequence number: poll it (a few microseconds
+        // after the kernel's last store) instead of a D2H copy + stream synchronisation; bounded, then the ordinary path takes over
+        volatile unsigned int* seq = &c->result_host->seq;
+        for (long spins = 0; spins < 4000000L; ++spins) { if (*seq == c->pose_seq) { got = true; break; } }
+        std::atomic_thread_fence(std::memory_order_acquire);
+    }
+    if (!got) {
+        KT_CUDA(cudaMemcpyAsync(c->result_host->Rcurr, (char*)c->state + offsetof(OdomState, Rcurr), 13 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        if (c->world > 1) KT_CUDA(cudaMemcpyAsync(c->mg_error_host, c->mg_error_dev, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        KT_CUDA(cudaStreamSynchronize(c->stream));
+    }
     if (c->world > 1 && *c->mg_error_host) { set_error("cross-GPU barrier timed out waiting for rank %d", *c->mg_error_host - 1); return KT_ERR_STATE; }
     if (c->result_host->timeout) {
         cudaMemsetAsync(&c->state->odo_timeout, 0, sizeof(int), c->stream);
@@ -603,7 +617,10 @@ int kt_create(const kt_config* cfg, kt_ctx** out)
     c->cloud_capacity = (size_t)c->cfg.cloud_capacity;
     KT_TRY(dev_alloc(c, &c->cloud_dev, c->cloud_capacity)); KT_TRY(dev_alloc(c, &c->counter_dev, 1));
     KT_TRY(kt::cuda_check(cudaMallocHost((void**)&c->pose12_host, 12 * sizeof(float)), "pinned", __FILE__, __LINE__));
-    KT_TRY(kt::cuda_check(cudaMallocHost((void**)&c->result_host, sizeof(OdomResult)), "pinned", __FILE__, __LINE__));
+    KT_TRY(kt::cuda_check(cudaHostAlloc((void**)&c->result_host, sizeof(OdomResult), cudaHostAllocMapped), "pinned", __FILE__, __LINE__));
+    std::memset(c->result_host, 0, sizeof(OdomResult));
+    { void* dp = 0; KT_TRY(kt::cuda_check(cudaHostGetDevicePointer(&dp, c->result_host, 0), "mapped", __FILE__, __LINE__)); c->result_dev_alias = (float*)dp; }
+    c->pose_seq = 0; c->pose_spin = getenv("KT_NO_POSE_SPIN") == nullptr;
     KT_TRY(kt::cuda_check(cudaMallocHost((void**)&c->trace_host, (size_t)MAX_TRACE_ITERS * TRACE_STRIDE * sizeof(float)), "pinned", __FILE__, __LINE__));
     KT_TRY(kt::cuda_check(cudaMallocHost((void**)&c->counter_host, sizeof(unsigned int)), "pinned", __FILE__, __LINE__));
     for (int i = 0; i < 7; ++i) KT_TRY(kt::cuda_check(cudaEventCreate(&c->ev[i]), "event", __FILE__, __LINE__));
@@ -817,13 +834,14 @@ int kt_volume_export_reference_layout(kt_ctx* c, int16_t* tsdf_host, uint8_t* co
 
 int kt_download_map(kt_ctx* c, int which, int level, void* dst)
 {
-    if (!c || !dst || level < 0 || level >= LEVELS || which < 0 || which > 5) return KT_ERR_INVALID;
+    if (!c || !dst || level < 0 || level >= LEVELS || which < 0 || which > 8) return KT_ERR_INVALID;
     KT_CUDA(cudaSetDevice(c->cfg.device));
     const size_t Pl = ((size_t)c->cfg.rows * c->cfg.cols) >> (2 * level);
     const void* src = which == 0 ? (void*)c->vmaps_curr[level] : which == 1 ? (void*)c->nmaps_curr[level] :
                       which == 2 ? (void*)c->vmaps_g_prev[level] : which == 3 ? (void*)c->nmaps_g_prev[level] :
-                      which == 4 ? (void*)c->depths_curr[level] : (void*)c->vmap_curr_color;
-    const size_t bytes = which <= 3 ? Pl * 12 : which == 4 ? Pl * 2 : Pl * 4;
+                      which == 4 ? (void*)c->depths_curr[level] : which == 5 ? (void*)c->vmap_curr_color :
+                      which == 6 ? (void*)c->depth_scaled : which == 7 ? (void*)c->cw_scratch : (void*)c->rgbf_scratch;      // 6-8: integration inputs, level 0
+    const size_t bytes = which <= 3 ? Pl * 12 : which == 4 ? Pl * 2 : which == 8 ? Pl * 16 : Pl * 4;
     KT_CUDA(cudaStreamSynchronize(c->stream));
     KT_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
     return KT_OK;
@@ -923,6 +941,62 @@ float kt_span_elapsed_ms(kt_ctx* c)
     float t = 0.f;
     if (cudaEventSynchronize(c->ev_span[1]) != cudaSuccess || cudaEventElapsedTime(&t, c->ev_span[0], c->ev_span[1]) != cudaSuccess) { cudaGetLastError(); return -1.f; }
     return t;
+}
+
+// ---- OdometryProvider at the ABI (OdometryProvider.h:42-52): one call = ICPOdometry / RGBDOdometry::getIncrementalTransformation
+// (ICPOdometry.cpp:68-186, RGBDOdometry.cpp:165-393) on the whole-frame kernels, for a caller that owns the pose history and the maps (the
+// reference's KintinuousTracker, or a fork of it).  The context only lends its odometry scratch and, for the photometric modes, keeps the
+// last / next pyramids between calls like the RGBDOdometry object does.
+int kt_odometry_first_run(kt_ctx* c, const uint16_t* depth_dev, const uint8_t* rgb_dev)             // RGBDOdometry::firstRun (RGBDOdometry.cpp:160-163)
+{
+    if (!c || !depth_dev || !rgb_dev) { set_error("kt_odometry_first_run: null argument"); return KT_ERR_INVALID; }
+    KT_CUDA(cudaSetDevice(c->cfg.device));
+    if (c->cfg.odometry == 0) return KT_OK;
+    FrontendArgs fa; std::memset(&fa, 0, sizeof(fa));
+    fa.depth_raw = depth_dev; fa.rgb = rgb_dev; fa.rows = c->cfg.rows; fa.cols = c->cfg.cols; fa.k.fx = c->cfg.fx; fa.k.fy = c->cfg.fy; fa.k.cx = c->cfg.cx; fa.k.cy = c->cfg.cy;
+    fa.depths = c->depths_curr; fa.cut_off = 6000; fa.depth_m = c->lastDepth; fa.intensity = c->lastImage; fa.dIdx = c->nextdIdx; fa.dIdy = c->nextdIdy;
+    int r = frontend_pyramid(fa, c->stream); if (r) return r;
+    KT_CUDA(cudaStreamSynchronize(c->stream));
+    return KT_OK;
+}
+
+int kt_odometry_increment(kt_ctx* c, const uint16_t* depth_dev, const uint8_t* rgb_dev, const float* Rprev9, const float* tprev3,
+                          const float* const* vmaps_g_prev4, const float* const* nmaps_g_prev4,
+                          const float* const* vmaps_curr4, const float* const* nmaps_curr4, float* Rcurr9, float* tcurr3)
+{
+    if (!c || !Rprev9 || !tprev3 || !vmaps_g_prev4 || !nmaps_g_prev4 || !Rcurr9 || !tcurr3) { set_error("kt_odometry_increment: null argument"); return KT_ERR_INVALID; }
+    if ((!vmaps_curr4 || !nmaps_curr4 || c->cfg.odometry != 0) && (!depth_dev || !rgb_dev)) { set_error("kt_odometry_increment: this mode needs the depth / colour frame"); return KT_ERR_INVALID; }
+    KT_CUDA(cudaSetDevice(c->cfg.device));
+    int r;
+    float* keep[4][LEVELS];
+    for (int l = 0; l < LEVELS; ++l) { keep[0][l] = c->vmaps_g_prev[l]; keep[1][l] = c->nmaps_g_prev[l]; keep[2][l] = c->vmaps_curr[l]; keep[3][l] = c->nmaps_curr[l]; }
+    auto restore = [&]() { for (int l = 0; l < LEVELS; ++l) { c->vmaps_g_prev[l] = keep[0][l]; c->nmaps_g_prev[l] = keep[1][l]; c->vmaps_curr[l] = keep[2][l]; c->nmaps_curr[l] = keep[3][l]; } };
+    if (vmaps_curr4 && nmaps_curr4) {
+        // the caller's current maps (createVMap / createNMap of its own pyramid); the photometric set still comes from the frame
+        if (c->cfg.odometry != 0) {
+            FrontendArgs fa; std::memset(&fa, 0, sizeof(fa));
+            fa.depth_raw = depth_dev; fa.rgb = rgb_dev; fa.rows = c->cfg.rows; fa.cols = c->cfg.cols; fa.k.fx = c->cfg.fx; fa.k.fy = c->cfg.fy; fa.k.cx = c->cfg.cx; fa.k.cy = c->cfg.cy;
+            fa.depths = c->depths_curr; fa.cut_off = 6000; fa.depth_m = c->nextDepth; fa.intensity = c->nextImage; fa.dIdx = c->nextdIdx; fa.dIdy = c->nextdIdy;
+            if ((r = frontend_pyramid(fa, c->stream))) return r;
+        }
+        for (int l = 0; l < LEVELS; ++l) { c->vmaps_curr[l] = const_cast<float*>(vmaps_curr4[l]); c->nmaps_curr[l] = const_cast<float*>(nmaps_curr4[l]); }
+    } else {
+        if ((r = build_frontend(c, depth_dev, rgb_dev, c->depth_scaled, c->depths_curr, c->vmaps_curr, c->nmaps_curr, 0, 0, c->cw_scratch, c->rgbf_scratch,
+                                c->cfg.odometry != 0 ? c->nextDepth : 0, c->cfg.odometry != 0 ? c->nextImage : 0, c->stream))) return r;
+    }
+    for (int l = 0; l < LEVELS; ++l) { c->vmaps_g_prev[l] = const_cast<float*>(vmaps_g_prev4[l]); c->nmaps_g_prev[l] = const_cast<float*>(nmaps_g_prev4[l]); }
+    M3 Rp, Rc; V3 tp, tc;
+    for (int k = 0; k < 9; ++k) Rp.m[k] = Rprev9[k];
+    for (int k = 0; k < 3; ++k) tp.v[k] = tprev3[k];
+    Rc = Rp; tc = tp;
+    const bool fr = c->frontend_ready; c->frontend_ready = true;          // the front end of this call is already built
+    r = run_odometry(c, Rp, tp, &Rc, &tc);
+    c->frontend_ready = fr;
+    restore();
+    if (r) return r;
+    for (int k = 0; k < 9; ++k) Rcurr9[k] = Rc.m[k];
+    for (int k = 0; k < 3; ++k) tcurr3[k] = tc.v[k];
+    return KT_OK;
 }
 
 // getLiveImage (KintinuousTracker.cpp:835-862, 960-981, 1125-1154): shaded weight image, colour image and model depth of the predicted

@@ -103,6 +103,7 @@ struct IntegrateParams {
     int lz_lo, lz_hi;          // LOGICAL z range walked by this launch
     int z_far_first;           // schedule the z chunks from high z to low z (see integrate())
     VolumeView vv;             // shared volume (MG instances): plane ownership and the peers' TSDF replicas
+    int seq_replay;            // test hook: replay the running sums one addition at a time instead of replay_add()
 };
 
 #define KT_MAX_WEIGHT 128          // Tsdf::MAX_WEIGHT (tsdf_volume.cu:486)
@@ -169,8 +170,13 @@ integrate_kernel(const IntegrateParams p)
     float v_y = __fmul_rn(__fmaf_rn(Rcurr_inv.r1.z, v_g_z, __fmaf_rn(Rcurr_inv.r1.x, v_g_x, __fmul_rn(Rcurr_inv.r1.y, v_g_y))), intr.fy);
     float v_z = __fmaf_rn(Rcurr_inv.r2.z, v_g_z, __fmaf_rn(Rcurr_inv.r2.x, v_g_x, __fmul_rn(Rcurr_inv.r2.y, v_g_y)));
 
-    float Rcurr_inv_0_z_scaled = Rcurr_inv.r0.z * cell_size.z * intr.fx;
+    float Rcurr_inv_0_z_scaled = Rcurr_inv.r0.z * cell_size.z * intr.fx;      // used by the conservative frustum interval only
     float Rcurr_inv_1_z_scaled = Rcurr_inv.r1.z * cell_size.z * intr.fy;
+    // The z step of the running sums, as the reference build executes it (its SASS: FMUL m = cell.z * R.z once, then FFMA v = m * f + v per z):
+    // nvcc contracts  v_x += Rcurr_inv.z * cell_size.z * intr.fx  (tsdf_volume.cu:574), so the addend is the EXACT product m * f, not
+    // its float rounding.  Adding the rounded product instead differs in the last bit of v_x about once per 10^7 voxel updates, enough
+    // to pick the neighbouring depth pixel for a few voxels per frame (found by the 512^3 replay test).
+    const float m0z = __fmul_rn(Rcurr_inv.r0.z, cell_size.z), m1z = __fmul_rn(Rcurr_inv.r1.z, cell_size.z);
 
     float tranc_dist_inv = 1.0f / tranc_dist;
 
@@ -219,10 +225,14 @@ integrate_kernel(const IntegrateParams p)
         if (zlo >= zhi) return;
     }
 
-    // the running sums at zlo: exactly the bits the reference reaches after zlo additions, in O(binades crossed) instead of O(zlo)
-    // dependent FADDs (kt_replay.cuh; the one-by-one replay was about a quarter of this kernel's issued instructions)
-    v_x = replay_add(v_x, Rcurr_inv_0_z_scaled, zlo);
-    v_y = replay_add(v_y, Rcurr_inv_1_z_scaled, zlo);
+    // the running sums at zlo: exactly the bits the reference reaches after zlo steps, in O(binades crossed) instead of O(zlo)
+    // dependent FFMAs (kt_replay.cuh; the one-by-one replay was about a quarter of this kernel's issued instructions)
+    if (p.seq_replay) {            // KT_INT_SEQ_REPLAY (test hook): the additions one by one, as the reference performs them
+        for (int z = 0; z < zlo; ++z) { v_x = __fmaf_rn(m0z, intr.fx, v_x); v_y = __fmaf_rn(m1z, intr.fy, v_y); }
+    } else {
+        v_x = replay_fma(v_x, m0z, intr.fx, zlo);
+        v_y = replay_fma(v_y, m1z, intr.fy, zlo);
+    }
 
     const float* __restrict__ zt = p.ztable;
     const float* __restrict__ depthScaled = p.depth_scaled;
@@ -245,8 +255,8 @@ integrate_kernel(const IntegrateParams p)
                 const int foreign = (p.vv.rank - blk - 1) & (p.vv.world - 1);          // whole foreign blocks between this one and mine
                 int skip = (((blk + 1) << p.vv.bshift) - sz) + (foreign << p.vv.bshift);
                 skip = min(skip, zhi - zb);
-                v_x = replay_add(v_x, Rcurr_inv_0_z_scaled, skip);
-                v_y = replay_add(v_y, Rcurr_inv_1_z_scaled, skip);
+                v_x = replay_fma(v_x, m0z, intr.fx, skip);
+                v_y = replay_fma(v_y, m1z, intr.fy, skip);
                 zb += skip - ZU;
                 continue;
             }
@@ -275,8 +285,8 @@ integrate_kernel(const IntegrateParams p)
                         Dp[u] = depthScaled[pix[u]];
                     }
                 }
-                v_x += Rcurr_inv_0_z_scaled;
-                v_y += Rcurr_inv_1_z_scaled;
+                v_x = __fmaf_rn(m0z, intr.fx, v_x);
+                v_y = __fmaf_rn(m1z, intr.fy, v_y);
             }
         }
         bool upd[ZU], nocol[ZU];
@@ -324,9 +334,9 @@ integrate_kernel(const IntegrateParams p)
                 if ((__float_as_int(cwv) >= 0 && !nocol[u]) || (c.x == 0 && c.y == 0 && c.z == 0)) {
                     const float Wrkc = fabsf(cwv);
                     const float4 rgb = rgbq[u];
-                    float new_x = __fmaf_rn(c.x, weight_prev, __fmul_rn(Wrkc, rgb.x)) / (weight_prev + Wrkc);   // (c * W + Wrkc * rgb) / (W + Wrkc)
-                    float new_y = __fmaf_rn(c.y, weight_prev, __fmul_rn(Wrkc, rgb.y)) / (weight_prev + Wrkc);
-                    float new_z = __fmaf_rn(c.z, weight_prev, __fmul_rn(Wrkc, rgb.z)) / (weight_prev + Wrkc);
+                    float new_x = __fmaf_rn(Wrkc, rgb.x, __fmul_rn(c.x, weight_prev)) / (weight_prev + Wrkc);   // (c * W + Wrkc * rgb) / (W + Wrkc): the reference build fuses Wrkc * rgb into the sum (SASS: FMUL W * c, then FFMA Wrkc * rgb + that)
+                    float new_y = __fmaf_rn(Wrkc, rgb.y, __fmul_rn(c.y, weight_prev)) / (weight_prev + Wrkc);
+                    float new_z = __fmaf_rn(Wrkc, rgb.z, __fmul_rn(c.z, weight_prev)) / (weight_prev + Wrkc);
                     c.x = sat_u8_rn(new_x);
                     c.y = sat_u8_rn(new_y);
                     c.z = sat_u8_rn(new_z);
@@ -337,9 +347,9 @@ integrate_kernel(const IntegrateParams p)
                 if ((!isnan(ncurr.x) && !nocol[u]) || (c.x == 0 && c.y == 0 && c.z == 0)) {
                     const float Wrkc = (p.angle_color ? min(1.0f, ncurr.z / KT_RGB_VIEW_ANGLE_WEIGHT) : 1.0f) * 2.0f;
                     uchar3 rgb = rgbv[u];
-                    float new_x = __fmaf_rn(c.x, weight_prev, __fmul_rn(Wrkc, rgb.x)) / (weight_prev + Wrkc);   // (c * W + Wrkc * rgb) / (W + Wrkc)
-                    float new_y = __fmaf_rn(c.y, weight_prev, __fmul_rn(Wrkc, rgb.y)) / (weight_prev + Wrkc);
-                    float new_z = __fmaf_rn(c.z, weight_prev, __fmul_rn(Wrkc, rgb.z)) / (weight_prev + Wrkc);
+                    float new_x = __fmaf_rn(Wrkc, rgb.x, __fmul_rn(c.x, weight_prev)) / (weight_prev + Wrkc);   // (c * W + Wrkc * rgb) / (W + Wrkc): the reference build fuses Wrkc * rgb into the sum (SASS: FMUL W * c, then FFMA Wrkc * rgb + that)
+                    float new_y = __fmaf_rn(Wrkc, rgb.y, __fmul_rn(c.y, weight_prev)) / (weight_prev + Wrkc);
+                    float new_z = __fmaf_rn(Wrkc, rgb.z, __fmul_rn(c.z, weight_prev)) / (weight_prev + Wrkc);
                     c.x = min(255, max(0, __float2int_rn(new_x)));
                     c.y = min(255, max(0, __float2int_rn(new_y)));
                     c.z = min(255, max(0, __float2int_rn(new_z)));
@@ -458,6 +468,8 @@ int integrate(const IntegrateArgs& a, float* ztable_dev, cudaStream_t s)
     static const bool force64 = getenv("KT_FORCE_IDX64") != nullptr;
     const bool idx32 = !force64 && (size_t)V * V * V <= ((size_t)1 << 31);
     p.lz_lo = 0; p.lz_hi = V;
+    static const bool seq_replay = getenv("KT_INT_SEQ_REPLAY") != nullptr;
+    p.seq_replay = seq_replay ? 1 : 0;
     dim3 block(32, 8), grid(div_up(V, 32), div_up(V, 8), div_up(V, p.zchunk));
     if (multi) {
         if (V & (V - 1)) { set_error("integrate: the shared volume needs a power-of-two resolution"); return -1; }

@@ -269,12 +269,14 @@ def test_kernel_variants_are_bit_identical(built):
       cannot run there, its int index overflows -- SURVEY.md D5), here on a 256^3 volume;
     * KT_INT_PREP=0: the colour update with the reference's per-voxel arithmetic (the operator-level golden tests pin that form against
       the reference) versus the default, which prepares the per-pixel colour weight and float RGB once per frame;
-    * KT_INT_ZU=1: one voxel per step at 6 CTAs/SM (the default for volumes >= 1024^3)."""
+    * KT_INT_ZU=1: one voxel per step at 6 CTAs/SM (the default for volumes >= 1024^3);
+    * KT_INT_SEQ_REPLAY=1: the running sums of a column replayed one float addition at a time up to its first voxel, as the reference
+      does, versus the default exact fast-forward (kt_replay.cuh, replay_add)."""
     import subprocess
     import sys
     from conftest import ROOT
     out = {}
-    for tag, extra in (("default", {}), ("idx64", {"KT_FORCE_IDX64": "1"}), ("noprep", {"KT_INT_PREP": "0"}), ("zu1", {"KT_INT_ZU": "1"}),
+    for tag, extra in (("default", {}), ("idx64", {"KT_FORCE_IDX64": "1"}), ("noprep", {"KT_INT_PREP": "0"}), ("zu1", {"KT_INT_ZU": "1"}), ("seqreplay", {"KT_INT_SEQ_REPLAY": "1"}),
                        ("idx64_noprep", {"KT_FORCE_IDX64": "1", "KT_INT_PREP": "0"})):
         env = dict(os.environ, PYTHONPATH=ROOT, **extra)
         r = subprocess.run([sys.executable, "-c", _IDX64_SCRIPT], env=env, capture_output=True, text=True, timeout=600, cwd=ROOT)

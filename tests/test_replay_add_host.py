@@ -72,3 +72,30 @@ def test_stress_rounded_values(lib):
     a = np.where(rng.random(n) < 0.3, np.round(a * 2.0 ** rng.integers(0, 20, n)) / 2.0 ** rng.integers(0, 20, n), a)
     x = np.where(rng.random(n) < 0.2, np.round(x * 4) / 4, x)
     assert _check(lib, x, a, rng.integers(0, 1200, n)) == 0
+
+
+def _check_fma(lib, x, m, f, k):
+    x = np.ascontiguousarray(x, np.float32); m = np.ascontiguousarray(m, np.float32); f = np.ascontiguousarray(f, np.float32); k = np.ascontiguousarray(k, np.int32)
+    return lib.ktr_check_many_fma(x.ctypes.data_as(C.c_void_p), m.ctypes.data_as(C.c_void_p), f.ctypes.data_as(C.c_void_p), k.ctypes.data_as(C.c_void_p), len(x))
+
+
+def test_replay_fma_matches_the_fused_loop(lib):
+    """The step the reference build really executes along z is v = fma(m, f, v) (nvcc contracts v += R.z * cell * f, tsdf_volume.cu:574): the
+    addend is the exact 48-bit product.  replay_fma(x, m, f, k) against k sequential fmaf: random magnitudes, rounded operands (exact
+    products, ties), zeros, and the kernel's ranges (m = R.z * cell ~ 1e-6 .. 1e-2, f = fx ~ 528, x = fx * p_x up to a few thousand)."""
+    rng = np.random.default_rng(5)
+    n = 800000
+    x = rng.standard_normal(n) * 2.0 ** rng.integers(-12, 14, n)
+    m = rng.standard_normal(n) * 2.0 ** rng.integers(-14, 2, n)
+    f = rng.standard_normal(n) * 2.0 ** rng.integers(-2, 11, n)
+    m = np.where(rng.random(n) < 0.3, np.round(m * 2.0 ** rng.integers(0, 16, n)) / 2.0 ** rng.integers(0, 16, n), m)
+    f = np.where(rng.random(n) < 0.3, np.round(f * 4) / 4, f)
+    x = np.where(rng.random(n) < 0.2, np.round(x * 4) / 4, x)
+    assert _check_fma(lib, x, m, f, rng.integers(0, 1200, n)) == 0
+    n = 600000
+    x = rng.uniform(-3500, 3500, n); m = rng.uniform(-1, 1, n) * 0.0117 * rng.choice([1, 0.1, 0.01, 1e-4], n)
+    f = np.full(n, 528.0144) * rng.choice([1, 2, 0.5], n)
+    assert _check_fma(lib, x, m, f, rng.integers(0, 2049, n)) == 0
+    z = np.zeros(2000)
+    assert _check_fma(lib, z, rng.standard_normal(2000), rng.standard_normal(2000), rng.integers(0, 50, 2000)) == 0
+    assert _check_fma(lib, rng.standard_normal(2000), z, rng.standard_normal(2000), rng.integers(0, 50, 2000)) == 0

@@ -8,6 +8,7 @@ for step in "$@"; do
     tail)  timeout 300 tools/bin/tail_bench > gpurun_out/${TAG}_tail_bench.txt 2>&1; tail -40 gpurun_out/${TAG}_tail_bench.txt ;;
     tests) timeout 2400 python -m pytest tests -m gpu -x -q --tb=short > gpurun_out/${TAG}_pytest_full.log 2>&1; grep -E "^E |Error|passed|failed" gpurun_out/${TAG}_pytest_full.log | head -40 | tee gpurun_out/${TAG}_pytest.log ;;
     tests_all) timeout 3000 python -m pytest tests -m gpu -q --tb=short > gpurun_out/${TAG}_pytest_full.log 2>&1; grep -E "^E  +(Assert|assert)|Error|passed|failed|FAILED|^cfg odometry|colour mismatches" gpurun_out/${TAG}_pytest_full.log | cut -c1-400 | head -60 | tee gpurun_out/${TAG}_pytest.log ;;
+    replayab) python tools/replay_ab.py 1 12 2>&1 | tail -30 | cut -c1-300 | tee gpurun_out/${TAG}_replayab.txt ;;
     mg2) timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/mgpu_check.py --vol 256 --frames 10 --voxel-shift 2 2>&1 | grep -E "MGPU_CHECK|mismatch|Error|error|slice" | cut -c1-400 | tee gpurun_out/${TAG}_mg2.log
          timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 tools/mgpu_check.py --vol 256 --frames 8 --voxel-shift 2 --odometry 2 2>&1 | grep -E "MGPU_CHECK|mismatch|Error|error|slice" | cut -c1-400 | tee -a gpurun_out/${TAG}_mg2.log ;;
     mgbench) NG=${NG:-2}; timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus $NG --steps 100 --warmup 10 --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/${TAG}_bench_${NG}gpu.json

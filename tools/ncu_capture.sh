@@ -4,7 +4,7 @@
 #   tools/ncu_capture.sh <tag> [odometry] [kernel ...]
 set -u
 TAG=${1:-r1}; ODO=${2:-0}; shift 2 || true
-KERNELS=${@:-icp_frame_kernel integrate_kernel raycast_kernel bilateral_kernel}
+KERNELS=${@:-icp_frame_kernel integrate_kernel raycast_kernel bilateral_scale_kernel frontend_pyramid_kernel}
 export KT_BENCH_FRAMES=8
 mkdir -p gpurun_out
 BENCH="python bench.py --steps 4 --warmup 3 --no-cpu-baseline --odometry $ODO"
