@@ -4,14 +4,19 @@ odometry modes -- against the reference's CUDA path compiled for VOL=512 (oracle
 Three statements per run, each exact or with its tolerance written here:
 
 1. POSES (north_star: <= 1e-4 m / 1e-4 rad).  Frame by frame against the reference tracker (KintinuousTracker.cpp:444-915 restated in
-   oracle/kt_host_logic.hpp driving the reference's own kernels).  ICP-only: rotation <= 1e-4 rad and the y / z translation <= 1e-4 m on
-   EVERY frame; the full translation <= 1e-4 m and its per-frame increment <= 2e-5 m through frame 40 (two -t 14 shifts).  After that the
-   synthetic camera has left the sphere and the cube behind and the direction of travel (x) is constrained by little geometry: the
-   normal matrix is ill-conditioned along x, the 1e-7 differences of the two summation orders are amplified, and the x translations drift
-   apart by up to ~1.5e-4 m in a single frame (y and z stay at 3e-6) -- frames 41..71 are held to 1e-3 m in x and the worst values are
-   printed.  The photometric modes (-r, -ri) pick discrete
-   correspondences, so the reference itself amplifies 1e-7 input differences: the first frames are held to 1e-4,
-   later ones to 2e-3.  The shift events (voxelWrap per frame) must be identical throughout in every mode.
+   oracle/kt_host_logic.hpp driving the reference's own kernels).  The tracker is a closed loop (pose -> fused volume -> predicted
+   surface -> next pose), so a long sequence can only be compared while the REFERENCE ITSELF is stable; that horizon is measured, not
+   assumed: a second reference instance ("ref'") gets the same stream with ONE depth pixel of frame 1 raised by 1 mm (the smallest
+   possible input change), and the stable horizon K* is the first frame where ref' has moved more than 2e-5 m away from ref.  On this
+   synthetic stream (tools/pose_sensitivity.py, B200): through frame 45 -- three -t 14 shifts -- ref' stays within 6e-6 m of ref and the
+   product within 8.1e-6 m; from frame 46 the camera has left the sphere and the cube behind, only the back wall is in view, x (the
+   direction of travel) is unconstrained, and at the shift of frame 51 ref' jumps 7.5 cm away from ref (the product 4 cm): no two
+   implementations -- nor two runs of the reference on inputs differing by one LSB -- agree beyond that point.
+   ICP-only: for every frame k < K* (K* >= 40 is asserted): translation <= 1e-4 m, rotation <= 1e-4 rad, per-frame increment of the
+   global position <= 2e-5 m, identical shift events.  For k >= K* only statements 2 and 3 (which do not depend on the reference's
+   trajectory) and a gross sanity bound continue.  The photometric modes (-r, -ri) pick discrete correspondences, so the reference
+   amplifies 1e-7 differences from the start: the first frames are held to 1e-4, later ones to 2e-3; shift
+   events identical throughout.
 
 2. VOLUME, EXACT.  The sequence-level TSDF bar cannot be "every voxel within 1 LSB of the reference's run": the two trackers' poses differ
    in the 7th digit, which moves a handful of voxel projections across a pixel boundary, and such a voxel fuses a DIFFERENT pixel's depth
@@ -87,6 +92,7 @@ def test_baseline_config_512_live_replay_exact(built, frames26, odometry, nframe
     assert cfg.voxel_shift == 14 and cfg.overlap == 2
     mine = kb.Tracker(cfg)
     rt = ref.tracker(refbind.TrackerConfig.from_kt(cfg))
+    rp = ref.tracker(refbind.TrackerConfig.from_kt(cfg)) if odometry == 0 else None      # ref': 1-LSB perturbed input (statement 1)
     intr = np.array(synth.intrinsics(COLS, ROWS), np.float32)
     vs = [SIZE] * 3
     trunc = mine.trunc_dist
@@ -104,26 +110,45 @@ def test_baseline_config_512_live_replay_exact(built, frames26, odometry, nframe
     slice_points = 0
     shifted_frames = []
     prev = None
-    worst_t = worst_inc = 0.0
+    worst_t = worst_inc = worst_self = 0.0
+    horizon = None                                                      # K*: first frame where the reference is unstable under a 1-LSB input change
+    slices_at_horizon = None
     for k in range(nframes):
         d, c = frames26[k]
         p = mine.process_frame(d, c, k); rt.process(d, c, k)
         Ra, ta, ga, wa = p.as_tuple(); Rb, tb, gb, wb = rt.pose()
+        if rp is not None:
+            dp = d
+            if k == 1:
+                dp = d.copy(); dp[ROWS // 2, COLS // 2] += 1
+            rp.process(dp, c, k)
+            _, _, gp, wp = rp.pose()
+            self_dev = float(np.abs(gp - gb).max())
+            if horizon is None and (self_dev > 2e-5 or not (wp == wb).all()):
+                horizon = k; slices_at_horizon = n_slices
+                print(f"stable horizon K* = {k}: the reference moved {self_dev:.2e} m under a 1-LSB change of one depth pixel of frame 1")
+            if horizon is None:
+                worst_self = max(worst_self, self_dev)
+        stable = horizon is None
         # ---- 1. poses ----
-        assert (wa == wb).all(), (odometry, k, wa, wb)                  # identical shift events
-        dt = float(np.abs(ta - tb).max()); worst_t = max(worst_t, dt)
+        dt = float(np.abs(ta - tb).max())
         if odometry == 0:
-            assert rot_angle(Ra, Rb) <= 1e-4, (k, rot_angle(Ra, Rb))
-            dyz = float(np.abs(ta - tb)[1:].max())
-            assert dt <= (1e-4 if k <= 40 else 1e-3) and dyz <= 1e-4, (k, dt, dyz)
-            if prev is not None:
-                inc = float(np.abs((ga - prev[0]) - (gb - prev[1])).max()); worst_inc = max(worst_inc, inc)
-                assert inc <= (2e-5 if k <= 40 else 5e-4), (k, inc)
-            tol = 1e-4 if k <= 40 else 1e-3
+            if stable:
+                assert (wa == wb).all(), (odometry, k, wa, wb)          # identical shift events
+                worst_t = max(worst_t, dt)
+                assert rot_angle(Ra, Rb) <= 1e-4, (k, rot_angle(Ra, Rb))
+                assert dt <= 1e-4 and np.abs(ga - gb).max() <= 1e-4, (k, dt)
+                if prev is not None:
+                    inc = float(np.abs((ga - prev[0]) - (gb - prev[1])).max()); worst_inc = max(worst_inc, inc)
+                    assert inc <= 2e-5, (k, inc)
+            else:
+                assert np.abs(ga - gb).max() <= 0.25, (k, ga, gb)       # gross sanity only: see the module docstring
         else:
+            assert (wa == wb).all(), (odometry, k, wa, wb)
+            worst_t = max(worst_t, dt)
             tol = 1e-4 if k < 4 else 2e-3
             assert dt <= tol and rot_angle(Ra, Rb) <= tol, (odometry, k, dt, rot_angle(Ra, Rb))
-        assert np.abs(ga - gb).max() <= tol
+            assert np.abs(ga - gb).max() <= tol
         prev = (ga.copy(), gb.copy())
         # ---- 2./3. replay this frame with the reference's operators on the product's pose ----
         dd = torch.from_numpy(d.view(np.int16)).cuda(); cc = torch.from_numpy(c).cuda()
@@ -155,11 +180,18 @@ def test_baseline_config_512_live_replay_exact(built, frames26, odometry, nframe
         Rinv, tint, wint = mine.last_integrate()
         assert list(wint) == (vwrap_nonneg(cur) if k > 0 else [0, 0, 0])
         ref.integrate(dd, ROWS, COLS, intr, vs, Rinv, tint, trunc, ts, cs, wint, cc, nm, 1, ds)
-    assert mine.num_slices() == n_slices == rt.num_slices()
+    assert mine.num_slices() == n_slices
+    if odometry == 0:
+        assert horizon is None or horizon >= 40, horizon               # the synthetic scene is well conditioned for at least 40 frames
+        n_cmp = n_slices if horizon is None else slices_at_horizon
+    else:
+        n_cmp = n_slices
+        assert rt.num_slices() == n_slices
     assert n_slices >= 1, "the run must cross the -t 14 shift threshold"
     if odometry == 0:
         assert n_slices >= 4 and slice_points > 1000, (n_slices, slice_points)      # a leaving slab that really contains surface
-    for i in range(n_slices):                                           # the reference tracker's own slices: same events, same sizes to 1 %
+        assert n_cmp >= 3, n_cmp                                        # three shifts inside the stable horizon
+    for i in range(n_cmp):                                              # the reference tracker's own slices: same events, same sizes to 1 %
         a, dim_a, _ = mine.get_slice(i); b, dim_b, _ = rt.get_slice(i)
         assert dim_a == dim_b and abs(len(a) - len(b)) <= 0.01 * len(b) + 5, (i, len(a), len(b))
     torch.cuda.synchronize()
@@ -177,11 +209,13 @@ def test_baseline_config_512_live_replay_exact(built, frames26, odometry, nframe
     tb_, cb_ = rt.export_volume()
     dlsb = np.abs(ta_.astype(np.int32) - tb_.astype(np.int32))[cb_[..., 3] != 0]
     frac = float((dlsb <= 1).mean())
-    print(f"cfg odometry={odometry}: worst |dt| {worst_t:.3e} m, worst per-frame increment difference {worst_inc:.3e} m; {nframes} frames, shifts at {shifted_frames} ({slice_points} slice points), touched {touched}, replay mismatches 0/0, "
+    print(f"cfg odometry={odometry}: stable horizon {horizon}, worst |dt| {worst_t:.3e} m (reference vs its 1-LSB-perturbed self: {worst_self:.3e} m), worst per-frame increment difference {worst_inc:.3e} m; {nframes} frames, shifts at {shifted_frames} ({slice_points} slice points), touched {touched}, replay mismatches 0/0, "
           f"vs reference tracker: {frac:.6f} of touched voxels within 1 LSB, worst {int(dlsb.max())} LSB")
-    if odometry == 0:
+    if odometry == 0 and horizon is None:
         assert frac >= 0.999
     mine.close(); rt.close()
+    if rp is not None:
+        rp.close()
 
 
 _PI_SCRIPT = r"""
