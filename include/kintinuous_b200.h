@@ -78,6 +78,16 @@ typedef struct kt_point_xyzrgb {
     uint8_t _pad1[12];
 } kt_point_xyzrgb;
 
+/* 48-byte point, byte-compatible with pcl::PointXYZRGBNormal: what CloudSliceProcessor hands to the deformation / meshing backend
+ * (backend/CloudSliceProcessor.cpp:162, CloudSlice::processedCloud, CloudSlice.h:57). */
+typedef struct kt_point_xyzrgbnormal {
+    float x, y, z, data3;            /* data3 = 1 (PCL's homogeneous coordinate) */
+    float nx, ny, nz, data_n3;
+    uint8_t b, g, r, a;
+    float curvature;
+    float pad[2];
+} kt_point_xyzrgbnormal;
+
 typedef struct kt_ctx kt_ctx;
 
 KT_API const char* kt_last_error(void);
@@ -111,11 +121,27 @@ KT_API int kt_num_slices(kt_ctx* ctx);
 /* Copies up to max_points points of slice idx; *count = the slice's size; dimension = CloudSlice::Dimension
  * (CloudSlice.h:33-44: XPlus..ZMinus, FIRST, FINAL, TSDF); camera_t = 3 floats, may be NULL. */
 KT_API int kt_get_slice(kt_ctx* ctx, int idx, kt_point_xyzrgb* points, size_t max_points, size_t* count, int* dimension, float* camera_t);
+/* CloudSliceProcessor on the device (backend/CloudSliceProcessor.cpp:97-162; kt_op_process_slice below): when enabled, every slice
+ * recorded from now on is also culled by weight (alpha >= weight_cull, the reference's -cw, default 8), voxel-grid filtered at one
+ * voxel and given 20-nearest-neighbour normals BEFORE it leaves the GPU; kt_get_processed_slice returns CloudSlice::processedCloud.
+ * Slices are downloaded asynchronously into pinned memory; both getters wait for the slice they are asked for, not for the tracker. */
+KT_API int kt_set_slice_processing(kt_ctx* ctx, int enabled, int weight_cull);
+KT_API int kt_get_processed_slice(kt_ctx* ctx, int idx, kt_point_xyzrgbnormal* points, size_t max_points, size_t* count);
 /* The rest of the CloudSlice record (CloudSlice.h:47-60): which odometry produced the pose (CloudSlice::Odometry: 0 ICP, 2 RGBD --
  * KintinuousTracker.cpp:137-176,565: the kind of the active OdometryProvider), the camera pose at hand-over (volume-global
  * translation, row-major rotation) and the frame's timestamp. */
 typedef struct kt_slice_info { int dimension; int odometry; float camera_t[3]; float camera_R[9]; uint64_t utime; size_t count; } kt_slice_info;
 KT_API int kt_get_slice_info(kt_ctx* ctx, int idx, kt_slice_info* info);
+/* Dense pose graph (KintinuousTracker::DensePose / densePoseGraph / latestDensePoseId, KintinuousTracker.h:151-172): one record per
+ * processed frame -- the frame's timestamp, the 4x4 camera pose [R | currentGlobalCamera] (row-major) and the loop-pose flag (true for the
+ * first frame, KintinuousTracker.cpp:534) -- what the deformation backend samples (backend/Deformation.cpp:134-169). */
+typedef struct kt_dense_pose { uint64_t timestamp; float pose[16]; int is_loop_pose; } kt_dense_pose;
+KT_API int kt_num_dense_poses(kt_ctx* ctx);                                /* latestDensePoseId */
+KT_API int kt_get_dense_pose(kt_ctx* ctx, int idx, kt_dense_pose* out);    /* densePoseGraph.at(idx) */
+/* KintinuousTracker::outputPose (.cpp:199-218, :911-914): append one line per tracked frame to `path` ("<saveFile>.poses" in the
+ * reference: "utime/1e6 gx gy gz qx qy qz qw").  NULL closes the log.  kt_format_pose_line formats one such line into buf. */
+KT_API int kt_set_pose_log(kt_ctx* ctx, const char* path);
+KT_API int kt_format_pose_line(uint64_t timestamp, const float* global_t3, const float* R9, char* buf, size_t capacity);
 /* Per-iteration normal equations of the last frame, n x 44 floats (A 6x6 row-major, b 6, residual, inliers):
  * what icpStep / rgbStep hand back to the host each iteration (cuda/reduce.cu:404-418). */
 KT_API int kt_get_trace(kt_ctx* ctx, float* dst, int max_iters, int* n_iters);
@@ -212,6 +238,14 @@ KT_API int kt_op_raycast(const float* intr4, const float* Rcurr9, const float* t
 KT_API int kt_op_extract_slice(const int16_t* tsdf_dev, const float* volume_size3, int vol, kt_point_xyzrgb* out_dev, size_t capacity,
                         const int* voxel_wrap3, const uint8_t* color_dev, int minX, int maxX, int minY, int maxY, int minZ, int maxZ,
                         int subsample, const int* real_voxel_wrap3, size_t* count, void* stream);
+/* What CloudSliceProcessor::process does to every slice before the backend sees it (backend/CloudSliceProcessor.cpp:97-162): weight cull
+ * (alpha >= weight_cull, -cw, default 8; 0 = off), pcl::VoxelGrid with leaf = the voxel edge, pcl::NormalEstimation with k_search = 20
+ * nearest neighbours and the viewpoint at the origin, pcl::concatenateFields -- on the device, on a slice that is still there.
+ * points_dev: n extracted points; out_dev: room for `capacity` 48-byte points (n is always enough); *count = processed points, in
+ * pcl::VoxelGrid's output order (ascending leaf index).  KT_ERR_INVALID if the leaf grid would exceed INT_MAX cells (PCL skips the
+ * filter in that case). */
+KT_API int kt_op_process_slice(const kt_point_xyzrgb* points_dev, size_t n, int weight_cull, float leaf, int k_search,
+                               kt_point_xyzrgbnormal* out_dev, size_t capacity, size_t* count, void* stream);
 /* clearVolume{X,Y,Z}[Back] + ...c on both volumes (tsdf_volume.cu:117-448). axis 0..2, back 0/1. */
 KT_API int kt_op_clear_volume(int axis, int back, int16_t* tsdf_dev, uint8_t* color_dev, int vol, int current_wrap, int delta_wrap, void* stream);
 /* initVolume + initColorVolume (tsdf_volume.cu:469, :77) */
@@ -236,6 +270,31 @@ KT_API int kt_op_generate_image(const float* vmap_dev, const float* nmap_dev, co
                          uint8_t* dst_rgb_dev, uint8_t* dst_color_rgb_dev, int rows, int cols, void* stream);
 KT_API int kt_op_generate_depth(const float* Rcurr_inv9, const float* tcurr3, const float* vmap_dev, const float* nmap_dev, uint16_t* dst_dev,
                          int rows, int cols, float max_depth, void* stream);
+
+/* ---- .klg log reader: replaces RawLogReader (src/utils/RawLogReader.cpp:20-133) and the upload + processFrame body of
+ * TrackerInterface::process (src/backend/TrackerInterface.cpp:82-104).  File layout: int32 numFrames, then per frame int64 timestamp,
+ * int32 depthSize, int32 imageSize, depth bytes (zlib stream or raw u16), image bytes (JPEG, raw 24-bit, or none).  Depth is inflated
+ * into pinned memory and copied asynchronously; a JPEG is decoded ON THE DEVICE (nvJPEG) into the interleaved B,G,R bytes cvDecodeImage
+ * produces.  The pointers of a frame stay valid until the next-but-one kt_klg_read_next. ---- */
+typedef struct kt_klg kt_klg;
+typedef struct kt_klg_frame {
+    int64_t timestamp;                 /* RawLogReader::timestamp */
+    int32_t depth_size, image_size;    /* compressedDepthSize / compressedImageSize */
+    int is_compressed;                 /* RawLogReader::isCompressed */
+    int frame;                         /* currentFrame after the read */
+    const uint16_t* depth_dev;         /* rows*cols u16, device (valid after kt_klg_wait) */
+    const uint8_t* rgb_dev;            /* rows*cols*3 u8, device */
+    const uint16_t* depth_host;        /* decompressedDepth, pinned host memory */
+    const unsigned char* compressed_depth; const unsigned char* compressed_image;   /* the frame's stored bytes (place-recognition inputs of processFrame) */
+} kt_klg_frame;
+KT_API int kt_klg_open(const char* path, int rows, int cols, int device, kt_klg** out);   /* RawLogReader::RawLogReader (:20-41) */
+KT_API int kt_klg_close(kt_klg* log);                                                     /* ~RawLogReader (:43-49) */
+KT_API int kt_klg_num_frames(kt_klg* log);                                                /* numFrames */
+KT_API int kt_klg_has_more(kt_klg* log);                                                  /* hasMore */
+KT_API int kt_klg_set_flip_colors(kt_klg* log, int flip);                                 /* ConfigArgs::flipColors (-f), :117-125 */
+KT_API int kt_klg_read_next(kt_klg* log, kt_klg_frame* out);                              /* readNext (:52-133); transfers are in flight on return */
+KT_API int kt_klg_wait(kt_klg* log);                                                      /* the last frame read has landed on the device */
+KT_API int kt_klg_track_next(kt_klg* log, kt_ctx* ctx, kt_pose* out);                     /* TrackerInterface::process (:82-104): read, upload, processFrame */
 
 #ifdef __cplusplus
 }

@@ -66,6 +66,10 @@ class Config(C.Structure):
         return c
 
 
+class DensePose(C.Structure):
+    _fields_ = [("timestamp", C.c_uint64), ("pose", C.c_float * 16), ("is_loop_pose", C.c_int)]
+
+
 class SliceInfo(C.Structure):
     _fields_ = [("dimension", C.c_int), ("odometry", C.c_int), ("camera_t", C.c_float * 3), ("camera_R", C.c_float * 9),
                 ("utime", C.c_uint64), ("count", C.c_size_t)]
@@ -83,6 +87,10 @@ class Pose(C.Structure):
 POINT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("_p0", "<f4"),
                         ("b", "u1"), ("g", "u1"), ("r", "u1"), ("a", "u1"), ("_p1", "u1", (12,))])
 assert POINT_DTYPE.itemsize == 32
+# kt_point_xyzrgbnormal == pcl::PointXYZRGBNormal (48 bytes)
+POINT_NORMAL_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("_p0", "<f4"), ("nx", "<f4"), ("ny", "<f4"), ("nz", "<f4"), ("_p1", "<f4"),
+                               ("b", "u1"), ("g", "u1"), ("r", "u1"), ("a", "u1"), ("curvature", "<f4"), ("_p2", "<f4", (2,))])
+assert POINT_NORMAL_DTYPE.itemsize == 48
 
 
 def _ptr(a):
@@ -164,6 +172,30 @@ class Tracker:
         if n.value:
             _check(self.lib.kt_get_slice(self.h, idx, _ptr(pts), C.c_size_t(n.value), C.byref(n), C.byref(dim), cam))
         return pts, dim.value, np.array(cam, dtype=np.float32)
+
+    def num_dense_poses(self):
+        return int(self.lib.kt_num_dense_poses(self.h))
+
+    def dense_pose(self, idx):
+        """(timestamp, 4x4 pose [R | currentGlobalCamera], is_loop_pose) of densePoseGraph[idx]."""
+        d = DensePose()
+        _check(self.lib.kt_get_dense_pose(self.h, idx, C.byref(d)))
+        return int(d.timestamp), np.array(d.pose, np.float32).reshape(4, 4), bool(d.is_loop_pose)
+
+    def set_pose_log(self, path):
+        _check(self.lib.kt_set_pose_log(self.h, path.encode() if path else None))
+
+    def set_slice_processing(self, enabled=True, weight_cull=8):
+        """CloudSliceProcessor on the device for every slice recorded from now on (kt_set_slice_processing)."""
+        _check(self.lib.kt_set_slice_processing(self.h, int(enabled), int(weight_cull)))
+
+    def get_processed_slice(self, idx):
+        n = C.c_size_t(0)
+        _check(self.lib.kt_get_processed_slice(self.h, idx, None, C.c_size_t(0), C.byref(n)))
+        pts = np.zeros(n.value, dtype=POINT_NORMAL_DTYPE)
+        if n.value:
+            _check(self.lib.kt_get_processed_slice(self.h, idx, _ptr(pts), C.c_size_t(n.value), C.byref(n)))
+        return pts
 
     def slice_info(self, idx):
         """The rest of the CloudSlice record: dimension, odometry kind, camera pose at hand-over, timestamp, point count."""
@@ -342,6 +374,13 @@ class _Ops:
         _check(self._l().kt_op_extract_slice(_ptr(tsdf), _ptr(vs), vol, _ptr(out), C.c_size_t(capacity), _ptr(w), _ptr(color),
                                              box[0], box[1], box[2], box[3], box[4], box[5], subsample, _ptr(rw), C.byref(n), None))
         return n.value
+
+    def process_slice(self, points_dev, n, weight_cull, leaf, out_dev, capacity, k_search=20):
+        """kt_op_process_slice: weight cull + voxel grid + 20-NN normals of n device-resident 32-byte points into 48-byte points."""
+        cnt = C.c_size_t(0)
+        _check(self._l().kt_op_process_slice(_ptr(points_dev), C.c_size_t(n), int(weight_cull), C.c_float(leaf), int(k_search), _ptr(out_dev), C.c_size_t(capacity),
+                                             C.byref(cnt), None))
+        return cnt.value
 
     def clear_volume(self, axis, back, tsdf, color, vol, current, delta):
         _check(self._l().kt_op_clear_volume(axis, back, _ptr(tsdf), _ptr(color), vol, current, delta, None))

@@ -19,7 +19,7 @@ cudaStream_t st(void* s) { return (cudaStream_t)s; }
 // either: internal.h:299-536 has static state in computeDerivativeImages and __device__ globals in extract.cu).  One set PER DEVICE
 // (the device current at the call), and the calls that use it are serialised by a process-wide mutex, so operator calls from several
 // host threads / on several devices are safe, just not concurrent.
-struct OpScratch { OdomState* state; float* partials; int* ipartials; float* ztable; int ztable_n; unsigned int* counter; OdomState* host_state; };
+struct OpScratch { OdomState* state; float* partials; int* ipartials; float* ztable; int ztable_n; unsigned int* counter; OdomState* host_state; SliceWorkspace slice_ws; };
 enum { KT_MAX_DEVICES = 64 };
 OpScratch g_ops_dev[KT_MAX_DEVICES];
 std::mutex g_ops_mu;
@@ -177,6 +177,13 @@ int kt_op_extract_slice(const int16_t* tsdf, const float* vs, int vol, kt_point_
     KT_CUDA(cudaStreamSynchronize(st(s)));
     if (count) *count = n < capacity ? n : capacity;
     return KT_OK;
+}
+
+int kt_op_process_slice(const kt_point_xyzrgb* points_dev, size_t n, int weight_cull, float leaf, int k_search, kt_point_xyzrgbnormal* out_dev, size_t capacity,
+                        size_t* count, void* s)
+{
+    KT_OPS_LOCK();
+    return process_slice(points_dev, n, weight_cull, leaf, k_search, out_dev, capacity, count, &g_ops.slice_ws, st(s));
 }
 
 int kt_op_clear_volume(int axis, int back, int16_t* tsdf, uint8_t* color, int vol, int current, int delta, void* s)

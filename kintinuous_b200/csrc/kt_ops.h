@@ -159,6 +159,11 @@ int extract_slice(const int16_t* tsdf, const float3& volume_size, int vol, void*
 int extract_slice_mg(const VolumeView& vv, const float3& volume_size, int vol, void* out, size_t capacity, const int3& wrap,
                      int minX, int maxX, int minY, int maxY, int minZ, int maxZ, int subsample,
                      const int3& real_wrap, unsigned int* counter_dev, cudaStream_t s);
+// ---- slice post-processing (kt_slice.cu): CloudSliceProcessor.cpp:97-162 on the device ----
+struct SliceWorkspace { unsigned int* mask; unsigned int* word_off; unsigned int* block_tot; size_t words_cap; void* acc; size_t acc_cap; unsigned int* bounds; unsigned int* bounds_host; };
+int process_slice(const void* points_dev /* kt_point_xyzrgb */, size_t n, int weight_cull, float leaf, int k_search, void* out_dev /* kt_point_xyzrgbnormal */,
+                  size_t capacity, size_t* count, SliceWorkspace* ws, cudaStream_t s);
+void slice_ws_free(SliceWorkspace* ws);
 // cross-GPU barrier: every rank writes `epoch` into slot [rank] of every peer's flag array, then waits until all slots of its own
 // array reach `epoch` (bounded spin: returns through *error_dev != 0 instead of hanging the GPU if a peer never arrives)
 int xgpu_barrier(unsigned int* const* peer_flags_dev /* [world] device array of pointers */, unsigned int* my_flags, int rank, int world,

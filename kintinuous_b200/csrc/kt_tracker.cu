@@ -14,6 +14,7 @@
 // current frame is being fused.  The CUDA-free bookkeeping of the shifting volume lives in kt_shift.hpp (CPU-tested).
 #include "kt_ops.h"
 #include "kt_shift.hpp"
+#include "kt_posegraph.hpp"
 #include <cstdlib>
 #include "../../include/kintinuous_b200.h"
 #include <vector>
@@ -79,7 +80,34 @@ static M3 m3_inverse(const M3& a)      // Eigen::Matrix3f::inverse(): cofactors 
 }
 static Mat33 to_mat33(const float* m) { Mat33 r; r.r0 = make_float3(m[0], m[1], m[2]); r.r1 = make_float3(m[3], m[4], m[5]); r.r2 = make_float3(m[6], m[7], m[8]); return r; }
 
-struct SliceRec { int dimension; std::vector<kt_point_xyzrgb> points; float camera_t[3]; float camera_R[9]; uint64_t utime; };
+// A slice lives in PINNED host memory carved from the context's arena; its device -> host copy is asynchronous (side stream) and
+// `ready` fires when the bytes have landed.  The reference downloads into a pageable std::vector with a blocking cudaMemcpy inside
+// processFrame (KintinuousTracker.cpp:1166, containers/device_memory.cpp:146-157).
+struct SliceRec { int dimension; kt_point_xyzrgb* points; size_t count; kt_point_xyzrgbnormal* processed; size_t processed_count; bool has_processed;
+                  cudaEvent_t ready; float camera_t[3]; float camera_R[9]; uint64_t utime; };
+
+// Pinned host memory handed out in slabs (one cudaHostAlloc per 64 MB, not per slice); everything is released together by kt_reset.
+struct PinnedArena {
+    std::vector<std::pair<char*, size_t> > chunks; size_t chunk_used; size_t current;
+    PinnedArena() : chunk_used(0), current(0) {}
+    void* alloc(size_t bytes)
+    {
+        bytes = (bytes + 255) & ~(size_t)255;
+        while (current < chunks.size() && chunk_used + bytes > chunks[current].second) { ++current; chunk_used = 0; }
+        if (current >= chunks.size()) {
+            const size_t sz = std::max(bytes, (size_t)64 << 20);
+            void* q = 0;
+            if (cudaHostAlloc(&q, sz, cudaHostAllocDefault) != cudaSuccess) return 0;
+            chunks.push_back(std::make_pair((char*)q, sz));
+            current = chunks.size() - 1; chunk_used = 0;
+        }
+        void* r = chunks[current].first + chunk_used;
+        chunk_used += bytes;
+        return r;
+    }
+    void rewind() { current = 0; chunk_used = 0; }
+    void release() { for (auto& c : chunks) cudaFreeHost(c.first); chunks.clear(); rewind(); }
+};
 
 // what the host reads back after the odometry of a frame
 struct OdomResult { float Rcurr[9]; float tcurr[3]; int timeout; unsigned int seq; int pad[2]; };     // seq: written last by the odometry kernel (mapped host memory)
@@ -99,6 +127,8 @@ struct kt_ctx {
     int overlap, parked;
     std::vector<M3> rmats; std::vector<V3> tvecs;
     std::vector<SliceRec> slices;
+    std::vector<kt_dense_pose> dense_poses;      // densePoseGraph (KintinuousTracker.h:171)
+    FILE* pose_log;                              // <saveFile>.poses (outputPose)
     int iterations[LEVELS];
     // device memory
     int16_t* tsdf; uint8_t* color;
@@ -118,6 +148,10 @@ struct kt_ctx {
     unsigned long long* xwords_dev; bool xwords_clean;      // exchange words of the whole-frame odometry kernels; zero between frames
     OdomState* state; float* partials; int* ipartials; float* trace_dev; float* pose12_dev; unsigned int* bar_dev; unsigned int bar_count; long long* prof_dev;
     kt_point_xyzrgb* cloud_dev; unsigned int* counter_dev; size_t cloud_capacity; size_t cloud_count;
+    // slice hand-off: pinned arena, asynchronous download on stream_slices; ev_cloud_free = the last download has left cloud_dev / proc_dev
+    PinnedArena* slice_arena; cudaStream_t stream_slices; cudaEvent_t ev_cloud_ready, ev_cloud_free; bool cloud_busy;
+    // CloudSliceProcessor on the device (kt_slice.cu): weight cull + voxel grid + normals of every slice before it leaves the GPU
+    int slice_processing, slice_weight_cull; SliceWorkspace slice_ws; kt_point_xyzrgbnormal* proc_dev; size_t proc_count;
     // RGB-D
     float* lastDepth[LEVELS]; float* nextDepth[LEVELS]; uint8_t* lastImage[LEVELS]; uint8_t* nextImage[LEVELS];
     int16_t* nextdIdx[LEVELS]; int16_t* nextdIdy[LEVELS]; float* pointClouds[LEVELS]; void* corresImg[LEVELS];
@@ -161,6 +195,8 @@ void vwrap_copy(const kt_ctx* c, int* w)       // KintinuousTracker::vWrapCopyUp
 
 int fetch_cloud(kt_ctx* c, const int* vWrapCopy, const int* lo, const int* hi)      // TsdfVolume::fetchCloud (TSDFVolume.cpp:131-172)
 {
+    // the previous slice's asynchronous download may still be reading cloud_dev
+    if (c->cloud_busy) { KT_CUDA(cudaStreamWaitEvent(c->stream, c->ev_cloud_free, 0)); c->cloud_busy = false; }
     KT_CUDA(cudaMemsetAsync(c->counter_dev, 0, sizeof(unsigned int), c->stream));
     float3 vs = make_float3(c->size, c->size, c->size);
     int r = c->world > 1
@@ -175,16 +211,48 @@ int fetch_cloud(kt_ctx* c, const int* vWrapCopy, const int* lo, const int* hi)  
     return 0;
 }
 
+// mutexOutCloudBuffer (KintinuousTracker.cpp:1156-1208): record the extracted cloud as a CloudSlice.  The points go to pinned host
+// memory with an ASYNCHRONOUS copy on a side stream -- the frame's clear / integrate / ray cast do not wait for it; readers of the slice
+// do (kt_get_slice waits on the slice's event).  With slice processing on, the slice is culled, voxel-gridded and given normals on the
+// device first (kt_slice.cu) and both clouds are handed out.
 int push_slice(kt_ctx* c, int dimension)
 {
-    SliceRec s; s.dimension = dimension;
-    s.points.resize(c->cloud_count);
-    if (c->cloud_count) KT_CUDA(cudaMemcpy(s.points.data(), c->cloud_dev, c->cloud_count * sizeof(kt_point_xyzrgb), cudaMemcpyDeviceToHost));
+    SliceRec s; s.dimension = dimension; s.points = 0; s.count = c->cloud_count; s.processed = 0; s.processed_count = 0; s.has_processed = false; s.ready = 0;
+    c->proc_count = 0;
+    if (c->slice_processing && c->cloud_count) {
+        if (!c->proc_dev) { void* q = 0; KT_CUDA(cudaMalloc(&q, c->cloud_capacity * sizeof(kt_point_xyzrgbnormal))); c->allocs.push_back(q); c->proc_dev = (kt_point_xyzrgbnormal*)q; }
+        int r = process_slice(c->cloud_dev, c->cloud_count, c->slice_weight_cull, c->voxel, 20, c->proc_dev, c->cloud_capacity, &c->proc_count, &c->slice_ws, c->stream);
+        if (r) return r;
+    }
+    s.has_processed = c->slice_processing != 0;
+    s.processed_count = c->proc_count;
+    if (c->cloud_count) {
+        s.points = (kt_point_xyzrgb*)c->slice_arena->alloc(c->cloud_count * sizeof(kt_point_xyzrgb));
+        if (c->proc_count) s.processed = (kt_point_xyzrgbnormal*)c->slice_arena->alloc(c->proc_count * sizeof(kt_point_xyzrgbnormal));
+        if (!s.points || (c->proc_count && !s.processed)) { set_error("pinned host memory for a slice of %zu points", c->cloud_count); return KT_ERR_CUDA; }
+        KT_CUDA(cudaEventCreateWithFlags(&s.ready, cudaEventDisableTiming));
+        KT_CUDA(cudaEventRecord(c->ev_cloud_ready, c->stream));
+        KT_CUDA(cudaStreamWaitEvent(c->stream_slices, c->ev_cloud_ready, 0));
+        KT_CUDA(cudaMemcpyAsync(s.points, c->cloud_dev, c->cloud_count * sizeof(kt_point_xyzrgb), cudaMemcpyDeviceToHost, c->stream_slices));
+        if (c->proc_count) KT_CUDA(cudaMemcpyAsync(s.processed, c->proc_dev, c->proc_count * sizeof(kt_point_xyzrgbnormal), cudaMemcpyDeviceToHost, c->stream_slices));
+        KT_CUDA(cudaEventRecord(s.ready, c->stream_slices));
+        KT_CUDA(cudaEventRecord(c->ev_cloud_free, c->stream_slices));
+        c->cloud_busy = true;
+    }
     for (int i = 0; i < 3; ++i) s.camera_t[i] = c->currentGlobalCamera[i];
     for (int i = 0; i < 9; ++i) s.camera_R[i] = c->rmats.back().m[i];
     s.utime = c->current_utime;
-    c->slices.push_back(std::move(s));
+    c->slices.push_back(s);
     return 0;
+}
+
+void drop_slices(kt_ctx* c)
+{
+    if (c->stream_slices) cudaStreamSynchronize(c->stream_slices);
+    for (auto& s : c->slices) if (s.ready) cudaEventDestroy(s.ready);
+    c->slices.clear();
+    if (c->slice_arena) c->slice_arena->rewind();
+    c->cloud_busy = false;
 }
 
 int do_integrate(kt_ctx* c, const M3& Rinv, const V3& t, const int* wrap)
@@ -359,6 +427,23 @@ int build_frontend(kt_ctx* c, const uint16_t* depth_raw, const uint8_t* rgb, flo
     return 0;
 }
 
+// densePoseGraph.push_back(DensePose(current_utime, [Rcurr | currentGlobalCamera], isLoopPose)); latestDensePoseId++ and, for tracked
+// frames, outputPose (KintinuousTracker.cpp:529-536, :901-914)
+void record_dense_pose(kt_ctx* c, bool first)
+{
+    kt_dense_pose d;
+    d.timestamp = c->current_utime; d.is_loop_pose = first ? 1 : 0;
+    const M3& R = c->rmats.back();
+    for (int r = 0; r < 3; ++r) { for (int k = 0; k < 3; ++k) d.pose[r * 4 + k] = R.m[r * 3 + k]; d.pose[r * 4 + 3] = c->currentGlobalCamera[r]; }
+    d.pose[12] = d.pose[13] = d.pose[14] = 0.f; d.pose[15] = 1.f;
+    c->dense_poses.push_back(d);
+    if (!first && c->pose_log) {
+        char line[256];
+        const int n = format_pose_line(c->current_utime, c->currentGlobalCamera, R.m, line, sizeof(line));
+        if (n > 0) { fwrite(line, 1, (size_t)n, c->pose_log); fflush(c->pose_log); }
+    }
+}
+
 void mark(kt_ctx* c, int i) { if (c->timing) cudaEventRecord(c->ev[i], c->stream); }
 
 int process_frame_device(kt_ctx* c, uint64_t utime, kt_pose* out)
@@ -392,6 +477,7 @@ int process_frame_device(kt_ctx* c, uint64_t utime, kt_pose* out)
         mark(c, 5);
         ++c->global_time;
         c->current_utime = utime;
+        record_dense_pose(c, true);                                                      // .cpp:529-536 (no outputPose on the first frame)
         if (out) kt_get_pose(c, out);
         return 0;
     }
@@ -467,6 +553,7 @@ int process_frame_device(kt_ctx* c, uint64_t utime, kt_pose* out)
     if ((r = mg_barrier(c))) return r;                                                   // all tiles of the predicted surface have landed everywhere
     mark(c, 5);
     ++c->global_time;
+    record_dense_pose(c, false);                                                         // .cpp:901-914
     if (out) kt_get_pose(c, out);
     return 0;
 }
@@ -494,7 +581,8 @@ int kt_reset(kt_ctx* c)
     V3 tb = {{c->volumeBasis[0], c->volumeBasis[1], c->volumeBasis[2]}};
     c->tvecs.push_back(tb);
     for (int i = 0; i < 3; ++i) { c->voxelWrap[i] = 0; c->currentGlobalCamera[i] = c->volumeBasis[i] - c->size * 0.5f; }
-    c->slices.clear();
+    drop_slices(c);
+    c->dense_poses.clear();                      // reset(): densePoseGraph.clear(), latestDensePoseId = 0 (.cpp:300-301)
     c->trace_iters = 0; c->shifted_last = 0; c->cloud_count = 0;
     c->pf_valid = false; c->pf_built = false; c->frontend_ready = false; c->maps_on_stream = false;
     if (c->stream_copy) cudaStreamSynchronize(c->stream_copy);
@@ -616,6 +704,9 @@ int kt_create(const kt_config* cfg, kt_ctx** out)
     KT_TRY(dev_alloc(c, &c->trace_dev, (size_t)MAX_TRACE_ITERS * TRACE_STRIDE)); KT_TRY(dev_alloc(c, &c->pose12_dev, 12));
     c->cloud_capacity = (size_t)c->cfg.cloud_capacity;
     KT_TRY(dev_alloc(c, &c->cloud_dev, c->cloud_capacity)); KT_TRY(dev_alloc(c, &c->counter_dev, 1));
+    c->slice_arena = new PinnedArena();
+    KT_CUDA(cudaStreamCreateWithFlags(&c->stream_slices, cudaStreamNonBlocking));
+    KT_CUDA(cudaEventCreateWithFlags(&c->ev_cloud_ready, cudaEventDisableTiming)); KT_CUDA(cudaEventCreateWithFlags(&c->ev_cloud_free, cudaEventDisableTiming));
     KT_TRY(kt::cuda_check(cudaMallocHost((void**)&c->pose12_host, 12 * sizeof(float)), "pinned", __FILE__, __LINE__));
     KT_TRY(kt::cuda_check(cudaHostAlloc((void**)&c->result_host, sizeof(OdomResult), cudaHostAllocMapped), "pinned", __FILE__, __LINE__));
     std::memset(c->result_host, 0, sizeof(OdomResult));
@@ -640,6 +731,13 @@ int kt_destroy(kt_ctx* c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (int g = 0; g < MAX_GPUS; ++g) if (c->peer_arena[g] && c->peer_arena[g] != c->arena) cudaIpcCloseMemHandle(c->peer_arena[g]);
     if (c->mg_error_host) cudaFreeHost(c->mg_error_host);
+    drop_slices(c);
+    if (c->pose_log) fclose(c->pose_log);
+    if (c->slice_arena) { c->slice_arena->release(); delete c->slice_arena; }
+    slice_ws_free(&c->slice_ws);
+    if (c->stream_slices) cudaStreamDestroy(c->stream_slices);
+    if (c->ev_cloud_ready) cudaEventDestroy(c->ev_cloud_ready);
+    if (c->ev_cloud_free) cudaEventDestroy(c->ev_cloud_free);
     for (void* p : c->allocs) cudaFree(p);
     if (c->pose12_host) cudaFreeHost(c->pose12_host);
     if (c->result_host) cudaFreeHost(c->result_host);
@@ -773,11 +871,58 @@ int kt_get_slice(kt_ctx* c, int idx, kt_point_xyzrgb* points, size_t max_points,
 {
     if (!c || idx < 0 || idx >= (int)c->slices.size()) { set_error("kt_get_slice: bad index"); return KT_ERR_INVALID; }
     const SliceRec& s = c->slices[idx];
-    if (count) *count = s.points.size();
+    if (count) *count = s.count;
     if (dimension) *dimension = s.dimension;
     if (camera_t) for (int i = 0; i < 3; ++i) camera_t[i] = s.camera_t[i];
-    size_t n = std::min(max_points, s.points.size());
-    if (points && n) std::memcpy(points, s.points.data(), n * sizeof(kt_point_xyzrgb));
+    size_t n = std::min(max_points, s.count);
+    if (points && n) {
+        KT_CUDA(cudaEventSynchronize(s.ready));                  // the asynchronous download of this slice has landed
+        std::memcpy(points, s.points, n * sizeof(kt_point_xyzrgb));
+    }
+    return KT_OK;
+}
+
+int kt_num_dense_poses(kt_ctx* c) { return c ? (int)c->dense_poses.size() : 0; }
+int kt_get_dense_pose(kt_ctx* c, int idx, kt_dense_pose* out)
+{
+    if (!c || !out || idx < 0 || idx >= (int)c->dense_poses.size()) { set_error("kt_get_dense_pose: bad argument"); return KT_ERR_INVALID; }
+    *out = c->dense_poses[idx];
+    return KT_OK;
+}
+int kt_set_pose_log(kt_ctx* c, const char* path)
+{
+    if (!c) return KT_ERR_INVALID;
+    if (c->pose_log) { fclose(c->pose_log); c->pose_log = 0; }
+    if (path && *path) {
+        c->pose_log = fopen(path, "a");                       // std::fstream::app (.cpp:205)
+        if (!c->pose_log) { set_error("kt_set_pose_log: cannot open %s", path); return KT_ERR_INVALID; }
+    }
+    return KT_OK;
+}
+int kt_format_pose_line(uint64_t timestamp, const float* global_t3, const float* R9, char* buf, size_t capacity)
+{
+    if (!global_t3 || !R9 || !buf) return KT_ERR_INVALID;
+    return format_pose_line(timestamp, global_t3, R9, buf, capacity) < 0 ? KT_ERR_CAPACITY : KT_OK;
+}
+
+int kt_set_slice_processing(kt_ctx* c, int enabled, int weight_cull)
+{
+    if (!c) return KT_ERR_INVALID;
+    c->slice_processing = enabled != 0; c->slice_weight_cull = weight_cull;
+    return KT_OK;
+}
+
+int kt_get_processed_slice(kt_ctx* c, int idx, kt_point_xyzrgbnormal* points, size_t max_points, size_t* count)
+{
+    if (!c || idx < 0 || idx >= (int)c->slices.size()) { set_error("kt_get_processed_slice: bad index"); return KT_ERR_INVALID; }
+    const SliceRec& s = c->slices[idx];
+    if (!s.has_processed) { set_error("kt_get_processed_slice: slice %d was recorded with slice processing off (kt_set_slice_processing)", idx); return KT_ERR_STATE; }
+    if (count) *count = s.processed_count;
+    size_t n = std::min(max_points, s.processed_count);
+    if (points && n) {
+        KT_CUDA(cudaEventSynchronize(s.ready));
+        std::memcpy(points, s.processed, n * sizeof(kt_point_xyzrgbnormal));
+    }
     return KT_OK;
 }
 
@@ -790,7 +935,7 @@ int kt_get_slice_info(kt_ctx* c, int idx, kt_slice_info* info)
     for (int i = 0; i < 3; ++i) info->camera_t[i] = s.camera_t[i];
     for (int i = 0; i < 9; ++i) info->camera_R[i] = s.camera_R[i];
     info->utime = s.utime;
-    info->count = s.points.size();
+    info->count = s.count;
     return KT_OK;
 }
 

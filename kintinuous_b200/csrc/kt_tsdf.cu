@@ -22,6 +22,7 @@
 // Roofline: HBM by nature (12 B per updated voxel + image-side gathers), instruction-issue bound in practice.
 #include "kt_ops.h"
 #include "kt_replay.cuh"
+#include "kt_frustum.hpp"
 
 namespace kt {
 
@@ -104,6 +105,7 @@ struct IntegrateParams {
     int z_far_first;           // schedule the z chunks from high z to low z (see integrate())
     VolumeView vv;             // shared volume (MG instances): plane ownership and the peers' TSDF replicas
     int seq_replay;            // test hook: replay the running sums one addition at a time instead of replay_add()
+    int tile_x0, tiles_x, tile_y0, tiles_y;    // the launch covers the cyclic range of 32-wide / 8-high storage tiles [tile0, tile0 + gridDim) mod tiles (kt_frustum.hpp)
 };
 
 #define KT_MAX_WEIGHT 128          // Tsdf::MAX_WEIGHT (tsdf_volume.cu:486)
@@ -141,8 +143,10 @@ __global__ void __launch_bounds__(256, MINB)
 integrate_kernel(const IntegrateParams p)
 {
     const int V = p.V;
-    const int sx = blockIdx.x * 32 + threadIdx.x;          // STORAGE x, y
-    const int sy = blockIdx.y * 8 + threadIdx.y;
+    int bx = p.tile_x0 + (int)blockIdx.x; if (bx >= p.tiles_x) bx -= p.tiles_x;      // the grid spans only the frustum's box of storage tiles (cyclic)
+    int by = p.tile_y0 + (int)blockIdx.y; if (by >= p.tiles_y) by -= p.tiles_y;
+    const int sx = bx * 32 + threadIdx.x;          // STORAGE x, y
+    const int sy = by * 8 + threadIdx.y;
     if (sx >= V || sy >= V) return;
     int x = sx - p.wrap.x; if (x < 0) x += V;             // logical voxel
     int y = sy - p.wrap.y; if (y < 0) y += V;
@@ -470,7 +474,21 @@ int integrate(const IntegrateArgs& a, float* ztable_dev, cudaStream_t s)
     p.lz_lo = 0; p.lz_hi = V;
     static const bool seq_replay = getenv("KT_INT_SEQ_REPLAY") != nullptr;
     p.seq_replay = seq_replay ? 1 : 0;
-    dim3 block(32, 8), grid(div_up(V, 32), div_up(V, 8), div_up(V, p.zchunk));
+    p.tiles_x = div_up(V, 32); p.tiles_y = div_up(V, 8); p.tile_x0 = 0; p.tile_y0 = 0;
+    dim3 block(32, 8), grid(p.tiles_x, p.tiles_y, div_up(V, p.zchunk));
+    // Launch only the storage tiles and z chunks the view frustum can reach (kt_frustum.hpp: a conservative box in logical voxel
+    // coordinates; the per-column test in the kernel stays).  KT_INT_NOBOX=1 (test hook) launches the whole volume as before.
+    static const bool no_box = getenv("KT_INT_NOBOX") != nullptr;
+    if (!no_box) {
+        const float Rinv9[9] = {a.Rinv.r0.x, a.Rinv.r0.y, a.Rinv.r0.z, a.Rinv.r1.x, a.Rinv.r1.y, a.Rinv.r1.z, a.Rinv.r2.x, a.Rinv.r2.y, a.Rinv.r2.z};
+        const float t3[3] = {a.t.x, a.t.y, a.t.z}, k4[4] = {a.k.fx, a.k.fy, a.k.cx, a.k.cy}, cell3[3] = {cell.x, cell.y, cell.z};
+        const VoxelBox box = frustum_voxel_box(Rinv9, t3, k4, a.rows, a.cols, V, cell3);
+        if (box.empty) return 0;                                       // the camera sees no voxel of the cube: nothing to integrate
+        p.lz_lo = box.lo[2]; p.lz_hi = box.hi[2] + 1;
+        grid.z = div_up(p.lz_hi - p.lz_lo, p.zchunk);
+        if (V % 32 == 0) { int n; cyclic_tile_range(box.lo[0], box.hi[0], p.wrap.x, V, 32, &p.tile_x0, &n); grid.x = n; }
+        if (V % 8 == 0) { int n; cyclic_tile_range(box.lo[1], box.hi[1], p.wrap.y, V, 8, &p.tile_y0, &n); grid.y = n; }
+    }
     if (multi) {
         if (V & (V - 1)) { set_error("integrate: the shared volume needs a power-of-two resolution"); return -1; }
         // one voxel per step: the walk alternates between owned blocks and exact jumps over foreign ones

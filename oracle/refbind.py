@@ -224,3 +224,45 @@ class CpuOracle:
         t.prefix = "ktoracle_tracker_"
         _TrackerBase.__init__(t, self.lib, cfg)
         return t
+
+
+POINT_NORMAL_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("_p0", "<f4"), ("nx", "<f4"), ("ny", "<f4"), ("nz", "<f4"), ("_p1", "<f4"),
+                               ("b", "u1"), ("g", "u1"), ("r", "u1"), ("a", "u1"), ("curvature", "<f4"), ("_p2", "<f4", (2,))])
+
+
+class SliceOracle:
+    """CPU restatement of CloudSliceProcessor's per-slice post-processing (oracle/kt_slice_oracle.cpp: weight cull, pcl::VoxelGrid,
+    pcl::NormalEstimation of PCL 1.7.2).  Host numpy arrays of POINT_DTYPE in, POINT_NORMAL_DTYPE out."""
+
+    def __init__(self):
+        p = os.path.join(_HERE, "libkt_slice_oracle.so")
+        if not os.path.exists(p):
+            raise FileNotFoundError(f"{p}: run make -C oracle")
+        self.lib = C.CDLL(p)
+        for f in ("ktslice_weight_cull", "ktslice_voxel_grid", "ktslice_process"):
+            getattr(self.lib, f).restype = C.c_size_t
+
+    def weight_cull(self, pts, weight_cull):
+        out = np.zeros(len(pts), POINT_DTYPE)
+        n = self.lib.ktslice_weight_cull(_ptr(pts), C.c_size_t(len(pts)), int(weight_cull), _ptr(out))
+        return out[:n]
+
+    def voxel_grid(self, pts, leaf):
+        out = np.zeros(len(pts), POINT_DTYPE); mb = np.zeros(3, np.int32); db = np.zeros(3, np.int32)
+        n = self.lib.ktslice_voxel_grid(_ptr(pts), C.c_size_t(len(pts)), C.c_float(leaf), _ptr(out), C.c_size_t(len(pts)), _ptr(mb), _ptr(db))
+        return out[:n], mb, db
+
+    def normals(self, pts, k, cell):
+        out = np.zeros(len(pts), POINT_NORMAL_DTYPE)
+        self.lib.ktslice_normals(_ptr(pts), C.c_size_t(len(pts)), int(k), C.c_float(cell), _ptr(out))
+        return out
+
+    def process(self, pts, weight_cull, leaf, k=20):
+        out = np.zeros(max(1, len(pts)), POINT_NORMAL_DTYPE)
+        n = self.lib.ktslice_process(_ptr(pts), C.c_size_t(len(pts)), int(weight_cull), C.c_float(leaf), int(k), _ptr(out), C.c_size_t(len(out)))
+        return out[:n]
+
+    def eigen33(self, cov):
+        c = np.ascontiguousarray(np.asarray(cov, np.float32).reshape(9)); ev = C.c_float(0); vec = np.zeros(3, np.float32)
+        self.lib.ktslice_eigen33(_ptr(c), C.byref(ev), _ptr(vec))
+        return ev.value, vec

@@ -189,8 +189,20 @@ def test_baseline_config_512_live_replay_exact(built, frames26, odometry, nframe
         assert rt.num_slices() == n_slices
     assert n_slices >= 1, "the run must cross the -t 14 shift threshold"
     if odometry == 0:
-        assert n_slices >= 4 and slice_points > 1000, (n_slices, slice_points)      # a leaving slab that really contains surface
+        assert n_slices >= 4, n_slices
         assert n_cmp >= 3, n_cmp                                        # three shifts inside the stable horizon
+        # 3b. the leaving slabs of this stream are mostly free space (the camera moves away from what it saw), so a slab that certainly
+        # contains surface is extracted as well: 30 z planes around the room's back wall, on the replayed volume at the final cyclic
+        # offset, product operator against the reference's extractCloudSlice -- the same multiset of points.
+        import kintinuous_b200 as kb2
+        wall = int((5.5 - cur[2] * SIZE / V) / (SIZE / V))
+        box = (0, V, 0, V, max(0, wall - 15), min(V - 1, wall + 15))
+        oa = torch.zeros(cap * 32, dtype=torch.uint8, device="cuda")
+        n_b = ref.extract(ts, vs, ob, cap, vwrap_nonneg(cur), cs, box, 1, cur)
+        n_a = kb2.ops.extract_slice(ts, vs, V, oa, cap, vwrap_nonneg(cur), cs, box, 1, tuple(cur))
+        assert n_a == n_b and n_a > 20000, (n_a, n_b, box)
+        assert (canon(oa.cpu().numpy().view(refbind.POINT_DTYPE)[:n_a]) == canon(ob.cpu().numpy().view(refbind.POINT_DTYPE)[:n_b])).all()
+        print(f"back-wall slab {box}: {n_a} points, multiset identical to the reference's extraction")
     for i in range(n_cmp):                                              # the reference tracker's own slices: same events, same sizes to 1 %
         a, dim_a, _ = mine.get_slice(i); b, dim_b, _ = rt.get_slice(i)
         assert dim_a == dim_b and abs(len(a) - len(b)) <= 0.01 * len(b) + 5, (i, len(a), len(b))

@@ -270,13 +270,14 @@ def test_kernel_variants_are_bit_identical(built):
     * KT_INT_PREP=0: the colour update with the reference's per-voxel arithmetic (the operator-level golden tests pin that form against
       the reference) versus the default, which prepares the per-pixel colour weight and float RGB once per frame;
     * KT_INT_ZU=1: one voxel per step at 6 CTAs/SM (the default for volumes >= 1024^3);
+    * KT_INT_NOBOX=1: integrate launched over the whole volume instead of the frustum's box of storage tiles (kt_frustum.hpp);
     * KT_INT_SEQ_REPLAY=1: the running sums of a column replayed one float addition at a time up to its first voxel, as the reference
       does, versus the default exact fast-forward (kt_replay.cuh, replay_add)."""
     import subprocess
     import sys
     from conftest import ROOT
     out = {}
-    for tag, extra in (("default", {}), ("idx64", {"KT_FORCE_IDX64": "1"}), ("noprep", {"KT_INT_PREP": "0"}), ("zu1", {"KT_INT_ZU": "1"}), ("seqreplay", {"KT_INT_SEQ_REPLAY": "1"}),
+    for tag, extra in (("default", {}), ("idx64", {"KT_FORCE_IDX64": "1"}), ("noprep", {"KT_INT_PREP": "0"}), ("zu1", {"KT_INT_ZU": "1"}), ("seqreplay", {"KT_INT_SEQ_REPLAY": "1"}), ("nobox", {"KT_INT_NOBOX": "1"}),
                        ("idx64_noprep", {"KT_FORCE_IDX64": "1", "KT_INT_PREP": "0"})):
         env = dict(os.environ, PYTHONPATH=ROOT, **extra)
         r = subprocess.run([sys.executable, "-c", _IDX64_SCRIPT], env=env, capture_output=True, text=True, timeout=600, cwd=ROOT)
@@ -313,4 +314,46 @@ def test_config5_1280x960_into_2048(built):
     err = np.abs(z[ok] - d[ok] / 1000.0)
     assert np.median(err) < 1.0 * voxel, np.median(err)
     assert np.quantile(err, 0.95) < 4 * voxel
+    trk.close()
+
+
+def test_dense_pose_graph_and_pose_log(built, tmp_path):
+    """KintinuousTracker::densePoseGraph / latestDensePoseId (KintinuousTracker.h:151-172, .cpp:529-536, :901-909) and the <saveFile>.poses
+    trajectory outputPose appends per tracked frame (.cpp:199-218, :911-914): one DensePose per frame ([R | currentGlobalCamera], loop flag
+    on the first), one text line per frame after the first, formatted as the reference streams it."""
+    import kintinuous_b200 as kb
+    from kintinuous_b200 import synth
+    rows, cols = 120, 160
+    log = str(tmp_path / "run.klg.poses")
+    trk = kb.Tracker(kb.Config.default(rows=rows, cols=cols, vol=128, odometry=0, voxel_shift=2))
+    trk.set_pose_log(log)
+    poses = []
+    for k in range(12):
+        d, c = synth.render(k, cols, rows)
+        p = trk.process_frame(d, c, 1000000 + 33333 * k)
+        poses.append(p.as_tuple())
+    assert trk.num_dense_poses() == 12
+    for k in range(12):
+        ts, M, loop = trk.dense_pose(k)
+        R, t, g, w = poses[k]
+        assert ts == 1000000 + 33333 * k and loop == (k == 0)
+        assert np.array_equal(M[:3, :3], R) and np.array_equal(M[3], np.array([0, 0, 0, 1], np.float32))
+        if k > 0:
+            assert np.array_equal(M[:3, 3], g)                      # currentGlobalCamera of that frame (.cpp:581-596), before any shift of it
+    trk.set_pose_log(None)
+    lines = open(log).read().splitlines()
+    assert len(lines) == 11                                         # no line for the first frame (.cpp:529-557 returns before outputPose)
+    from scipy.spatial.transform import Rotation
+    for k, line in enumerate(lines, start=1):
+        f = line.split()
+        R, t, g, w = poses[k]
+        assert f[0] == "%.6f" % ((1000000 + 33333 * k) / 1000000.0)
+        assert f[1:4] == ["%g" % float(v) for v in g]
+        q = Rotation.from_matrix(R.astype(np.float64)).as_quat()
+        got = np.array([float(x) for x in f[4:]])
+        if np.dot(q, got) < 0:
+            q = -q
+        assert np.abs(got - q).max() < 2e-5
+    trk.reset()
+    assert trk.num_dense_poses() == 0
     trk.close()
