@@ -45,6 +45,7 @@ typedef boost::mutex mutex;
 typedef boost::condition_variable_any condition_variable_any;
 typedef boost::mutex::scoped_lock scoped_lock;
 typedef pcl::PointCloud<pcl::PointXYZRGB> PointCloud;
+typedef pcl::PointCloud<pcl::PointXYZRGBNormal> PointCloudNormal;
 }
 #else
 #include <condition_variable>
@@ -62,6 +63,7 @@ typedef std::mutex mutex;
 typedef std::condition_variable_any condition_variable_any;
 struct scoped_lock { std::unique_lock<std::mutex> l; explicit scoped_lock(std::mutex& m) : l(m) {} void unlock() { l.unlock(); } void lock() { l.lock(); } };
 struct PointCloud { std::vector<PointXYZRGB> points; };                                                                  // pcl::PointCloud<pcl::PointXYZRGB>::points
+struct PointCloudNormal { std::vector<kt_point_xyzrgbnormal> points; };                                                  // pcl::PointCloud<pcl::PointXYZRGBNormal>::points (48-byte points)
 }
 #endif
 
@@ -109,7 +111,12 @@ struct KtFrontendOptions {
     bool fastOdometry;    // -fo
     bool disableColorAngleWeight;   // -dc
     int gpu;              // -gpu
-    static KtFrontendOptions& get() { static KtFrontendOptions o = {512, 14, false, false, false, false, 0}; return o; }
+    // CloudSliceProcessor's work done on the device before a slice leaves it (backend/CloudSliceProcessor.cpp:97-162): when set, every
+    // CloudSlice arrives with processedCloud filled (weight cull at weightCull = -cw, voxel grid, 20-NN normals) and the backend thread
+    // has nothing left to do for it
+    bool processSlicesOnGpu; int weightCull;
+    const char* poseLog;  // "<saveFile>.poses" (outputPose, KintinuousTracker.cpp:199-218); NULL = off
+    static KtFrontendOptions& get() { static KtFrontendOptions o = {512, 14, false, false, false, false, 0, false, 8, 0}; return o; }
 };
 
 // ---- CloudSlice.h:28-129 ----
@@ -127,8 +134,8 @@ public:
         if (rgbImage) { this->rgbImage = new unsigned char[Resolution::get().numPixels() * 3]; std::memcpy(this->rgbImage, rgbImage, Resolution::get().numPixels() * 3); }
         if (depthData) { this->depthData = new unsigned short[Resolution::get().numPixels()]; std::memcpy(this->depthData, depthData, Resolution::get().numPixels() * 2); }
     }
-    virtual ~CloudSlice() { delete cloud; delete[] rgbImage; delete[] tsdfImageColor; delete[] tsdfImage; delete[] depthData; }
-    ktt::PointCloud* cloud; ktt::PointCloud* processedCloud;
+    virtual ~CloudSlice() { delete cloud; delete processedCloud; delete[] rgbImage; delete[] tsdfImageColor; delete[] tsdfImage; delete[] depthData; }
+    ktt::PointCloud* cloud; ktt::PointCloudNormal* processedCloud;                    // CloudSlice.h:84-85
     Dimension dimension; Odometry odometry;
     ktt::Vector3f cameraTranslation; ktt::Matrix3f cameraRotation;
     uint64_t utime, lagTime;
@@ -245,6 +252,8 @@ public:
         cfg.odometry = o.useRGBDICP ? 2 : (o.useRGBD ? 1 : 0); cfg.fast_odometry = o.fastOdometry ? 1 : 0;
         cfg.voxel_shift = o.voxelShift; cfg.overlap = 2; cfg.angle_color = o.disableColorAngleWeight ? 0 : 1; cfg.device = o.gpu; cfg.world = 1;
         kt::check(kt_create(&cfg, &ctx_));
+        if (o.processSlicesOnGpu) kt::check(kt_set_slice_processing(ctx_, 1, o.weightCull));
+        if (o.poseLog) kt::check(kt_set_pose_log(ctx_, o.poseLog));
         lastOdometry = cfg.odometry == 0 ? CloudSlice::ICP : CloudSlice::RGBD;
     }
     virtual ~KintinuousTracker()
@@ -263,11 +272,14 @@ public:
         if (p.frame == 1) { init_utime.assignValue(timestamp); firstRgbImage.assignValue(rgbImage); firstDepthData.assignValue(depthData); }     // .cpp:497-503
         // mutexOutCloudBuffer (.cpp:1156-1208): every slab that left the volume during this frame is handed to the backend
         while (handed_ < kt_num_slices(ctx_)) handOver(handed_++);
-        // dense pose graph (.cpp:901-909)
-        ktt::Matrix4f pose;
-        for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) pose(r, c) = p.R[r * 3 + c]; pose(r, 3) = p.global_t[r]; }
-        densePoseGraph.push_back(DensePose(timestamp, pose, false));
-        latestDensePoseId++;
+        // dense pose graph (.cpp:529-536, :901-909): mirrored from the context (the first frame carries the loop-pose flag)
+        while ((int)densePoseGraph.size() < kt_num_dense_poses(ctx_)) {
+            kt_dense_pose d; kt::check(kt_get_dense_pose(ctx_, (int)densePoseGraph.size(), &d));
+            ktt::Matrix4f pose;
+            for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) pose(r, c) = d.pose[r * 4 + c];
+            densePoseGraph.push_back(DensePose(d.timestamp, pose, d.is_loop_pose != 0));
+            latestDensePoseId++;
+        }
         // GUI taps (.cpp:835-862)
         if (tsdfRequest.getValue()) {
             bool needed; { ktt::scoped_lock l(tsdfMutex); needed = !tsdfAvailable; }
@@ -327,6 +339,11 @@ private:
         ktt::Matrix3f R; for (int k = 0; k < 9; ++k) R.data()[k] = info.camera_R[k];
         CloudSlice* s = new CloudSlice(cloud, (CloudSlice::Dimension)info.dimension, (CloudSlice::Odometry)info.odometry, t, R, info.utime, 0,
                                        info.dimension == CloudSlice::FINAL ? lastRgbImage : 0);
+        if (KtFrontendOptions::get().processSlicesOnGpu) {
+            size_t m = 0; kt::check(kt_get_processed_slice(ctx_, i, 0, 0, &m));
+            s->processedCloud = new ktt::PointCloudNormal(); s->processedCloud->points.resize(m);
+            if (m) kt::check(kt_get_processed_slice(ctx_, i, (kt_point_xyzrgbnormal*)&s->processedCloud->points[0], m, &m));
+        }
         { ktt::scoped_lock lock(cloudMutex); cycledMutex = true; sharedCloudSlices.push_back(s); }
         cloudSignal.notify_all();
     }

@@ -144,7 +144,7 @@ struct kt_ctx {
     cudaStream_t stream_copy; cudaEvent_t ev_prefetch, ev_done[2], ev_maps; int last_parity; bool maps_on_stream;   // ev_maps: this frame's front end (on `stream`) has written the current maps
     uint16_t* depths_curr[LEVELS];
     float* vmaps_g_prev[LEVELS]; float* nmaps_g_prev[LEVELS]; float* vmaps_curr[LEVELS]; float* nmaps_curr[LEVELS];
-    uint8_t* vmap_curr_color; float* depth_scaled; float* ztable; float* cw_scratch; float* rgbf_scratch; float* cw_alt; float* rgbf_alt;
+    uint8_t* vmap_curr_color; float* depth_scaled; float* cw_scratch; float* rgbf_scratch; float* cw_alt; float* rgbf_alt;
     unsigned long long* xwords_dev; bool xwords_clean;      // exchange words of the whole-frame odometry kernels; zero between frames
     OdomState* state; float* partials; int* ipartials; float* trace_dev; float* pose12_dev; unsigned int* bar_dev; unsigned int bar_count; long long* prof_dev;
     kt_point_xyzrgb* cloud_dev; unsigned int* counter_dev; size_t cloud_capacity; size_t cloud_count;
@@ -268,7 +268,7 @@ int do_integrate(kt_ctx* c, const M3& Rinv, const V3& t, const int* wrap)
     for (int k = 0; k < 3; ++k) { c->last_int_t[k] = t.v[k]; c->last_int_wrap[k] = wrap[k]; }
     a.reset_words = c->xwords_dev; a.reset_count = odom_exchange_used(&a.reset_stride); c->xwords_clean = true;       // the prologue launch of integrate() zeroes them
     a.multi = c->world > 1 ? 1 : 0; a.vv = c->vv; a.cw = c->color_prepared ? c->cw_scratch : 0; a.rgbf = c->color_prepared ? (float4*)c->rgbf_scratch : 0;
-    return integrate(a, c->ztable, c->stream);
+    return integrate(a, c->stream);
 }
 
 int run_odometry(kt_ctx* c, const M3& Rprev, const V3& tprev, M3* Rcurr, V3* tcurr)
@@ -642,9 +642,12 @@ int kt_create(const kt_config* cfg, kt_ctx** out)
     {   // shared arena: local volume slab, model maps, raycast colour, barrier flags -- one allocation, one IPC handle
         c->world = cfg->world > 1 ? cfg->world : 1; c->rank = cfg->world > 1 ? cfg->rank : 0;
         c->local_planes = cfg->vol / c->world;
-        // colour planes are dealt to the ranks in blocks of mg_block storage planes (KT_MG_BLOCK, default 8): small enough that any
-        // viewing frustum spreads evenly over the ranks, large enough to amortise the jump over the foreign blocks in integrate_kernel
-        c->mg_block = 8;
+        // colour planes are dealt to the ranks in blocks of mg_block storage planes (KT_MG_BLOCK, default max(8, V / 64)): small enough
+        // that any viewing frustum spreads evenly over the ranks (the frustum's cross-section grows with depth: with V / 16-plane blocks
+        // the farthest block alone would hold a third of the work), large enough to amortise the per-column set-up of integrate_kernel,
+        // which walks one ownership block per CTA
+        c->mg_block = cfg->vol / 64 > 8 ? cfg->vol / 64 : 8;
+        { int b = 1; while (b * 2 <= c->mg_block) b *= 2; c->mg_block = b; }
         if (const char* e = getenv("KT_MG_BLOCK")) { int b = atoi(e); if (b >= 1 && (b & (b - 1)) == 0) c->mg_block = b; }
         while (c->mg_block > 1 && c->mg_block * c->world > cfg->vol) c->mg_block >>= 1;
         if (c->world == 1) c->mg_block = 1;
@@ -694,7 +697,7 @@ int kt_create(const kt_config* cfg, kt_ctx** out)
         }
     }
     c->vmap_curr_color = c->arena + c->off_vcol; KT_TRY(dev_alloc(c, &c->depth_scaled, P)); KT_TRY(dev_alloc(c, &c->depth_scaled_alt, P)); c->pf_built = false; c->frontend_ready = false;
-    KT_TRY(dev_alloc(c, &c->ztable, (size_t)2 * cfg->vol)); KT_TRY(dev_alloc(c, &c->cw_scratch, P)); KT_TRY(dev_alloc(c, &c->rgbf_scratch, P * 4)); KT_TRY(dev_alloc(c, &c->cw_alt, P)); KT_TRY(dev_alloc(c, &c->rgbf_alt, P * 4));
+    KT_TRY(dev_alloc(c, &c->cw_scratch, P)); KT_TRY(dev_alloc(c, &c->rgbf_scratch, P * 4)); KT_TRY(dev_alloc(c, &c->cw_alt, P)); KT_TRY(dev_alloc(c, &c->rgbf_alt, P * 4));
     KT_TRY(dev_alloc(c, &c->xwords_dev, odom_exchange_words()));
     KT_TRY(kt::cuda_check(cudaMemset(c->xwords_dev, 0, odom_exchange_words() * sizeof(unsigned long long)), "memset", __FILE__, __LINE__)); c->xwords_clean = true;
     KT_TRY(dev_alloc(c, &c->state, 1)); KT_TRY(dev_alloc(c, &c->partials, (size_t)MAX_PARTIALS * 32));

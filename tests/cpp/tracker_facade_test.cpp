@@ -37,6 +37,7 @@ int main()
         Resolution::get(cols, rows);
         Volume::get(6.0f);
         KtFrontendOptions::get().vol = 128; KtFrontendOptions::get().voxelShift = 2;
+        KtFrontendOptions::get().processSlicesOnGpu = true;          // CloudSlice::processedCloud filled on the device (CloudSliceProcessor.cpp:97-162)
         ktt::Mat K;
         K.at<double>(0, 0) = 132.0; K.at<double>(1, 1) = 132.0; K.at<double>(0, 2) = 80.0; K.at<double>(1, 2) = 66.75; K.at<double>(2, 2) = 1.0;
         KintinuousTracker* frontend = new KintinuousTracker(&K);
@@ -93,6 +94,14 @@ int main()
         if (lit < rows * cols / 2 || !ltsdf || ltsdf->cloud->points.size() < 1000 || ltsdf->dimension != CloudSlice::TSDF) ++bad;
         frontend->finalise();
         if (frontend->getCloudSlices().back()->dimension != CloudSlice::FINAL) ++bad;
+        {
+            CloudSlice* fin = frontend->getCloudSlices().back();
+            const size_t np = fin->processedCloud ? fin->processedCloud->points.size() : 0;
+            float nn = 0.f;
+            if (np) { const kt_point_xyzrgbnormal& q = fin->processedCloud->points[np / 2]; nn = q.nx * q.nx + q.ny * q.ny + q.nz * q.nz; }
+            std::printf("FINAL slice: %zu points, processedCloud %zu points, |n|^2 of one = %.4f\n", fin->cloud->points.size(), np, nn);
+            if (np < 100 || np > fin->cloud->points.size() || std::fabs(nn - 1.f) > 1e-3f) ++bad;
+        }
 
         // ---- an OdometryProvider on its own: ICPOdometry over maps the caller owns (what KintinuousTracker.cpp:562-577 does) ----
         {

@@ -21,7 +21,6 @@ cap integrate_kernel integrate_kernel 3 $B0
 cap raycast_kernel raycast_kernel 3 $B0
 cap bilateral_scale_kernel bilateral_scale_kernel 3 $B0
 cap frontend_pyramid_kernel frontend_pyramid_kernel 3 $B0
-cap ztable_kernel ztable_kernel 3 $B0
 cap rgbd_frame_kernel rgbd_frame_kernel 3 $B2
 cap frontend_pyramid_kernel_rgbd frontend_pyramid_kernel 3 $B2
 cap integrate_kernel_1024 integrate_kernel 3 $B1024

@@ -7,6 +7,7 @@ import kintinuous_b200 as kb
 from kintinuous_b200 import synth
 vol = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 t = kb.Tracker(kb.Config.default(vol=vol, voxel_shift=2))
+t.set_slice_processing(True, 8)          # CloudSliceProcessor on the device (kt_slice.cu) for every slice, the FINAL one included
 fr = [synth.render(k) for k in range(24)]
 for k in range(24):
     t.process_frame(fr[k][0], fr[k][1], k)
