@@ -19,7 +19,7 @@ cudaStream_t st(void* s) { return (cudaStream_t)s; }
 // either: internal.h:299-536 has static state in computeDerivativeImages and __device__ globals in extract.cu).  One set PER DEVICE
 // (the device current at the call), and the calls that use it are serialised by a process-wide mutex, so operator calls from several
 // host threads / on several devices are safe, just not concurrent.
-struct OpScratch { OdomState* state; float* partials; int* ipartials; unsigned int* counter; OdomState* host_state; SliceWorkspace slice_ws; };
+struct OpScratch { OdomState* state; float* partials; int* ipartials; float* ztable; int ztable_n; unsigned int* counter; OdomState* host_state; SliceWorkspace slice_ws; };
 enum { KT_MAX_DEVICES = 64 };
 OpScratch g_ops_dev[KT_MAX_DEVICES];
 std::mutex g_ops_mu;
@@ -41,6 +41,14 @@ int ensure_scratch()
     KT_CUDA(cudaMalloc((void**)&g_ops.ipartials, (size_t)MAX_PARTIALS * 2 * sizeof(int)));
     KT_CUDA(cudaMalloc((void**)&g_ops.counter, sizeof(unsigned int)));
     KT_CUDA(cudaMallocHost((void**)&g_ops.host_state, sizeof(OdomState)));
+    return 0;
+}
+int ensure_ztable(int vol)
+{
+    if (g_ops.ztable_n >= 2 * vol) return 0;
+    if (g_ops.ztable) cudaFree(g_ops.ztable);
+    KT_CUDA(cudaMalloc((void**)&g_ops.ztable, (size_t)2 * vol * sizeof(float)));
+    g_ops.ztable_n = 2 * vol;
     return 0;
 }
 int unpack_to_host(const float* sums, float* A, float* b)       // cuda/reduce.cu:404-415
@@ -128,14 +136,14 @@ int kt_op_integrate(const uint16_t* depth_raw, int rows, int cols, const float* 
                     const int* wrap, const uint8_t* rgb, const float* nmap_curr, int angle_color, float* depth_scaled, void* s)
 {
     KT_OPS_LOCK();
-    int r;
+    int r = ensure_ztable(vol); if (r) return r;
     r = scale_depth(depth_raw, depth_scaled, rows, cols, intr4(k), angle_color != 0, st(s)); if (r) return r;
     IntegrateArgs a; a.cw = 0; a.rgbf = 0; a.reset_words = 0; a.reset_count = 0; a.reset_stride = 1;
     a.depth_scaled = depth_scaled; a.rows = rows; a.cols = cols; a.k = intr4(k); a.volume_size = make_float3(vs[0], vs[1], vs[2]);
     a.Rinv = mat33(Rinv); a.t = make_float3(t[0], t[1], t[2]); a.trunc = trunc; a.tsdf = tsdf; a.color = color; a.vol = vol;
     a.wrap = make_int3(wrap[0], wrap[1], wrap[2]); a.rgb = rgb; a.nmap_curr = nmap_curr; a.angle_color = angle_color != 0;
     a.multi = 0; a.vv = single_volume(tsdf, color, vol);
-    r = integrate(a, st(s)); if (r) return r;
+    r = integrate(a, g_ops.ztable, st(s)); if (r) return r;
     KT_CUDA(cudaStreamSynchronize(st(s)));
     return KT_OK;
 }

@@ -140,7 +140,7 @@ struct IntegrateArgs {
     float* cw; float4* rgbf;     // optional per-pixel scratch (rows*cols each): colour weight + float RGB prepared once per frame
     unsigned long long* reset_words; int reset_count, reset_stride;   // optional: reset_count 64-bit words, reset_stride apart, that the launch zeroes (the odometry's exchange words)
 };
-int integrate(const IntegrateArgs& a, cudaStream_t s);
+int integrate(const IntegrateArgs& a, float* ztable_dev /* 2*vol floats */, cudaStream_t s);
 // per-pixel colour weight (sign = normal invalid) + float RGB for IntegrateArgs::cw / rgbf; once per frame, after the normal map exists
 int color_prep(const float* nmap, const uint8_t* rgb, int rows, int cols, bool angle_color, float* cw, float4* rgbf, cudaStream_t s);
 struct RaycastArgs {

@@ -144,7 +144,7 @@ struct kt_ctx {
     cudaStream_t stream_copy; cudaEvent_t ev_prefetch, ev_done[2], ev_maps; int last_parity; bool maps_on_stream;   // ev_maps: this frame's front end (on `stream`) has written the current maps
     uint16_t* depths_curr[LEVELS];
     float* vmaps_g_prev[LEVELS]; float* nmaps_g_prev[LEVELS]; float* vmaps_curr[LEVELS]; float* nmaps_curr[LEVELS];
-    uint8_t* vmap_curr_color; float* depth_scaled; float* cw_scratch; float* rgbf_scratch; float* cw_alt; float* rgbf_alt;
+    uint8_t* vmap_curr_color; float* depth_scaled; float* ztable; float* cw_scratch; float* rgbf_scratch; float* cw_alt; float* rgbf_alt;
     unsigned long long* xwords_dev; bool xwords_clean;      // exchange words of the whole-frame odometry kernels; zero between frames
     OdomState* state; float* partials; int* ipartials; float* trace_dev; float* pose12_dev; unsigned int* bar_dev; unsigned int bar_count; long long* prof_dev;
     kt_point_xyzrgb* cloud_dev; unsigned int* counter_dev; size_t cloud_capacity; size_t cloud_count;
@@ -268,7 +268,7 @@ int do_integrate(kt_ctx* c, const M3& Rinv, const V3& t, const int* wrap)
     for (int k = 0; k < 3; ++k) { c->last_int_t[k] = t.v[k]; c->last_int_wrap[k] = wrap[k]; }
     a.reset_words = c->xwords_dev; a.reset_count = odom_exchange_used(&a.reset_stride); c->xwords_clean = true;       // the prologue launch of integrate() zeroes them
     a.multi = c->world > 1 ? 1 : 0; a.vv = c->vv; a.cw = c->color_prepared ? c->cw_scratch : 0; a.rgbf = c->color_prepared ? (float4*)c->rgbf_scratch : 0;
-    return integrate(a, c->stream);
+    return integrate(a, c->ztable, c->stream);
 }
 
 int run_odometry(kt_ctx* c, const M3& Rprev, const V3& tprev, M3* Rcurr, V3* tcurr)
@@ -369,7 +369,7 @@ int run_odometry(kt_ctx* c, const M3& Rprev, const V3& tprev, M3* Rcurr, V3* tcu
     // one 64-byte read-back of the estimate (+ the trace when someone asked for it later: it stays on the device)
     static_assert(offsetof(OdomState, odo_timeout) == offsetof(OdomState, Rcurr) + 12 * sizeof(float), "the time-out flag travels with the pose");
     bool got = false;
-    if (c->pose_spin && !per_iteration_path && c->world == 1 && !c->timing) {
+    if (c->pose_spin && !per_iteration_path && !c->timing) {
         // the whole-frame kernel wrote the estimate into mapped host memory and then its sequence number: poll it (a few microseconds
         // after the kernel's last store) instead of a D2H copy + stream synchronisation; bounded, then the ordinary path takes over
         volatile unsigned int* seq = &c->result_host->seq;
@@ -378,10 +378,10 @@ int run_odometry(kt_ctx* c, const M3& Rprev, const V3& tprev, M3* Rcurr, V3* tcu
     }
     if (!got) {
         KT_CUDA(cudaMemcpyAsync(c->result_host->Rcurr, (char*)c->state + offsetof(OdomState, Rcurr), 13 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-        if (c->world > 1) KT_CUDA(cudaMemcpyAsync(c->mg_error_host, c->mg_error_dev, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         KT_CUDA(cudaStreamSynchronize(c->stream));
     }
-    if (c->world > 1 && *c->mg_error_host) { set_error("cross-GPU barrier timed out waiting for rank %d", *c->mg_error_host - 1); return KT_ERR_STATE; }
+    // mapped host memory: a timed-out barrier kernel wrote it in place
+    if (c->world > 1 && *(volatile int*)c->mg_error_host) { set_error("cross-GPU barrier timed out waiting for rank %d", *c->mg_error_host - 1); return KT_ERR_STATE; }
     if (c->result_host->timeout) {
         cudaMemsetAsync(&c->state->odo_timeout, 0, sizeof(int), c->stream);
         set_error("odometry kernel: a CTA never arrived at the grid-wide sum (bounded poll gave up)"); return KT_ERR_STATE;
@@ -586,7 +586,7 @@ int kt_reset(kt_ctx* c)
     c->trace_iters = 0; c->shifted_last = 0; c->cloud_count = 0;
     c->pf_valid = false; c->pf_built = false; c->frontend_ready = false; c->maps_on_stream = false;
     if (c->stream_copy) cudaStreamSynchronize(c->stream_copy);
-    if (c->mg_error_dev) { KT_CUDA(cudaMemsetAsync(c->mg_error_dev, 0, sizeof(int), c->stream)); *c->mg_error_host = 0; }      // a timed-out cross-GPU barrier is not sticky across resets
+    if (c->mg_error_host) { KT_CUDA(cudaStreamSynchronize(c->stream)); *c->mg_error_host = 0; }      // a timed-out cross-GPU barrier is not sticky across resets
     int r = init_shared(c->vv, c->cfg.vol, c->stream);
     if (r) return r;
     // Q7: stale y/z planes of invalid pixels start from a defined state (zeros)
@@ -670,9 +670,10 @@ int kt_create(const kt_config* cfg, kt_ctx** out)
         c->vv.world = c->world; c->vv.rank = c->rank;
         c->vv.bshift = 0; { int t = c->mg_block; while (t > 1) { t >>= 1; ++c->vv.bshift; } }
         c->vv.nshift = 0; { int t = c->world; while (t > 1) { t >>= 1; ++c->vv.nshift; } }
-        KT_TRY(dev_alloc(c, &c->peer_flags_dev, (size_t)MAX_GPUS)); KT_TRY(dev_alloc(c, &c->mg_error_dev, 1));
-        KT_TRY(kt::cuda_check(cudaMemset(c->mg_error_dev, 0, sizeof(int)), "memset", __FILE__, __LINE__));
-        KT_TRY(kt::cuda_check(cudaMallocHost((void**)&c->mg_error_host, sizeof(int)), "pinned", __FILE__, __LINE__)); *c->mg_error_host = 0;
+        KT_TRY(dev_alloc(c, &c->peer_flags_dev, (size_t)MAX_GPUS)); 
+        // the barrier's time-out flag lives in MAPPED host memory: the kernel writes it in place, the host reads it with the pose (no copy)
+        KT_TRY(kt::cuda_check(cudaHostAlloc((void**)&c->mg_error_host, sizeof(int), cudaHostAllocMapped), "mapped", __FILE__, __LINE__)); *c->mg_error_host = 0;
+        KT_TRY(kt::cuda_check(cudaHostGetDevicePointer((void**)&c->mg_error_dev, c->mg_error_host, 0), "mapped alias", __FILE__, __LINE__));
     }
     KT_TRY(dev_alloc(c, &c->depth_raw, P)); KT_TRY(dev_alloc(c, &c->rgb, P * 3));
     KT_TRY(dev_alloc(c, &c->depth_alt, P)); KT_TRY(dev_alloc(c, &c->rgb_alt, P * 3)); c->pf_valid = false; c->pf_depth = c->pf_rgb = 0;
@@ -697,7 +698,7 @@ int kt_create(const kt_config* cfg, kt_ctx** out)
         }
     }
     c->vmap_curr_color = c->arena + c->off_vcol; KT_TRY(dev_alloc(c, &c->depth_scaled, P)); KT_TRY(dev_alloc(c, &c->depth_scaled_alt, P)); c->pf_built = false; c->frontend_ready = false;
-    KT_TRY(dev_alloc(c, &c->cw_scratch, P)); KT_TRY(dev_alloc(c, &c->rgbf_scratch, P * 4)); KT_TRY(dev_alloc(c, &c->cw_alt, P)); KT_TRY(dev_alloc(c, &c->rgbf_alt, P * 4));
+    KT_TRY(dev_alloc(c, &c->ztable, (size_t)2 * cfg->vol)); KT_TRY(dev_alloc(c, &c->cw_scratch, P)); KT_TRY(dev_alloc(c, &c->rgbf_scratch, P * 4)); KT_TRY(dev_alloc(c, &c->cw_alt, P)); KT_TRY(dev_alloc(c, &c->rgbf_alt, P * 4));
     KT_TRY(dev_alloc(c, &c->xwords_dev, odom_exchange_words()));
     KT_TRY(kt::cuda_check(cudaMemset(c->xwords_dev, 0, odom_exchange_words() * sizeof(unsigned long long)), "memset", __FILE__, __LINE__)); c->xwords_clean = true;
     KT_TRY(dev_alloc(c, &c->state, 1)); KT_TRY(dev_alloc(c, &c->partials, (size_t)MAX_PARTIALS * 32));

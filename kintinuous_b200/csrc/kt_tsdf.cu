@@ -78,26 +78,33 @@ clear_planes_x_kernel(int16_t* __restrict__ tsdf, uchar4* __restrict__ color, in
 }
 
 // ------------------------------------------------------------------------------------------------
-// The reference's v_g_z(z) and z_scaled(z) are running float sums along z as well (tsdf_volume.cu:555,563,570-571); every thread brings them
-// to its first voxel with the exact fast-forward (kt_replay.cuh) and steps them with the reference's own additions -- round 1 built them
-// as a table in a separate one-thread launch (6 us on the critical path between the odometry and the integration).
-// Only when the camera sees no voxel at all (no integrate launch) the odometry's exchange words are reset by this little kernel.
-__global__ void __launch_bounds__(64) reset_words_kernel(unsigned long long* __restrict__ reset_words, int reset_count, int reset_stride)
+// z tables: v_g_z(z) and z_scaled(z) as the reference's running sums produce them (tsdf_volume.cu:555,563,570-571: they start at
+// (0 + 0.5f) * cell - t_z and 0 and grow by ONE float addition of cell per z step).  Prologue of the integration, one small launch: entry
+// z is brought there by thread z with the exact fast-forward of kt_replay.cuh (round 1: one thread adding 2 V times, 6 us on the critical
+// path between the odometry and the integration; building the entries inside integrate_kernel -- per thread, or per CTA in shared
+// memory -- was measured and is slower: 66 -> 77 .. 85 us at 512^3), and the other job of this launch is the reset of the odometry
+// kernels' exchange words for the next frame (grid_sum_words, kt_frame.cuh): it sits between two odometry launches anyway.
+__global__ void __launch_bounds__(256) ztable_kernel(float* __restrict__ table, int V, float cell_z, float t_z, unsigned long long* __restrict__ reset_words, int reset_count, int reset_stride, int seq)
 {
-    for (int i = threadIdx.x; i < reset_count; i += blockDim.x) reset_words[(size_t)i * reset_stride] = 0ull;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (blockIdx.x == 0) for (int k = threadIdx.x; k < reset_count; k += blockDim.x) reset_words[(size_t)k * reset_stride] = 0ull;
+    if (i >= 2 * V) return;
+    const int z = i < V ? i : i - V;
+    float v = i < V ? __fmaf_rn(0.5f, cell_z, -t_z) : 0.f;                 // (0 + 0.5f) * cell_z - t_z (0.5 * cell is exact, so fused or not is the same)
+    if (seq) { for (int k = 0; k < z; ++k) v = __fadd_rn(v, cell_z); }    // KT_INT_SEQ_REPLAY (test hook): the additions one by one
+    else v = replay_add(v, cell_z, z);
+    table[i] = v;
 }
 
 struct IntegrateParams {
     const float* depth_scaled; int rows, cols; Intr k; float3 cell; Mat33 Rinv; float3 t; float trunc;
     int16_t* tsdf; uchar4* color; int V; int3 wrap; const uint8_t* rgb; const float* nmap; bool angle_color;
-    int zchunk;
-    unsigned long long* reset_words; int reset_count, reset_stride;     // the odometry kernels' exchange words, zeroed by CTA (0,0,0) (grid_sum_words, kt_frame.cuh)
+    const float* ztable; int zchunk;
     const float* cw; const float4* rgbf;   // PREP: per-pixel colour weight (sign bit = normal invalid) and RGB as floats
     int lz_lo, lz_hi;          // LOGICAL z range walked by this launch
     int z_far_first;           // schedule the z chunks from high z to low z (see integrate())
     VolumeView vv;             // shared volume (MG instances): plane ownership and the peers' TSDF replicas
     int seq_replay;            // test hook: replay the running sums one addition at a time instead of replay_add()
-    int mg_first_block, mg_extra;               // shared volume: first owned ownership block of the launch (cyclic), 1 = the last z slot is the second part of the block the wrap splits
     int tile_x0, tiles_x, tile_y0, tiles_y;    // the launch covers the cyclic range of 32-wide / 8-high storage tiles [tile0, tile0 + gridDim) mod tiles (kt_frustum.hpp)
 };
 
@@ -128,48 +135,19 @@ __device__ __forceinline__ unsigned int sat_u8_rn(float x)       // == min(255, 
     return r;
 }
 
-// MG: the volume is shared by vv.world GPUs (VolumeView, kt_ops.h): this launch walks only the ownership blocks of storage planes this
-// rank owns (one block per z slot of the grid) and stores every CHANGED TSDF value into all ranks' replicas.
+// MG: the volume is shared by vv.world GPUs (VolumeView, kt_ops.h): this launch updates only the voxels of storage planes this rank owns
+// -- it steps over the foreign blocks of planes -- and stores every CHANGED TSDF value into all ranks' replicas.
 template <typename IdxT, int ZU, int MINB, bool PREP = false, bool MG = false>
 __global__ void __launch_bounds__(256, MINB)
 integrate_kernel(const IntegrateParams p)
 {
     const int V = p.V;
-    if (p.reset_count && (blockIdx.x | blockIdx.y | blockIdx.z) == 0) {
-        // this launch sits between two odometry launches on the tracker's stream: the reset of their exchange words costs no launch of its own
-        for (int i = threadIdx.y * 32 + threadIdx.x; i < p.reset_count; i += 256) p.reset_words[(size_t)i * p.reset_stride] = 0ull;
-    }
     int bx = p.tile_x0 + (int)blockIdx.x; if (bx >= p.tiles_x) bx -= p.tiles_x;      // the grid spans only the frustum's box of storage tiles (cyclic)
     int by = p.tile_y0 + (int)blockIdx.y; if (by >= p.tiles_y) by -= p.tiles_y;
     const int sx = bx * 32 + threadIdx.x;          // STORAGE x, y
     const int sy = by * 8 + threadIdx.y;
-    if (sx >= V || sy >= V) return;
-    int x = sx - p.wrap.x; if (x < 0) x += V;             // logical voxel
-    int y = sy - p.wrap.y; if (y < 0) y += V;
-    int z0, z1;
-    if (MG) {
-        // Shared volume: the z "chunks" of this launch are the ownership blocks of storage z planes that belong to THIS rank (every B-th
-        // block of 2^bshift planes, B = world): a CTA walks one whole block, so no voxel of a foreign plane is ever projected and the
-        // ranks split the frustum's voxels evenly whatever the camera looks at.  Logical z = storage z - wrap.z (mod V) is contiguous
-        // inside a block except for the one block the cyclic offset falls into; its second part has a grid slot of its own (mg_extra).
-        const int bs = p.vv.bshift, B = 1 << bs, nblocks = V >> bs, wz = p.wrap.z;
-        const bool second = p.mg_extra && blockIdx.z == gridDim.z - 1;
-        int b;
-        if (second) b = wz >> bs;
-        else { b = p.mg_first_block + (int)blockIdx.z * p.vv.world; if (b >= nblocks) b -= nblocks; }
-        const int sb = b << bs;
-        int a0, a1;
-        if (sb >= wz) { a0 = sb - wz; a1 = a0 + B; }
-        else if (sb + B <= wz) { a0 = sb - wz + V; a1 = a0 + B; }
-        else if (!second) { a0 = 0; a1 = sb + B - wz; }              // storage planes [wz, sb + B)
-        else { a0 = sb - wz + V; a1 = V; }                           // storage planes [sb, wz)
-        if (second && !(sb < wz && wz < sb + B)) return;
-        z0 = max(a0, p.lz_lo); z1 = min(a1, p.lz_hi);
-        if (z0 >= z1) return;
-    } else {
-        z0 = p.lz_lo + (p.z_far_first ? (int)(gridDim.z - 1 - blockIdx.z) : (int)blockIdx.z) * p.zchunk;
-        z1 = min(z0 + p.zchunk, p.lz_hi);
-    }
+    const int z0 = p.lz_lo + (p.z_far_first ? (int)(gridDim.z - 1 - blockIdx.z) : (int)blockIdx.z) * p.zchunk;
+    const int z1 = min(z0 + p.zchunk, p.lz_hi);
 
     const float3 cell_size = p.cell;
     const Intr intr = p.k;
@@ -177,6 +155,10 @@ integrate_kernel(const IntegrateParams p)
     const float3 tcurr = p.t;
     const float tranc_dist = p.trunc;
     const int cols = p.cols, rows = p.rows;
+
+    if (sx >= V || sy >= V) return;
+    int x = sx - p.wrap.x; if (x < 0) x += V;             // logical voxel
+    int y = sy - p.wrap.y; if (y < 0) y += V;
 
     // Parity-critical arithmetic is written with explicit round-to-nearest intrinsics in exactly the contraction nvcc chose for the
     // reference's expressions (tsdf_volume.cu:549-563; read off the SASS of both builds): a*b + c*d compiles to fma(a, b, c*d).  Left to
@@ -255,11 +237,7 @@ integrate_kernel(const IntegrateParams p)
         v_x = replay_fma(v_x, m0z, intr.fx, zlo);
         v_y = replay_fma(v_y, m1z, intr.fy, zlo);
     }
-    // v_g_z and z_scaled at zlo (tsdf_volume.cu:555,563: they start at (0 + 0.5f) * cell - t_z and 0 and grow by cell per z step, :570-571)
-    float z_scaled = 0.f;
-    if (p.seq_replay) { for (int z = 0; z < zlo; ++z) { v_g_z = __fadd_rn(v_g_z, cell_size.z); z_scaled = __fadd_rn(z_scaled, cell_size.z); } }
-    else { v_g_z = replay_add(v_g_z, cell_size.z, zlo); z_scaled = replay_add(z_scaled, cell_size.z, zlo); }
-
+    const float* __restrict__ zt = p.ztable;
     const float* __restrict__ depthScaled = p.depth_scaled;
     const float* __restrict__ nmap_curr = p.nmap;
     const uchar3* __restrict__ colors = reinterpret_cast<const uchar3*>(p.rgb);
@@ -271,6 +249,22 @@ integrate_kernel(const IntegrateParams p)
     // blend + stores) so that ZU independent memory round trips are in flight per thread; the per-voxel arithmetic and the
     // running sums are exactly the reference's (storage addresses of different z never alias, which the compiler cannot know).
     for (int zb = zlo; zb < zhi; zb += ZU) {
+        if (MG) {
+            // Shared volume: only the storage planes this rank owns are integrated here.  A run of foreign planes is crossed by STEPPING the
+            // running sums -- two FFMAs per plane, the reference's own arithmetic -- or, when the run is long (many ranks), by the exact
+            // fast-forward; the ownership pattern has period 2^bshift * world, which divides V, so it continues across the cyclic wrap.
+            int sz = zb + p.wrap.z; if (sz >= V) sz -= V;
+            if (vv_owner(p.vv, sz) != p.vv.rank) {
+                const int blk = sz >> p.vv.bshift;
+                const int foreign = (p.vv.rank - blk - 1) & (p.vv.world - 1);          // whole foreign blocks between this one and mine
+                int skip = (((blk + 1) << p.vv.bshift) - sz) + (foreign << p.vv.bshift);
+                skip = min(skip, zhi - zb);
+                if (skip <= 48) { for (int k = 0; k < skip; ++k) { v_x = __fmaf_rn(m0z, intr.fx, v_x); v_y = __fmaf_rn(m1z, intr.fy, v_y); } }
+                else { v_x = replay_fma(v_x, m0z, intr.fx, skip); v_y = replay_fma(v_y, m1z, intr.fy, skip); }
+                zb += skip - ZU;
+                continue;
+            }
+        }
         float vgz[ZU], Dp[ZU];
         IdxT pix[ZU], addr[ZU], caddr[ZU];
         bool ok[ZU];
@@ -281,7 +275,8 @@ integrate_kernel(const IntegrateParams p)
             const int z = zb + u;
             ok[u] = false;
             if (z < zhi) {
-                vgz[u] = v_g_z;
+                vgz[u] = zt[z];
+                const float z_scaled = zt[V + z];
                 float inv_z = 1.0f / __fmaf_rn(Rcurr_inv.r2.z, z_scaled, v_z);             // 1 / (v_z + Rcurr_inv.r2.z * z_scaled)
                 if (!(inv_z < 0)) {
                     int2 coo = { __float2int_rn(__fmaf_rn(v_x, inv_z, intr.cx)), __float2int_rn(__fmaf_rn(v_y, inv_z, intr.cy)) };
@@ -296,8 +291,6 @@ integrate_kernel(const IntegrateParams p)
                 }
                 v_x = __fmaf_rn(m0z, intr.fx, v_x);
                 v_y = __fmaf_rn(m1z, intr.fy, v_y);
-                v_g_z = __fadd_rn(v_g_z, cell_size.z);                                      // v_g_z += cell_size.z; z_scaled += cell_size.z (:570-571)
-                z_scaled = __fadd_rn(z_scaled, cell_size.z);
             }
         }
         bool upd[ZU], nocol[ZU];
@@ -450,12 +443,14 @@ int color_prep(const float* nmap, const uint8_t* rgb, int rows, int cols, bool a
     return 0;
 }
 
-int integrate(const IntegrateArgs& a, cudaStream_t s)
+int integrate(const IntegrateArgs& a, float* ztable_dev, cudaStream_t s)
 {
     const int V = a.vol;
     float3 cell = make_float3(a.volume_size.x / V, a.volume_size.y / V, a.volume_size.z / V);   // host division, tsdf_volume.cu:659-661
+    static const bool seq_replay = getenv("KT_INT_SEQ_REPLAY") != nullptr;
+    ztable_kernel<<<div_up(2 * V, 256), 256, 0, s>>>(ztable_dev, V, cell.z, a.t.z, a.reset_words, a.reset_words ? a.reset_count : 0, a.reset_stride, seq_replay ? 1 : 0);
+    KT_LAUNCH_CHECK();
     IntegrateParams p;
-    p.reset_words = a.reset_words; p.reset_count = a.reset_words ? a.reset_count : 0; p.reset_stride = a.reset_stride;
     p.depth_scaled = a.depth_scaled; p.rows = a.rows; p.cols = a.cols; p.k = a.k; p.cell = cell; p.Rinv = a.Rinv; p.t = a.t; p.trunc = a.trunc;
     p.tsdf = a.tsdf; p.color = (uchar4*)a.color; p.V = V; p.wrap = wrap_mod3(a.wrap, V); p.rgb = a.rgb; p.nmap = a.nmap_curr; p.angle_color = a.angle_color;
     static int n_chunks = -1, order = -1;          // tuning knobs: KT_INT_ZCHUNKS (default 16), KT_INT_ORDER (0 near-first = default, 1 far-first)
@@ -467,7 +462,7 @@ int integrate(const IntegrateArgs& a, cudaStream_t s)
     if (prep_knob < 0) { const char* e = getenv("KT_INT_PREP"); prep_knob = e ? atoi(e) : 1; }
     const bool prep = prep_knob != 0 && a.cw && a.rgbf;      // the caller ran color_prep() on this frame's normal map and image
     p.cw = a.cw; p.rgbf = a.rgbf;
-    p.zchunk = V >= 64 ? (V + n_chunks - 1) / n_chunks : V;
+    p.ztable = ztable_dev; p.zchunk = V >= 64 ? (V + n_chunks - 1) / n_chunks : V;
     // z chunks: a warp walks its columns' voxels serially, so a chunk's length is the scheduling quantum of the launch.  Measured on
     // B200 (640x480 into 512^3, tools/stage_ab.py): 8 chunks 100 us, 16 chunks 78 us, 32 chunks 96 us (per-chunk column setup);
     // dispatching the far chunks first was slower at every chunk count (89-109 us).
@@ -478,7 +473,6 @@ int integrate(const IntegrateArgs& a, cudaStream_t s)
     static const bool force64 = getenv("KT_FORCE_IDX64") != nullptr;
     const bool idx32 = !force64 && (size_t)V * V * V <= ((size_t)1 << 31);
     p.lz_lo = 0; p.lz_hi = V;
-    static const bool seq_replay = getenv("KT_INT_SEQ_REPLAY") != nullptr;
     p.seq_replay = seq_replay ? 1 : 0;
     p.tiles_x = div_up(V, 32); p.tiles_y = div_up(V, 8); p.tile_x0 = 0; p.tile_y0 = 0;
     dim3 block(32, 8), grid(p.tiles_x, p.tiles_y, div_up(V, p.zchunk));
@@ -489,34 +483,15 @@ int integrate(const IntegrateArgs& a, cudaStream_t s)
         const float Rinv9[9] = {a.Rinv.r0.x, a.Rinv.r0.y, a.Rinv.r0.z, a.Rinv.r1.x, a.Rinv.r1.y, a.Rinv.r1.z, a.Rinv.r2.x, a.Rinv.r2.y, a.Rinv.r2.z};
         const float t3[3] = {a.t.x, a.t.y, a.t.z}, k4[4] = {a.k.fx, a.k.fy, a.k.cx, a.k.cy}, cell3[3] = {cell.x, cell.y, cell.z};
         const VoxelBox box = frustum_voxel_box(Rinv9, t3, k4, a.rows, a.cols, V, cell3);
-        if (box.empty) {                                               // the camera sees no voxel of the cube: nothing to integrate
-            if (p.reset_count) { reset_words_kernel<<<1, 64, 0, s>>>(p.reset_words, p.reset_count, p.reset_stride); KT_LAUNCH_CHECK(); }
-            return 0;
-        }
+        if (box.empty) return 0;                                       // the camera sees no voxel of the cube: nothing to integrate
         p.lz_lo = box.lo[2]; p.lz_hi = box.hi[2] + 1;
         grid.z = div_up(p.lz_hi - p.lz_lo, p.zchunk);
         if (V % 32 == 0) { int n; cyclic_tile_range(box.lo[0], box.hi[0], p.wrap.x, V, 32, &p.tile_x0, &n); grid.x = n; }
         if (V % 8 == 0) { int n; cyclic_tile_range(box.lo[1], box.hi[1], p.wrap.y, V, 8, &p.tile_y0, &n); grid.y = n; }
     }
-    p.mg_first_block = 0; p.mg_extra = 0;
     if (multi) {
         if (V & (V - 1)) { set_error("integrate: the shared volume needs a power-of-two resolution"); return -1; }
-        // grid.z = this rank's ownership blocks among the storage planes of the box's z range (cyclic), + 1 slot for the split block
-        const int bs = p.vv.bshift, B = 1 << bs, nblocks = V >> bs, world = p.vv.world, wz = p.wrap.z;
-        const int s0 = (p.lz_lo + wz) % V, L = p.lz_hi - p.lz_lo;
-        const int b0 = s0 >> bs;
-        int nb = ((s0 & (B - 1)) + L + B - 1) >> bs; if (nb > nblocks) nb = nblocks;
-        const int lead = ((p.vv.rank - b0) % world + world) % world;          // blocks from b0 to the first one this rank owns
-        int count = nb > lead ? (nb - lead + world - 1) / world : 0;
-        p.mg_first_block = (b0 + lead) % nblocks;
-        const int split = (wz & (B - 1)) ? (wz >> bs) : -1;
-        p.mg_extra = (split >= 0 && (split & (world - 1)) == p.vv.rank) ? 1 : 0;
-        if (count + p.mg_extra == 0) {
-            if (p.reset_count) { reset_words_kernel<<<1, 64, 0, s>>>(p.reset_words, p.reset_count, p.reset_stride); KT_LAUNCH_CHECK(); }
-            return 0;
-        }
-        grid.z = count + p.mg_extra;
-        // one voxel per step at 6 CTAs / SM
+        // one voxel per step: the walk alternates between owned blocks and stepped-over foreign ones
         if (idx32) { if (prep) integrate_kernel<unsigned int, 1, 6, true, true><<<grid, block, 0, s>>>(p); else integrate_kernel<unsigned int, 1, 6, false, true><<<grid, block, 0, s>>>(p); }
         else { if (prep) integrate_kernel<size_t, 1, 6, true, true><<<grid, block, 0, s>>>(p); else integrate_kernel<size_t, 1, 6, false, true><<<grid, block, 0, s>>>(p); }
     } else if (idx32) {

@@ -20,3 +20,4 @@ cap slice_normals_kernel slice_normals_kernel 1 python tools/prof_shift.py
 cap slice_accumulate_kernel slice_accumulate_kernel 1 python tools/prof_shift.py
 cap slice_mark_kernel slice_mark_kernel 1 python tools/prof_shift.py
 cap extract_kernel extract_kernel 1 python tools/prof_shift.py
+cap ztable_kernel ztable_kernel 3 $B0
