@@ -16,8 +16,10 @@ integrate -> raycast + model pyramid.
           The reference has no CPU implementation of this path; if the library is missing, the CPU oracle port is timed.
 Timing: W>=3 warm-up frames, exactly K timed frames between barrier + cuda synchronize, max over ranks, CUDA clocks sampled
 with nvidia-smi during the timed region.  Inputs: 96 distinct frames (147 MB) cycled, i.e. larger than the 126 MB L2.
-Multi-GPU (torchrun): rank r tracks its own stream into its own volume (independent sessions, no data-path collective):
-weak scaling.  The z-slab single-stream mode of BASELINE configs[3] is selected with --mode zslab.
+Multi-GPU (torchrun): the headline line is weak scaling -- rank r tracks its own stream into its own volume (independent sessions, no
+data-path collective).  At every N the same JSON line carries a `zslab` sub-record: ONE stream fused into ONE 1024^3 volume shared by all
+N GPUs (BASELINE configs[3]; replicated TSDF with owner P2P stores, block-cyclic colour planes, banded ray cast with the model-map
+all-gather as P2P stores) -- strong scaling of one stream; --mode zslab runs the main legs in that mode instead.
 """
 import argparse
 import json
@@ -476,7 +478,7 @@ def main():
                 "traffic_source": f"ncu --set full capture {traffic_file} (dram__bytes_read.sum + dram__bytes_write.sum, one launch); not re-measured in this run" if traffic else None,
                 "compulsory_dram_bytes": compulsory, "frac_compulsory_dram": (compulsory / (icp_ms * 1e-3) / 1e9 / peak) if icp_ms > 0 else None,
                 "peak_source": peak_src, "bytes_per_launch": icp_bytes, "avg_launch_ms": icp_ms,
-                "note": "algorithmic bytes / CUDA-event time of that launch; the kernel is latency-bound by design at 640x480 (19 sequential reduce+solve steps separated by grid barriers, inputs L2-resident so DRAM traffic is far below the algorithmic bytes); see DESIGN.md section 4 and profiles/r1_ncu_summary.md",
+                "note": "algorithmic bytes / CUDA-event time of that launch; the kernel is latency-bound by design at 640x480 (19 sequential reduce+solve steps, each a grid-wide exchange; inputs L2- / shared-memory-resident so DRAM traffic equals one compulsory read of the maps, far below the algorithmic bytes); see DESIGN.md section 4 and profiles/r2_ncu_summary.md",
                 "dominant_stage": dom}
     dt = results["device"]["dt"]
     streams = 1 if zslab else world          # z-slab: all ranks work on ONE stream (strong scaling)

@@ -146,7 +146,9 @@ icp_kernel(const IcpParams p)
 //   solve    lane 0 of warp 0 of EVERY CTA: the same FP64 LDL^T + Rodrigues + pose composition on the same bit-identical totals
 //            (kt_solve.cuh, latency-trimmed form), so no pose broadcast is needed and all CTAs hold identical poses.
 // Two __syncthreads per iteration.  The totals are exact integer sums => deterministic run to run.
-enum { ICP_BATCH = 4 };          // pixels per thread whose model-map gathers are in flight together
+// ICP_BATCH = pixels per thread whose model-map gathers are in flight together (template parameter: 4, or 5 when the level-0 share of a
+// thread is 4 passes + a remainder -- 640x480 on 148 SMs: 4.05 pixels per thread -- so that the remainder does not cost a second batch's
+// worth of L2 latency per iteration; the sums are accumulated in pass order either way, so the result does not depend on it)
 
 struct IcpFrameParams {
     IcpLevelArgs lv[LEVELS];
@@ -161,6 +163,7 @@ struct IcpFrameParams {
     float* host_pose; unsigned int host_seq;      // optional mapped host record: pose (12), time-out (1), sequence number (1)
 };
 
+template <int ICP_BATCH>
 __global__ void __launch_bounds__(FRAME_THREADS, 1)
 icp_frame_kernel(const IcpFrameParams p)
 {
@@ -185,6 +188,15 @@ icp_frame_kernel(const IcpFrameParams p)
     tprev = make_float3(s_tp[0], s_tp[1], s_tp[2]);
 
     GridSumState gs; gs.prev[0] = 0ull; gs.prev[1] = 0ull;
+    // where lane l's component lands in a trace record: A(6x6 row-major, symmetric) | b(6) | residual | inliers -- component index -> (i, j) of the
+    // upper triangle with the b column, rows of 7, 6, 5, ... entries (internal.h:101-106)
+    int trace_a = -1, trace_b = -1;
+    if (lane < NSUM) {
+        int i = 0, base = 0;
+        while (lane >= base + (7 - i) && i < 6) { base += 7 - i; ++i; }
+        if (lane < 27) { const int jx = i + (lane - base); if (jx == 6) trace_a = 36 + i; else { trace_a = jx * 6 + i; trace_b = i * 6 + jx; } }
+        else trace_a = 42 + (lane - 27);
+    }
     int it = 0;
     unsigned int stage_parity = 0;
     for (int level = LEVELS - 1; level >= 0; --level) {
@@ -298,19 +310,12 @@ icp_frame_kernel(const IcpFrameParams p)
                     if (prof) p.prof[it * 8 + 3] = clock64();
                 }
                 if (p.trace && blockIdx.x == 0 && it < 64) {
-                    // the iteration's normal equations as the reference hands them to the host (reduce.cu:404-418), written after the
-                    // solve was issued so that the stores are off the critical path
+                    // the iteration's normal equations as the reference hands them to the host (reduce.cu:404-418); CTA 0 is on the critical
+                    // path of every exchange, so the component -> (row, column) mapping was worked out once per launch (trace_a / trace_b)
                     float* t = p.trace + (size_t)it * TRACE_STRIDE;
-                    if (lane < NSUM) {
-                        const float value = (float)total;
-                        // component index -> (i, j) of the upper triangle with the b column: rows of 7, 6, 5, ... entries
-                        int i = 0, base = 0;
-                        while (lane >= base + (7 - i) && i < 6) { base += 7 - i; ++i; }
-                        if (lane < 27) {
-                            const int jx = i + (lane - base);
-                            if (jx == 6) t[36 + i] = value; else { t[jx * 6 + i] = value; t[i * 6 + jx] = value; }
-                        } else t[42 + (lane - 27)] = value;
-                    }
+                    const float value = (float)total;
+                    if (trace_a >= 0) t[trace_a] = value;
+                    if (trace_b >= 0) t[trace_b] = value;
                 }
             }
             __syncthreads();
@@ -397,14 +402,21 @@ int icp_frame(const IcpLevelArgs* levels, const int* iters, const float* pose12_
     DeviceInfo& di = device_info();
     const int smem_optin = di.smem_optin;
     if (!(di.configured & 1u)) {
-        if (smem_optin > 0) cudaFuncSetAttribute((const void*)icp_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - 4096);
+        if (smem_optin > 0) {
+            cudaFuncSetAttribute((const void*)icp_frame_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - 4096);
+            cudaFuncSetAttribute((const void*)icp_frame_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - 4096);
+        }
         di.configured |= 1u;
     }
     const size_t stage_bytes = (size_t)6 * need_k * FRAME_THREADS * sizeof(float);
     const bool can_stage = need_k > 0 && need_k <= STAGE_MAX_K && smem_optin > 0 && stage_bytes <= (size_t)(smem_optin - 4096);
     p.stage_k = can_stage ? need_k : 0;
+    static int batch_knob = -1;                     // KT_ICP_BATCH = 4 | 5 (A/B); default: 5 when the largest level leaves a remainder pass after groups of 4
+    if (batch_knob < 0) { const char* e = getenv("KT_ICP_BATCH"); batch_knob = e ? atoi(e) : 0; }
+    const int batch = batch_knob == 4 || batch_knob == 5 ? batch_knob : ((need_k % 4 == 1) ? 5 : 4);
     void* args[] = {&p};
-    cudaError_t e = cudaLaunchCooperativeKernel((const void*)icp_frame_kernel, dim3(grid), dim3(FRAME_THREADS), args, can_stage ? stage_bytes : 0, s);
+    const void* fn = batch == 5 ? (const void*)icp_frame_kernel<5> : (const void*)icp_frame_kernel<4>;
+    cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(FRAME_THREADS), args, can_stage ? stage_bytes : 0, s);
     ++g_launches;
     if (e != cudaSuccess) return cuda_check(e, "cudaLaunchCooperativeKernel(icp_frame_kernel)", __FILE__, __LINE__);
     return 0;

@@ -13,8 +13,8 @@
 //   * centroids accumulate in 64-bit fixed point (2^-32 m) with integer atomics: order-independent, hence deterministic run to run
 //     (PCL's float sums depend on std::sort's unspecified order inside a leaf); colours are integer sums, divided as PCL divides them;
 //   * the 20 nearest neighbours are found EXACTLY by one warp per point scanning the cube of +-r leaves around the point's leaf
-//     (r = 2, 3, ...; a point outside the cube is farther than r leaves, so the search stops as soon as the 20th candidate is nearer),
-//     candidates ranked by (squared distance, slot) -- the order the oracle uses;
+//     (r = 3, 4, ...; a point outside the cube is farther than r leaves, so the search stops as soon as the 20th candidate is nearer),
+//     candidates ranked by (squared distance, slot) -- the order the oracle uses -- in ONE pass (rank = number of smaller candidates);
 //   * the 3x3 covariance is taken about the query point (PCL's single-pass float sum of raw coordinates loses ~3 digits to
 //     cancellation for clouds metres away from the origin) and its smallest eigenpair comes from PCL's analytic eigen33 in FP64;
 //     normal flipped towards the viewpoint (0,0,0), curvature = lambda0 / trace.
@@ -271,8 +271,10 @@ slice_normals_kernel(kt_point_xyzrgbnormal* __restrict__ pts, const SliceAcc* __
 {
     __shared__ float s_d[NRM_THREADS / 32][CAND_CAP];
     __shared__ unsigned int s_i[NRM_THREADS / 32][CAND_CAP];
+    __shared__ float s_sd[NRM_THREADS / 32][KNN_MAX];
+    __shared__ unsigned int s_si[NRM_THREADS / 32][KNN_MAX];
     const unsigned int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    float* cd = s_d[wid]; unsigned int* ci = s_i[wid];
+    float* cd = s_d[wid]; unsigned int* ci = s_i[wid]; float* sd = s_sd[wid]; unsigned int* si = s_si[wid];
     const int kk = min(k, (int)min(n_out, (unsigned int)KNN_MAX));
     for (unsigned int q = blockIdx.x * (NRM_THREADS / 32) + wid; q < n_out; q += gridDim.x * (NRM_THREADS / 32)) {
         const float qx = pts[q].x, qy = pts[q].y, qz = pts[q].z;
@@ -280,7 +282,9 @@ slice_normals_kernel(kt_point_xyzrgbnormal* __restrict__ pts, const SliceAcc* __
         const int c0 = (int)(l % g.div_b[0]), c1 = (int)((l / g.div_b[0]) % g.div_b[1]), c2 = (int)(l / ((unsigned long long)g.div_b[0] * g.div_b[1]));
         unsigned int ncand = 0;
         bool done = false;
-        for (int r = 2; r <= R_CAP && !done; ++r) {
+        // r starts at 3: on a surface sampled at one point per leaf the 20th neighbour sits ~2.5 leaves away, so the +-2 cube almost never
+        // passes the stop test and would only cost a second gather + ranking
+        for (int r = 3; r <= R_CAP && !done; ++r) {
             const bool covers = c0 - r <= 0 && c1 - r <= 0 && c2 - r <= 0 && c0 + r >= g.div_b[0] - 1 && c1 + r >= g.div_b[1] - 1 && c2 + r >= g.div_b[2] - 1;
             unsigned int m = 0;
             const int side = 2 * r + 1, ncell = side * side * side;
@@ -308,27 +312,22 @@ slice_normals_kernel(kt_point_xyzrgbnormal* __restrict__ pts, const SliceAcc* __
             __syncwarp();
             if (m > CAND_CAP) break;                                   // cannot happen with one point per leaf before r = 5; the whole-cloud path below is exact anyway
             if ((int)m >= kk || covers) {
-                // select the kk smallest (distance, slot) pairs: kk rounds of a warp arg-min; the winners move to the front
+                // the kk smallest (distance, slot) pairs by RANK: a candidate's rank is the number of candidates before it in (distance, slot)
+                // order (slots are unique, so ranks are); every lane ranks its candidates against all m (shared-memory broadcast reads) and
+                // the ones with rank < kk drop into place -- one pass, no kk rounds of warp arg-min
                 const int take = min(kk, (int)m);
-                float dk = 0.f;
-                for (int t = 0; t < take; ++t) {
-                    float bd = 3.0e38f; unsigned int bi = 0xffffffffu, bp = 0;
-                    for (unsigned int j = t + lane; j < m; j += 32) {
-                        const float d = cd[j]; const unsigned int sl = ci[j];
-                        if (d < bd || (d == bd && sl < bi)) { bd = d; bi = sl; bp = j; }
-                    }
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        const float od = __shfl_xor_sync(0xffffffffu, bd, o); const unsigned int oi = __shfl_xor_sync(0xffffffffu, bi, o), op = __shfl_xor_sync(0xffffffffu, bp, o);
-                        if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; bp = op; }
-                    }
-                    if (lane == 0) { const float td = cd[t]; const unsigned int ti = ci[t]; cd[t] = bd; ci[t] = bi; cd[bp] = td; ci[bp] = ti; }
-                    __syncwarp();
-                    dk = bd;
+                for (unsigned int j = lane; j < m; j += 32) {
+                    const float d = cd[j]; const unsigned int sl = ci[j];
+                    int rank = 0;
+                    for (unsigned int i = 0; i < m; ++i) { const float di = cd[i]; rank += (di < d || (di == d && ci[i] < sl)) ? 1 : 0; }
+                    if (rank < take) { sd[rank] = d; si[rank] = sl; }
                 }
+                __syncwarp();
+                const float dk = sd[take - 1];
                 // a point outside the cube of +-r leaves is farther than r leaves from the query along some axis
                 const float reach = ((float)r - 0.001f) * g.leaf;
                 if (covers || ((int)m >= kk && dk <= reach * reach)) { done = true; ncand = (unsigned int)take; }
+                __syncwarp();
             }
         }
         if (!done) {
@@ -347,7 +346,7 @@ slice_normals_kernel(kt_point_xyzrgbnormal* __restrict__ pts, const SliceAcc* __
                     const float od = __shfl_xor_sync(0xffffffffu, bd, o); const unsigned int oi = __shfl_xor_sync(0xffffffffu, bi, o);
                     if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
                 }
-                if (lane == 0) { cd[t] = bd; ci[t] = bi; }
+                if (lane == 0) { sd[t] = bd; si[t] = bi; }
                 ld = bd; li = bi;
             }
             __syncwarp();
@@ -356,7 +355,7 @@ slice_normals_kernel(kt_point_xyzrgbnormal* __restrict__ pts, const SliceAcc* __
         // covariance about the query point over the ncand selected neighbours (lanes 0 .. ncand-1), FP64
         double a[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
         if (lane < ncand) {
-            const unsigned int s = ci[lane];
+            const unsigned int s = si[lane];
             const double dx = (double)pts[s].x - (double)qx, dy = (double)pts[s].y - (double)qy, dz = (double)pts[s].z - (double)qz;
             a[0] = dx * dx; a[1] = dx * dy; a[2] = dx * dz; a[3] = dy * dy; a[4] = dy * dz; a[5] = dz * dz; a[6] = dx; a[7] = dy; a[8] = dz;
         }

@@ -487,7 +487,9 @@ int process_frame_device(kt_ctx* c, uint64_t utime, kt_pose* out)
     if ((r = run_odometry(c, Rprev, tprev, &Rcurr, &tcurr))) return r;
     mark(c, 2);
     c->current_utime = utime;
-    c->rmats.push_back(Rcurr); c->tvecs.push_back(tcurr);                                // .cpp:578-579
+    // rmats_.push_back / tvecs_.push_back (.cpp:578-579): only .back() is ever read (by the reference too), so the history is one entry deep --
+    // the full trajectory is the dense pose graph (kt_get_dense_pose)
+    c->rmats.back() = Rcurr; c->tvecs.back() = tcurr;
 
     for (int i = 0; i < 3; ++i) c->currentGlobalCamera[i] = global_camera(c->volumeBasis[i], c->size, c->voxelWrap[i], c->voxel, tcurr.v[i]);   // .cpp:581-596
     M3 Rcurr_inv = m3_inverse(Rcurr);                                                    // .cpp:627
@@ -552,6 +554,9 @@ int process_frame_device(kt_ctx* c, uint64_t utime, kt_pose* out)
     if ((r = raycast(ra, c->stream))) return r;
     if ((r = mg_barrier(c))) return r;                                                   // all tiles of the predicted surface have landed everywhere
     mark(c, 5);
+    // a cross-GPU barrier that timed out writes its flag straight into mapped host memory: report it with the frame it belongs to when it
+    // has already fired (free to check), else with the next frame's pose read-back (run_odometry)
+    if (c->world > 1 && *(volatile int*)c->mg_error_host) { set_error("cross-GPU barrier timed out waiting for rank %d", *c->mg_error_host - 1); return KT_ERR_STATE; }
     ++c->global_time;
     record_dense_pose(c, false);                                                         // .cpp:901-914
     if (out) kt_get_pose(c, out);
