@@ -269,12 +269,13 @@ __global__ void __launch_bounds__(NRM_THREADS)
 slice_normals_kernel(kt_point_xyzrgbnormal* __restrict__ pts, const SliceAcc* __restrict__ acc, unsigned int n_out, int k, const SliceGrid g,
                      const unsigned int* __restrict__ mask, const unsigned int* __restrict__ word_off)
 {
-    __shared__ float s_d[NRM_THREADS / 32][CAND_CAP];
-    __shared__ unsigned int s_i[NRM_THREADS / 32][CAND_CAP];
+    // a candidate = ONE 64-bit key (bits of the squared distance, which is >= 0 so its bit pattern orders like its value) << 32 | slot:
+    // (distance, slot) order is unsigned integer order, one shared-memory load and one compare per pair in the ranking pass
+    __shared__ unsigned long long s_key[NRM_THREADS / 32][CAND_CAP];
     __shared__ float s_sd[NRM_THREADS / 32][KNN_MAX];
     __shared__ unsigned int s_si[NRM_THREADS / 32][KNN_MAX];
     const unsigned int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    float* cd = s_d[wid]; unsigned int* ci = s_i[wid]; float* sd = s_sd[wid]; unsigned int* si = s_si[wid];
+    unsigned long long* ck = s_key[wid]; float* sd = s_sd[wid]; unsigned int* si = s_si[wid];
     const int kk = min(k, (int)min(n_out, (unsigned int)KNN_MAX));
     for (unsigned int q = blockIdx.x * (NRM_THREADS / 32) + wid; q < n_out; q += gridDim.x * (NRM_THREADS / 32)) {
         const float qx = pts[q].x, qy = pts[q].y, qz = pts[q].z;
@@ -288,11 +289,14 @@ slice_normals_kernel(kt_point_xyzrgbnormal* __restrict__ pts, const SliceAcc* __
             const bool covers = c0 - r <= 0 && c1 - r <= 0 && c2 - r <= 0 && c0 + r >= g.div_b[0] - 1 && c1 + r >= g.div_b[1] - 1 && c2 + r >= g.div_b[2] - 1;
             unsigned int m = 0;
             const int side = 2 * r + 1, ncell = side * side * side;
+            const float inv_side = 1.0f / (float)side;
             for (int cb = 0; cb < ncell; cb += 32) {
                 const int c = cb + lane;
                 bool hit = false; unsigned int slot = 0; float d = 0.f;
                 if (c < ncell) {
-                    const int x = c0 - r + c % side, y = c1 - r + (c / side) % side, z = c2 - r + c / (side * side);
+                    // c = (cz * side + cy) * side + cx without integer division (exact: c < 2^14, side <= 21)
+                    const int cq = __float2int_rz(((float)c + 0.5f) * inv_side), cz = __float2int_rz(((float)cq + 0.5f) * inv_side);
+                    const int x = c0 - r + (c - cq * side), y = c1 - r + (cq - cz * side), z = c2 - r + cz;
                     if ((unsigned)x < (unsigned)g.div_b[0] && (unsigned)y < (unsigned)g.div_b[1] && (unsigned)z < (unsigned)g.div_b[2]) {
                         const unsigned long long ll = leaf_index(g, x, y, z);
                         const unsigned int w = mask[ll >> 5];
@@ -306,7 +310,7 @@ slice_normals_kernel(kt_point_xyzrgbnormal* __restrict__ pts, const SliceAcc* __
                 }
                 const unsigned int b = __ballot_sync(0xffffffffu, hit);
                 const unsigned int pos = m + __popc(b & ((1u << lane) - 1u));
-                if (hit && pos < CAND_CAP) { cd[pos] = d; ci[pos] = slot; }
+                if (hit && pos < CAND_CAP) ck[pos] = ((unsigned long long)__float_as_uint(d) << 32) | slot;
                 m += __popc(b);
             }
             __syncwarp();
@@ -317,10 +321,10 @@ slice_normals_kernel(kt_point_xyzrgbnormal* __restrict__ pts, const SliceAcc* __
                 // the ones with rank < kk drop into place -- one pass, no kk rounds of warp arg-min
                 const int take = min(kk, (int)m);
                 for (unsigned int j = lane; j < m; j += 32) {
-                    const float d = cd[j]; const unsigned int sl = ci[j];
+                    const unsigned long long key = ck[j];
                     int rank = 0;
-                    for (unsigned int i = 0; i < m; ++i) { const float di = cd[i]; rank += (di < d || (di == d && ci[i] < sl)) ? 1 : 0; }
-                    if (rank < take) { sd[rank] = d; si[rank] = sl; }
+                    for (unsigned int i = 0; i < m; ++i) rank += ck[i] < key ? 1 : 0;
+                    if (rank < take) { sd[rank] = __uint_as_float((unsigned int)(key >> 32)); si[rank] = (unsigned int)key; }
                 }
                 __syncwarp();
                 const float dk = sd[take - 1];
