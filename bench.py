@@ -233,12 +233,12 @@ def shared_volume_leg(kb, torch, args, world, rank, local, device, dev_depth, de
     torch.cuda.synchronize(); barrier(world)
     dt = max_over_ranks(dt, world, device)
     trk.set_stage_timing(True)
-    acc = np.zeros(6); m = 0
+    acc = np.zeros(6); kacc = np.zeros(3); m = 0
     for _ in range(12):
         j = pingpong(i, n); p = trk.process_frame_device(dev_depth[j], dev_rgb[j], i); i += 1
         if p.shifted == 0:
-            acc += np.array(trk.stage_ms()); m += 1
-    st = (acc / max(1, m)).tolist()
+            acc += np.array(trk.stage_ms()); kacc += np.array(trk.kernel_ms()); m += 1
+    st = (acc / max(1, m)).tolist(); kst = (kacc / max(1, m)).tolist()
     info = trk.mgpu_info()
     trk.close()
     barrier(world)
@@ -251,6 +251,8 @@ def shared_volume_leg(kb, torch, args, world, rank, local, device, dev_depth, de
                             f"(blocks of {info['block']} storage z planes), ray cast split into {world} image bands with the model-map all-gather as P2P stores in the kernel epilogue, "
                             "flag barriers in peer memory, ICP replicated; no NCCL call on the data path"),
             "stages_ms_rank0": {nm: st[k] for k, nm in enumerate(["pyramid", "odometry", "shift", "integrate", "raycast"])},
+            "kernels_ms_rank0": {"icp": kst[0], "ztable+integrate": kst[1], "raycast": kst[2],
+                                 "note": "the launches alone; the stage timers above include the cross-GPU barriers, i.e. the wait for the slowest rank"},
             "p2p_model_map_bytes_per_frame": int(maps_bytes * (world - 1)) if world > 1 else 0,
             "arena_mb_per_gpu": info["arena_mb"]}
 
@@ -322,6 +324,7 @@ def main():
     ap.add_argument("--no-prefetch", action="store_true", help="do not give the kt_prefetch_frame hint (A/B)")
     ap.add_argument("--no-shared-volume", action="store_true", help="skip the extra one-stream / one-shared-1024^3-volume leg (the zslab sub-record)")
     ap.add_argument("--shared-vol", type=int, default=1024)
+    ap.add_argument("--shared-only", action="store_true", help="diagnostic: run only the shared-volume leg and print its record")
     ap.add_argument("--vol", type=int, default=VOL)
     ap.add_argument("--scale", type=int, default=1, help="image scale: 1 = 640x480 (configs 1-3), 2 = 1280x960 (configs[4])")
     ap.add_argument("--odometry", type=int, default=0, help="0 ICP (configs[1]), 2 ICP+RGB-D (configs[2])")
@@ -353,6 +356,14 @@ def main():
     dev_rgb = [torch.from_numpy(f[1]).to(device) for f in frames]
     pin_depth = [torch.from_numpy(f[0].view(np.int16)).pin_memory() for f in frames]
     pin_rgb = [torch.from_numpy(f[1]).pin_memory() for f in frames]
+    if args.shared_only:
+        rec = shared_volume_leg(kb, torch, args, world, rank, local, device, dev_depth, dev_rgb, n, warmup)
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier(); dist.destroy_process_group()
+        if rank == 0:
+            print(json.dumps({"zslab": rec}), flush=True)
+        return
     zslab = (args.mode == "zslab" and world > 1)
     cfg = kb.Config.default(rows=ROWS, cols=COLS, vol=args.vol, odometry=args.odometry, device=local,
                             rank=rank if zslab else 0, world=world if zslab else 1)

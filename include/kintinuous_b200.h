@@ -157,6 +157,9 @@ KT_API int kt_get_stage_ms(kt_ctx* ctx, float* ms6);
 KT_API int kt_set_stage_timing(kt_ctx* ctx, int enabled);
 /* CUDA-event duration of the last whole-frame ICP launch (icp_frame_kernel), ms; 0 unless stage timing is on and odometry == 0 */
 KT_API float kt_get_icp_kernel_ms(kt_ctx* ctx);
+/* The launches alone, ms: whole-frame ICP kernel, z table + integrate, ray cast -- without the cross-GPU barriers that the stage timers
+ * of a shared-volume context include (0 unless stage timing is on). */
+KT_API int kt_get_kernel_ms(kt_ctx* ctx, float* ms3);
 /* Device-side stopwatch on the tracker's own stream: mark(0) ... frames ... mark(1), then the CUDA-event time between the two
  * marks (ms, synchronises on mark 1; < 0 on error).  bench.py times its region with this, not with the host clock. */
 KT_API int kt_span_mark(kt_ctx* ctx, int which);

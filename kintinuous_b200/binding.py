@@ -268,6 +268,12 @@ class Tracker:
     def span_elapsed_ms(self):
         return float(self.lib.kt_span_elapsed_ms(self.h))
 
+    def kernel_ms(self):
+        """(icp, ztable + integrate, raycast) launches alone, ms (stage timing on)"""
+        a = (C.c_float * 3)()
+        _check(self.lib.kt_get_kernel_ms(self.h, a))
+        return [float(x) for x in a]
+
     def icp_kernel_ms(self):
         return float(self.lib.kt_get_icp_kernel_ms(self.h))
 

@@ -159,7 +159,7 @@ struct kt_ctx {
     float* pose12_host; OdomResult* result_host; float* result_dev_alias; unsigned int pose_seq; bool pose_spin; float* trace_host; unsigned int* counter_host;
     int trace_iters; int shifted_last;
     // timing
-    bool timing; cudaEvent_t ev[7]; float stage_ms[6]; cudaEvent_t ev_icp[2]; cudaEvent_t ev_span[2];
+    bool timing; cudaEvent_t ev[7]; float stage_ms[6]; cudaEvent_t ev_icp[2]; cudaEvent_t ev_krn[4]; cudaEvent_t ev_span[2];     // ev_krn: integrate / raycast launches alone (without the cross-GPU barriers the stage timers include)
     long long launches_at_create;
     std::vector<void*> allocs;
     // ONE volume shared by `world` GPUs (one process per GPU; peers' arenas are mapped through CUDA IPC): TSDF plane replicated, colour /
@@ -528,7 +528,9 @@ int process_frame_device(kt_ctx* c, uint64_t utime, kt_pose* out)
     if (c->shifted_last && (r = mg_barrier(c))) return r;
     mark(c, 3);
 
+    if (c->timing) cudaEventRecord(c->ev_krn[0], c->stream);
     if ((r = do_integrate(c, Rcurr_inv, tcurr, vWrapCopy))) return r;                    // .cpp:864-876
+    if (c->timing) cudaEventRecord(c->ev_krn[1], c->stream);
     if ((r = mg_barrier(c))) return r;                                                   // every slab holds this frame before any ray reads it
     mark(c, 4);
     vwrap_copy(c, vWrapCopy);
@@ -551,7 +553,9 @@ int process_frame_device(kt_ctx* c, uint64_t utime, kt_pose* out)
             ra.peer_vcol[g] = c->peer_arena[g] + c->off_vcol;
         }
     }
+    if (c->timing) cudaEventRecord(c->ev_krn[2], c->stream);
     if ((r = raycast(ra, c->stream))) return r;
+    if (c->timing) cudaEventRecord(c->ev_krn[3], c->stream);
     if ((r = mg_barrier(c))) return r;                                                   // all tiles of the predicted surface have landed everywhere
     mark(c, 5);
     // a cross-GPU barrier that timed out writes its flag straight into mapped host memory: report it with the frame it belongs to when it
@@ -725,6 +729,7 @@ int kt_create(const kt_config* cfg, kt_ctx** out)
     KT_TRY(kt::cuda_check(cudaMallocHost((void**)&c->counter_host, sizeof(unsigned int)), "pinned", __FILE__, __LINE__));
     for (int i = 0; i < 7; ++i) KT_TRY(kt::cuda_check(cudaEventCreate(&c->ev[i]), "event", __FILE__, __LINE__));
     for (int i = 0; i < 2; ++i) KT_TRY(kt::cuda_check(cudaEventCreate(&c->ev_icp[i]), "event", __FILE__, __LINE__));
+    for (int i = 0; i < 4; ++i) KT_TRY(kt::cuda_check(cudaEventCreate(&c->ev_krn[i]), "event", __FILE__, __LINE__));
     for (int i = 0; i < 2; ++i) KT_TRY(kt::cuda_check(cudaEventCreate(&c->ev_span[i]), "event", __FILE__, __LINE__));
     for (int i = 0; i < 6; ++i) c->stage_ms[i] = 0.f;
     KT_TRY(kt_reset(c));
@@ -754,6 +759,7 @@ int kt_destroy(kt_ctx* c)
     if (c->counter_host) cudaFreeHost(c->counter_host);
     for (int i = 0; i < 7; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (int i = 0; i < 2; ++i) if (c->ev_icp[i]) cudaEventDestroy(c->ev_icp[i]);
+    for (int i = 0; i < 4; ++i) if (c->ev_krn[i]) cudaEventDestroy(c->ev_krn[i]);
     for (int i = 0; i < 2; ++i) if (c->ev_span[i]) cudaEventDestroy(c->ev_span[i]);
     if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
     if (c->stream_copy) { cudaStreamSynchronize(c->stream_copy); cudaStreamDestroy(c->stream_copy); }
@@ -1079,6 +1085,18 @@ float kt_get_icp_kernel_ms(kt_ctx* c)
     float t = 0.f;
     if (cudaEventElapsedTime(&t, c->ev_icp[0], c->ev_icp[1]) != cudaSuccess) { cudaGetLastError(); return 0.f; }
     return t;
+}
+
+int kt_get_kernel_ms(kt_ctx* c, float* ms3)
+{
+    if (!c || !ms3) return KT_ERR_INVALID;
+    ms3[0] = ms3[1] = ms3[2] = 0.f;
+    if (!c->timing) return KT_OK;
+    cudaStreamSynchronize(c->stream);
+    if (cudaEventElapsedTime(&ms3[0], c->ev_icp[0], c->ev_icp[1]) != cudaSuccess) { cudaGetLastError(); ms3[0] = 0.f; }
+    if (cudaEventElapsedTime(&ms3[1], c->ev_krn[0], c->ev_krn[1]) != cudaSuccess) { cudaGetLastError(); ms3[1] = 0.f; }
+    if (cudaEventElapsedTime(&ms3[2], c->ev_krn[2], c->ev_krn[3]) != cudaSuccess) { cudaGetLastError(); ms3[2] = 0.f; }
+    return KT_OK;
 }
 
 int kt_span_mark(kt_ctx* c, int which)

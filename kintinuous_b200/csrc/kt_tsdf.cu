@@ -105,6 +105,7 @@ struct IntegrateParams {
     int z_far_first;           // schedule the z chunks from high z to low z (see integrate())
     VolumeView vv;             // shared volume (MG instances): plane ownership and the peers' TSDF replicas
     int seq_replay;            // test hook: replay the running sums one addition at a time instead of replay_add()
+    int mg_no_publish;         // KT_MG_NO_PUBLISH (diagnostic only, results are wrong): skip the P2P stores of changed TSDF values
     int tile_x0, tiles_x, tile_y0, tiles_y;    // the launch covers the cyclic range of 32-wide / 8-high storage tiles [tile0, tile0 + gridDim) mod tiles (kt_frustum.hpp)
 };
 
@@ -328,7 +329,7 @@ integrate_kernel(const IntegrateParams p)
             const float Wrk = 1;
             const short tnew = pack_tsdf(__fmaf_rn(tsdf_prev, weight_prev, tsdf) / (weight_prev + Wrk));   // (F * W + Wrk * tsdf) / (W + Wrk), Wrk = 1
             p.tsdf[addr[u]] = tnew;
-            if (MG && tnew != tprev[u]) {
+            if (MG && !p.mg_no_publish && tnew != tprev[u]) {
                 // the owner publishes a changed value to every replica (free-space voxels that stay at 32767 cause no traffic)
                 for (int g = 0; g < p.vv.world; ++g) if (g != p.vv.rank) p.vv.tsdf[g][addr[u]] = tnew;
             }
@@ -474,6 +475,8 @@ int integrate(const IntegrateArgs& a, float* ztable_dev, cudaStream_t s)
     const bool idx32 = !force64 && (size_t)V * V * V <= ((size_t)1 << 31);
     p.lz_lo = 0; p.lz_hi = V;
     p.seq_replay = seq_replay ? 1 : 0;
+    static const bool no_publish = getenv("KT_MG_NO_PUBLISH") != nullptr;
+    p.mg_no_publish = no_publish ? 1 : 0;
     p.tiles_x = div_up(V, 32); p.tiles_y = div_up(V, 8); p.tile_x0 = 0; p.tile_y0 = 0;
     dim3 block(32, 8), grid(p.tiles_x, p.tiles_y, div_up(V, p.zchunk));
     // Launch only the storage tiles and z chunks the view frustum can reach (kt_frustum.hpp: a conservative box in logical voxel
