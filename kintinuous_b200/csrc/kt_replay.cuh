@@ -100,6 +100,16 @@ KT_HD __forceinline__ float rp_fma(float m, float f, float x) {
 #endif
 }
 
+// 2^e as a double, e in [-1022, 1023], from its exponent bits
+KT_HD __forceinline__ double rp_pow2(int e) {
+    const uint64_t b = (uint64_t)(1023 + e) << 52;
+#ifdef __CUDA_ARCH__
+    return __longlong_as_double((long long)b);
+#else
+    double d; memcpy(&d, &b, 8); return d;
+#endif
+}
+
 KT_HD inline float replay_fma(float x, float m, float f, int k)
 {
     if (k <= 0) return x;
@@ -113,8 +123,8 @@ KT_HD inline float replay_fma(float x, float m, float f, int k)
         const int ex = (int)((xb >> 23) & 0xffu);
         if (ex != 0 && ex != 255) {
             // q = P / u scaled into the magnitude direction of x: positive q_m grows |x|.  u = 2^(ex - 150).
-            const double scale = ex >= 150 ? 1.0 / (double)(1ull << (ex - 150 < 63 ? ex - 150 : 62)) : (double)(1ull << (150 - ex < 63 ? 150 - ex : 62));
             if (ex > 150 - 62 && ex < 150 + 62) {
+                const double scale = rp_pow2(150 - ex);          // 1 / u as an exact power of two, built from its exponent bits (no division)
                 double q = P * scale;                           // exact (power-of-two scaling, no overflow in these ranges)
                 if (xb >> 31) q = -q;
                 if (q < 16777216.0 && q > -16777216.0) {
@@ -126,13 +136,15 @@ KT_HD inline float replay_fma(float x, float m, float f, int k)
                             // |P| < u/2: x is a fixed point -- unless x sits on its binade's lower edge and shrinks (finer ulp below)
                             if (q >= 0.0 || X != 0x800000u) return x;
                         } else {
-                            const long long Ai = (long long)A;
-                            long long n;
-                            if (Ai > 0) n = (long long)(0xffffffu - X) / Ai;
-                            else n = X > 0x800000u ? (long long)(X - 0x800001u) / (-Ai) : 0;
-                            if (n > k) n = k;
+                            // |A| < 2^24 and the room inside the binade < 2^24: 32-bit unsigned division (the 64-bit one is a long emulated
+                            // sequence on the GPU, and this chain is the set-up latency of every integrate_kernel thread)
+                            const int32_t Ai = (int32_t)A;
+                            uint32_t n;
+                            if (Ai > 0) n = (0xffffffu - X) / (uint32_t)Ai;
+                            else n = X > 0x800000u ? (X - 0x800001u) / (uint32_t)(-Ai) : 0u;
+                            if (n > (uint32_t)k) n = (uint32_t)k;
                             if (n > 0) {
-                                const uint32_t Xn = (uint32_t)((long long)X + n * Ai);
+                                const uint32_t Xn = (uint32_t)((int32_t)X + (int32_t)n * Ai);
                                 x = rp_float((xb & 0xff800000u) | (Xn & 0x7fffffu));
                                 k -= (int)n;
                             }
