@@ -312,6 +312,15 @@ rgbd_frame_kernel(const RgbdFrameParams p)
 
     int it = 0, ex = 0;                      // iteration / exchange counters (two exchanges per iteration)
     GridSumState gs; gs.prev[0] = 0ull; gs.prev[1] = 0ull;
+    // where lane l's component of the photometric sums lands in a trace record (A 6x6 row-major symmetric | b): rows of 7, 6, 5, ... entries
+    int trace_a = -1, trace_b = -1;
+    if ((threadIdx.x & 31) < 27) {
+        const int ln = threadIdx.x & 31;
+        int i = 0, base = 0;
+        while (ln >= base + (7 - i) && i < 6) { base += 7 - i; ++i; }
+        const int j = i + (ln - base);
+        if (j == 6) trace_a = 36 + i; else { trace_a = j * 6 + i; trace_b = i * 6 + j; }
+    }
     double icp_total = 0.0;                  // warp 0, lane l: grid total of ICP component l of this iteration
     unsigned int stage_parity = 0;
     for (int level = LEVELS - 1; level >= 0; --level) {
@@ -516,15 +525,9 @@ rgbd_frame_kernel(const RgbdFrameParams p)
                 }
                 if (p.trace && blockIdx.x == 0 && it < 64) {            // the photometric part alone, like the reference's A_rgb / b_rgb
                     float* t = p.trace + (size_t)it * TRACE_STRIDE;
-                    if (lane < NSUM) {
-                        const float value = (float)total;
-                        int i = 0, base = 0;
-                        while (lane >= base + (7 - i) && i < 6) { base += 7 - i; ++i; }
-                        if (lane < 27) {
-                            const int j = i + (lane - base);
-                            if (j == 6) t[36 + i] = value; else { t[j * 6 + i] = value; t[i * 6 + j] = value; }
-                        }
-                    }
+                    const float value = (float)total;              // component -> (row, column) worked out once per launch (trace_a / trace_b): CTA 0 is on every exchange's critical path
+                    if (trace_a >= 0) t[trace_a] = value;
+                    if (trace_b >= 0) t[trace_b] = value;
                     if (lane == 0) { t[42] = (float)rgb_sigma; t[43] = (float)rgb_count; }
                 }
             }

@@ -718,8 +718,11 @@ int kt_create(const kt_config* cfg, kt_ctx** out)
     c->cloud_capacity = (size_t)c->cfg.cloud_capacity;
     KT_TRY(dev_alloc(c, &c->cloud_dev, c->cloud_capacity)); KT_TRY(dev_alloc(c, &c->counter_dev, 1));
     c->slice_arena = new PinnedArena();
-    KT_CUDA(cudaStreamCreateWithFlags(&c->stream_slices, cudaStreamNonBlocking));
-    KT_CUDA(cudaEventCreateWithFlags(&c->ev_cloud_ready, cudaEventDisableTiming)); KT_CUDA(cudaEventCreateWithFlags(&c->ev_cloud_free, cudaEventDisableTiming));
+    if (!c->slice_arena->alloc(256)) { set_error("kt_create: pinned slice arena"); kt_destroy(c); return KT_ERR_CUDA; }      // the first 64 MB slab now, not inside the first shift frame
+    c->slice_arena->rewind();
+    KT_TRY(kt::cuda_check(cudaStreamCreateWithFlags(&c->stream_slices, cudaStreamNonBlocking), "stream_slices", __FILE__, __LINE__));
+    KT_TRY(kt::cuda_check(cudaEventCreateWithFlags(&c->ev_cloud_ready, cudaEventDisableTiming), "event", __FILE__, __LINE__));
+    KT_TRY(kt::cuda_check(cudaEventCreateWithFlags(&c->ev_cloud_free, cudaEventDisableTiming), "event", __FILE__, __LINE__));
     KT_TRY(kt::cuda_check(cudaMallocHost((void**)&c->pose12_host, 12 * sizeof(float)), "pinned", __FILE__, __LINE__));
     KT_TRY(kt::cuda_check(cudaHostAlloc((void**)&c->result_host, sizeof(OdomResult), cudaHostAllocMapped), "pinned", __FILE__, __LINE__));
     std::memset(c->result_host, 0, sizeof(OdomResult));
