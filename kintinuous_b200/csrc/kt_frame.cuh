@@ -76,6 +76,47 @@ __device__ __forceinline__ double grid_sum_words(unsigned long long* words, int 
     return from_fixed32(grid_sum_fixed(words, ex, lane, lane < NSUM, to_fixed32(partial), st, G, timeout));
 }
 
+
+// ---- the same exchange ACROSS GPUs (shared-volume mode with the pixel rows of every level split over the ranks): every CTA of every rank
+// adds its partial to the word of EVERY rank -- one system-scope red.add per rank over NVLink peer memory, fire-and-forget -- and polls its
+// LOCAL word until all world * G contributions are in.  This is the north_star's per-iteration all-reduce of the 29 normal-equation sums,
+// fused into the kernel: no collective library call, no second kernel, and because integer addition commutes every rank reads
+// bit-identical totals (hence identical poses) whatever the arrival order.  12 count bits (up to 4095 CTAs), so partials are rounded to
+// 2^-20 instead of 2^-24 (still far below the float partials' own rounding for every entry that matters to the solve).
+__device__ __forceinline__ void red_add_sys_u64(unsigned long long* p, unsigned long long v)
+{ asm volatile("red.relaxed.sys.global.add.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p)
+{ unsigned long long v; asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
+
+struct PeerWords { unsigned long long* w[8]; int world; };
+
+__device__ __forceinline__ double grid_sum_words_mg(const PeerWords& pw, int rank, int ex, int lane, float partial, GridSumState& st, unsigned int G_total, int* timeout)
+{
+    long long total = 0;
+    if (lane < NSUM) {
+        const int par = ex & 1;
+        const size_t off = ((size_t)par * 32 + lane) * XW_STRIDE;
+        const long long q = __double2ll_rn((double)partial * 4294967296.0) & ~0xFFFll;
+        for (int g = 0; g < pw.world; ++g) red_add_sys_u64(pw.w[g] + off, (unsigned long long)(q + 1));
+        const unsigned long long* w = pw.w[rank] + off;
+        const unsigned long long prev = par ? st.prev[1] : st.prev[0];
+        unsigned long long now, d;
+        unsigned int spins = 0; long long t0 = 0;
+        for (;;) {
+            now = ld_relaxed_sys_u64(w); d = now - prev;
+            if ((unsigned int)(d & 0xFFFull) == G_total) break;
+            if ((++spins & 0x3FFFu) == 0) {
+                const long long t = clock64();
+                if (t0 == 0) t0 = t;
+                else if (t - t0 > 4000000000LL) { if (timeout) *timeout = 1; break; }
+            }
+        }
+        if (par) st.prev[1] = now; else st.prev[0] = now;
+        total = (long long)(d - (unsigned long long)G_total);
+    }
+    return from_fixed32(total);
+}
+
 // ---- TMA (bulk async copy engine) helpers: global -> shared 1-D bulk copies completing on an mbarrier ----
 __device__ __forceinline__ unsigned int smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned int count)

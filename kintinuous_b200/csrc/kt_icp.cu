@@ -161,6 +161,7 @@ struct IcpFrameParams {
     long long* prof;           // optional: clock64() stamps per iteration from CTA 0 (debug)
     int stage_k;               // passes of FRAME_THREADS pixels per CTA that fit the shared-memory stage (0 = no staging)
     float* host_pose; unsigned int host_seq;      // optional mapped host record: pose (12), time-out (1), sequence number (1)
+    PeerWords pw; int rank;                       // pw.world > 1: the pixel rows are split over the ranks of a shared volume (grid_sum_words_mg)
 };
 
 template <int ICP_BATCH>
@@ -211,8 +212,10 @@ icp_frame_kernel(const IcpFrameParams p)
         const float dist_thres = a.dist_thres, angle_thres = a.angle_thres;
         // pixels of this CTA: ONE contiguous range of q = ceil(N / G) pixels (rounded up to the 16-byte TMA granule), so that every SM
         // gets the same share
-        const int q = (((N + G - 1) / G) + 3) & ~3;
-        const int i_begin = min(N, (int)blockIdx.x * q), cnt = min(N, i_begin + q) - i_begin;
+        // (split over the ranks of a shared volume: world * G CTAs, this one is number rank * G + blockIdx.x)
+        const int GT = G * p.pw.world, gci = p.rank * G + (int)blockIdx.x;
+        const int q = (((N + GT - 1) / GT) + 3) & ~3;
+        const int i_begin = min(N, gci * q), cnt = min(N, i_begin + q) - i_begin;
         const int n_pass = (q + FRAME_THREADS - 1) / FRAME_THREADS;
         const int ps = p.stage_k * FRAME_THREADS;                    // floats per staged plane
         const bool staged = (p.stage_k > 0) && (n_pass <= p.stage_k) && ((N & 3) == 0);
@@ -272,7 +275,7 @@ icp_frame_kernel(const IcpFrameParams p)
                     }
                 }
             } else {
-                for (int i = blockIdx.x * FRAME_THREADS + tid; i < N; i += G * FRAME_THREADS) {
+                for (int i = gci * FRAME_THREADS + tid; i < N; i += GT * FRAME_THREADS) {
                     const float3 vc = make_float3(__ldg(&vmap_curr[i]), __ldg(&vmap_curr[i + N]), __ldg(&vmap_curr[i + 2 * N]));
                     const float3 nc = make_float3(__ldg(&nmap_curr[i]), __ldg(&nmap_curr[i + N]), __ldg(&nmap_curr[i + 2 * N]));
                     icp_pixel_staged(vc, nc, N, cols, rows, vmap_g_prev, nmap_g_prev, intr, Rcurr, tcurr, Rprev_inv, tprev, dist_thres, angle_thres, sum);
@@ -289,7 +292,8 @@ icp_frame_kernel(const IcpFrameParams p)
 #pragma unroll
                 for (int w = 0; w < FRAME_THREADS / 32; ++w) v += s_red[w][lane];
                 if (prof) p.prof[it * 8 + 1] = clock64();
-                const double total = grid_sum_words(p.xwords, it, lane, v, gs, (unsigned int)G, p.timeout);
+                const double total = p.pw.world > 1 ? grid_sum_words_mg(p.pw, p.rank, it, lane, v, gs, (unsigned int)GT, p.timeout)
+                                                    : grid_sum_words(p.xwords, it, lane, v, gs, (unsigned int)G, p.timeout);
                 s_sumd[lane] = total;
                 __syncwarp();
                 if (prof) p.prof[it * 8 + 2] = clock64();
@@ -385,9 +389,12 @@ int odom_begin_frame(OdomState* state, const float* pose12_dev, cudaStream_t s)
 // Whole-frame ICP (ICP-only odometry).  pose12 = Rprev (9) + tprev (3) on the host; the result lands in state->Rcurr/tcurr.
 // xwords_dev: XW_WORDS 64-bit exchange words, ZERO when the launch starts (the tracker resets them once per frame, kt_tracker.cu).
 int icp_frame(const IcpLevelArgs* levels, const int* iters, const float* pose12_host, OdomState* state, unsigned long long* xwords_dev,
-              float* trace, int* timeout_dev, long long* prof_dev, float* host_pose, unsigned int host_seq, cudaStream_t s)
+              float* trace, int* timeout_dev, long long* prof_dev, float* host_pose, unsigned int host_seq, cudaStream_t s,
+              unsigned long long* const* peer_words, int world, int rank)
 {
     IcpFrameParams p;
+    p.pw.world = (peer_words && world > 1) ? world : 1; p.rank = p.pw.world > 1 ? rank : 0;
+    for (int g = 0; g < 8; ++g) p.pw.w[g] = (p.pw.world > 1 && g < world) ? peer_words[g] : xwords_dev;
     p.host_pose = host_pose; p.host_seq = host_seq;
     p.prof = prof_dev;
     for (int l = 0; l < LEVELS; ++l) { p.lv[l] = levels[l]; p.iters[l] = iters[l]; }
@@ -398,7 +405,7 @@ int icp_frame(const IcpLevelArgs* levels, const int* iters, const float* pose12_
     // shared-memory stage for the current maps: 6 planes x stage_k x 2 KB (one contiguous pixel range per CTA), sized for the largest level in use
     int need_k = 0;
     for (int l = 0; l < LEVELS; ++l)
-        if (iters[l] > 0) { int q = (div_up(levels[l].rows * levels[l].cols, grid) + 3) & ~3; int k = div_up(q, FRAME_THREADS); if (k > need_k) need_k = k; }
+        if (iters[l] > 0) { int q = (div_up(levels[l].rows * levels[l].cols, grid * p.pw.world) + 3) & ~3; int k = div_up(q, FRAME_THREADS); if (k > need_k) need_k = k; }
     DeviceInfo& di = device_info();
     const int smem_optin = di.smem_optin;
     if (!(di.configured & 1u)) {

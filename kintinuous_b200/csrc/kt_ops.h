@@ -102,8 +102,11 @@ struct IcpLevelArgs {
 //   mode 1: reduce + LDLT solve + pose update on device (ICP-only odometry)
 int icp_iteration(const IcpLevelArgs& a, OdomState* state, float* partials, float* trace, int mode, cudaStream_t s);
 
+// peer_words / world / rank (optional): the exchange words of every rank of a shared volume (NVLink peer memory) -- the pixel rows of every
+// level are then split over the ranks and the 29 sums are all-reduced inside the kernel (grid_sum_words_mg, kt_frame.cuh)
 int icp_frame(const IcpLevelArgs* levels, const int* iters, const float* pose12_host, OdomState* state, unsigned long long* xwords_dev,
-              float* trace, int* timeout_dev, long long* prof_dev, float* host_pose, unsigned int host_seq, cudaStream_t s);
+              float* trace, int* timeout_dev, long long* prof_dev, float* host_pose, unsigned int host_seq, cudaStream_t s,
+              unsigned long long* const* peer_words = 0, int world = 1, int rank = 0);
 // exchange words of the whole-frame odometry kernels (grid_sum_words, kt_frame.cuh): their count, and the reset (zero) of a word array --
 // stream-ordered, once per frame between two odometry launches
 size_t odom_exchange_words();          // allocation size (64-bit words)

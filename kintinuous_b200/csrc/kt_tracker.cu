@@ -166,7 +166,8 @@ struct kt_ctx {
     // weight plane sharded block-cyclically by storage z (VolumeView, kt_ops.h)
     int world, rank, local_planes, mg_block;
     uint8_t* arena; size_t arena_bytes;
-    size_t off_tsdf, off_color, off_vmap[LEVELS], off_nmap[LEVELS], off_vcol, off_flags;
+    size_t off_tsdf, off_color, off_vmap[LEVELS], off_nmap[LEVELS], off_vcol, off_flags, off_xwords;
+    bool split_icp;            // KT_MG_SPLIT_ICP: pixel rows of the ICP split over the ranks, normal equations all-reduced in the kernel over peer memory
     uint8_t* peer_arena[MAX_GPUS]; bool connected;
     unsigned int** peer_flags_dev; unsigned int epoch; int* mg_error_dev; int* mg_error_host;
     VolumeView vv;
@@ -297,8 +298,10 @@ int run_odometry(kt_ctx* c, const M3& Rprev, const V3& tprev, M3* Rcurr, V3* tcu
         if (!c->xwords_clean && (r = odom_exchange_reset(c->xwords_dev, c->stream))) return r;
         c->xwords_clean = false;
         ++c->pose_seq;
+        unsigned long long* peers[MAX_GPUS];
+        for (int g = 0; g < MAX_GPUS; ++g) peers[g] = (unsigned long long*)(c->peer_arena[g] + c->off_xwords);
         if ((r = icp_frame(la, c->iterations, c->pose12_host, c->state, c->xwords_dev, c->trace_dev, &c->state->odo_timeout, c->timing ? c->prof_dev : 0,
-                           c->pose_spin ? c->result_dev_alias : 0, c->pose_seq, c->stream))) return r;
+                           c->pose_spin ? c->result_dev_alias : 0, c->pose_seq, c->stream, c->split_icp ? peers : 0, c->world, c->rank))) return r;
         if (c->timing) cudaEventRecord(c->ev_icp[1], c->stream);
     }
     const double SOBEL_SCALE = 1.0 / std::pow(2.0, 3);
@@ -668,9 +671,13 @@ int kt_create(const kt_config* cfg, kt_ctx** out)
         for (int l = 0; l < LEVELS; ++l) { size_t Pl = P >> (2 * l); c->off_vmap[l] = off; off = al(off + Pl * 12); c->off_nmap[l] = off; off = al(off + Pl * 12); }
         c->off_vcol = off; off = al(off + P * 4);
         c->off_flags = off; off = al(off + 256);
+        c->off_xwords = off; off = al(off + odom_exchange_words() * sizeof(unsigned long long));      // in the arena so that peers can add to them
         c->arena_bytes = off;
         KT_TRY(dev_alloc(c, &c->arena, off));
         KT_TRY(kt::cuda_check(cudaMemset(c->arena + c->off_flags, 0, 256), "memset", __FILE__, __LINE__));
+        c->xwords_dev = (unsigned long long*)(c->arena + c->off_xwords);
+        KT_TRY(kt::cuda_check(cudaMemset(c->xwords_dev, 0, odom_exchange_words() * sizeof(unsigned long long)), "memset", __FILE__, __LINE__)); c->xwords_clean = true;
+        c->split_icp = c->world > 1 && getenv("KT_MG_SPLIT_ICP") != nullptr;
         c->tsdf = (int16_t*)(c->arena + c->off_tsdf); c->color = c->arena + c->off_color;
         for (int g = 0; g < MAX_GPUS; ++g) c->peer_arena[g] = c->arena;
         c->connected = (c->world == 1);
@@ -708,8 +715,7 @@ int kt_create(const kt_config* cfg, kt_ctx** out)
     }
     c->vmap_curr_color = c->arena + c->off_vcol; KT_TRY(dev_alloc(c, &c->depth_scaled, P)); KT_TRY(dev_alloc(c, &c->depth_scaled_alt, P)); c->pf_built = false; c->frontend_ready = false;
     KT_TRY(dev_alloc(c, &c->ztable, (size_t)2 * cfg->vol)); KT_TRY(dev_alloc(c, &c->cw_scratch, P)); KT_TRY(dev_alloc(c, &c->rgbf_scratch, P * 4)); KT_TRY(dev_alloc(c, &c->cw_alt, P)); KT_TRY(dev_alloc(c, &c->rgbf_alt, P * 4));
-    KT_TRY(dev_alloc(c, &c->xwords_dev, odom_exchange_words()));
-    KT_TRY(kt::cuda_check(cudaMemset(c->xwords_dev, 0, odom_exchange_words() * sizeof(unsigned long long)), "memset", __FILE__, __LINE__)); c->xwords_clean = true;
+
     KT_TRY(dev_alloc(c, &c->state, 1)); KT_TRY(dev_alloc(c, &c->partials, (size_t)MAX_PARTIALS * 32));
     KT_TRY(kt::cuda_check(cudaMemset(c->partials, 0, (size_t)MAX_PARTIALS * 32 * sizeof(float)), "memset", __FILE__, __LINE__));   // tags start at 0
     KT_TRY(dev_alloc(c, &c->bar_dev, 1)); KT_TRY(kt::cuda_check(cudaMemset(c->bar_dev, 0, sizeof(unsigned int)), "memset", __FILE__, __LINE__)); c->bar_count = 0;
