@@ -85,6 +85,8 @@ struct kt_klg {
 
 extern "C" {
 
+int kt_klg_close(kt_klg* k);
+
 int kt_klg_open(const char* path, int rows, int cols, int device, kt_klg** out)
 {
     if (!path || !out || rows <= 0 || cols <= 0) { set_error("kt_klg_open: bad argument"); return KT_ERR_INVALID; }
@@ -98,12 +100,16 @@ int kt_klg_open(const char* path, int rows, int cols, int device, kt_klg** out)
     k->fp = fp; k->rows = rows; k->cols = cols; k->device = device; k->num_frames = n; k->current = 0; k->flip_colors = 0; k->set = 1;
     k->P = (size_t)rows * cols;
     k->comp_depth.resize(k->P * 2); k->comp_image.resize(k->P * 3);
-    for (int i = 0; i < 2; ++i) {
-        KT_CUDA(cudaMallocHost((void**)&k->depth_pinned[i], k->P * 2)); KT_CUDA(cudaMallocHost((void**)&k->image_pinned[i], k->P * 3));
-        KT_CUDA(cudaMalloc((void**)&k->depth_dev[i], k->P * 2)); KT_CUDA(cudaMalloc((void**)&k->rgb_dev[i], k->P * 3));
-        KT_CUDA(cudaEventCreateWithFlags(&k->done[i], cudaEventDisableTiming));
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        if ((e = cudaMallocHost((void**)&k->depth_pinned[i], k->P * 2)) != cudaSuccess) break;
+        if ((e = cudaMallocHost((void**)&k->image_pinned[i], k->P * 3)) != cudaSuccess) break;
+        if ((e = cudaMalloc((void**)&k->depth_dev[i], k->P * 2)) != cudaSuccess) break;
+        if ((e = cudaMalloc((void**)&k->rgb_dev[i], k->P * 3)) != cudaSuccess) break;
+        if ((e = cudaEventCreateWithFlags(&k->done[i], cudaEventDisableTiming)) != cudaSuccess) break;
     }
-    KT_CUDA(cudaStreamCreateWithFlags(&k->stream, cudaStreamNonBlocking));
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&k->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { kt_klg_close(k); return cuda_check(e, "kt_klg_open: buffers", __FILE__, __LINE__); }
     memset(&k->last, 0, sizeof(k->last));
     *out = k;
     return KT_OK;
