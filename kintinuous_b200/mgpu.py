@@ -49,3 +49,14 @@ def connect(tracker, group=None):
     tracker.mgpu_connect(handles)
     dist.barrier(group)
     return handles
+
+
+def icp_pixel_range(rank: int, world: int, cta: int, ctas: int, n_pixels: int):
+    """Pixel range [begin, begin + count) of one CTA of icp_frame_kernel at a pyramid level with n_pixels pixels when the rows are split over
+    the ranks of a shared volume (KT_MG_SPLIT_ICP; kt_icp.cu: GT = G * world CTAs, this one is number rank * G + cta, q pixels each, rounded
+    up to the 16-byte TMA granule).  world = 1 is the single-GPU partition."""
+    gt = ctas * world
+    gci = rank * ctas + cta
+    q = (((n_pixels + gt - 1) // gt) + 3) & ~3
+    begin = min(n_pixels, gci * q)
+    return begin, min(n_pixels, begin + q) - begin

@@ -64,3 +64,25 @@ def test_control_plane_world2_gloo(tmp_path):
                           str(script), ROOT], capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count("ok") == 2
+
+
+def test_split_icp_pixel_partition_covers_every_pixel_once():
+    """KT_MG_SPLIT_ICP: world * 148 CTAs split the pixels of every pyramid level; the ranges must tile [0, N) exactly, be 4-pixel aligned (the
+    TMA bulk copies need 16-byte granules) and fit the shared-memory stage the host sizes for them."""
+    from kintinuous_b200 import mgpu
+    for rows, cols in ((480, 640), (960, 1280)):
+        for level in range(3):
+            n = (rows >> level) * (cols >> level)
+            for world in (1, 2, 4, 8):
+                ctas = 148
+                seen = 0
+                worst = 0
+                for rank in range(world):
+                    for cta in range(ctas):
+                        b, c = mgpu.icp_pixel_range(rank, world, cta, ctas, n)
+                        assert b == min(n, seen) and c >= 0 and b % 4 == 0
+                        seen += c
+                        worst = max(worst, c)
+                assert seen == n
+                # the stage holds ceil(q / 512) passes of 512 pixels x 6 planes x 4 bytes (kt_icp.cu, STAGE_MAX_K = 17)
+                assert -(-worst // 512) <= 17
